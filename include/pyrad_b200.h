@@ -1,0 +1,139 @@
+/* pyrad_b200.h -- C ABI of libpyrad_b200.so, the B200 (sm_100a) engine behind PyRad's
+ * gas-cell / atmosphere line-by-line path.
+ *
+ * The reference (bschrag620/PyRad) is pure Python + numpy and has NO plugin / FFI
+ * interface.  The seam this library replaces is the method
+ * edge between the host object model and the numpy physics:
+ *
+ *   pyradClasses.py:361-407  Isotope.createCrossSection   -> prb_upload_lines + prb_set_grid
+ *                                                            + prb_layer_prepass + prb_line_sum
+ *   pyradClasses.py:252-263  Line.broadenedLine/lorentzHW/gaussianHW      \
+ *   pyradIntensity.py:16-32  intensityFactor                               > prb_layer_prepass (K1)
+ *   pyradLineshape.py:22-29,58-71 half widths, pseudo-Voigt f and eta      /
+ *   pyradLineshape.py:32-76  gaussian/lorentz/pseudoVoigt shapes + the scatter loop
+ *                            pyradClasses.py:392-400                       -> prb_line_sum (K2)
+ *   pyradClasses.py:581-587,707-716 absCoef / transmittance                \
+ *   pyradPlanck.py:38-44     planckWavenumber                               > prb_layer_stream (K3)
+ *   pyradClasses.py:784-787  Layer.transmission                            /
+ *   pyradClasses.py:159-162,493-500 xsc np.interp + aligned placement      -> prb_xsc_place
+ *   (absent upstream) multi-layer fold of Layer.transmission   -> prb_atmosphere
+ *
+ * Conventions: every entry point is extern "C", returns int (0 = PRB_OK, < 0 = error) unless
+ * noted, takes plain pointers and sizes.  Pointers named *_host / unmarked are caller-owned host
+ * buffers (C-contiguous); pointers named *_dev are CUDA device pointers valid on the engine's
+ * device.  Host-buffer entry points copy H2D/D2H internally and block until the result is in the
+ * caller's buffer.  *_dev entry points only enqueue on the engine's stream (prb_stream) and
+ * return; call prb_synchronize (which also reports deferred device-side errors).
+ * One engine per process per device; an engine is not re-entrant.  There is NO CPU fallback:
+ * prb_create fails when no sm_100-class CUDA device is usable.
+ */
+#ifndef PYRAD_B200_H
+#define PYRAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRB_OK               0
+#define PRB_ERR_CUDA        -1   /* CUDA runtime error (see prb_last_error) */
+#define PRB_ERR_ARG         -2   /* invalid argument */
+#define PRB_ERR_STATE       -3   /* call order violated (e.g. line_sum before prepass) */
+#define PRB_ERR_RANGE       -4   /* grid segment too large for exact FP32 offsets, or coefficient overflow */
+#define PRB_ERR_NODEVICE    -5   /* no usable CUDA device: there is no CPU fallback */
+
+#define PRB_ABI_VERSION      1
+
+/* prb_line_sum output modes */
+#define PRB_OUT_F64          0   /* double per grid point */
+#define PRB_OUT_F32          1   /* float per grid point (atmosphere k-matrix rows) */
+
+/* K2 kernel variants (for A/B parity tests and profiling) */
+#define PRB_K2_GENERAL       0   /* every staged line through the predicated two-term path */
+#define PRB_K2_CLASSED       1   /* per-warp window classes + paired-reciprocal far path (default) */
+
+typedef struct prb_engine prb_engine;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int         prb_abi_version(void);
+const char *prb_last_error(void);                       /* thread-local, never NULL */
+int         prb_create(int device, prb_engine **out);
+int         prb_destroy(prb_engine *e);
+void       *prb_stream(prb_engine *e);                  /* the engine's cudaStream_t */
+int         prb_synchronize(prb_engine *e);             /* stream sync + deferred device status */
+int         prb_device_info(prb_engine *e, int *sm_count, int *cc_major, int *cc_minor,
+                            int *sm_clock_khz, size_t *free_bytes, size_t *total_bytes);
+int         prb_set_k2_variant(prb_engine *e, int variant, int points_per_thread /* 0 = auto */);
+
+/* ---- line list (a1): SoA float64, ascending nu0; group[i] in [0, n_groups) or NULL (all 0) - */
+int prb_upload_lines(prb_engine *e, int64_t n,
+                     const double *nu0, const double *s296,
+                     const double *gamma_air, const double *gamma_self,
+                     const double *elower, const double *n_air, const double *delta_air,
+                     const int32_t *group, int32_t n_groups);
+
+/* ---- grid (a10/a11): point i of the FULL grid sits at range_min + i*res, i in [0, n_total).
+ * This engine (rank) owns the contiguous chunk [i_begin, i_end).  Computes every line's
+ * arrayIndex = int((nu0 - range_min)/res) (FP64 divide, truncation toward zero) on the device. */
+int prb_set_grid(prb_engine *e, double range_min, double res,
+                 int64_t n_total, int64_t i_begin, int64_t i_end);
+
+/* ---- K1 (a2-a6, a9 coefficients): per-layer, per-line prepass.
+ * Per group g: conc[g] = molecule mole fraction, molmass[g] in g/mol, q_t[g] = Q(T), q_296[g] = Q(296),
+ * weight[g] multiplies the group's contribution (1.0 for a cross section; conc*P/1e4/k/T for an
+ * absorption coefficient).  window_len = W = len(np.arange(0, cutoff, res)). */
+int prb_layer_prepass(prb_engine *e, double T, double P, int32_t n_groups,
+                      const double *conc, const double *molmass,
+                      const double *q_t, const double *q_296, const double *weight,
+                      int64_t window_len);
+
+/* ---- K2 (a7-a10): sum of line shapes into the owned grid chunk; out has i_end-i_begin entries. */
+int prb_line_sum(prb_engine *e, double *out_host);
+int prb_line_sum_dev(prb_engine *e, void *out_dev, int out_mode);
+int64_t prb_pair_count(prb_engine *e);                  /* accumulations of the last prepass' window on the owned chunk; <0 = error */
+
+/* ---- K1 introspection for parity tests: FP64 per-line values of the last prepass (host buffers,
+ * n entries each, any may be NULL): shifted nu, gamma_L, gamma_D, S(T), regime (0 G, 1 L, 2 V), index */
+int prb_debug_line_params(prb_engine *e, double *nu_shift, double *gamma_l, double *gamma_d,
+                          double *s_t, int32_t *regime, int64_t *index);
+
+/* ---- K3 (a13-a16): fused pointwise layer physics on host buffers, FP64.
+ * sigma: n_mol rows of n points (row-major).  weight[m] = conc*P/1e4/k/T.  nu_i = x0 + i*dx for
+ * i < n-1 and x_last for i = n-1 (np.linspace semantics; pass the values of Layer.xAxis).
+ * Outputs (any may be NULL): abs_coef, transmittance, radiance_out = T*radiance_in + (1-T)*B(nu,t_layer).
+ * radiance_in may be NULL when radiance_out is NULL. */
+int prb_layer_stream(prb_engine *e, int64_t n, int32_t n_mol, const double *sigma,
+                     const double *weight, double depth_cm, double t_layer,
+                     double x0, double dx, double x_last,
+                     const double *radiance_in,
+                     double *abs_coef, double *transmittance, double *radiance_out);
+
+/* planckWavenumber on the same axis convention (pyradPlanck.py:38-44) */
+int prb_planck(prb_engine *e, int64_t n, double x0, double dx, double x_last, double temp, double *out);
+
+/* ---- xsc (a17): out[n_out]: zeros, except out[dst0 + j] = src(src0 + j) for j in [0, count), where
+ * src(m) = file_y[m] when interp == 0, else np.interp(ax0 + m*adelta, file_x, file_y). */
+int prb_xsc_place(prb_engine *e, int64_t n_out, int64_t dst0, int64_t src0, int64_t count,
+                  int interp, double ax0, double adelta,
+                  int64_t n_file, const double *file_x, const double *file_y, double *out);
+
+/* ---- atmosphere (cfg 4): L layers bottom -> top on the owned chunk, everything on the device:
+ * per layer K1 + K2 (absorption-coefficient mode, FP32 row of the k matrix), then ONE K3 pass
+ * folding I <- T_l*I + (1-T_l)*B(nu, t[l]) with I_0 = B(nu, t_surface).  Per-layer arrays have L
+ * entries; per-(layer, group) arrays are L x n_groups row-major.  nu for Planck follows the
+ * reference's Layer.xAxis: linspace(range_min, range_max, n_total).
+ * Results stay on the device (prb_atmosphere_result_dev) or are copied out (prb_atmosphere_read). */
+int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
+                   const double *depth_cm, const double *t_layer, const double *p_layer,
+                   const double *conc, const double *molmass, const double *q_t, const double *q_296,
+                   const int64_t *window_len, double t_surface, double range_max);
+int prb_atmosphere_result_dev(prb_engine *e, void **radiance_dev, void **transmittance_dev); /* float[chunk] each */
+int prb_atmosphere_read(prb_engine *e, double *radiance_host, double *transmittance_host);
+int prb_atmosphere_kmatrix_dev(prb_engine *e, void **kmat_dev, int64_t *ld);                 /* float[L][ld] */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYRAD_B200_H */

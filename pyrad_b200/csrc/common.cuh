@@ -1,0 +1,45 @@
+// common.cuh -- shared definitions for libpyrad_b200 (sm_100a only; no other backend exists).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace prb {
+
+// Physical constants exactly as the reference spells them
+// (pyradIntensity.py:3-13, pyradLineshape.py:14-19, pyradPlanck.py:4-9, pyradClasses.py:15-23).
+constexpr double kBoltz = 1.38064852E-23;
+constexpr double cLight = 299792458.0;
+constexpr double hPlanck = 6.62607004e-34;
+constexpr double kPi = 3.141592653589793;
+constexpr double kT0 = 296.0;
+constexpr double kP0 = 1013.25;
+constexpr double kAvogadro = 6.022140857E23;
+
+constexpr int REGIME_GAUSS = 0, REGIME_LORENTZ = 1, REGIME_VOIGT = 2;
+
+// Per-group (isotopologue) scalars for one layer, built on the host in FP64.
+struct GroupParams {
+    double conc;     // molecule mole fraction q            (pyradClasses.py:258)
+    double dopp;     // sqrt(2 k T / m / c^2)               (pyradClasses.py:263)
+    double qratio;   // Q(296) / Q(T)                       (pyradIntensity.py:31)
+    double weight;   // output weight folded into the coefficients
+};
+
+// Small device-resident state block, cleared before every prepass.
+struct DevState {
+    unsigned int dg_max_bits;   // max near-zone radius (float bits, >= 0) over the processed lines
+    unsigned int flags;         // bit0: coefficient overflow, bit1: non-finite coefficient
+    unsigned int tile_counter;  // dynamic tile scheduler of K2 (work distribution only, never data)
+    unsigned int pad;
+};
+
+constexpr unsigned int FLAG_OVERFLOW = 1u, FLAG_NONFINITE = 2u;
+
+// K2 geometry
+constexpr int K2_THREADS = 256;          // 8 warps per CTA
+constexpr int K2_CHUNK = 512;            // lines staged per TMA bulk copy
+constexpr int K2_FLUSH = 64;             // lines accumulated in FP32 before flushing into FP64
+constexpr float K2_SENTINEL = 3.0e38f;   // fidx of padding records: outside every window
+
+}  // namespace prb

@@ -1,0 +1,146 @@
+// k1_prepass.cuh -- K0 (line -> grid index) and K1 (per-layer, per-line prepass), FP64.
+//
+// K1 restates, per line, in FP64 (one thread per line, SoA loads fully coalesced):
+//   shifted nu          pyradClasses.py:252-254   nu* = nu0 + delta * P / p0
+//   Lorentz half width  pyradClasses.py:256-259   ((1-q) g_air + q g_self) (P/p0) (t0/T)^n
+//   Doppler half width  pyradClasses.py:261-263   nu* sqrt(2kT/m/c^2)          (1/e half width)
+//   regime select       pyradClasses.py:378-387   ratio < .01 Gauss, > 100 Lorentz, else pseudo-Voigt
+//   S(T)                pyradIntensity.py:16-32   S296 (Q296/QT) stim(nu*,T) boltz(E'',T)
+//   pseudo-Voigt f, eta pyradLineshape.py:58-71
+// and packs what K2 needs into two FP32 records per line.  With d = i - idx (grid units):
+//   contribution(d) = A / (d^2 + B) + G * exp2(C * d^2)
+//   Voigt  : h = f/2;  A = S eta h / pi / res^2;  B = (h/res)^2;  G = S (1-eta) / (h sqrt(pi));  C = -log2(e)/B
+//   Lorentz: h = gL;   A = S h / pi / res^2;      B = (h/res)^2;  G = 0
+//   Gauss  : h = gD;   A = 0, B = 1;              G = S / (h sqrt(pi));  C = -log2(e) res^2 / h^2
+// which is algebraically the reference's S * shape(d * res) (pyradLineshape.py:32-76).
+// A and G additionally carry the group weight and a power-of-two scale (FP32 range), undone
+// exactly in K2's FP64 epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace prb {
+
+struct LinesSoA {
+    const double *nu0, *s296, *gair, *gself, *elower, *nair, *delta;
+    const int32_t *group;   // may be nullptr (single group)
+};
+
+struct DebugOut {
+    double *nu_shift, *gl, *gd, *st;
+    int32_t *regime;
+};
+
+// K0: arrayIndex = int((nu0 - rangeMin) / res)   (pyradClasses.py:390; FP64 divide, truncation
+// toward zero, UN-shifted nu0).  Saturated to int32; padding entries get INT32_MAX.
+__global__ void k0_line_index(const double *__restrict__ nu0, int64_t n, int64_t n_alloc,
+                              double range_min, double res, int32_t *__restrict__ idx) {
+    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_alloc) return;
+    if (l >= n) { idx[l] = INT32_MAX; return; }
+    double q = __ddiv_rn(__dsub_rn(nu0[l], range_min), res);
+    double t = trunc(q);
+    t = fmin(fmax(t, -2147483647.0), 2147483646.0);
+    idx[l] = (int32_t)t;
+}
+
+__device__ __forceinline__ double pow5(double x) { double x2 = x * x; return x2 * x2 * x; }
+
+__global__ void __launch_bounds__(256)
+k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__restrict__ gp,
+           int64_t l_begin, int64_t l_end, int64_t n_lines,
+           double T, double P, double res, double scale, int64_t i_base, double wm,
+           float4 *__restrict__ rec4, float2 *__restrict__ rec2, DevState *st, DebugOut dbg) {
+    const double c2 = cLight * hPlanck * 100 / kBoltz;          // pyradIntensity.py:13
+    int64_t l = l_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float dg = -1.0f;
+    unsigned int flags = 0;
+    if (l < l_end) {
+        if (l >= n_lines) {                                       // padding record: never in a window
+            rec4[l] = make_float4(K2_SENTINEL, 0.f, 1.f, 0.f);
+            rec2[l] = make_float2(-1.f, -1.f);
+        } else {
+            const int g = L.group ? L.group[l] : 0;
+            const GroupParams p = gp[g];
+            const double nu = L.nu0[l];
+            const double nus = nu + L.delta[l] * P / kP0;
+            const double gl = ((1 - p.conc) * L.gair[l] + p.conc * L.gself[l]) * (P / kP0) *
+                              pow(kT0 / T, L.nair[l]);
+            const double gd = nus * p.dopp;
+            const double ratio = gl / gd;                         // gd == 0 -> inf -> Lorentz, as numpy
+            const double stim = (1 - exp(-c2 * nus / T)) / (1 - exp(-c2 * nus / kT0));
+            const double boltz = exp(-c2 * L.elower[l] / T) / exp(-c2 * L.elower[l] / kT0);
+            const double S = L.s296[l] * p.qratio * stim * boltz;
+            const double sw = S * p.weight * scale;
+            const double res2 = res * res;
+            const double log2e = 1.4426950408889634;
+            const double sqrtpi = sqrt(kPi);
+            double A, B, G, C, bg;                                // bg: Gaussian (h/res)^2
+            int regime;
+            if (ratio < .01) {
+                regime = REGIME_GAUSS;
+                A = 0.0; B = 1.0;
+                G = sw / gd / sqrtpi;
+                bg = gd * gd / res2;
+                C = -log2e / bg;
+            } else if (ratio > 100) {
+                regime = REGIME_LORENTZ;
+                A = sw * gl / kPi / res2;
+                B = gl * gl / res2;
+                G = 0.0; C = -1.0; bg = 0.0;
+            } else {
+                regime = REGIME_VOIGT;
+                const double gFW = 2 * gd, lFW = 2 * gl;
+                const double g2 = gFW * gFW, l2 = lFW * lFW;
+                const double f = pow(pow5(gFW) + 2.69269 * g2 * g2 * lFW + 2.42843 * g2 * gFW * l2 +
+                                     4.47163 * g2 * l2 * lFW + .07842 * gFW * l2 * l2 + pow5(lFW), .2);
+                const double rho = lFW / f;
+                const double eta = 1.36603 * rho - .47719 * rho * rho + .11116 * rho * rho * rho;
+                const double hh = f / 2;
+                A = sw * eta * hh / kPi / res2;
+                B = hh * hh / res2;
+                G = sw * (1 - eta) / hh / sqrtpi;
+                bg = B;
+                C = -log2e / B;
+            }
+            // near-zone radius: beyond it the Gaussian term is < 1e-9 of the same line's Lorentz term
+            // (or below the scaled FP32 floor for Gaussian-only lines), so K2 may skip it.
+            if (G > 0.0) {
+                double t2 = 160.0;
+                if (A > 0.0) {
+                    const double rho9 = 1e-9 * A / (B * G);
+                    if (rho9 >= 1.0) t2 = -1.0;
+                    else {
+                        const double ln = -log(rho9);
+                        t2 = ln;
+                        for (int it = 0; it < 4; ++it) t2 = ln + log1p(t2);
+                        t2 = fmin(t2 + 0.5, 160.0);
+                    }
+                }
+                if (t2 > 0.0) dg = (float)fmin(ceil(sqrt(t2 * bg)) + 1.0, 3.0e7);
+            }
+            // FP32 range guards: the paired far path forms A*(d^2+B) with |d| <= wm.
+            const double qmax = wm * wm + B;
+            if (!(isfinite(A) && isfinite(G) && isfinite(B) && isfinite(C))) flags |= FLAG_NONFINITE;
+            else if (A * qmax > 8.0e37 || G > 8.0e37 || B > 1.0e18 || qmax * qmax > 8.0e37) flags |= FLAG_OVERFLOW;
+            const double fi = (double)((int64_t)idx[l] - i_base);
+            rec4[l] = make_float4((float)fi, (float)A, (float)B, (float)G);
+            rec2[l] = make_float2((float)C, dg);
+            if (dbg.nu_shift) dbg.nu_shift[l] = nus;
+            if (dbg.gl) dbg.gl[l] = gl;
+            if (dbg.gd) dbg.gd[l] = gd;
+            if (dbg.st) dbg.st[l] = S;
+            if (dbg.regime) dbg.regime[l] = regime;
+        }
+    }
+    // block-level max of dg (>= 0 floats order like their bit patterns) and OR of flags; one
+    // atomic per block.  max / or are order-independent, so the result is deterministic.
+    unsigned int bits = dg > 0.f ? __float_as_uint(dg) : 0u;
+    bits = __reduce_max_sync(0xffffffffu, bits);
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if ((threadIdx.x & 31) == 0) {
+        if (bits) atomicMax(&st->dg_max_bits, bits);
+        if (flags) atomicOr(&st->flags, flags);
+    }
+}
+
+}  // namespace prb

@@ -1,0 +1,137 @@
+// k3_stream.cuh -- K3: fused pointwise layer physics (HBM-bound streaming kernels).
+//
+//   absCoef        pyradClasses.py:581-583, 707-712   k = sum_m sigma_m * (conc_m P / 1e4 / kB / T)
+//   transmittance  pyradClasses.py:585-587, 714-716   T = exp(-k * depth)
+//   Planck         pyradPlanck.py:38-44, 12-15        B = 2e8 h c^2 nu^3 / (exp(100 h c nu / kB / T) - 1)
+//   transmission   pyradClasses.py:784-787            I_out = T * I_in + (1 - T) * B(nu, T_layer)
+//   xsc ingest     pyradClasses.py:159-162, 493-500   np.interp + aligned placement
+//   multi-layer    fold of Layer.transmission over the layers (absent upstream)
+//
+// Two flavours: an FP64 kernel behind the host-buffer API (bit-faithful formulas, used by the
+// pyradClasses mirror), and the FP32 float4-vectorised fold over the resident k matrix used by
+// the atmosphere path (algorithmic traffic L*N*4 + N*8 bytes).
+#pragma once
+#include "common.cuh"
+
+namespace prb {
+
+// nu_i of np.linspace(start, stop, n): i*step + start (two roundings, as numpy), last = stop.
+__device__ __forceinline__ double axis_value(int64_t i, int64_t n, double x0, double dx, double x_last) {
+    if (i == n - 1) return x_last;
+    return __dadd_rn(__dmul_rn((double)i, dx), x0);
+}
+
+__device__ __forceinline__ double planck_f64(double nu, double temp) {
+    const double a = 2E8 * hPlanck * (cLight * cLight) * (nu * nu * nu);
+    const double b = 100 * hPlanck * cLight * nu / kBoltz / temp;
+    return a / (exp(b) - 1);                              // nu = 0 -> 0/0 = NaN, as the reference
+}
+
+__global__ void __launch_bounds__(256)
+k3_layer_stream_f64(int64_t n, int n_mol, const double *__restrict__ sigma, const double *__restrict__ weight,
+                    double depth, double t_layer, double x0, double dx, double x_last,
+                    const double *__restrict__ rad_in, double *__restrict__ absc, double *__restrict__ trans,
+                    double *__restrict__ rad_out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double k = 0.0;
+        for (int m = 0; m < n_mol; ++m) k += sigma[(int64_t)m * n + i] * weight[m];
+        const double t = exp(-k * depth);
+        if (absc) absc[i] = k;
+        if (trans) trans[i] = t;
+        if (rad_out) {
+            const double b = planck_f64(axis_value(i, n, x0, dx, x_last), t_layer);
+            rad_out[i] = t * rad_in[i] + (1 - t) * b;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k3_planck_f64(int64_t n, double x0, double dx, double x_last, double temp, double *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = planck_f64(axis_value(i, n, x0, dx, x_last), temp);
+}
+
+// np.interp(x, xp, fp) for one x: clamps outside, slope form inside (numpy's arithmetic, no FMA).
+__device__ __forceinline__ double np_interp(double x, const double *__restrict__ xp, const double *__restrict__ fp,
+                                            int64_t n) {
+    if (x <= xp[0]) return x < xp[0] ? fp[0] : fp[0];
+    if (x >= xp[n - 1]) return fp[n - 1];
+    int64_t lo = 0, hi = n - 1;                            // xp[lo] <= x < xp[hi]
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (xp[mid] <= x) lo = mid; else hi = mid;
+    }
+    const double slope = __ddiv_rn(__dsub_rn(fp[lo + 1], fp[lo]), __dsub_rn(xp[lo + 1], xp[lo]));
+    return __dadd_rn(__dmul_rn(slope, __dsub_rn(x, xp[lo])), fp[lo]);
+}
+
+__global__ void __launch_bounds__(256)
+k3_xsc_place(int64_t n_out, int64_t dst0, int64_t src0, int64_t count, int interp, double ax0, double adelta,
+             int64_t n_file, const double *__restrict__ fx, const double *__restrict__ fy, double *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = i - dst0;
+        double v = 0.0;
+        if (j >= 0 && j < count) {
+            const int64_t m = src0 + j;
+            if (interp) v = np_interp(__dadd_rn(ax0, __dmul_rn((double)m, adelta)), fx, fy, n_file);
+            else v = (m >= 0 && m < n_file) ? fy[m] : 0.0;
+        }
+        out[i] = v;
+    }
+}
+
+// ---- atmosphere fold, FP32 storage, float4 per thread --------------------------------------------
+struct FoldLayer {
+    float neg_depth_log2e;   // -depth * log2(e): T = exp2(k * this)
+    float c2_over_t;         // 100 h c / kB / T_layer
+};
+
+__device__ __forceinline__ float planck_f32(float a_nu3, float x) {
+    // a nu^3 / (e^x - 1); expm1f keeps the small-x end (first few hundred grid points) accurate.
+    return a_nu3 / expm1f(x);
+}
+
+__global__ void __launch_bounds__(256)
+k3_fold_f32(const float *__restrict__ kmat, int64_t ld, int n_layers, const FoldLayer *__restrict__ layers,
+            int64_t n_chunk, int64_t i_begin, int64_t n_total, double x0, double dx, double x_last,
+            float c2_over_tsurf, float *__restrict__ rad_out, float *__restrict__ trans_out) {
+    const int64_t nvec = (n_chunk + 3) >> 2;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = v << 2;
+        float nu[4], a3[4], rad[4], tau[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double x = axis_value(i_begin + i0 + q, n_total, x0, dx, x_last);
+            nu[q] = (float)x;
+            a3[q] = (float)(2E8 * hPlanck * (cLight * cLight) * (x * x * x));
+            rad[q] = planck_f32(a3[q], c2_over_tsurf * nu[q]);   // I_0 = B(nu, T_surface)
+            tau[q] = 0.f;
+        }
+#pragma unroll 4
+        for (int l = 0; l < n_layers; ++l) {
+            const float4 k4 = __ldg(reinterpret_cast<const float4 *>(kmat + (int64_t)l * ld + i0));
+            const FoldLayer fl = layers[l];
+            const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float e = kk[q] * fl.neg_depth_log2e;       // -tau_l * log2(e)
+                const float t = exp2f(e);
+                const float b = planck_f32(a3[q], fl.c2_over_t * nu[q]);
+                rad[q] = fmaf(t, rad[q] - b, b);                  // T*I + (1-T)*B
+                tau[q] += e;
+            }
+        }
+        if (i0 + 3 < n_chunk) {
+            *reinterpret_cast<float4 *>(rad_out + i0) = make_float4(rad[0], rad[1], rad[2], rad[3]);
+            *reinterpret_cast<float4 *>(trans_out + i0) =
+                make_float4(exp2f(tau[0]), exp2f(tau[1]), exp2f(tau[2]), exp2f(tau[3]));
+        } else {
+            for (int q = 0; q < 4 && i0 + q < n_chunk; ++q) {
+                rad_out[i0 + q] = rad[q];
+                trans_out[i0 + q] = exp2f(tau[q]);
+            }
+        }
+    }
+}
+
+}  // namespace prb

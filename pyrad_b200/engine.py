@@ -1,0 +1,221 @@
+"""Thin numpy-facing wrapper over the C ABI (include/pyrad_b200.h).  Holds no physics."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+K_BOLTZ = 1.38064852E-23          # pyradClasses.py:16
+P0 = 1013.25
+
+OUT_F64, OUT_F32 = 0, 1
+K2_GENERAL, K2_CLASSED = 0, 1
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def window_len(cutoff, res):
+    """W = len(np.arange(0, cutoff, res)) (pyradClasses.py:377) -- numpy's own length rule."""
+    return len(np.arange(0, cutoff, res))
+
+
+def grid_len(range_min, range_max, res):
+    """N = int((rangeMax - rangeMin) / res) (pyradClasses.py:672, 700)."""
+    return int((range_max - range_min) / res)
+
+
+def number_density_weight(conc, P, T):
+    """absCoef factor conc * P / 1E4 / k / T, left to right (pyradClasses.py:583)."""
+    return conc * P / 1E4 / K_BOLTZ / T
+
+
+class Engine:
+    """One engine per process per device (the C ABI's contract)."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.prb_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.n_lines = 0
+        self.n_groups = 0
+        self.n_chunk = 0
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.prb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def stream(self):
+        """Raw cudaStream_t of the engine (wrap with torch.cuda.ExternalStream for CUDA events)."""
+        return int(self._lib.prb_stream(self._h) or 0)
+
+    def synchronize(self):
+        _lib.check(self._lib.prb_synchronize(self._h))
+
+    def device_info(self):
+        sm, ma, mi, khz = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        fr, to = C.c_size_t(), C.c_size_t()
+        _lib.check(self._lib.prb_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(khz),
+                                             C.byref(fr), C.byref(to)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "sm_clock_khz": khz.value,
+                "free_bytes": fr.value, "total_bytes": to.value}
+
+    def set_k2_variant(self, variant=K2_CLASSED, points_per_thread=0):
+        _lib.check(self._lib.prb_set_k2_variant(self._h, int(variant), int(points_per_thread)))
+
+    # -- data
+    def upload_lines(self, lines, n_groups=1):
+        """lines: dict with nu, sw, gamma_air, gamma_self, elower, n_air, delta_air (+ optional int32 group),
+        ascending in nu."""
+        cols = [_f64(lines[k]) for k in ("nu", "sw", "gamma_air", "gamma_self", "elower", "n_air", "delta_air")]
+        n = cols[0].size
+        grp = lines.get("group") if hasattr(lines, "get") else None
+        gp = None
+        if grp is not None:
+            grp = np.ascontiguousarray(grp, dtype=np.int32)
+            gp = grp.ctypes.data_as(C.POINTER(C.c_int32))
+        _lib.check(self._lib.prb_upload_lines(self._h, n, *[_dp(c) for c in cols], gp, int(n_groups)))
+        self.n_lines = n
+        self.n_groups = int(n_groups)
+
+    def set_grid(self, range_min, res, n_total, i_begin=0, i_end=None):
+        i_end = n_total if i_end is None else i_end
+        _lib.check(self._lib.prb_set_grid(self._h, float(range_min), float(res), int(n_total), int(i_begin),
+                                          int(i_end)))
+        self.n_chunk = int(i_end) - int(i_begin)
+        self.n_total = int(n_total)
+        self.i_begin, self.i_end = int(i_begin), int(i_end)
+        self._res = float(res)
+        self.range_min = float(range_min)
+
+    # -- kernels
+    def layer_prepass(self, T, P, conc, molmass, q_t, q_296, window, weight=None):
+        g = self.n_groups
+        arrs = [_f64(np.broadcast_to(np.asarray(a, dtype=np.float64), (g,))) for a in (conc, molmass, q_t, q_296)]
+        w = _f64(np.broadcast_to(np.asarray(weight, dtype=np.float64), (g,))) if weight is not None else None
+        _lib.check(self._lib.prb_layer_prepass(self._h, float(T), float(P), g, *[_dp(a) for a in arrs], _dp(w),
+                                               int(window)))
+
+    def line_sum(self):
+        out = np.empty(self.n_chunk, dtype=np.float64)
+        _lib.check(self._lib.prb_line_sum(self._h, _dp(out)))
+        return out
+
+    def line_sum_dev(self, dev_ptr, out_mode=OUT_F64):
+        _lib.check(self._lib.prb_line_sum_dev(self._h, C.c_void_p(int(dev_ptr)), int(out_mode)))
+
+    def pair_count(self):
+        n = self._lib.prb_pair_count(self._h)
+        if n < 0:
+            raise _lib.EngineError(int(n), _lib.last_error())
+        return int(n)
+
+    def debug_line_params(self):
+        n = self.n_lines
+        out = {k: np.empty(n, dtype=np.float64) for k in ("nu_shift", "gamma_l", "gamma_d", "s_t")}
+        reg = np.empty(n, dtype=np.int32)
+        idx = np.empty(n, dtype=np.int64)
+        _lib.check(self._lib.prb_debug_line_params(
+            self._h, _dp(out["nu_shift"]), _dp(out["gamma_l"]), _dp(out["gamma_d"]), _dp(out["s_t"]),
+            reg.ctypes.data_as(C.POINTER(C.c_int32)), idx.ctypes.data_as(C.POINTER(C.c_int64))))
+        out["regime"] = reg
+        out["index"] = idx
+        return out
+
+    def cross_section(self, T, P, conc, molmass, q_t, q_296, cutoff, res=None, weight=None):
+        """prepass + line sum on the current grid: Isotope.createCrossSection (pyradClasses.py:361-400)."""
+        res = self._res if res is None else res
+        self.layer_prepass(T, P, conc, molmass, q_t, q_296, window_len(cutoff, res), weight)
+        return self.line_sum()
+
+    def layer_stream(self, sigma, weight, depth_cm, t_layer, axis, radiance_in=None,
+                     want=("abs_coef", "transmittance", "radiance")):
+        """axis = (x0, dx, x_last, n) of the np.linspace grid (Layer.xAxis)."""
+        sigma = _f64(np.atleast_2d(sigma))
+        n_mol, n = sigma.shape
+        x0, dx, x_last, n_axis = axis
+        assert n_axis == n
+        w = _f64(weight)
+        rin = _f64(radiance_in) if radiance_in is not None else None
+        k = np.empty(n) if "abs_coef" in want else None
+        t = np.empty(n) if "transmittance" in want else None
+        r = np.empty(n) if ("radiance" in want and rin is not None) else None
+        _lib.check(self._lib.prb_layer_stream(self._h, n, n_mol, _dp(sigma), _dp(w), float(depth_cm), float(t_layer),
+                                              float(x0), float(dx), float(x_last), _dp(rin), _dp(k), _dp(t), _dp(r)))
+        return k, t, r
+
+    def planck(self, axis, temp):
+        x0, dx, x_last, n = axis
+        out = np.empty(n)
+        _lib.check(self._lib.prb_planck(self._h, n, float(x0), float(dx), float(x_last), float(temp), _dp(out)))
+        return out
+
+    def xsc_place(self, n_out, dst0, src0, count, file_x, file_y, interp, ax0=0.0, adelta=0.0):
+        fy = _f64(file_y)
+        fx = _f64(file_x) if file_x is not None else None
+        out = np.empty(n_out)
+        _lib.check(self._lib.prb_xsc_place(self._h, n_out, int(dst0), int(src0), int(count), int(bool(interp)),
+                                           float(ax0), float(adelta), fy.size, _dp(fx), _dp(fy), _dp(out)))
+        return out
+
+    def atmosphere(self, depth_cm, t_layer, p_layer, conc, molmass, q_t, q_296, window, t_surface, range_max):
+        """conc, q_t: (L, G); molmass, q_296: (G,).  Runs K1+K2 per layer and the K3 fold on the device."""
+        L = len(t_layer)
+        g = self.n_groups
+        conc = _f64(np.broadcast_to(np.asarray(conc, dtype=np.float64), (L, g)))
+        q_t = _f64(np.broadcast_to(np.asarray(q_t, dtype=np.float64), (L, g)))
+        molmass = _f64(np.broadcast_to(np.asarray(molmass, dtype=np.float64), (g,)))
+        q_296 = _f64(np.broadcast_to(np.asarray(q_296, dtype=np.float64), (g,)))
+        depth = _f64(np.broadcast_to(np.asarray(depth_cm, dtype=np.float64), (L,)))
+        win = np.ascontiguousarray(window, dtype=np.int64)
+        _lib.check(self._lib.prb_atmosphere(self._h, L, g, _dp(depth), _dp(_f64(t_layer)), _dp(_f64(p_layer)),
+                                            _dp(conc), _dp(molmass), _dp(q_t), _dp(q_296),
+                                            win.ctypes.data_as(C.POINTER(C.c_int64)), float(t_surface),
+                                            float(range_max)))
+
+    def atmosphere_read(self):
+        rad = np.empty(self.n_chunk)
+        tr = np.empty(self.n_chunk)
+        _lib.check(self._lib.prb_atmosphere_read(self._h, _dp(rad), _dp(tr)))
+        return rad, tr
+
+    def atmosphere_result_dev(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        _lib.check(self._lib.prb_atmosphere_result_dev(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def atmosphere_kmatrix_dev(self):
+        p, ld = C.c_void_p(), C.c_int64()
+        _lib.check(self._lib.prb_atmosphere_kmatrix_dev(self._h, C.byref(p), C.byref(ld)))
+        return p.value, ld.value
+
+
+def linspace_axis(range_min, range_max, n):
+    """(x0, dx, x_last, n) reproducing np.linspace(range_min, range_max, n, endpoint=True) bit for bit:
+    numpy forms arange(n) * step + start and overwrites the last sample with stop (Layer.xAxis,
+    pyradClasses.py:703-705)."""
+    n = int(n)
+    step = (range_max - range_min) / (n - 1) if n > 1 else 0.0
+    return float(range_min), float(step), float(range_max), n

@@ -1,0 +1,71 @@
+"""The BASELINE.json configurations as seeded synthetic workloads.
+
+A workload is a plain dict: merged SoA `lines` (with int32 `group`), per-group species info, the
+grid (range_min, range_max, res) and the layer(s).  No physics here -- only inputs.
+"""
+import numpy as np
+
+from . import synth
+
+P0 = 1013.25
+
+
+def _layer_cutoff(P):
+    return P / 1013.25 * 5            # Layer.__init__ pyradClasses.py:655
+
+
+def gas_cell(names, n_lines_total, rmin, rmax, res, T, P, conc, depth_cm, seed, margin=None, cutoff=None):
+    """Single layer, one isotopologue (group) per named molecule."""
+    cutoff = _layer_cutoff(P) if cutoff is None else cutoff
+    margin = cutoff if margin is None else margin
+    lo, hi = max(rmin - margin, 0.0), rmax + margin
+    per = []
+    sp = [synth.species(n) for n in names]
+    for g, s in enumerate(sp):
+        per.append(synth.make_lines(n_lines_total // len(names), lo, hi, seed + 101 * g))
+    lines = synth.merge_species_lines(per)
+    return {
+        "lines": lines, "per_group_lines": per, "species": sp,
+        "range_min": rmin, "range_max": rmax, "res": res,
+        "T": T, "P": P, "conc": list(conc), "depth_cm": depth_cm, "cutoff": cutoff,
+    }
+
+
+def cfg1(n_lines=50_000):
+    """single CO2 gas cell 10 cm, 296 K, 1013 hPa, 400 ppm, 500-800 cm-1 at 0.01 cm-1."""
+    return gas_cell(["co2"], n_lines, 500.0, 800.0, 0.01, 296, 1013.0, [400e-6], 10.0, synth.SEED0 + 1)
+
+
+def cfg2(n_lines=500_000, rmax=3000.0):
+    """mixed H2O+CO2+CH4+O3 gas cell 0-3000 cm-1 at 0.001 cm-1 (~3M points, ~500k lines)."""
+    return gas_cell(["h2o", "co2", "ch4", "o3"], n_lines, 0.0, rmax, 0.001, 296, 1013.25,
+                    [0.01, 400e-6, 1.8e-6, 5e-8], 10.0, synth.SEED0 + 2)
+
+
+def cfg5(n_lines=5_000_000, rmax=5000.0, res=0.001, cutoff=25.0):
+    """stress sweep: 5M synthetic lines, 0-5000 cm-1 at 0.001 cm-1, 25 cm-1 cutoff."""
+    return gas_cell(["h2o", "co2", "ch4", "o3"], n_lines, 0.0, rmax, res, 296, 1013.25,
+                    [0.01, 400e-6, 1.8e-6, 5e-8], 10.0, synth.SEED0 + 5, cutoff=cutoff)
+
+
+def atmosphere(n_layers=100, n_lines=5_000_000, rmin=0.0, rmax=5000.0, res=0.001, top_km=70.0,
+               fixed_cutoff=None, seed=synth.SEED0 + 4):
+    """cfg4: L-layer US-standard-atmosphere column, per-layer T/p, reference cutoff 5*P/p0."""
+    depth_cm, T, P = synth.atmosphere_profile(n_layers, top_km)
+    names = ["h2o", "co2", "ch4", "o3"]
+    sp = [synth.species(n) for n in names]
+    cut_max = fixed_cutoff if fixed_cutoff is not None else _layer_cutoff(P.max())
+    lo, hi = max(rmin - cut_max, 0.0), rmax + cut_max
+    per = [synth.make_lines(n_lines // len(names), lo, hi, seed + 101 * g) for g in range(len(names))]
+    lines = synth.merge_species_lines(per)
+    # simple composition profile: H2O falls off with height, the others well mixed
+    z = (np.arange(n_layers) + 0.5) * top_km / n_layers
+    conc = np.stack([np.maximum(0.01 * np.exp(-z / 2.0), 4e-6), np.full(n_layers, 400e-6),
+                     np.full(n_layers, 1.8e-6), 5e-8 + 8e-6 * np.exp(-((z - 25.0) / 8.0) ** 2)], axis=1)
+    cutoff = np.full(n_layers, fixed_cutoff) if fixed_cutoff is not None else _layer_cutoff(P)
+    return {
+        "lines": lines, "per_group_lines": per, "species": sp,
+        "range_min": rmin, "range_max": rmax, "res": res,
+        "depth_cm": np.full(n_layers, depth_cm), "T": T, "P": P, "conc": conc, "cutoff": cutoff,
+        "t_surface": 288.0,
+    }
