@@ -416,10 +416,10 @@ static int pick_ppt(const prb_engine *e, int64_t wm) {
 
 template <int P>
 static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
-    const int tile = K2_THREADS * P;
+    const int tile = K2_CONSUMERS * 32 * P;
     a.n_tiles = (int)((a.n_chunk + tile - 1) / tile);
     if (a.n_tiles == 0) return cudaSuccess;
-    const size_t smem = sizeof(K2Smem<P>);
+    const size_t smem = sizeof(K2Smem);
     const int grid = std::min(a.n_tiles, 2 * e->prop.multiProcessorCount);
     k2_line_sum<P><<<grid, K2_THREADS, smem, e->stream>>>(a);
     return cudaGetLastError();
@@ -458,7 +458,7 @@ extern "C" int prb_line_sum_dev(prb_engine *e, void *out_dev, int out_mode) {
     if (!out_dev) return fail(PRB_ERR_ARG, "prb_line_sum_dev: NULL output");
     if (out_mode != PRB_OUT_F64 && out_mode != PRB_OUT_F32) return fail(PRB_ERR_ARG, "prb_line_sum_dev: bad out_mode");
     CK(cudaSetDevice(e->device));
-    // the tile scheduler counter is consumed by a launch: reset it (dg_max and flags must survive)
+    // the tile scheduler counter is consumed by a launch: reset it (the status flags must survive)
     CK(cudaMemsetAsync(&e->st.p->tile_counter, 0, sizeof(unsigned int), e->stream));
     return launch_line_sum(e, e->last, e->st.p, out_dev, out_mode);
 }

@@ -28,7 +28,7 @@ struct GroupParams {
 
 // Small device-resident state block, cleared before every prepass.
 struct DevState {
-    unsigned int dg_max_bits;   // max near-zone radius (float bits, >= 0) over the processed lines
+    unsigned int reserved0;
     unsigned int flags;         // bit0: coefficient overflow, bit1: non-finite coefficient
     unsigned int tile_counter;  // dynamic tile scheduler of K2 (work distribution only, never data)
     unsigned int pad;
@@ -37,8 +37,10 @@ struct DevState {
 constexpr unsigned int FLAG_OVERFLOW = 1u, FLAG_NONFINITE = 2u;
 
 // K2 geometry
-constexpr int K2_THREADS = 256;          // 8 warps per CTA
-constexpr int K2_CHUNK = 512;            // lines staged per TMA bulk copy
+constexpr int K2_CONSUMERS = 8;          // math warps per CTA
+constexpr int K2_THREADS = 32 * (K2_CONSUMERS + 1);   // + one TMA producer warp
+constexpr int K2_CHUNK = 256;            // lines staged per ring slot (one pair of TMA bulk copies)
+constexpr int K2_STAGES = 6;             // ring depth
 constexpr int K2_FLUSH = 64;             // lines accumulated in FP32 before flushing into FP64
 constexpr float K2_SENTINEL = 3.0e38f;   // fidx of padding records: outside every window
 

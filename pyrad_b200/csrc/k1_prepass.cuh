@@ -52,7 +52,6 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__res
            float4 *__restrict__ rec4, float2 *__restrict__ rec2, DevState *st, DebugOut dbg) {
     const double c2 = cLight * hPlanck * 100 / kBoltz;          // pyradIntensity.py:13
     int64_t l = l_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    float dg = -1.0f;
     unsigned int flags = 0;
     if (l < l_end) {
         if (l >= n_lines) {                                       // padding record: never in a window
@@ -76,6 +75,7 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__res
             const double sqrtpi = sqrt(kPi);
             double A, B, G, C, bg;                                // bg: Gaussian (h/res)^2
             int regime;
+            float dg = -1.0f;
             if (ratio < .01) {
                 regime = REGIME_GAUSS;
                 A = 0.0; B = 1.0;
@@ -132,15 +132,9 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__res
             if (dbg.regime) dbg.regime[l] = regime;
         }
     }
-    // block-level max of dg (>= 0 floats order like their bit patterns) and OR of flags; one
-    // atomic per block.  max / or are order-independent, so the result is deterministic.
-    unsigned int bits = dg > 0.f ? __float_as_uint(dg) : 0u;
-    bits = __reduce_max_sync(0xffffffffu, bits);
+    // OR of the status flags, one atomic per warp that has something to report (order independent).
     flags = __reduce_or_sync(0xffffffffu, flags);
-    if ((threadIdx.x & 31) == 0) {
-        if (bits) atomicMax(&st->dg_max_bits, bits);
-        if (flags) atomicOr(&st->flags, flags);
-    }
+    if ((threadIdx.x & 31) == 0 && flags) atomicOr(&st->flags, flags);
 }
 
 }  // namespace prb

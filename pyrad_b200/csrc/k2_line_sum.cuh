@@ -50,6 +50,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -109,12 +112,21 @@ struct K2Args {
     DevState *st;
 };
 
-template <int P>
+// One ring slot: a chunk of staged line records plus its descriptor.
+struct K2Desc {
+    int tile0;      // chunk-local index of the first point of the tile this chunk belongs to
+    int cnt;        // staged lines to process (padding excluded)
+    int flags;      // K2_FIRST | K2_LAST | K2_END
+    int pad;
+};
+constexpr int K2_FIRST = 1, K2_LAST = 2, K2_END = 4;
+
 struct K2Smem {
-    float4 r4[2][K2_CHUNK];
-    float2 r2[2][K2_CHUNK];
-    uint64_t full[2];
-    int tile, lo, hi;
+    float4 r4[K2_STAGES][K2_CHUNK];
+    float2 r2[K2_STAGES][K2_CHUNK];
+    K2Desc desc[K2_STAGES];
+    uint64_t full[K2_STAGES];      // producer -> consumers: TMA bytes landed (+ descriptor written)
+    uint64_t empty[K2_STAGES];     // consumers -> producer: all 8 consumer warps are done with the slot
 };
 
 template <int P>
@@ -141,7 +153,7 @@ __device__ __forceinline__ void path_general(const float4 *s4, const float2 *s2,
             if (use_g) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    const float e = d0 + (float)(32 * p);
+                    const float e = p ? d0 + (float)(32 * p) : d0;
                     const float e2 = e * e;
                     float t = r.y * rcp_approx(e2 + r.z);
                     t = fmaf(r.w, ex2_approx(g.x * e2), t);
@@ -150,7 +162,7 @@ __device__ __forceinline__ void path_general(const float4 *s4, const float2 *s2,
             } else {
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    const float e = d0 + (float)(32 * p);
+                    const float e = p ? d0 + (float)(32 * p) : d0;
                     const float t = r.y * rcp_approx(fmaf(e, e, r.z));
                     a32[p] += (fabsf(e) <= wmf) ? t : 0.f;
                 }
@@ -174,7 +186,7 @@ __device__ __forceinline__ void path_near(const float4 *s4, const float2 *s2, in
             if (use_g) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    const float e = d0 + (float)(32 * p);
+                    const float e = p ? d0 + (float)(32 * p) : d0;
                     const float e2 = e * e;
                     a32[p] = fmaf(r.y, rcp_approx(e2 + r.z), a32[p]);
                     a32[p] = fmaf(r.w, ex2_approx(g.x * e2), a32[p]);
@@ -182,7 +194,7 @@ __device__ __forceinline__ void path_near(const float4 *s4, const float2 *s2, in
             } else {
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    const float e = d0 + (float)(32 * p);
+                    const float e = p ? d0 + (float)(32 * p) : d0;
                     a32[p] = fmaf(r.y, rcp_approx(fmaf(e, e, r.z)), a32[p]);
                 }
             }
@@ -205,8 +217,8 @@ __device__ __forceinline__ void path_far(const float4 *s4, int js, int je, float
             const float d2 = fi0 - r2.x;
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const float e1 = d1 + (float)(32 * p);
-                const float e2 = d2 + (float)(32 * p);
+                const float e1 = p ? d1 + (float)(32 * p) : d1;
+                const float e2 = p ? d2 + (float)(32 * p) : d2;
                 const float q1 = fmaf(e1, e1, r1.z);
                 const float q2 = fmaf(e2, e2, r2.z);
                 const float num = fmaf(r2.y, q1, r1.y * q2);
@@ -218,7 +230,7 @@ __device__ __forceinline__ void path_far(const float4 *s4, int js, int je, float
             const float d0 = fi0 - r.x;
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const float e = d0 + (float)(32 * p);
+                const float e = p ? d0 + (float)(32 * p) : d0;
                 a32[p] = fmaf(r.y, rcp_approx(fmaf(e, e, r.z)), a32[p]);
             }
         }
@@ -226,115 +238,151 @@ __device__ __forceinline__ void path_far(const float4 *s4, int js, int je, float
     }
 }
 
+// Warp-specialised persistent kernel: warps 0..7 consume (math), warp 8 produces (tile scheduling,
+// line-range search, TMA issue).  Slots of the ring are handed over with mbarriers only -- there is
+// no CTA-wide barrier in the steady state, so a warp that is in its slow near-zone does not hold up
+// the other seven (each warp's near-zone sits at a different place in the line stream).
 template <int P>
 __global__ void __launch_bounds__(K2_THREADS, 2) k2_line_sum(const K2Args a) {
-    constexpr int TILE = K2_THREADS * P;
-    constexpr int SPAN = 32 * P;                      // points per warp
+    constexpr int TILE = K2_CONSUMERS * 32 * P;
+    constexpr int SPAN = 32 * P;                      // points per consumer warp
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    K2Smem<P> &sm = *reinterpret_cast<K2Smem<P> *>(smem_raw);
+    K2Smem &sm = *reinterpret_cast<K2Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
-        mbar_init(&sm.full[0], 1);
-        mbar_init(&sm.full[1], 1);
+        for (int s = 0; s < K2_STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], K2_CONSUMERS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
-    const float wmf = (float)a.wm;
-    const float dgmax = fmaxf(__uint_as_float(a.st->dg_max_bits), 0.f);
-    uint32_t it = 0;                                   // chunk counter: stage = it&1, parity = (it>>1)&1
-
-    while (true) {
-        if (tid == 0) sm.tile = (int)atomicAdd(&a.st->tile_counter, 1u);
-        __syncthreads();
-        const int tile = sm.tile;
-        if (tile >= a.n_tiles) break;
-        const int tile0 = tile * TILE;                 // chunk-local index of the tile's first point
-
-        if (warp == 0) {
+    if (warp == K2_CONSUMERS) {
+        // ------------------------------------------------------------------ producer warp
+        uint32_t it = 0;
+        auto slot_acquire = [&](uint32_t &stage) {
+            stage = it % K2_STAGES;
+            mbar_wait(&sm.empty[stage], ((it / K2_STAGES) & 1) ^ 1);   // fresh barrier: passes at once
+        };
+        while (true) {
+            int tile = 0;
+            if (lane == 0) tile = (int)atomicAdd(&a.st->tile_counter, 1u);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= a.n_tiles) break;
+            const int tile0 = tile * TILE;
             const long long k_lo = a.i_begin + tile0 - a.wm;
             const long long k_hi = a.i_begin + tile0 + TILE - 1 + a.wm + 1;
-            const int lo = warp_lower_bound(a.idx, a.l_begin, a.l_end, k_lo);
+            int lo = warp_lower_bound(a.idx, a.l_begin, a.l_end, k_lo);
             const int hi = warp_lower_bound(a.idx, lo, a.l_end, k_hi);
-            if (lane == 0) { sm.lo = lo; sm.hi = hi; }
-        }
-        __syncthreads();
-        const int lo = sm.lo & ~1;                     // 16-byte alignment of the float2 stream
-        const int hi = sm.hi;
-        const int nch = hi > lo ? (hi - lo + K2_CHUNK - 1) / K2_CHUNK : 0;
-
-        float a32[P];
-        double a64[P];
-#pragma unroll
-        for (int p = 0; p < P; ++p) { a32[p] = 0.f; a64[p] = 0.0; }
-
-        const int wb = tile0 + warp * SPAN;            // first point of this warp's span
-        const float wbf = (float)wb, we1f = (float)(wb + SPAN - 1);
-        const float fi0 = (float)(wb + lane);
-
-        auto issue = [&](int c, uint32_t stage) {
-            const int first = lo + c * K2_CHUNK;
-            int cnt = min(K2_CHUNK, hi - first);
-            cnt = (cnt + 1) & ~1;                      // padding records exist past l_end (K1 wrote them)
-            mbar_expect_tx(&sm.full[stage], (uint32_t)cnt * 24u);
-            tma_bulk_g2s(sm.r4[stage], a.rec4 + first, (uint32_t)cnt * 16u, &sm.full[stage]);
-            tma_bulk_g2s(sm.r2[stage], a.rec2 + first, (uint32_t)cnt * 8u, &sm.full[stage]);
-        };
-
-        if (tid == 0 && nch > 0) issue(0, it & 1);
-        for (int c = 0; c < nch; ++c, ++it) {
-            const uint32_t stage = it & 1;
-            if (tid == 0 && c + 1 < nch) issue(c + 1, stage ^ 1);
-            mbar_wait(&sm.full[stage], (it >> 1) & 1);
-            const int cnt = min(K2_CHUNK, hi - (lo + c * K2_CHUNK));
-            const float4 *s4 = sm.r4[stage];
-            const float2 *s2 = sm.r2[stage];
-
-            if (a.variant == 0) {
-                path_general<P>(s4, s2, 0, cnt, fi0, wbf, we1f, wmf, a32, a64);
-            } else {
-                // class boundaries of the sorted staged lines relative to this warp's span, by counting
-                const float t0 = wbf - wmf;                       // idx <  t0 : window ends before the span
-                const float t5 = we1f + 1.f + wmf;                // idx >= t5 : window starts after the span
-                const float fl = we1f - wmf, fr1 = wbf + wmf + 1.f;   // full cover: fl <= idx < fr1
-                float t1, t2, t3, t4;
-                if (fl >= fr1) { t1 = t2 = t3 = t4 = t5; }       // window narrower than the span
-                else {
-                    t1 = fl;
-                    t4 = fr1;
-                    t2 = fminf(fmaxf(wbf - dgmax, fl), fr1);
-                    t3 = fminf(fmaxf(we1f + 1.f + dgmax, t2), fr1);
+            lo &= ~1;                                  // 16-byte alignment of the float2 stream
+            const int nch = hi > lo ? (hi - lo + K2_CHUNK - 1) / K2_CHUNK : 1;   // empty tile: one empty chunk
+            for (int c = 0; c < nch; ++c, ++it) {
+                uint32_t stage;
+                slot_acquire(stage);
+                if (lane == 0) {
+                    const int first = lo + c * K2_CHUNK;
+                    const int cnt = max(min(K2_CHUNK, hi - first), 0);
+                    sm.desc[stage] = K2Desc{tile0, cnt, (c == 0 ? K2_FIRST : 0) | (c == nch - 1 ? K2_LAST : 0), 0};
+                    if (cnt > 0) {
+                        const uint32_t ce = (uint32_t)((cnt + 1) & ~1);   // padding records exist past l_end
+                        mbar_expect_tx(&sm.full[stage], ce * 24u);
+                        tma_bulk_g2s(sm.r4[stage], a.rec4 + first, ce * 16u, &sm.full[stage]);
+                        tma_bulk_g2s(sm.r2[stage], a.rec2 + first, ce * 8u, &sm.full[stage]);
+                    } else {
+                        mbar_arrive(&sm.full[stage]);
+                    }
                 }
-                int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
-                for (int j = lane; j < cnt; j += 32) {
-                    const float f = s4[j].x;
-                    c0 += f < t0; c1 += f < t1; c2 += f < t2; c3 += f < t3; c4 += f < t4; c5 += f < t5;
-                }
-                const int b0 = __reduce_add_sync(0xffffffffu, c0);
-                const int b1 = __reduce_add_sync(0xffffffffu, c1);
-                const int b2 = __reduce_add_sync(0xffffffffu, c2);
-                const int b3 = __reduce_add_sync(0xffffffffu, c3);
-                const int b4 = __reduce_add_sync(0xffffffffu, c4);
-                const int b5 = __reduce_add_sync(0xffffffffu, c5);
-                path_general<P>(s4, s2, b0, b1, fi0, wbf, we1f, wmf, a32, a64);
-                path_far<P>(s4, b1, b2, fi0, a32, a64);
-                path_near<P>(s4, s2, b2, b3, fi0, wbf, we1f, a32, a64);
-                path_far<P>(s4, b3, b4, fi0, a32, a64);
-                path_general<P>(s4, s2, b4, b5, fi0, wbf, we1f, wmf, a32, a64);
+                __syncwarp();
             }
-            __syncthreads();                           // stage may be refilled two iterations later
         }
+        uint32_t stage;
+        slot_acquire(stage);
+        if (lane == 0) {
+            sm.desc[stage] = K2Desc{0, 0, K2_END, 0};
+            mbar_arrive(&sm.full[stage]);
+        }
+        return;
+    }
 
-        // epilogue: undo the power-of-two scale exactly and store (coalesced 32-point rows)
+    // ---------------------------------------------------------------------- consumer warps
+    const float wmf = (float)a.wm;
+    float a32[P];
+    double a64[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const int i = wb + 32 * p + lane;
-            if (i < a.n_chunk) {
-                const double v = a64[p] * a.inv_scale;
-                if (a.out_mode == 0) reinterpret_cast<double *>(a.out)[i] = v;
-                else reinterpret_cast<float *>(a.out)[i] = (float)v;
+    for (int p = 0; p < P; ++p) { a32[p] = 0.f; a64[p] = 0.0; }
+    int wb = 0;
+    float wbf = 0.f, we1f = 0.f, fi0 = 0.f;
+
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t stage = it % K2_STAGES;
+        mbar_wait(&sm.full[stage], (it / K2_STAGES) & 1);
+        const K2Desc d = sm.desc[stage];
+        if (d.flags & K2_END) break;
+        if (d.flags & K2_FIRST) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) { a32[p] = 0.f; a64[p] = 0.0; }
+            wb = d.tile0 + warp * SPAN;                // first point of this warp's span
+            wbf = (float)wb;
+            we1f = (float)(wb + SPAN - 1);
+            fi0 = (float)(wb + lane);
+        }
+        const int cnt = d.cnt;
+        const float4 *s4 = sm.r4[stage];
+        const float2 *s2 = sm.r2[stage];
+
+        if (a.variant == 0) {
+            path_general<P>(s4, s2, 0, cnt, fi0, wbf, we1f, wmf, a32, a64);
+        } else if (cnt > 0) {
+            // near-zone radius of THIS staged chunk (max over its lines): a function of the tile
+            // geometry only, so the classes -- and the FP32 rounding -- do not depend on the sharding.
+            float dgl = 0.f;
+            for (int j = lane; j < cnt; j += 32) dgl = fmaxf(dgl, s2[j].y);
+            const float dgmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(dgl)));
+            // class boundaries of the sorted staged lines relative to this warp's span, by counting
+            const float t0 = wbf - wmf;                       // idx <  t0 : window ends before the span
+            const float t5 = we1f + 1.f + wmf;                // idx >= t5 : window starts after the span
+            const float fl = we1f - wmf, fr1 = wbf + wmf + 1.f;   // full cover: fl <= idx < fr1
+            float t1, t2, t3, t4;
+            if (fl >= fr1) { t1 = t2 = t3 = t4 = t5; }       // window narrower than the span
+            else {
+                t1 = fl;
+                t4 = fr1;
+                t2 = fminf(fmaxf(wbf - dgmax, fl), fr1);
+                t3 = fminf(fmaxf(we1f + 1.f + dgmax, t2), fr1);
+            }
+            int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+            for (int j = lane; j < cnt; j += 32) {
+                const float f = s4[j].x;
+                c0 += f < t0; c1 += f < t1; c2 += f < t2; c3 += f < t3; c4 += f < t4; c5 += f < t5;
+            }
+            const int b0 = __reduce_add_sync(0xffffffffu, c0);
+            const int b1 = __reduce_add_sync(0xffffffffu, c1);
+            const int b2 = __reduce_add_sync(0xffffffffu, c2);
+            const int b3 = __reduce_add_sync(0xffffffffu, c3);
+            const int b4 = __reduce_add_sync(0xffffffffu, c4);
+            const int b5 = __reduce_add_sync(0xffffffffu, c5);
+            path_general<P>(s4, s2, b0, b1, fi0, wbf, we1f, wmf, a32, a64);
+            path_far<P>(s4, b1, b2, fi0, a32, a64);
+            path_near<P>(s4, s2, b2, b3, fi0, wbf, we1f, a32, a64);
+            path_far<P>(s4, b3, b4, fi0, a32, a64);
+            path_general<P>(s4, s2, b4, b5, fi0, wbf, we1f, wmf, a32, a64);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[stage]);  // slot may be refilled
+
+        if (d.flags & K2_LAST) {
+            // epilogue: undo the power-of-two scale exactly and store (coalesced 32-point rows)
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int i = wb + 32 * p + lane;
+                if (i < a.n_chunk) {
+                    const double v = a64[p] * a.inv_scale;
+                    if (a.out_mode == 0) reinterpret_cast<double *>(a.out)[i] = v;
+                    else reinterpret_cast<float *>(a.out)[i] = (float)v;
+                }
             }
         }
     }

@@ -23,8 +23,12 @@ def main():
     wts = [eng.number_density_weight(c, P, T) for c in w["conc"]]
     res = {}
     ref = None
-    for variant in (1, 0):
-        for ppt in (4, 8, 16):
+    only = os.environ.get("QK_ONLY")
+    combos = [(v, p) for v in (1, 0) for p in (4, 8, 16)]
+    if only:
+        combos = [tuple(int(x) for x in c.split(":")) for c in only.split(",")]
+    for variant, ppt in combos:
+        if True:
             e.set_k2_variant(variant, ppt)
             t0 = time.time()
             e.layer_prepass(T, P, w["conc"], [s.molmass for s in sp], [s.q(T) for s in sp], [s.q296 for s in sp], win, wts)
