@@ -1,0 +1,469 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement of pyrad-b200 (contract in the task statement / DESIGN.md).
+
+Metric (BASELINE.json): line-gridpoint evals/s on the cfg2 gas cell (mixed H2O+CO2+CH4+O3, 0-3000 cm-1
+at 0.001 cm-1, ~3M grid points, ~500k lines, Voigt, P = 1013.25 hPa => W = 5000), plus the 100-layer
+atmosphere as a secondary object.  A "step" is one pass of the hot path over the cell: K1 prepass ->
+K2 line sum -> K3 (exp(-k u), Planck, transmission).  With N ranks the spectrum is N consecutive
+cfg2-sized wavenumber chunks (weak scaling, one chunk per GPU) and the finished transmittance spectra
+are all-gathered once per step (the only collective).
+
+  python bench.py [--gpus N --steps K --warmup W]          our arm (CUDA engine through the C ABI)
+  python bench.py --impl reference [...]                   the reference's CPU path (oracle port) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "line-gridpoint evals/s"
+UNIT = "pairs/s"
+WORKLOAD = "cfg2: mixed H2O+CO2+CH4+O3 gas cell, 0-3000 cm-1 @ 0.001 cm-1 per GPU (3.0M points, ~500k lines, W=5000)"
+SM_COUNT = 148
+SM_MAX_MHZ_DEFAULT = 1965.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            d = json.load(open(p))
+            return d, "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": SM_MAX_MHZ_DEFAULT}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (recipe in B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.rows = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+                pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "power_w_max": float(np.max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU side
+def _oracle_window(args):
+    """One bounded sample of the cfg2 workload on one core: the oracle's slice-add restatement of
+    Isotope.createCrossSection on a `width` cm-1 sub-window of the cell, all four species."""
+    lo, width, seed = args
+    from oracle import physics as ph
+    from pyrad_b200 import workloads
+    w = workloads.gas_cell(["h2o", "co2", "ch4", "o3"], int(500_000 * (width + 10.0) / 3005.0), lo, lo + width, 0.001,
+                           296, 1013.25, [0.01, 400e-6, 1.8e-6, 5e-8], 10.0, seed)
+    t0 = time.perf_counter()
+    pairs = 0
+    n = ph.grid_len(w["range_min"], w["range_max"], w["res"])
+    W = ph.window_len(w["cutoff"], w["res"])
+    for g, sp in enumerate(w["species"]):
+        ln = w["per_group_lines"][g]
+        ph.cross_section(ln, w["T"], w["P"], w["conc"][g], sp.molmass, sp.q(w["T"]), sp.q296,
+                         w["range_min"], w["range_max"], w["res"], w["cutoff"])
+        pairs += ph.pair_count(ph.line_index(ln["nu"], w["range_min"], w["res"]), n, W)
+    return pairs, time.perf_counter() - t0
+
+
+def _literal_loop_rate():
+    """The reference's OWN loop structure (pure-Python per-element scatter, pyradClasses.py:394-400) on a tiny
+    sample -- context for how much faster the slice-add port is than the code it restates."""
+    from oracle import physics as ph
+    from pyrad_b200 import workloads
+    w = workloads.gas_cell(["co2"], 60, 1000.0, 1010.0, 0.001, 296, 1013.25, [400e-6], 10.0, 4242)
+    sp = w["species"][0]
+    ln = w["per_group_lines"][0]
+    t0 = time.perf_counter()
+    ph.cross_section_scalar(ln, 296, 1013.25, 400e-6, sp.molmass, sp.q(296), sp.q296, 1000.0, 1010.0, 0.001, w["cutoff"])
+    dt = time.perf_counter() - t0
+    n = ph.grid_len(1000.0, 1010.0, 0.001)
+    pairs = ph.pair_count(ph.line_index(ln["nu"], 1000.0, 0.001), n, ph.window_len(w["cutoff"], 0.001))
+    return pairs / dt
+
+
+def cpu_baseline_sample(budget_s=12.0):
+    """Single-core oracle on successive 10 cm-1 windows of cfg2 until ~budget_s of CPU work is done."""
+    pairs, secs, k = 0, 0.0, 0
+    while secs < budget_s and k < 64:
+        p, s = _oracle_window((1000.0 + 10.0 * k, 10.0, 777 + k))
+        pairs += p
+        secs += s
+        k += 1
+    lit = _literal_loop_rate()
+    return {"value": pairs / secs, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d x 10 cm-1 windows of cfg2 (%.3g pairs, %.1f s) with the oracle's numpy slice-add restatement of "
+                      "Isotope.createCrossSection; the reference's literal per-element Python loop runs at %.3g pairs/s "
+                      "on the same core" % (k, pairs, secs, lit)}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python that cannot
+    travel to the GPU box) on all host cores; each step = one 10 cm-1 cfg2 window per core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        def step(s):
+            jobs = [(1000.0 + 10.0 * ((s * cores + c) % 180), 10.0, 1000 + s * cores + c) for c in range(cores)]
+            t0 = time.perf_counter()
+            res = pool.map(_oracle_window, jobs)
+            return sum(r[0] for r in res), time.perf_counter() - t0
+        for s in range(args.warmup):
+            step(s)
+        pairs, secs = 0, 0.0
+        for s in range(args.steps):
+            p, t = step(args.warmup + s)
+            pairs += p
+            secs += t
+    value = pairs / secs
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": WORKLOAD, "sample": "each step: one 10 cm-1 window of the cell per host core"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "oracle numpy slice-add restatement of pyradClasses.py:361-400 (bitwise-equivalent "
+                                   "order, ~15x faster than the reference's literal loop), %d processes, %d steps x %d "
+                                   "windows of 10 cm-1" % (cores, args.steps, cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-atmosphere", action="store_true", help="skip the secondary 100-layer atmosphere object")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--atm-layers", type=int, default=100)
+    ap.add_argument("--atm-lines", type=int, default=5_000_000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from pyrad_b200 import distributed as pd
+    from pyrad_b200 import engine as eng
+    from pyrad_b200 import workloads
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d "
+                             "--master-addr 127.0.0.1 --master-port P bench.py --gpus %d ..." % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks, peaks_kind = load_peaks()
+
+    # ------------------------------------------------------------------ workload (resident in HBM)
+    w = workloads.cfg2_shard(rank, world)
+    sp = w["species"]
+    e = eng.Engine(local)
+    e.upload_lines(w["lines"], n_groups=len(sp))
+    e.set_grid(w["range_min"], w["res"], w["n_total"], w["i_begin"], w["i_end"])
+    n_chunk = e.n_chunk
+    T, P = w["T"], w["P"]
+    win = eng.window_len(w["cutoff"], w["res"])
+    molmass = [s.molmass for s in sp]
+    q296 = [s.q296 for s in sp]
+    qt = [[s.q(T) for s in sp]]
+    conc = [w["conc"]]
+
+    ext = torch.cuda.ExternalStream(e.stream)
+    torch.cuda.set_stream(ext)                      # torch work (L2 flush, NCCL sync, events) follows the engine stream
+    flush_buf = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # 512 MiB > 126 MB L2
+    hold = {"gather": None}
+
+    def step_device():
+        """K1 -> K2 -> K3 on resident inputs (+ the all-gather of the finished transmittance spectrum)."""
+        e.atmosphere([w["depth_cm"]], [T], [P], conc, molmass, qt, q296, [win], w["t_surface"], w["range_max"])
+        if world > 1:
+            _, tr_ptr = e.atmosphere_result_dev()
+            tr = pd.device_tensor(tr_ptr, n_chunk)
+            if hold["gather"] is None:
+                hold["gather"] = torch.empty(world * n_chunk, dtype=torch.float32, device="cuda")
+            dist.all_gather_into_tensor(hold["gather"], tr)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # pair count of one step on this rank (exact, int64, computed by the library from the device's own indices)
+    e.layer_prepass(T, P, conc[0], molmass, qt[0], q296, win)
+    pairs_rank = e.pair_count()
+    pairs_all = pairs_rank
+    if world > 1:
+        t = torch.tensor([pairs_rank], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        pairs_all = int(t.item())
+
+    for _ in range(args.warmup):
+        flush_buf.zero_()
+        step_device()
+    sync_all()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region: K steps, CUDA events on the launching stream around every step, L2 flushed between steps
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    wall0 = time.perf_counter()
+    for a, b in evs:
+        flush_buf.zero_()
+        a.record(ext)
+        step_device()
+        b.record(ext)
+    sync_all()
+    wall = time.perf_counter() - wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tm = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms = float(tm.item())
+    ms_per_step = dev_ms / args.steps
+    value = pairs_all / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel alone (K2) for the roofline: events around prb_line_sum_dev only, L2 flushed
+    kbuf = torch.empty(n_chunk, dtype=torch.float32, device="cuda")
+    wts = [eng.number_density_weight(c, P, T) for c in w["conc"]]
+    e.layer_prepass(T, P, conc[0], molmass, qt[0], q296, win, wts)
+    k2_ms = []
+    for i in range(3 + 10):
+        flush_buf.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(ext)
+        e.line_sum_dev(kbuf.data_ptr(), eng.OUT_F32)
+        b.record(ext)
+        torch.cuda.synchronize()
+        if i >= 3:
+            k2_ms.append(a.elapsed_time(b))
+    k2_t = float(np.mean(k2_ms)) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: the same step through the C ABI with HOST buffers (pinned), copies inside the timed region
+    host_lines = {}
+    for kname, v in w["lines"].items():
+        tns = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+        host_lines[kname] = tns.numpy()
+        host_lines["_keep_" + kname] = tns
+    h_rad = torch.empty(n_chunk, dtype=torch.float32).pin_memory()
+    h_tr = torch.empty(n_chunk, dtype=torch.float32).pin_memory()
+    lines_view = {k: v for k, v in host_lines.items() if not k.startswith("_keep_")}
+
+    def step_e2e():
+        e.upload_lines(lines_view, n_groups=len(sp))                                  # H2D: the step's inputs
+        e.set_grid(w["range_min"], w["res"], w["n_total"], w["i_begin"], w["i_end"])
+        step_device()
+        e.atmosphere_read_f32(h_rad.numpy(), h_tr.numpy())                            # D2H: the step's result
+
+    for _ in range(2):
+        step_e2e()
+    sync_all()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    n_l = e.n_lines
+    h2d = n_l * (7 * 8 + 4) + 4 * 32 * len(sp)
+    d2h = 4 * (n_l + 8) + 2 * 4 * n_chunk + 16
+    e2e = {"value": pairs_all / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / e2e_steps * 1e3,
+           "api": "prb_upload_lines + prb_set_grid + prb_atmosphere(L=1) + prb_atmosphere_read_f32, pinned host buffers"}
+
+    # ---- secondary object: the 100-layer atmosphere (cfg4), strong-sharded by wavenumber chunk
+    atm = None
+    if not args.no_atmosphere:
+        atm = run_atmosphere(e, args, rank, world, ext, peaks)
+
+    # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_sample()
+
+    if rank == 0:
+        sm_max = float(peaks.get("sm_max_mhz", SM_MAX_MHZ_DEFAULT))
+        f_hz = sm_max * 1e6
+        # FP32-pipe roofline of K2 (the binding pipe of the paired-reciprocal formulation): the far path needs
+        # 8 FP32-pipe instructions per TWO (line, point) pairs = 4 lane-slots = 8 flop-slots per pair.
+        fp32_peak = SM_COUNT * 128 * 2 * f_hz / 1e12
+        k2_pairs_s = pairs_rank / k2_t
+        fp32_ach = k2_pairs_s * 8 / 1e12
+        mufu_naive_peak = SM_COUNT * 16 * f_hz / 2.0          # 2 MUFU per Voigt pair
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": "wavenumber chunks x%d, one all-gather" % world,
+                       "pairs_per_step": pairs_all, "lines_per_gpu": n_l, "points_per_gpu": n_chunk,
+                       "l2": "flushed between timed steps (512 MiB write)",
+                       "numerics": "FP64 prepass, FP32 lineshape evaluation, FP64 accumulation; k stored FP32"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * args.steps,
+            "roofline": {"bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": fp32_ach / fp32_peak, "traffic": None, "kernel": "k2_line_sum<8>",
+                         "k2_ms": k2_t * 1e3, "k2_pairs_per_s": k2_pairs_s,
+                         "peak_source": "nominal: 148 SM x 128 FP32 lanes x 2 x %.0f MHz (MEASURED_PEAKS.json has no FP32 "
+                                        "figure; %s file used for the clock)" % (sm_max, peaks_kind),
+                         "algorithmic": "8 FP32 flop-slots per (line, gridpoint) pair (paired-reciprocal far path, DESIGN.md)"},
+            "roofline_sfu": {"bound": "sfu", "achieved": k2_pairs_s / 1e9, "peak": mufu_naive_peak / 1e9, "unit": "Gpair/s",
+                             "frac": k2_pairs_s / mufu_naive_peak,
+                             "note": "SURVEY 8(d) naive bound (2 MUFU per Voigt pair, 16 MUFU/clk/SM); the kernel issues "
+                                     "0.5 MUFU per far pair, hence > 1"},
+            "wall_s_timed_region": wall,
+        }
+        if atm:
+            line["atmosphere"] = atm
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_atmosphere(e, args, rank, world, ext, peaks):
+    """100-layer standard atmosphere, 0-5000 cm-1 @ 0.001 cm-1, ~5M lines: K1+K2 per layer, one K3 fold, one
+    all-gather.  Strong scaling: the N ranks split ONE spectrum by pair-count-balanced wavenumber chunks."""
+    import torch
+    import torch.distributed as dist
+    from pyrad_b200 import distributed as pd
+    from pyrad_b200 import engine as eng
+    from pyrad_b200 import workloads
+
+    w = workloads.atmosphere(n_layers=args.atm_layers, n_lines=args.atm_lines)
+    sp = w["species"]
+    n_total = eng.grid_len(w["range_min"], w["range_max"], w["res"])
+    win = [eng.window_len(c, w["res"]) for c in w["cutoff"]]
+    plan = pd.ShardPlan(w["lines"]["nu"], w["range_min"], w["res"], n_total, win, rank, world)
+    e.upload_lines(plan.subset(w["lines"]), n_groups=len(sp))
+    e.set_grid(w["range_min"], w["res"], n_total, plan.i_begin, plan.i_end)
+    e.set_timing(True)
+    qt = np.array([[s.q(T) for s in sp] for T in w["T"]])
+    molmass = [s.molmass for s in sp]
+    q296 = [s.q296 for s in sp]
+    nc = plan.i_end - plan.i_begin
+
+    def run():
+        e.atmosphere(w["depth_cm"], w["T"], w["P"], w["conc"], molmass, qt, q296, win, w["t_surface"], w["range_max"])
+        rad_p, tr_p = e.atmosphere_result_dev()
+        rad = pd.device_tensor(rad_p, nc)
+        tr = pd.device_tensor(tr_p, nc)
+        g1 = pd.all_gather_spectra(rad, plan, dist if world > 1 else None)
+        g2 = pd.all_gather_spectra(tr, plan, dist if world > 1 else None)
+        return g1, g2
+
+    run()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    times = []
+    for _ in range(2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a.record(ext)
+        run()
+        b.record(ext)
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ms = float(np.mean(times))
+    tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm.item())
+    idx = np.trunc((w["lines"]["nu"] - w["range_min"]) / w["res"]).astype(np.int64)
+    from pyrad_b200 import partition as pt
+    pairs = float(pt.block_pair_cost(idx, n_total, win).sum())
+    tim = e.atmosphere_timing()
+    e.set_timing(False)
+    k3_bytes = len(win) * nc * 4 + nc * 8
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    return {"workload": "cfg4: %d-layer US-std atmosphere 0-70 km, 0-5000 cm-1 @ 0.001 cm-1 (%d points, %d lines), "
+                        "reference cutoff 5*P/p0 per layer" % (len(win), n_total, len(w["lines"]["nu"])),
+            "spectra_per_s": 1e3 / ms, "ms_per_spectrum": ms, "pairs": pairs, "pairs_per_s": pairs / (ms * 1e-3),
+            "scaling": "strong", "n_gpus": world, "chunk_points_rank0": nc,
+            "rank0_stage_ms": tim,
+            "roofline_k3": {"bound": "hbm", "achieved": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                            "frac": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9 / hbm, "traffic": None,
+                            "algorithmic_bytes": k3_bytes}}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -131,6 +131,10 @@ int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
                    const int64_t *window_len, double t_surface, double range_max);
 int prb_atmosphere_result_dev(prb_engine *e, void **radiance_dev, void **transmittance_dev); /* float[chunk] each */
 int prb_atmosphere_read(prb_engine *e, double *radiance_host, double *transmittance_host);
+int prb_atmosphere_read_f32(prb_engine *e, float *radiance_host, float *transmittance_host);   /* no widening */
+/* stage timing: CUDA events on the engine stream, summed over layers, of the last prb_atmosphere */
+int prb_set_timing(prb_engine *e, int enabled);
+int prb_atmosphere_timing(prb_engine *e, float *k1_ms, float *k2_ms, float *k3_ms);
 int prb_atmosphere_kmatrix_dev(prb_engine *e, void **kmat_dev, int64_t *ld);                 /* float[L][ld] */
 
 #ifdef __cplusplus

@@ -53,6 +53,9 @@ PROTOTYPES = {
     "prb_atmosphere": (C.c_int, [_vp, _i32, _i32, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _lp, _d, _d]),
     "prb_atmosphere_result_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "prb_atmosphere_read": (C.c_int, [_vp, _dp, _dp]),
+    "prb_atmosphere_read_f32": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "prb_set_timing": (C.c_int, [_vp, C.c_int]),
+    "prb_atmosphere_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "prb_atmosphere_kmatrix_dev": (C.c_int, [_vp, C.POINTER(_vp), _lp]),
 }
 

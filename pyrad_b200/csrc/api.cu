@@ -97,6 +97,10 @@ struct prb_engine {
     DevBuf<FoldLayer> fold;
     int64_t kmat_ld = 0;
     int atm_layers = 0;
+    // optional stage timing of prb_atmosphere (CUDA events on the engine stream)
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    float t_k1 = 0, t_k2 = 0, t_k3 = 0;
 };
 
 static int64_t chunk_len(const prb_engine *e) { return e->i_end - e->i_begin; }
@@ -145,6 +149,7 @@ extern "C" int prb_destroy(prb_engine *e) {
     e->out64.release(); e->scratch_a.release(); e->scratch_b.release(); e->scratch_c.release();
     e->scratch_d.release(); e->scratch_w.release();
     e->kmat.release(); e->rad.release(); e->trans.release(); e->fold.release();
+    for (auto x : e->ev) cudaEventDestroy(x);
     cudaStreamDestroy(e->stream);
     delete e;
     return PRB_OK;
@@ -615,14 +620,25 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
         CK(cudaMemsetAsync(e->kmat.p, 0, sizeof(float) * e->kmat_ld * n_layers, e->stream));
         e->atm_layers = n_layers;
     }
+    const size_t n_ev = (size_t)2 * n_layers + 2;
+    if (e->timing) {
+        while (e->ev.size() < n_ev) {
+            cudaEvent_t x;
+            CK(cudaEventCreate(&x));
+            e->ev.push_back(x);
+        }
+    }
     for (int l = 0; l < n_layers; ++l) {
         PrepassArgs pa;
+        if (e->timing) CK(cudaEventRecord(e->ev[2 * l], e->stream));
         rc = launch_prepass(e, t_layer[l], p_layer[l], window_len[l], e->gp.p + (size_t)l * n_groups, scale[l],
                             e->st.p + l, DebugOut{}, &pa);
         if (rc) return rc;
+        if (e->timing) CK(cudaEventRecord(e->ev[2 * l + 1], e->stream));
         rc = launch_line_sum(e, pa, e->st.p + l, e->kmat.p + (size_t)l * e->kmat_ld, PRB_OUT_F32);
         if (rc) return rc;
     }
+    if (e->timing) CK(cudaEventRecord(e->ev[2 * n_layers], e->stream));
     if (nc > 0) {
         const double dx = e->n_total > 1 ? (range_max - e->range_min) / (double)(e->n_total - 1) : 0.0;
         k3_fold_f32<<<stream_grid(e, nc, 4), 256, 0, e->stream>>>(e->kmat.p, e->kmat_ld, n_layers, e->fold.p, nc,
@@ -630,7 +646,19 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
                                                                  (float)(c2 / t_surface), e->rad.p, e->trans.p);
         CK(cudaGetLastError());
     }
+    if (e->timing) CK(cudaEventRecord(e->ev[2 * n_layers + 1], e->stream));
     CK(cudaStreamSynchronize(e->stream));                       // pageable staging vectors go out of scope
+    if (e->timing) {
+        e->t_k1 = e->t_k2 = e->t_k3 = 0;
+        for (int l = 0; l < n_layers; ++l) {
+            float a = 0, b = 0;
+            CK(cudaEventElapsedTime(&a, e->ev[2 * l], e->ev[2 * l + 1]));
+            CK(cudaEventElapsedTime(&b, e->ev[2 * l + 1], e->ev[2 * l + 2]));
+            e->t_k1 += a;
+            e->t_k2 += b;
+        }
+        CK(cudaEventElapsedTime(&e->t_k3, e->ev[2 * n_layers], e->ev[2 * n_layers + 1]));
+    }
     e->last.valid = false;
     return check_flags(e, n_layers);
 }
@@ -662,5 +690,30 @@ extern "C" int prb_atmosphere_read(prb_engine *e, double *radiance_host, double 
         CK(cudaStreamSynchronize(e->stream));
         for (int64_t i = 0; i < nc; ++i) dst[k][i] = (double)tmp[i];
     }
+    return PRB_OK;
+}
+
+extern "C" int prb_atmosphere_read_f32(prb_engine *e, float *radiance_host, float *transmittance_host) {
+    if (!e || !e->atm_layers) return fail(PRB_ERR_STATE, "prb_atmosphere_read_f32: run prb_atmosphere first");
+    CK(cudaSetDevice(e->device));
+    const int64_t nc = chunk_len(e);
+    if (radiance_host) CK(cudaMemcpyAsync(radiance_host, e->rad.p, sizeof(float) * nc, cudaMemcpyDeviceToHost, e->stream));
+    if (transmittance_host)
+        CK(cudaMemcpyAsync(transmittance_host, e->trans.p, sizeof(float) * nc, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PRB_OK;
+}
+
+extern "C" int prb_set_timing(prb_engine *e, int enabled) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    e->timing = enabled != 0;
+    return PRB_OK;
+}
+
+extern "C" int prb_atmosphere_timing(prb_engine *e, float *k1_ms, float *k2_ms, float *k3_ms) {
+    if (!e || !e->atm_layers || !e->timing) return fail(PRB_ERR_STATE, "prb_atmosphere_timing: enable timing and run prb_atmosphere first");
+    if (k1_ms) *k1_ms = e->t_k1;
+    if (k2_ms) *k2_ms = e->t_k2;
+    if (k3_ms) *k3_ms = e->t_k3;
     return PRB_OK;
 }

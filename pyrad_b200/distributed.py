@@ -1,0 +1,68 @@
+"""Multi-GPU plumbing: one process per GPU, wavenumber-chunk sharding, ONE all-gather of the
+finished spectra (torch.distributed; NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+The compute is injected (`compute_chunk`) so that the host-side logic -- partition, per-rank line
+subsetting, padded all-gather, assembly -- is exercised on CPU with gloo, and runs unchanged on
+B200s with the CUDA engine behind it.
+"""
+import numpy as np
+
+from . import partition as pt
+
+
+class ShardPlan:
+    """Everything a rank needs to know about its chunk."""
+
+    def __init__(self, nu0, range_min, res, n_total, windows, rank, world, balance=True):
+        idx = pt.line_index(nu0, range_min, res)
+        if balance and world > 1:
+            cost = pt.block_pair_cost(idx, n_total, windows)
+            self.chunks = pt.balanced_chunks(cost, n_total, world)
+        else:
+            self.chunks = pt.equal_chunks(n_total, world)
+        self.rank, self.world = rank, world
+        self.i_begin, self.i_end = self.chunks[rank]
+        self.wmax = max(max(int(w) - 2, 0) for w in np.atleast_1d(windows))
+        # lines whose window reaches the chunk (+1 line of slack each side, harmless)
+        l0 = int(np.searchsorted(idx, self.i_begin - self.wmax, side="left"))
+        l1 = int(np.searchsorted(idx, self.i_end - 1 + self.wmax, side="right"))
+        self.l0, self.l1 = l0, max(l1, l0)
+        self.max_chunk = max(b - a for a, b in self.chunks)
+        self.n_total = n_total
+
+    def subset(self, lines):
+        return {k: np.ascontiguousarray(np.asarray(v)[self.l0:self.l1]) for k, v in lines.items()}
+
+
+def all_gather_spectra(local, plan, dist=None, device=None):
+    """local: torch tensor of the rank's finished chunk (any float dtype, on `device`).
+    Pads to the widest chunk, runs ONE all_gather_into_tensor, returns the (world, max_chunk) tensor."""
+    import torch
+    n = plan.i_end - plan.i_begin
+    pad = torch.zeros(plan.max_chunk, dtype=local.dtype, device=local.device)
+    pad[:n] = local[:n]
+    out = torch.empty(plan.world * plan.max_chunk, dtype=local.dtype, device=local.device)
+    if dist is None or plan.world == 1:
+        out[:plan.max_chunk] = pad
+    else:
+        dist.all_gather_into_tensor(out, pad)
+    return out.view(plan.world, plan.max_chunk)
+
+
+def assemble(gathered, plan):
+    import torch
+    parts = [gathered[r, : b - a] for r, (a, b) in enumerate(plan.chunks)]
+    return torch.cat(parts) if parts else gathered.new_zeros(0)
+
+
+class CudaArrayView:
+    """Zero-copy view of engine-owned device memory for torch (``torch.as_tensor(view, device='cuda')``)."""
+
+    def __init__(self, ptr, n, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def device_tensor(ptr, n, typestr="<f4", device="cuda"):
+    import torch
+    return torch.as_tensor(CudaArrayView(ptr, n, typestr), device=device)

@@ -201,6 +201,21 @@ class Engine:
         _lib.check(self._lib.prb_atmosphere_read(self._h, _dp(rad), _dp(tr)))
         return rad, tr
 
+    def atmosphere_read_f32(self, rad=None, tr=None):
+        """Copy the FP32 device results into caller-owned float32 host arrays (pinned or not), no widening."""
+        fp = C.POINTER(C.c_float)
+        _lib.check(self._lib.prb_atmosphere_read_f32(
+            self._h, rad.ctypes.data_as(fp) if rad is not None else None,
+            tr.ctypes.data_as(fp) if tr is not None else None))
+
+    def set_timing(self, enabled=True):
+        _lib.check(self._lib.prb_set_timing(self._h, int(bool(enabled))))
+
+    def atmosphere_timing(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        _lib.check(self._lib.prb_atmosphere_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"k1_ms": a.value, "k2_ms": b.value, "k3_ms": c.value}
+
     def atmosphere_result_dev(self):
         a, b = C.c_void_p(), C.c_void_p()
         _lib.check(self._lib.prb_atmosphere_result_dev(self._h, C.byref(a), C.byref(b)))

@@ -1,0 +1,94 @@
+"""Wavenumber-chunk sharding of the grid across ranks.
+
+Every grid point is independent given the line list, so the path shards with NO exchange step:
+each rank owns a contiguous chunk of grid points, reads the lines whose cutoff window reaches the
+chunk (read-only duplication at chunk edges) and the only collective is one all-gather of the
+finished spectra.  Chunks are
+  * aligned to ALIGN grid points (the largest K2 tile), which makes the sharded result bitwise
+    identical to the unsharded one (per-point summation order is a function of the tile only), and
+  * balanced by (line, grid point) pair count -- not by width -- because real line density is very
+    non-uniform in wavenumber.
+Pure numpy; no device code here.
+"""
+import numpy as np
+
+ALIGN = 4096          # 8 consumer warps x 32 lanes x 16 points: the largest K2 tile
+
+
+def line_index(nu0, range_min, res):
+    """arrayIndex of pyradClasses.py:390 (FP64 divide, truncation toward zero) -- host copy used only to
+    plan the sharding; the engine recomputes it on the device."""
+    return np.trunc((np.asarray(nu0, dtype=np.float64) - range_min) / res).astype(np.int64)
+
+
+def block_pair_cost(idx, n_total, windows, block=ALIGN):
+    """cost[b] = number of (line, point) accumulations falling into grid block b, summed over the layers'
+    windows (W = len(arange(0, cutoff, res)); |d| <= max(W-2, 0))."""
+    idx = np.asarray(idx, dtype=np.int64)
+    windows = [int(w) for w in np.atleast_1d(windows)]
+    nb = (n_total + block - 1) // block
+    cost = np.zeros(nb, dtype=np.float64)
+    if idx.size == 0 or n_total == 0:
+        return cost
+    wmax = max(max(w - 2, 0) for w in windows)
+    off = wmax + 2
+    size = n_total + 2 * off
+    hist = np.bincount(np.clip(idx + off, 0, size - 1), minlength=size)
+    # lines clipped onto the borders lie outside every window of in-range points only if they are
+    # further than wmax away; drop them instead of piling them on the border cells
+    far = (idx + off < 0) | (idx + off > size - 1)
+    if far.any():
+        hist = np.bincount((idx + off)[~far], minlength=size)
+    C = np.cumsum(hist)                       # C[j] = #lines with idx+off <= j
+    D = np.concatenate([[0], np.cumsum(C)])   # D[j+1] = sum_{t<=j} C[t]
+    a = np.arange(nb, dtype=np.int64) * block            # block start (grid index)
+    b = np.minimum(a + block, n_total)                   # block end (exclusive)
+    for w in set(windows):
+        mult = windows.count(w)
+        wm = max(w - 2, 0)
+        # sum_{i=a}^{b-1} [C(i+wm) - C(i-wm-1)]   (arguments shifted by off)
+        hi = D[b + wm + off] - D[a + wm + off]
+        lo = D[b - wm - 1 + off] - D[a - wm - 1 + off]
+        cost += mult * (hi - lo)
+    return cost
+
+
+def balanced_chunks(cost, n_total, nranks, block=ALIGN):
+    """Contiguous, block-aligned chunks [(i_begin, i_end)] with near-equal cost.  A rank may get an
+    empty chunk when there are fewer blocks than ranks."""
+    nb = len(cost)
+    total = float(np.sum(cost))
+    if total <= 0:
+        cum = np.arange(1, nb + 1, dtype=np.float64)
+        total = float(nb)
+    else:
+        cum = np.cumsum(cost)
+    cuts = [0]
+    for r in range(1, nranks):
+        target = total * r / nranks
+        k = int(np.searchsorted(cum, target, side="left")) + 1   # blocks [0, k) reach the target
+        # pick the nearer of k-1 / k
+        if k - 1 >= 1 and abs(cum[k - 2] - target) <= abs(cum[min(k - 1, nb - 1)] - target):
+            k -= 1
+        cuts.append(min(max(k, cuts[-1]), nb))
+    cuts.append(nb)
+    return [(min(c0 * block, n_total), min(c1 * block, n_total)) for c0, c1 in zip(cuts[:-1], cuts[1:])]
+
+
+def equal_chunks(n_total, nranks, block=ALIGN):
+    nb = (n_total + block - 1) // block
+    return balanced_chunks(np.ones(nb), n_total, nranks, block)
+
+
+def lines_for_chunk(nu0, range_min, res, i_begin, i_end, wmax):
+    """Slice [l0, l1) of the (sorted) line list whose windows can reach [i_begin, i_end) with |d| <= wmax."""
+    idx = line_index(nu0, range_min, res)
+    l0 = int(np.searchsorted(idx, i_begin - wmax, side="left"))
+    l1 = int(np.searchsorted(idx, i_end - 1 + wmax, side="right"))
+    return l0, max(l1, l0)
+
+
+def assemble(gathered, chunks):
+    """gathered: (nranks, max_chunk) padded rows from the all-gather -> the full spectrum."""
+    parts = [np.asarray(gathered[r])[: b - a] for r, (a, b) in enumerate(chunks)]
+    return np.concatenate(parts) if parts else np.zeros(0)

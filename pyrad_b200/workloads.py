@@ -69,3 +69,34 @@ def atmosphere(n_layers=100, n_lines=5_000_000, rmin=0.0, rmax=5000.0, res=0.001
         "depth_cm": np.full(n_layers, depth_cm), "T": T, "P": P, "conc": conc, "cutoff": cutoff,
         "t_surface": 288.0,
     }
+
+
+def cfg2_shard(rank, world, n_lines_per_chunk=500_000, chunk_width=3000.0, res=0.001):
+    """Weak-scaling form of cfg2: the spectrum is `world` consecutive 3000 cm-1 chunks of the cfg2 cell
+    (same line density, T, P and mixing ratios), rank r owns chunk r.  Returns the lines rank r needs
+    (its chunk plus the cutoff margin on both sides) and the global grid description."""
+    names = ["h2o", "co2", "ch4", "o3"]
+    sp = [synth.species(n) for n in names]
+    P, T = 1013.25, 296
+    cutoff = _layer_cutoff(P)
+    lo, hi = chunk_width * rank, chunk_width * (rank + 1)
+    per = []
+    for g in range(len(names)):
+        parts = []
+        for c in (rank - 1, rank, rank + 1):
+            if c < 0:
+                continue
+            d = synth.make_lines(n_lines_per_chunk // len(names), chunk_width * c, chunk_width * (c + 1),
+                                 synth.SEED0 + 2 + 1009 * c + 101 * g)
+            m = (d["nu"] > max(lo - cutoff, 0.0)) & (d["nu"] < hi + cutoff)
+            parts.append({k: v[m] for k, v in d.items()})
+        per.append({k: np.concatenate([p[k] for p in parts]) for k in parts[0]})
+    lines = synth.merge_species_lines(per)
+    n_chunk = int(round(chunk_width / res))
+    return {
+        "lines": lines, "per_group_lines": per, "species": sp,
+        "range_min": 0.0, "range_max": chunk_width * world, "res": res,
+        "n_total": n_chunk * world, "i_begin": n_chunk * rank, "i_end": n_chunk * (rank + 1),
+        "T": T, "P": P, "conc": [0.01, 400e-6, 1.8e-6, 5e-8], "depth_cm": 10.0, "cutoff": cutoff,
+        "t_surface": 288.0,
+    }
