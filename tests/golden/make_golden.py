@@ -1,0 +1,156 @@
+"""Generate tests/golden/*.npz by running the REAL, UNMODIFIED reference (bschrag620/PyRad mounted at
+/root/reference) through oracle/ref_harness.py on seeded synthetic HITRAN-format data.
+
+Run in the build container only:   python tests/golden/make_golden.py
+The reference is Python and cannot travel to the GPU box, so these vectors are the pin that does:
+the oracle is checked against them on CPU, the CUDA engine on the GPU.  Every file stores the inputs
+(line columns, species constants, layer scalars) next to the reference's outputs, so no test needs
+/root/reference at run time.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh          # noqa: E402
+from pyrad_b200 import synth                  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+LOCAL_ISO = 1
+
+
+def seed_species(wd, sp, lines, seg_lo, seg_hi):
+    rh.write_params(wd, sp.global_iso, sp.name, sp.mol_id, 1, 0.99, sp.q296, 1, sp.molmass)
+    rh.write_q_table(wd, sp.global_iso, range(100, 501), [sp.q(t) for t in range(100, 501)])
+    rh.write_line_segments(wd, sp.global_iso, sp.mol_id, LOCAL_ISO, lines, seg_lo, seg_hi)
+
+
+def pack_lines(prefix, lines):
+    return {"%s_%s" % (prefix, k): np.asarray(v) for k, v in lines.items()}
+
+
+def case_gas_cell(name, species_names, conc, n_lines, rmin, rmax, T, P, depth, seed, base=None, dynamic=True,
+                  surface_T=288):
+    wd = tempfile.mkdtemp(prefix="pyrad_golden_")
+    sps = [synth.species(s) for s in species_names]
+    rh.seed_workdir(wd)
+    cutoff = P / 1013.25 * 5
+    lo, hi = max(rmin - cutoff, 0.0), rmax + cutoff
+    all_lines = []
+    for g, sp in enumerate(sps):
+        ln = synth.make_lines(n_lines, max(lo - 1.0, 0.0), hi + 1.0, seed + 17 * g)   # some lines fall outside the kept range
+        seed_species(wd, sp, ln, int(max(lo - 1.0, 0.0) / 100) * 100, hi + 101.0)
+        all_lines.append(ln)
+    ref = rh.load_reference(wd)
+    if base is not None:
+        ref.set_base_resolution(base)
+    C = ref.classes
+    out = {"species": np.array(species_names), "conc": np.array(conc, dtype=np.float64),
+           "molmass": np.array([s.molmass for s in sps]), "q296": np.array([s.q296 for s in sps]),
+           "qT": np.array([s.q(T) for s in sps]),
+           "T": T, "P": P, "depth": depth, "range_min": rmin, "range_max": rmax, "surface_T": surface_T,
+           "base": ref.utils.BASE_RESOLUTION, "dynamic": dynamic}
+    with rh.quiet():
+        layer = C.Layer(depth, T, P, rmin, rmax, dynamicResolution=dynamic)
+        mols = []
+        for sp, c in zip(sps, conc):
+            mols.append(layer.addMolecule(sp.name, concentration=c))
+        out["res"] = layer.resolution
+        out["cutoff"] = layer.distanceFromCenter
+        out["xaxis"] = np.asarray(layer.xAxis)
+        for g, m in enumerate(mols):
+            iso = m[0]
+            out["kept_nu_%d" % g] = np.array([l.wavenumber for l in iso])
+            out["sigma_%d" % g] = np.asarray(C.getCrossSection(iso))
+            out["abscoef_%d" % g] = np.asarray(C.getAbsCoef(m))
+        out["layer_abscoef"] = np.asarray(C.getAbsCoef(layer))
+        out["layer_transmittance"] = np.asarray(C.getTransmittance(layer))
+        surf = ref.planck.planckWavenumber(layer.xAxis, surface_T)
+        out["surface"] = np.asarray(surf)
+        out["layer_transmission"] = np.asarray(layer.transmission(surf))
+        out["layer_planck"] = np.asarray(layer.planck(layer.T))
+    for g, ln in enumerate(all_lines):
+        out.update(pack_lines("lines%d" % g, ln))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "N=%d res=%g W-cutoff=%g kept=%s" % (len(out["layer_abscoef"]), out["res"], out["cutoff"],
+                                                    [len(out["kept_nu_%d" % g]) for g in range(len(sps))]))
+
+
+def case_xsc(name, file_res, rmin_f, rmax_f, layer_rmin, layer_rmax, seed):
+    """xsc molecule next to a line-by-line molecule (cfg3 in miniature).  The xsc branch overwrites the layer's
+    T and P with the file's (pyradClasses.py:488-491)."""
+    wd = tempfile.mkdtemp(prefix="pyrad_golden_")
+    rh.seed_workdir(wd)
+    sp = synth.species("co2")
+    T_file, torr = 296, 760.0
+    P_file = torr / 0.75006
+    cutoff = P_file / 1013.25 * 5
+    ln = synth.make_lines(300, max(layer_rmin - cutoff, 0), layer_rmax + cutoff, seed)
+    seed_species(wd, sp, ln, int(max(layer_rmin - cutoff, 0) / 100) * 100, layer_rmax + cutoff + 101)
+    fx, fy = synth.make_xsc_table(rmin_f, rmax_f, file_res, seed + 1)
+    fname = rh.write_xsc_file(wd, "CFC11", float(T_file), torr, rmin_f, rmax_f, file_res, fx, fy)
+    ref = rh.load_reference(wd)
+    C = ref.classes
+    out = {"file_x": fx, "file_y": fy, "file_res": file_res, "file_rmin": rmin_f, "file_rmax": rmax_f,
+           "layer_rmin": layer_rmin, "layer_rmax": layer_rmax, "molmass": sp.molmass, "q296": sp.q296,
+           "conc_xsc": 250e-12, "conc_co2": 400e-6, "depth": 100.0}
+    with rh.quiet():
+        layer = C.Layer(100.0, 250, 500.0, layer_rmin, layer_rmax)
+        xm = layer.addMolecule({"CFC11": fname}, concentration=250e-12)
+        out["T_after"] = layer.T
+        out["P_after"] = layer.P
+        m = layer.addMolecule("co2", concentration=400e-6)
+        out["qT"] = sp.q(layer.T)
+        out["xaxis"] = np.asarray(layer.xAxis)
+        out["xsc_sigma"] = np.asarray(C.getCrossSection(xm), dtype=np.float64)
+        out["co2_sigma"] = np.asarray(C.getCrossSection(m[0]))
+        out["layer_abscoef"] = np.asarray(C.getAbsCoef(layer))
+        out["layer_transmittance"] = np.asarray(C.getTransmittance(layer))
+        out["res"] = layer.resolution
+        out["cutoff"] = layer.distanceFromCenter
+    out.update(pack_lines("lines0", ln))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "N=%d xsc nonzero=%d T,P after=%s,%s" % (len(out["xsc_sigma"]), int(np.count_nonzero(out["xsc_sigma"])),
+                                                        out["T_after"], out["P_after"]))
+
+
+def case_kat(name):
+    """Known-answer values straight from the real physics modules."""
+    wd = tempfile.mkdtemp(prefix="pyrad_golden_")
+    ref = rh.load_reference(wd)
+    I, L, Pk = ref.intensity, ref.lineshape, ref.planck
+    m = 43.98983 / 1000 / 6.022140857E23
+    g = L.gaussianHW(667.661, 250, m)
+    l = L.lorentzHW(.07, .09, 500., 250, 4e-4, .7)
+    l2 = L.lorentzHW(.07, .09, 10., 250, 4e-4, .7)
+    x = np.array([0, .01, .1, 1])
+    x2 = np.array([0, .001, .002, .01])
+    out = {
+        "c2": I.c2, "boltz": I.boltzmannFactors(100, 250), "stim": I.stimulatedEmissions(667.661, 250),
+        "intensity": I.intensityFactor(3.0e-19, 667.661, 250, 100.0, 220.0, 286.09),
+        "m": m, "gHW": g, "lHW": l, "lHW2": l2,
+        "x": x, "x2": x2,
+        "lorentz": L.lorentzLineShape(l, x), "voigt": L.pseudoVoigtShape(g, l, x), "gauss0": L.gaussianLineShape(g, 0),
+        "gauss": L.gaussianLineShape(g, x2), "voigt2": L.pseudoVoigtShape(g, l2, x2),
+        "planck": Pk.planckWavenumber(np.array([1., 667., 2000.]), 288),
+    }
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: (v if np.ndim(v) == 0 else "...") for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    if not rh.available():
+        raise SystemExit("the reference is not mounted at %s" % rh.REFERENCE_DIR)
+    case_kat("kat")
+    case_gas_cell("cell_co2_1atm", ["co2"], [400e-6], 1500, 600.0, 700.0, 296, 1013.0, 10.0, 101)
+    case_gas_cell("cell_lowp", ["co2", "h2o"], [400e-6, 0.005], 900, 640.0, 690.0, 220, 5.0, 1000.0, 202)
+    case_gas_cell("cell_tiny_window", ["co2"], [400e-6], 600, 660.0, 680.0, 200, 0.05, 1e5, 303)
+    case_gas_cell("cell_fine_grid", ["h2o", "co2"], [0.01, 400e-6], 700, 1000.0, 1008.0, 280, 800.0, 50.0, 404,
+                  base=0.001, dynamic=False)
+    case_gas_cell("cell_highp_dynres", ["co2"], [0.02], 400, 600.0, 700.0, 300, 20000.0, 5.0, 505)
+    case_xsc("xsc_native_res", 0.01, 830.0, 860.0, 800.0, 900.0, 606)
+    case_xsc("xsc_coarse_res", 0.05, 830.0, 860.0, 800.0, 900.0, 707)

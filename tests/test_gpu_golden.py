@@ -1,0 +1,86 @@
+"""GPU tests: the drop-in host mirror (pyrad_b200.classes, same API as the reference's pyradClasses) driven
+through the C ABI on the same on-disk data tree the reference read, compared with the golden vectors the
+REAL reference produced (tests/golden/make_golden.py).  Reads like the reference's own usage (main.py:35-46)."""
+import numpy as np
+import pytest
+
+from oracle import ref_harness as rh          # only its data-tree writers (test infrastructure)
+from pyrad_b200 import classes as C
+from pyrad_b200 import synth
+from tests import golden_util as G
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def data_root(tmp_path, engine):
+    C.set_engine(engine)
+    C.DATA_ROOT = str(tmp_path)
+    C.Layer.hasAtmosphere = False
+    old = C.BASE_RESOLUTION
+    yield str(tmp_path)
+    C.BASE_RESOLUTION = old
+    C.DATA_ROOT = None
+
+
+def seed(root, g, group, name):
+    sp = synth.species(name)
+    ln = G.lines_of(g, group)
+    rh.write_params(root, sp.global_iso, sp.name, sp.mol_id, 1, 0.99, sp.q296, 1, sp.molmass)
+    rh.write_q_table(root, sp.global_iso, range(100, 501), [sp.q(t) for t in range(100, 501)])
+    rh.write_line_segments(root, sp.global_iso, sp.mol_id, 1, ln, int(ln["nu"].min() / 100) * 100, ln["nu"].max() + 101)
+
+
+@pytest.mark.parametrize("name", G.CELL_CASES)
+def test_mirror_matches_reference_gas_cell(name, data_root):
+    g = G.load(name)
+    species = [str(s) for s in g["species"]]
+    for i, s in enumerate(species):
+        seed(data_root, g, i, s)
+    C.BASE_RESOLUTION = float(g["base"])
+    T = int(g["T"])
+    layer = C.Layer(float(g["depth"]), T, float(g["P"]), float(g["range_min"]), float(g["range_max"]),
+                    dynamicResolution=bool(g["dynamic"]))
+    mols = [layer.addMolecule(s, concentration=float(c)) for s, c in zip(species, g["conc"])]
+    assert layer.resolution == float(g["res"]) and layer.distanceFromCenter == float(g["cutoff"])
+    np.testing.assert_array_equal(layer.xAxis, g["xaxis"])
+    for i, m in enumerate(mols):
+        np.testing.assert_array_equal([l.wavenumber for l in m[0]], g["kept_nu_%d" % i])
+        sig = C.getCrossSection(m[0])
+        assert H.k_rel_err(sig, g["sigma_%d" % i]).max() <= H.K_REL_TOL
+        assert H.k_rel_err(C.getAbsCoef(m), g["abscoef_%d" % i]).max() <= H.K_REL_TOL
+    assert H.k_rel_err(C.getAbsCoef(layer), g["layer_abscoef"]).max() <= H.K_REL_TOL
+    assert np.abs(C.getTransmittance(layer) - g["layer_transmittance"]).max() <= H.T_ABS_TOL
+    np.testing.assert_allclose(layer.planck(T), g["layer_planck"], rtol=1e-12)
+    out = layer.transmission(g["surface"])
+    np.testing.assert_allclose(out, g["layer_transmission"], rtol=2e-5)
+
+
+@pytest.mark.parametrize("name", G.XSC_CASES)
+def test_mirror_matches_reference_xsc(name, data_root):
+    g = G.load(name)
+    seed(data_root, g, 0, "co2")
+    fname = rh.write_xsc_file(data_root, "CFC11", 296.0, 760.0, float(g["file_rmin"]), float(g["file_rmax"]),
+                              float(g["file_res"]), g["file_x"], g["file_y"])
+    layer = C.Layer(100.0, 250, 500.0, float(g["layer_rmin"]), float(g["layer_rmax"]))
+    xm = layer.addMolecule({"CFC11": fname}, concentration=250e-12)
+    assert layer.T == int(g["T_after"]) and layer.P == float(g["P_after"])     # forced to the file's T, P
+    m = layer.addMolecule("co2", concentration=400e-6)
+    np.testing.assert_allclose(C.getCrossSection(xm), g["xsc_sigma"], rtol=1e-14, atol=0)
+    assert H.k_rel_err(C.getCrossSection(m[0]), g["co2_sigma"]).max() <= H.K_REL_TOL
+    assert H.k_rel_err(C.getAbsCoef(layer), g["layer_abscoef"]).max() <= H.K_REL_TOL
+    assert np.abs(C.getTransmittance(layer) - g["layer_transmittance"]).max() <= H.T_ABS_TOL
+
+
+def test_mirror_error_behaviour(data_root):
+    g = G.load("cell_co2_1atm")
+    seed(data_root, g, 0, "co2")
+    layer = C.Layer(10.0, 296.5, 1013.0, 600.0, 700.0)            # non-integer T: Q lookup fails like the reference
+    m = layer.addMolecule("co2", ppm=400)
+    with pytest.raises(KeyError):
+        C.getCrossSection(m[0])
+    layer.changeTemperature(296)
+    assert H.k_rel_err(C.getCrossSection(m[0]), g["sigma_0"]).max() <= H.K_REL_TOL
+    layer.changePressure(500.0)                                    # invalidates and recomputes (lazy cache)
+    assert not m[0].progressCrossSection

@@ -1,0 +1,105 @@
+"""CPU tests of host-side logic that needs no device: numpy-compatible helpers, workloads, the mirror's
+bookkeeping, bench plumbing."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from oracle import physics as ph
+from pyrad_b200 import classes as C
+from pyrad_b200 import engine as eng
+from pyrad_b200 import synth
+from pyrad_b200 import workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_linspace_axis_reproduces_numpy_bitwise():
+    for a, b, n in [(600.0, 700.0, 10000), (0.0, 3000.0, 3000000), (1000.0, 1008.0, 8000)]:
+        x0, dx, xl, n_ = eng.linspace_axis(a, b, n)
+        ref = np.linspace(a, b, n, endpoint=True)
+        mine = np.arange(n) * dx + x0
+        mine[-1] = xl
+        assert np.array_equal(mine, ref)
+
+
+def test_window_and_grid_rules_follow_numpy():
+    assert eng.window_len(5 * 1013 / 1013.25, .01) == 500
+    assert eng.window_len(25, .001) == 25000
+    assert eng.window_len(0.000246731, .01) == 1
+    assert eng.grid_len(600.0, 607.77, 0.01) == int((607.77 - 600.0) / 0.01)
+    assert eng.number_density_weight(4e-4, 1013.25, 296) == 4e-4 * 1013.25 / 1E4 / 1.38064852E-23 / 296
+
+
+def test_workloads_are_seeded_sorted_and_shaped():
+    w1, w2 = workloads.cfg1(2000), workloads.cfg1(2000)
+    assert np.array_equal(w1["lines"]["nu"], w2["lines"]["nu"])
+    assert np.all(np.diff(w1["lines"]["nu"]) > 0)
+    w = workloads.cfg2(4000, 30.0)
+    assert set(np.unique(w["lines"]["group"])) == {0, 1, 2, 3}
+    assert np.all(np.diff(w["lines"]["nu"]) >= 0)
+    a = workloads.atmosphere(n_layers=10, n_lines=1000, rmax=50.0)
+    assert a["conc"].shape == (10, 4) and np.all(np.diff(a["P"]) < 0)
+    assert np.all(a["T"] == np.round(a["T"]))                # integer K: the reference's Q lookup needs it
+    s0, s1 = workloads.cfg2_shard(0, 2, 4000, 30.0), workloads.cfg2_shard(1, 2, 4000, 30.0)
+    assert s0["n_total"] == s1["n_total"] == 60000 and s0["i_end"] == s1["i_begin"] == 30000
+    # the margin lines of neighbouring shards are the same physical lines
+    edge0 = s0["lines"]["nu"][s0["lines"]["nu"] > 30.0 - 5]
+    edge1 = s1["lines"]["nu"][s1["lines"]["nu"] < 30.0 + s0["cutoff"]]
+    both = np.intersect1d(edge0, edge1)
+    assert both.size > 0 and np.all((both > 30.0 - s0["cutoff"]) & (both < 30.0 + s0["cutoff"]))
+
+
+def test_us_standard_atmosphere_anchor_points():
+    t, p = synth.us_standard_atmosphere(0.0)
+    assert abs(t - 288.15) < 1e-9 and abs(p - 1013.25) < 1e-9
+    t, p = synth.us_standard_atmosphere(11.0)
+    assert abs(t - 216.65) < 1e-6 and abs(p - 226.32) < 0.05
+    t, p = synth.us_standard_atmosphere(47.0)
+    assert abs(t - 270.65) < 1e-6 and abs(p - 1.1091) < 0.002
+
+
+def test_merge_plan_matches_oracle_merge_array():
+    rng = np.random.default_rng(3)
+    new_x = np.linspace(800.0, 900.0, 10000)
+    for lo, hi in [(830.0, 860.0), (800.0, 900.0), (805.5, 806.5)]:
+        old_x = np.arange(lo, hi, .01)
+        old_y = rng.uniform(1, 2, old_x.size)
+        ref = ph.merge_array(new_x, old_x, old_y)
+        dst0, src0, count, out_len = C._merge_plan(new_x, old_x)
+        assert out_len == len(ref)
+        mine = np.zeros(out_len)
+        mine[dst0:dst0 + count] = old_y[src0:src0 + count]
+        assert np.array_equal(mine, ref)
+    # new range inside the old one
+    old_x = np.arange(700.0, 1000.0, .01)
+    old_y = rng.uniform(1, 2, old_x.size)
+    ref = ph.merge_array(new_x, old_x, old_y)
+    dst0, src0, count, out_len = C._merge_plan(new_x, old_x)
+    mine = np.zeros(out_len)
+    mine[dst0:dst0 + count] = old_y[src0:src0 + count]
+    assert np.array_equal(mine, ref)
+
+
+def test_unit_conversions_and_concentration_setters():
+    assert C.convertLength(2, "m") == 200 and C.convertPressure(1, "atm") == 1013.25
+    assert C.convertRange(10, "um") == 1000 and C.convertTemperature(27, "C") == 300
+    layer = C.Layer(10, 296, 1013.25, 600, 700)
+    assert layer.distanceFromCenter == 5.0 and layer.resolution == .01
+    assert len(layer.xAxis) == 10000 and layer.xAxis[1] - layer.xAxis[0] != .01      # linspace spacing, not res
+    layer.changePressure(500.0)
+    assert layer.distanceFromCenter == 500.0 / 1013.25 * 5
+    assert layer.effectiveRangeMax == 705.0                                         # quirk: not updated
+
+
+def test_reference_arm_prints_one_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "line-gridpoint evals/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0

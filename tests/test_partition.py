@@ -1,0 +1,103 @@
+"""CPU tests of the multi-GPU host logic: pair-count-balanced, tile-aligned wavenumber chunks, per-rank line
+subsets and the padded all-gather -- including a real world_size-2 run over gloo."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import physics as ph
+from pyrad_b200 import distributed as pd
+from pyrad_b200 import partition as pt
+from pyrad_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_block_cost_equals_reference_pair_count():
+    rng = np.random.default_rng(0)
+    n_total = 20000
+    idx = np.sort(rng.integers(-600, n_total + 600, 3000))
+    for windows in ([500], [3, 50, 500], [1], [2, 700, 700]):
+        cost = pt.block_pair_cost(idx, n_total, windows, block=1024)
+        assert cost.sum() == sum(ph.pair_count(idx, n_total, w) for w in windows)
+        b = 5
+        brute = 0
+        for w in windows:
+            wm = max(w - 2, 0)
+            lo = np.maximum(idx - wm, b * 1024)
+            hi = np.minimum(idx + wm, min((b + 1) * 1024, n_total) - 1)
+            brute += np.maximum(hi - lo + 1, 0).sum()
+        assert cost[b] == brute
+
+
+def test_chunks_are_aligned_contiguous_and_balanced():
+    rng = np.random.default_rng(1)
+    n_total = 1_000_000
+    # strongly non-uniform line density: a band head
+    nu = np.sort(np.concatenate([rng.uniform(0, 1000, 20000), rng.normal(650, 15, 80000)]))
+    idx = pt.line_index(nu, 0.0, 0.001)
+    cost = pt.block_pair_cost(idx, n_total, [5000, 2000, 300])
+    for world in (2, 4, 8):
+        ch = pt.balanced_chunks(cost, n_total, world)
+        assert ch[0][0] == 0 and ch[-1][1] == n_total
+        assert all(a[1] == b[0] for a, b in zip(ch[:-1], ch[1:]))
+        assert all(a % pt.ALIGN == 0 for a, _ in ch)
+        per = [cost[a // pt.ALIGN:(b + pt.ALIGN - 1) // pt.ALIGN].sum() for a, b in ch]
+        assert max(per) <= 1.15 * cost.sum() / world + cost.max()
+        eq = pt.equal_chunks(n_total, world)
+        per_eq = [cost[a // pt.ALIGN:(b + pt.ALIGN - 1) // pt.ALIGN].sum() for a, b in eq]
+        assert max(per) <= max(per_eq)
+
+
+def test_line_subset_reaches_every_window():
+    ln = synth.make_lines(5000, 0.0, 100.0, 5)
+    idx = pt.line_index(ln["nu"], 0.0, 0.01)
+    l0, l1 = pt.lines_for_chunk(ln["nu"], 0.0, 0.01, 4096, 8192, 498)
+    inside = (idx >= 4096 - 498) & (idx <= 8191 + 498)
+    assert np.array_equal(np.nonzero(inside)[0], np.arange(l0, l1))
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ln = synth.make_lines(800, 598.0, 642.0, 21)
+        rmin, rmax, res, P, T = 600.0, 640.0, 0.0025, 300.0, 250
+        cutoff = ph.layer_cutoff(P)
+        n_total = ph.grid_len(rmin, rmax, res)
+        W = ph.window_len(cutoff, res)
+        plan = pd.ShardPlan(ln["nu"], rmin, res, n_total, [W], rank, world)
+        sub = plan.subset(ln)
+        # stand-in for the CUDA engine: the oracle evaluates ONLY this rank's chunk from ONLY its line subset
+        pts = np.arange(plan.i_begin, plan.i_end)
+        local = ph.cross_section_at(pts, sub, T, P, 4e-4, 43.98983, 250.0, 286.09, rmin, rmax, res, cutoff)
+        g = pd.all_gather_spectra(torch.from_numpy(local), plan, dist)
+        full = pd.assemble(g, plan).numpy()
+        ref = ph.cross_section(ln, T, P, 4e-4, 43.98983, 250.0, 286.09, rmin, rmax, res, cutoff)
+        ok = full.shape == ref.shape and np.allclose(full, ref, rtol=1e-12, atol=0)
+        q.put((rank, bool(ok), plan.chunks))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_all_gather_assembles_the_unsharded_spectrum():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    assert res[0][2] == res[1][2]                       # both ranks derived the same plan
