@@ -66,6 +66,8 @@ int         prb_synchronize(prb_engine *e);             /* stream sync + deferre
 int         prb_device_info(prb_engine *e, int *sm_count, int *cc_major, int *cc_minor,
                             int *sm_clock_khz, size_t *free_bytes, size_t *total_bytes);
 int         prb_set_k2_variant(prb_engine *e, int variant, int points_per_thread /* 0 = auto */);
+/* windows with W-2 < wm_below use the thread-per-point kernel k2_narrow (0 = never, <0 = default 128) */
+int         prb_set_narrow_threshold(prb_engine *e, int64_t wm_below);
 
 /* ---- line list (a1): SoA float64, ascending nu0; group[i] in [0, n_groups) or NULL (all 0) - */
 int prb_upload_lines(prb_engine *e, int64_t n,
@@ -135,6 +137,7 @@ int prb_atmosphere_read_f32(prb_engine *e, float *radiance_host, float *transmit
 /* stage timing: CUDA events on the engine stream, summed over layers, of the last prb_atmosphere */
 int prb_set_timing(prb_engine *e, int enabled);
 int prb_atmosphere_timing(prb_engine *e, float *k1_ms, float *k2_ms, float *k3_ms);
+int prb_atmosphere_layer_timing(prb_engine *e, int32_t n_layers, float *k1_ms, float *k2_ms);   /* per layer */
 int prb_atmosphere_kmatrix_dev(prb_engine *e, void **kmat_dev, int64_t *ld);                 /* float[L][ld] */
 
 #ifdef __cplusplus

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpyrad_b200.so")
+LIB_PATH = os.environ.get("PRB_LIB") or os.path.join(_HERE, "libpyrad_b200.so")   # PRB_LIB: development A/B builds only
 
 
 class EngineUnavailable(RuntimeError):
@@ -40,6 +40,7 @@ PROTOTYPES = {
     "prb_device_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "prb_set_k2_variant": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "prb_set_narrow_threshold": (C.c_int, [_vp, _i64]),
     "prb_upload_lines": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _i32]),
     "prb_set_grid": (C.c_int, [_vp, _d, _d, _i64, _i64, _i64]),
     "prb_layer_prepass": (C.c_int, [_vp, _d, _d, _i32, _dp, _dp, _dp, _dp, _dp, _i64]),
@@ -56,6 +57,7 @@ PROTOTYPES = {
     "prb_atmosphere_read_f32": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "prb_set_timing": (C.c_int, [_vp, C.c_int]),
     "prb_atmosphere_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "prb_atmosphere_layer_timing": (C.c_int, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "prb_atmosphere_kmatrix_dev": (C.c_int, [_vp, C.POINTER(_vp), _lp]),
 }
 

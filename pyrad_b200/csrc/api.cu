@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "k1_prepass.cuh"
 #include "k2_line_sum.cuh"
+#include "k2_narrow.cuh"
 #include "k3_stream.cuh"
 
 using namespace prb;
@@ -57,6 +58,7 @@ struct DevBuf {
 struct PrepassArgs {
     double T = 0, P = 0, scale = 1;
     int64_t W = 0, wm = 0, l0 = 0, l1 = 0, k1_begin = 0, k1_end = 0;
+    int narrow = 0;              // record layout / kernel: 1 = k2_narrow (thread-per-point gather)
     bool valid = false;
 };
 
@@ -82,12 +84,13 @@ struct prb_engine {
     std::vector<int32_t> h_idx;
 
     // per-layer
-    DevBuf<float4> rec4;
-    DevBuf<float2> rec2;
+    DevBuf<float4> recA, recB;
+    DevBuf<float> recD;
     DevBuf<GroupParams> gp;       // n_layers * n_groups
     DevBuf<DevState> st;          // one per layer
     PrepassArgs last;
     int k2_variant = PRB_K2_CLASSED, k2_ppt = 0;
+    int64_t narrow_wm = 128;     // windows with W-2 below this use k2_narrow
 
     // outputs / scratch
     DevBuf<double> out64;
@@ -101,6 +104,7 @@ struct prb_engine {
     bool timing = false;
     std::vector<cudaEvent_t> ev;
     float t_k1 = 0, t_k2 = 0, t_k3 = 0;
+    std::vector<float> t_layer_k1, t_layer_k2;
 };
 
 static int64_t chunk_len(const prb_engine *e) { return e->i_end - e->i_begin; }
@@ -145,7 +149,7 @@ extern "C" int prb_destroy(prb_engine *e) {
     cudaStreamSynchronize(e->stream);
     e->nu0.release(); e->s296.release(); e->gair.release(); e->gself.release();
     e->elower.release(); e->nair.release(); e->delta.release(); e->group.release();
-    e->idx.release(); e->rec4.release(); e->rec2.release(); e->gp.release(); e->st.release();
+    e->idx.release(); e->recA.release(); e->recB.release(); e->recD.release(); e->gp.release(); e->st.release();
     e->out64.release(); e->scratch_a.release(); e->scratch_b.release(); e->scratch_c.release();
     e->scratch_d.release(); e->scratch_w.release();
     e->kmat.release(); e->rad.release(); e->trans.release(); e->fold.release();
@@ -202,8 +206,8 @@ extern "C" int prb_device_info(prb_engine *e, int *sm_count, int *cc_major, int 
 extern "C" int prb_set_k2_variant(prb_engine *e, int variant, int ppt) {
     if (!e) return fail(PRB_ERR_ARG, "null engine");
     if (variant != PRB_K2_GENERAL && variant != PRB_K2_CLASSED) return fail(PRB_ERR_ARG, "unknown K2 variant");
-    if (ppt != 0 && ppt != 1 && ppt != 2 && ppt != 4 && ppt != 8 && ppt != 16)
-        return fail(PRB_ERR_ARG, "points_per_thread must be 0 (auto), 1, 2, 4, 8 or 16");
+    if (ppt != 0 && ppt != 2 && ppt != 4 && ppt != 8 && ppt != 16)
+        return fail(PRB_ERR_ARG, "points_per_thread must be 0 (auto), 2, 4, 8 or 16");
     e->k2_variant = variant;
     e->k2_ppt = ppt;
     return PRB_OK;
@@ -227,7 +231,7 @@ extern "C" int prb_upload_lines(prb_engine *e, int64_t n, const double *nu0, con
         for (int64_t i = 0; i < n; ++i)
             if (group[i] < 0 || group[i] >= n_groups) return fail(PRB_ERR_ARG, "prb_upload_lines: group id out of range");
     CK(cudaSetDevice(e->device));
-    const int64_t na = n + 8;                                   // padding records for even-sized TMA copies
+    const int64_t na = n + 16;                                  // padding records: TMA copies are 16-byte granular
     DevBuf<double> *cols[7] = {&e->nu0, &e->s296, &e->gair, &e->gself, &e->elower, &e->nair, &e->delta};
     const double *src[7] = {nu0, s296, gamma_air, gamma_self, elower, n_air, delta_air};
     for (int c = 0; c < 7; ++c) {
@@ -240,8 +244,9 @@ extern "C" int prb_upload_lines(prb_engine *e, int64_t n, const double *nu0, con
         if (n) CK(cudaMemcpyAsync(e->group.p, group, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
     }
     CK(e->idx.ensure(na));
-    CK(e->rec4.ensure(na));
-    CK(e->rec2.ensure(na));
+    CK(e->recA.ensure(na));
+    CK(e->recB.ensure(na));
+    CK(e->recD.ensure(na));
     CK(cudaStreamSynchronize(e->stream));
     e->n_lines = n;
     e->n_alloc = na;
@@ -303,6 +308,14 @@ static double pick_scale(double s_max, double w_max) {
     return std::ldexp(1.0, 20 - std::ilogb(m));
 }
 
+static LayerConsts layer_consts(double T, double res) {
+    LayerConsts lc;
+    lc.log_t0_over_t = std::log(kT0 / T);
+    lc.inv_t_minus_inv_t0 = 1.0 / T - 1.0 / kT0;
+    lc.inv_res2 = 1.0 / (res * res);
+    return lc;
+}
+
 static int launch_prepass(prb_engine *e, double T, double P, int64_t W, const GroupParams *gp_dev, double scale,
                           DevState *st_dev, DebugOut dbg, PrepassArgs *pa) {
     const int64_t wm = std::max<int64_t>(W - 2, 0);
@@ -313,19 +326,21 @@ static int launch_prepass(prb_engine *e, double T, double P, int64_t W, const Gr
     int64_t l0 = std::lower_bound(hb, hb + n, klo, [](int32_t a, int64_t k) { return (int64_t)a < k; }) - hb;
     int64_t l1 = std::upper_bound(hb, hb + n, khi, [](int64_t k, int32_t a) { return k < (int64_t)a; }) - hb;
     if (l1 < l0) l1 = l0;
-    const int64_t kb = l0 & ~int64_t(1);
-    const int64_t ke = std::min<int64_t>(l1 + 4, e->n_alloc);
+    const int narrow = (e->k2_variant == PRB_K2_CLASSED && wm < e->narrow_wm) ? 1 : 0;
+    const int64_t kb = l0 & ~int64_t(3);
+    const int64_t ke = std::min<int64_t>(l1 + 8, e->n_alloc);
     LinesSoA L{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
                e->has_group ? e->group.p : nullptr};
     const int64_t cnt = ke - kb;
     if (cnt > 0) {
         k1_prepass<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(
-            L, e->idx.p, gp_dev, kb, ke, n, T, P, e->res, scale, e->i_begin, (double)wm, e->rec4.p, e->rec2.p,
-            st_dev, dbg);
+            L, e->idx.p, gp_dev, kb, ke, n, T, P, layer_consts(T, e->res), scale, e->i_begin, (double)wm, narrow, e->recA.p, e->recB.p,
+            e->recD.p, st_dev, dbg);
         CK(cudaGetLastError());
     }
     pa->T = T; pa->P = P; pa->scale = scale; pa->W = W; pa->wm = wm;
     pa->l0 = l0; pa->l1 = l1; pa->k1_begin = kb; pa->k1_end = ke;
+    pa->narrow = narrow;
     pa->valid = true;
     return PRB_OK;
 }
@@ -391,11 +406,11 @@ extern "C" int prb_debug_line_params(prb_engine *e, double *nu_shift, double *ga
     LinesSoA L{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
                e->has_group ? e->group.p : nullptr};
     // records are scratch here: use temporaries so the live prepass is not disturbed
-    DevBuf<float4> r4; DevBuf<float2> r2;
-    CK(r4.ensure(na)); CK(r2.ensure(na));
+    DevBuf<float4> r4, r5; DevBuf<float> r2;
+    CK(r4.ensure(na)); CK(r5.ensure(na)); CK(r2.ensure(na));
     k1_prepass<<<(unsigned)((na + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, e->gp.p, 0, na, n, e->last.T, e->last.P,
-                                                                   e->res, e->last.scale, save_b, (double)e->last.wm,
-                                                                   r4.p, r2.p, st.p, dbg);
+                                                                   layer_consts(e->last.T, e->res), e->last.scale, save_b, (double)e->last.wm, 0,
+                                                                   r4.p, r5.p, r2.p, st.p, dbg);
     e->i_begin = save_b; e->i_end = save_e;
     CK(cudaGetLastError());
     if (nu_shift) CK(cudaMemcpyAsync(nu_shift, e->scratch_a.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
@@ -405,7 +420,7 @@ extern "C" int prb_debug_line_params(prb_engine *e, double *nu_shift, double *ga
     if (regime) CK(cudaMemcpyAsync(regime, reg.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (index) for (int64_t i = 0; i < n; ++i) index[i] = e->h_idx[i];
-    r4.release(); r2.release(); reg.release(); st.release();
+    r4.release(); r5.release(); r2.release(); reg.release(); st.release();
     return PRB_OK;
 }
 
@@ -415,8 +430,7 @@ static int pick_ppt(const prb_engine *e, int64_t wm) {
     // a warp spans 32*P points: keep the span well inside the window so most lines cover it fully
     if (wm >= 1024) return 8;
     if (wm >= 256) return 4;
-    if (wm >= 64) return 2;
-    return 1;
+    return 2;
 }
 
 template <int P>
@@ -425,15 +439,22 @@ static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
     a.n_tiles = (int)((a.n_chunk + tile - 1) / tile);
     if (a.n_tiles == 0) return cudaSuccess;
     const size_t smem = sizeof(K2Smem);
-    const int grid = std::min(a.n_tiles, 2 * e->prop.multiProcessorCount);
+    static bool attr_set = false;                               // per template instance
+    if (!attr_set) {
+        cudaError_t ce = cudaFuncSetAttribute(k2_line_sum<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return ce;
+        attr_set = true;
+    }
+    const int grid = std::min(a.n_tiles, K2_MIN_CTAS * e->prop.multiProcessorCount);
     k2_line_sum<P><<<grid, K2_THREADS, smem, e->stream>>>(a);
     return cudaGetLastError();
 }
 
 static int launch_line_sum(prb_engine *e, const PrepassArgs &pa, DevState *st_dev, void *out_dev, int out_mode) {
     K2Args a{};
-    a.rec4 = e->rec4.p;
-    a.rec2 = e->rec2.p;
+    a.recA = e->recA.p;
+    a.recB = e->recB.p;
+    a.recD = e->recD.p;
     a.idx = e->idx.p;
     a.l_begin = (int)pa.l0;
     a.l_end = (int)pa.l1;
@@ -446,8 +467,14 @@ static int launch_line_sum(prb_engine *e, const PrepassArgs &pa, DevState *st_de
     a.out = out_dev;
     a.st = st_dev;
     cudaError_t ce;
+    if (pa.narrow) {
+        a.n_tiles = (a.n_chunk + KN_TILE - 1) / KN_TILE;
+        if (a.n_tiles > 0) k2_narrow<<<a.n_tiles, KN_THREADS, sizeof(KNSmem), e->stream>>>(a);
+        ce = cudaGetLastError();
+        if (ce != cudaSuccess) return fail(PRB_ERR_CUDA, std::string("k2_narrow launch failed: ") + cudaGetErrorString(ce));
+        return PRB_OK;
+    }
     switch (pick_ppt(e, pa.wm)) {
-        case 1: ce = launch_k2_t<1>(e, a); break;
         case 2: ce = launch_k2_t<2>(e, a); break;
         case 4: ce = launch_k2_t<4>(e, a); break;
         case 16: ce = launch_k2_t<16>(e, a); break;
@@ -650,12 +677,16 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
     CK(cudaStreamSynchronize(e->stream));                       // pageable staging vectors go out of scope
     if (e->timing) {
         e->t_k1 = e->t_k2 = e->t_k3 = 0;
+        e->t_layer_k1.assign(n_layers, 0.f);
+        e->t_layer_k2.assign(n_layers, 0.f);
         for (int l = 0; l < n_layers; ++l) {
             float a = 0, b = 0;
             CK(cudaEventElapsedTime(&a, e->ev[2 * l], e->ev[2 * l + 1]));
             CK(cudaEventElapsedTime(&b, e->ev[2 * l + 1], e->ev[2 * l + 2]));
             e->t_k1 += a;
             e->t_k2 += b;
+            e->t_layer_k1[l] = a;
+            e->t_layer_k2[l] = b;
         }
         CK(cudaEventElapsedTime(&e->t_k3, e->ev[2 * n_layers], e->ev[2 * n_layers + 1]));
     }
@@ -715,5 +746,22 @@ extern "C" int prb_atmosphere_timing(prb_engine *e, float *k1_ms, float *k2_ms, 
     if (k1_ms) *k1_ms = e->t_k1;
     if (k2_ms) *k2_ms = e->t_k2;
     if (k3_ms) *k3_ms = e->t_k3;
+    return PRB_OK;
+}
+
+extern "C" int prb_atmosphere_layer_timing(prb_engine *e, int32_t n_layers, float *k1_ms, float *k2_ms) {
+    if (!e || !e->atm_layers || !e->timing || (int)e->t_layer_k1.size() != n_layers)
+        return fail(PRB_ERR_STATE, "prb_atmosphere_layer_timing: enable timing, run prb_atmosphere, pass its layer count");
+    for (int l = 0; l < n_layers; ++l) {
+        if (k1_ms) k1_ms[l] = e->t_layer_k1[l];
+        if (k2_ms) k2_ms[l] = e->t_layer_k2[l];
+    }
+    return PRB_OK;
+}
+
+extern "C" int prb_set_narrow_threshold(prb_engine *e, int64_t wm_below) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    e->narrow_wm = wm_below < 0 ? 128 : wm_below;
+    e->last.valid = false;                                      // record layout may change: redo the prepass
     return PRB_OK;
 }

@@ -39,8 +39,18 @@ constexpr unsigned int FLAG_OVERFLOW = 1u, FLAG_NONFINITE = 2u;
 // K2 geometry
 constexpr int K2_CONSUMERS = 8;          // math warps per CTA
 constexpr int K2_THREADS = 32 * (K2_CONSUMERS + 1);   // + one TMA producer warp
-constexpr int K2_CHUNK = 256;            // lines staged per ring slot (one pair of TMA bulk copies)
-constexpr int K2_STAGES = 6;             // ring depth
+#ifndef PRB_K2_CHUNK
+#define PRB_K2_CHUNK 256
+#endif
+#ifndef PRB_K2_STAGES
+#define PRB_K2_STAGES 6
+#endif
+#ifndef PRB_K2_MIN_CTAS
+#define PRB_K2_MIN_CTAS 2
+#endif
+constexpr int K2_CHUNK = PRB_K2_CHUNK;   // lines staged per ring slot (three TMA bulk copies)
+constexpr int K2_STAGES = PRB_K2_STAGES; // ring depth
+constexpr int K2_MIN_CTAS = PRB_K2_MIN_CTAS;   // resident CTAs per SM the register budget is sized for
 constexpr int K2_FLUSH = 64;             // lines accumulated in FP32 before flushing into FP64
 constexpr float K2_SENTINEL = 3.0e38f;   // fidx of padding records: outside every window
 

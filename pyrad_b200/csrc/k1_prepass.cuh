@@ -7,7 +7,7 @@
 //   regime select       pyradClasses.py:378-387   ratio < .01 Gauss, > 100 Lorentz, else pseudo-Voigt
 //   S(T)                pyradIntensity.py:16-32   S296 (Q296/QT) stim(nu*,T) boltz(E'',T)
 //   pseudo-Voigt f, eta pyradLineshape.py:58-71
-// and packs what K2 needs into two FP32 records per line.  With d = i - idx (grid units):
+// and packs what K2 needs into FP32 records (36 B per line, see k2_line_sum.cuh).  With d = i - idx (grid units):
 //   contribution(d) = A / (d^2 + B) + G * exp2(C * d^2)
 //   Voigt  : h = f/2;  A = S eta h / pi / res^2;  B = (h/res)^2;  G = S (1-eta) / (h sqrt(pi));  C = -log2(e)/B
 //   Lorentz: h = gL;   A = S h / pi / res^2;      B = (h/res)^2;  G = 0
@@ -23,6 +23,13 @@ namespace prb {
 struct LinesSoA {
     const double *nu0, *s296, *gair, *gself, *elower, *nair, *delta;
     const int32_t *group;   // may be nullptr (single group)
+};
+
+// Per-layer constants evaluated once on the host in FP64.
+struct LayerConsts {
+    double log_t0_over_t;          // log(296 / T)
+    double inv_t_minus_inv_t0;     // 1/T - 1/296
+    double inv_res2;               // 1 / res^2
 };
 
 struct DebugOut {
@@ -48,83 +55,101 @@ __device__ __forceinline__ double pow5(double x) { double x2 = x * x; return x2 
 __global__ void __launch_bounds__(256)
 k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__restrict__ gp,
            int64_t l_begin, int64_t l_end, int64_t n_lines,
-           double T, double P, double res, double scale, int64_t i_base, double wm,
-           float4 *__restrict__ rec4, float2 *__restrict__ rec2, DevState *st, DebugOut dbg) {
+           double T, double P, LayerConsts lc, double scale, int64_t i_base, double wm, int narrow,
+           float4 *__restrict__ recA, float4 *__restrict__ recB, float *__restrict__ recD, DevState *st,
+           DebugOut dbg) {
     const double c2 = cLight * hPlanck * 100 / kBoltz;          // pyradIntensity.py:13
     int64_t l = l_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int flags = 0;
     if (l < l_end) {
         if (l >= n_lines) {                                       // padding record: never in a window
-            rec4[l] = make_float4(K2_SENTINEL, 0.f, 1.f, 0.f);
-            rec2[l] = make_float2(-1.f, -1.f);
+            if (narrow) {
+                recA[l] = make_float4(-K2_SENTINEL, 0.f, 1.f, 0.f);
+            } else {
+                recA[l] = make_float4(-K2_SENTINEL, -K2_SENTINEL, 0.f, 0.f);
+                recB[l] = make_float4(1.f, 1.f, 0.f, -1.f);
+            }
+            recD[l] = -1.f;
         } else {
             const int g = L.group ? L.group[l] : 0;
             const GroupParams p = gp[g];
             const double nu = L.nu0[l];
             const double nus = nu + L.delta[l] * P / kP0;
+            // (t0/T)^n = exp(n * log(t0/T)): the log is a per-layer constant (lc.log_t0_over_t)
             const double gl = ((1 - p.conc) * L.gair[l] + p.conc * L.gself[l]) * (P / kP0) *
-                              pow(kT0 / T, L.nair[l]);
+                              exp(L.nair[l] * lc.log_t0_over_t);
             const double gd = nus * p.dopp;
             const double ratio = gl / gd;                         // gd == 0 -> inf -> Lorentz, as numpy
             const double stim = (1 - exp(-c2 * nus / T)) / (1 - exp(-c2 * nus / kT0));
-            const double boltz = exp(-c2 * L.elower[l] / T) / exp(-c2 * L.elower[l] / kT0);
+            // exp(-c2 E/T) / exp(-c2 E/t0) evaluated as one exponential (same value to ~1e-16)
+            const double boltz = exp(-c2 * L.elower[l] * lc.inv_t_minus_inv_t0);
             const double S = L.s296[l] * p.qratio * stim * boltz;
             const double sw = S * p.weight * scale;
-            const double res2 = res * res;
+            const double inv_res2 = lc.inv_res2;
             const double log2e = 1.4426950408889634;
-            const double sqrtpi = sqrt(kPi);
+            const double inv_sqrtpi = 0.5641895835477563;         // 1/sqrt(pi)
             double A, B, G, C, bg;                                // bg: Gaussian (h/res)^2
             int regime;
             float dg = -1.0f;
             if (ratio < .01) {
                 regime = REGIME_GAUSS;
                 A = 0.0; B = 1.0;
-                G = sw / gd / sqrtpi;
-                bg = gd * gd / res2;
+                G = sw / gd * inv_sqrtpi;
+                bg = gd * gd * inv_res2;
                 C = -log2e / bg;
             } else if (ratio > 100) {
                 regime = REGIME_LORENTZ;
-                A = sw * gl / kPi / res2;
-                B = gl * gl / res2;
+                A = sw * gl * (inv_res2 / kPi);
+                B = gl * gl * inv_res2;
                 G = 0.0; C = -1.0; bg = 0.0;
             } else {
                 regime = REGIME_VOIGT;
                 const double gFW = 2 * gd, lFW = 2 * gl;
                 const double g2 = gFW * gFW, l2 = lFW * lFW;
-                const double f = pow(pow5(gFW) + 2.69269 * g2 * g2 * lFW + 2.42843 * g2 * gFW * l2 +
-                                     4.47163 * g2 * l2 * lFW + .07842 * gFW * l2 * l2 + pow5(lFW), .2);
+                const double f5 = pow5(gFW) + 2.69269 * g2 * g2 * lFW + 2.42843 * g2 * gFW * l2 +
+                                  4.47163 * g2 * l2 * lFW + .07842 * gFW * l2 * l2 + pow5(lFW);
+                const double f = exp(.2 * log(f5));               // f5 ** .2
                 const double rho = lFW / f;
                 const double eta = 1.36603 * rho - .47719 * rho * rho + .11116 * rho * rho * rho;
                 const double hh = f / 2;
-                A = sw * eta * hh / kPi / res2;
-                B = hh * hh / res2;
-                G = sw * (1 - eta) / hh / sqrtpi;
+                A = sw * eta * hh * (inv_res2 / kPi);
+                B = hh * hh * inv_res2;
+                G = sw * (1 - eta) / hh * inv_sqrtpi;
                 bg = B;
                 C = -log2e / B;
             }
             // near-zone radius: beyond it the Gaussian term is < 1e-9 of the same line's Lorentz term
-            // (or below the scaled FP32 floor for Gaussian-only lines), so K2 may skip it.
-            if (G > 0.0) {
-                double t2 = 160.0;
-                if (A > 0.0) {
-                    const double rho9 = 1e-9 * A / (B * G);
-                    if (rho9 >= 1.0) t2 = -1.0;
+            // (or below the scaled FP32 floor for Gaussian-only lines), so K2 may skip it.  FP32 is
+            // plenty here (the radius is rounded up and padded): solve e^{-t2}(1+t2) <= rho9 with one
+            // fixed-point step from t2 = -ln(rho9) plus a margin of 1 (the step undershoots by < 1).
+            // (G can be negative: a line whose pressure-shifted wavenumber is < 0 gets a negative Doppler width
+            // in the reference, pyradClasses.py:261-263 -- reproduced, so the test is on |G|.)
+            if (G != 0.0) {
+                float t2 = 160.f;
+                if (A != 0.0) {
+                    const float rho9 = (float)fabs(1e-9 * A / (B * G));
+                    if (rho9 >= 1.f) t2 = -1.f;
                     else {
-                        const double ln = -log(rho9);
-                        t2 = ln;
-                        for (int it = 0; it < 4; ++it) t2 = ln + log1p(t2);
-                        t2 = fmin(t2 + 0.5, 160.0);
+                        const float ln = -__logf(fmaxf(rho9, 1e-37f));
+                        t2 = fminf(ln + __logf(1.f + ln) + 1.5f, 160.f);
                     }
                 }
-                if (t2 > 0.0) dg = (float)fmin(ceil(sqrt(t2 * bg)) + 1.0, 3.0e7);
+                if (t2 > 0.f) dg = fminf(ceilf(sqrtf(t2 * (float)bg)) + 2.f, 3.0e7f);
             }
             // FP32 range guards: the paired far path forms A*(d^2+B) with |d| <= wm.
-            const double qmax = wm * wm + B;
+            const double qmax = (wm + 4096.0) * (wm + 4096.0) + B;   // partial lines reach one warp span past the window
             if (!(isfinite(A) && isfinite(G) && isfinite(B) && isfinite(C))) flags |= FLAG_NONFINITE;
             else if (A * qmax > 8.0e37 || G > 8.0e37 || B > 1.0e18 || qmax * qmax > 8.0e37) flags |= FLAG_OVERFLOW;
             const double fi = (double)((int64_t)idx[l] - i_base);
-            rec4[l] = make_float4((float)fi, (float)A, (float)B, (float)G);
-            rec2[l] = make_float2((float)C, dg);
+            const float nf = -(float)fi, Af = (float)A, Bf = (float)B;
+            if (narrow) {                                         // compact layout of k2_narrow
+                recA[l] = make_float4(nf, Af, Bf, (float)G);
+                recD[l] = (float)C;
+            } else {
+                recA[l] = make_float4(nf, nf, Af, Af);
+                recB[l] = make_float4(Bf, Bf, (float)G, (float)C);
+                recD[l] = dg;
+            }
             if (dbg.nu_shift) dbg.nu_shift[l] = nus;
             if (dbg.gl) dbg.gl[l] = gl;
             if (dbg.gd) dbg.gd[l] = gd;

@@ -7,22 +7,24 @@
 // reference's bounds checks becoming "grid point exists").
 //
 // Design (B200 / sm_100a):
-//   * a CTA owns a tile of 256*P consecutive grid points; tiles are handed out by a dynamic counter
-//     (work distribution only).  Every thread keeps P points in registers (FP32 partial sums that are
-//     flushed into FP64 accumulators every <= 64 lines).  No atomics touch data; the per-point
-//     summation order depends only on the tile geometry, so results are deterministic and
-//     independent of how the grid is sharded across GPUs (shards are tile aligned).
-//   * the wavenumber-sorted lines overlapping the tile's cutoff window are found with a 32-ary
-//     warp-ballot search over the sorted index array, then streamed through shared memory in
-//     chunks of 512 records with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), double
-//     buffered so the copy of chunk c+1 overlaps the math of chunk c.
-//   * per chunk every warp classifies the staged (sorted) lines against its own 32*P-point span
-//     by counting (six warp reductions): lines whose window only partly covers the span take a
-//     predicated path; lines that may need their Gaussian core take a two-term path; all other
-//     lines ("far": window covers the span, Gaussian term < 1e-9 of the Lorentz term) take the
-//     paired-reciprocal path  A1/q1 + A2/q2 = (A1 q2 + A2 q1) * rcp(q1 q2):  one MUFU per TWO
-//     (line, point) pairs instead of the naive one to two per pair.  The SFU pipe (16 lanes/clk/SM)
-//     is what bounds the naive formulation, so this is where the kernel gains its speed.
+//   * persistent CTAs of 8 consumer warps + 1 TMA producer warp.  A CTA owns a tile of 256*P consecutive
+//     grid points; tiles are handed out by a dynamic counter (work distribution only).  Every consumer
+//     thread keeps P points in registers (FP32 partial sums flushed into FP64 accumulators every <= 64
+//     lines).  No atomics touch data; the per-point summation order depends only on the tile geometry,
+//     so results are deterministic and independent of how the grid is sharded (shards are tile aligned).
+//   * the producer finds the wavenumber-sorted lines overlapping the tile's cutoff window with a 32-ary
+//     warp-ballot search over the sorted index array and streams their records through a shared-memory
+//     ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP).  Slots are handed
+//     over with full/empty mbarriers only: there is no CTA-wide barrier in the steady state.
+//   * per slot every consumer warp classifies the staged (sorted) lines against its own 32*P-point span
+//     by counting (warp reductions): lines whose window only partly covers the span are evaluated with
+//     a per-point mask, the rest without.
+//   * the Lorentz term of EVERY line goes through the paired reciprocal
+//         A1/q1 + A2/q2 = (A1 q2 + A2 q1) * rcp(q1 q2),   q = d^2 + B
+//     (one MUFU.RCP per TWO (line, point) pairs), written with Blackwell's packed FP32x2 instructions
+//     (FADD2/FMUL2/FFMA2: two grid points per instruction), so a (line, point) pair costs 2 issue slots
+//     of FP32-pipe work + 0.5 MUFU.  The Gaussian core G*exp2(C d^2) is a separate pass over the few
+//     lines whose near zone (|d| <= Dg: beyond it the term is < 1e-9 of the Lorentz term) meets the span.
 //   * tensor cores are deliberately unused: this is not a dense contraction.
 #pragma once
 #include "common.cuh"
@@ -96,12 +98,18 @@ __device__ __forceinline__ int warp_lower_bound(const int32_t *__restrict__ idx,
     return lo;
 }
 
+// Per-line records written by K1 (36 B/line).  Values needed as packed operands are stored twice so
+// that one LDS.128 delivers them as aligned register pairs.
+//   recA = {-fidx, -fidx, A, A}      fidx = line index relative to the shard's first point (exact integer)
+//   recB = {B, B, G, C}
+//   recD = Dg                         near-zone radius in grid points (-1: no Gaussian term)
 struct K2Args {
-    const float4 *rec4;        // {fidx, A, B, G} per line, fidx relative to the chunk's first point
-    const float2 *rec2;        // {C, Dg}
+    const float4 *recA;
+    const float4 *recB;
+    const float *recD;
     const int32_t *idx;        // sorted absolute grid index per line
-    int l_begin, l_end;        // line range prepared by K1 for this chunk
-    long long i_begin;         // absolute index of the chunk's first grid point
+    int l_begin, l_end;        // line range prepared by K1 for this shard
+    long long i_begin;         // absolute index of the shard's first grid point
     int n_chunk;               // grid points owned
     int wm;                    // W-2 clamped at 0: max |d| that still accumulates
     int n_tiles;
@@ -114,7 +122,7 @@ struct K2Args {
 
 // One ring slot: a chunk of staged line records plus its descriptor.
 struct K2Desc {
-    int tile0;      // chunk-local index of the first point of the tile this chunk belongs to
+    int tile0;      // shard-local index of the first point of the tile this chunk belongs to
     int cnt;        // staged lines to process (padding excluded)
     int flags;      // K2_FIRST | K2_LAST | K2_END
     int pad;
@@ -122,128 +130,144 @@ struct K2Desc {
 constexpr int K2_FIRST = 1, K2_LAST = 2, K2_END = 4;
 
 struct K2Smem {
-    float4 r4[K2_STAGES][K2_CHUNK];
-    float2 r2[K2_STAGES][K2_CHUNK];
+    float4 rA[K2_STAGES][K2_CHUNK];
+    float4 rB[K2_STAGES][K2_CHUNK];
+    float rD[K2_STAGES][K2_CHUNK];
     K2Desc desc[K2_STAGES];
     uint64_t full[K2_STAGES];      // producer -> consumers: TMA bytes landed (+ descriptor written)
-    uint64_t empty[K2_STAGES];     // consumers -> producer: all 8 consumer warps are done with the slot
+    uint64_t empty[K2_STAGES];     // consumers -> producer: all consumer warps are done with the slot
 };
 
-template <int P>
-__device__ __forceinline__ void flush(float (&a32)[P], double (&a64)[P]) {
+// Per-thread state of a consumer: H = P/2 packed point pairs.
+template <int H>
+struct Acc {
+    float2 fi[H];       // grid coordinates of the thread's points: (p even, p odd) = (fi0+64j, fi0+64j+32)
+    float2 a32[H];      // FP32 partial sums
+    double a64[2 * H];  // FP64 accumulators
+    __device__ __forceinline__ void flush() {
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-        a64[p] += (double)a32[p];
-        a32[p] = 0.f;
+        for (int j = 0; j < H; ++j) {
+            a64[2 * j] += (double)a32[j].x;
+            a64[2 * j + 1] += (double)a32[j].y;
+            a32[j] = make_float2(0.f, 0.f);
+        }
+    }
+};
+
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 lo2(const float4 &v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4 &v) { return make_float2(v.z, v.w); }
+
+// One paired-reciprocal step: lines 1 and 2 at the thread's 2*H points.
+template <int H, bool MASKED>
+__device__ __forceinline__ void pair_step(const float4 &a1, const float4 &a2, const float2 &B1, const float2 &B2,
+                                          float wmf, Acc<H> &s) {
+    const float2 nf1 = lo2(a1), nf2 = lo2(a2);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const float2 e1 = __fadd2_rn(s.fi[h], nf1);
+        const float2 e2 = __fadd2_rn(s.fi[h], nf2);
+        const float2 q1 = __ffma2_rn(e1, e1, B1);
+        const float2 q2 = __ffma2_rn(e2, e2, B2);
+        float2 A1 = hi2(a1), A2 = hi2(a2);
+        if (MASKED) {
+            A1.x = fabsf(e1.x) <= wmf ? A1.x : 0.f;
+            A1.y = fabsf(e1.y) <= wmf ? A1.y : 0.f;
+            A2.x = fabsf(e2.x) <= wmf ? A2.x : 0.f;
+            A2.y = fabsf(e2.y) <= wmf ? A2.y : 0.f;
+        }
+        const float2 num = __ffma2_rn(A2, q1, __fmul2_rn(A1, q2));
+        const float2 den = __fmul2_rn(q1, q2);
+        const float2 r = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+        s.a32[h] = __ffma2_rn(num, r, s.a32[h]);
     }
 }
 
-// predicated two-term path: window may cover only part of the span
-template <int P>
-__device__ __forceinline__ void path_general(const float4 *s4, const float2 *s2, int js, int je, float fi0,
-                                             float wbf, float we1f, float wmf, float (&a32)[P],
-                                             double (&a64)[P]) {
-    for (int jb = js; jb < je; jb += K2_FLUSH) {
-        const int jend = min(jb + K2_FLUSH, je);
+__device__ __forceinline__ float2 ldB(const float4 *sB, int j) { return *reinterpret_cast<const float2 *>(sB + j); }
+
+// Lorentz terms of lines [js, je), two lines per reciprocal, two points per instruction.  The record
+// loads of pair k+1 are issued before the math of pair k (register double buffering), so the LDS latency
+// is not exposed with only ~4 warps per scheduler.
+// MASKED: the window |d| <= wm may cover only part of the span -> zero A per point outside it.
+template <int H, bool MASKED>
+__device__ __forceinline__ void lorentz_paired(const float4 *sA, const float4 *sB, int js, int je, float wmf,
+                                               Acc<H> &s) {
+    const int n = je - js;
+    if (n <= 0) return;
+    const int npairs = n >> 1;
+    if (npairs) {
+        float4 a1 = sA[js], a2 = sA[js + 1];
+        float2 B1 = ldB(sB, js), B2 = ldB(sB, js + 1);
+        int since = 0;
+        for (int k = 0; k < npairs; ++k) {
+            const int jn = js + 2 * min(k + 1, npairs - 1);        // last step re-reads itself (harmless)
+            const float4 na1 = sA[jn], na2 = sA[jn + 1];
+            const float2 nB1 = ldB(sB, jn), nB2 = ldB(sB, jn + 1);
+            pair_step<H, MASKED>(a1, a2, B1, B2, wmf, s);
+            a1 = na1; a2 = na2; B1 = nB1; B2 = nB2;
+            if (++since == K2_FLUSH / 2) { s.flush(); since = 0; }
+        }
+    }
+    if (n & 1) {                                                    // odd line: partner with the same q and zero weight
+        const float4 a1 = sA[je - 1];
+        const float2 B1 = ldB(sB, je - 1);
+        pair_step<H, MASKED>(a1, make_float4(a1.x, a1.y, 0.f, 0.f), B1, B1, wmf, s);
+    }
+    s.flush();
+}
+
+// Gaussian cores of lines [js, je): only lines whose near zone meets the span (warp-uniform test).
+template <int H>
+__device__ __forceinline__ void gauss_pass(const float4 *sA, const float4 *sB, const float *sD, int js, int je,
+                                           float wbf, float we1f, float wmf, Acc<H> &s) {
+    int since = 0;
+    for (int j = js; j < je; ++j) {
+        const float dg = sD[j];
+        const float f = -sA[j].x;
+        if (!((dg >= 0.f) && (f + dg >= wbf) && (f - dg <= we1f))) continue;
+        const float4 b = sB[j];
+        const float2 nf = splat(-f), C2 = splat(b.w);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const float2 e = __fadd2_rn(s.fi[h], nf);
+            const float2 arg = __fmul2_rn(C2, __fmul2_rn(e, e));
+            float2 g;
+            g.x = fabsf(e.x) <= wmf ? b.z : 0.f;
+            g.y = fabsf(e.y) <= wmf ? b.z : 0.f;
+            s.a32[h] = __ffma2_rn(g, make_float2(ex2_approx(arg.x), ex2_approx(arg.y)), s.a32[h]);
+        }
+        if (++since == K2_FLUSH) { s.flush(); since = 0; }
+    }
+    if (since) s.flush();
+}
+
+// Plain one-line-at-a-time evaluation of every staged line (variant PRB_K2_GENERAL): the A/B check
+// for the classed path, and a measurement of what the naive formulation costs.
+template <int H>
+__device__ __forceinline__ void general_all(const float4 *sA, const float4 *sB, int cnt, float wmf, Acc<H> &s) {
+    for (int jb = 0; jb < cnt; jb += K2_FLUSH) {
+        const int jend = min(jb + K2_FLUSH, cnt);
         for (int j = jb; j < jend; ++j) {
-            const float4 r = s4[j];
-            const float2 g = s2[j];
-            const float d0 = fi0 - r.x;
-            const bool use_g = (r.w != 0.f) && (r.x + g.y >= wbf) && (r.x - g.y <= we1f);   // warp uniform
-            if (use_g) {
+            const float4 a = sA[j], b = sB[j];
 #pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const float e = p ? d0 + (float)(32 * p) : d0;
-                    const float e2 = e * e;
-                    float t = r.y * rcp_approx(e2 + r.z);
-                    t = fmaf(r.w, ex2_approx(g.x * e2), t);
-                    a32[p] += (fabsf(e) <= wmf) ? t : 0.f;
-                }
-            } else {
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const float e = p ? d0 + (float)(32 * p) : d0;
-                    const float t = r.y * rcp_approx(fmaf(e, e, r.z));
-                    a32[p] += (fabsf(e) <= wmf) ? t : 0.f;
-                }
+            for (int h = 0; h < H; ++h) {
+                const float ex = s.fi[h].x + a.x, ey = s.fi[h].y + a.x;
+                const float e2x = ex * ex, e2y = ey * ey;
+                float tx = a.z * rcp_approx(e2x + b.x), ty = a.z * rcp_approx(e2y + b.x);
+                tx = fmaf(b.z, ex2_approx(b.w * e2x), tx);
+                ty = fmaf(b.z, ex2_approx(b.w * e2y), ty);
+                s.a32[h].x += (fabsf(ex) <= wmf) ? tx : 0.f;
+                s.a32[h].y += (fabsf(ey) <= wmf) ? ty : 0.f;
             }
         }
-        flush<P>(a32, a64);
+        s.flush();
     }
 }
 
-// window covers the whole span; Gaussian core may be needed (per-line, warp-uniform test)
 template <int P>
-__device__ __forceinline__ void path_near(const float4 *s4, const float2 *s2, int js, int je, float fi0,
-                                          float wbf, float we1f, float (&a32)[P], double (&a64)[P]) {
-    for (int jb = js; jb < je; jb += K2_FLUSH) {
-        const int jend = min(jb + K2_FLUSH, je);
-        for (int j = jb; j < jend; ++j) {
-            const float4 r = s4[j];
-            const float2 g = s2[j];
-            const float d0 = fi0 - r.x;
-            const bool use_g = (r.w != 0.f) && (r.x + g.y >= wbf) && (r.x - g.y <= we1f);
-            if (use_g) {
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const float e = p ? d0 + (float)(32 * p) : d0;
-                    const float e2 = e * e;
-                    a32[p] = fmaf(r.y, rcp_approx(e2 + r.z), a32[p]);
-                    a32[p] = fmaf(r.w, ex2_approx(g.x * e2), a32[p]);
-                }
-            } else {
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const float e = p ? d0 + (float)(32 * p) : d0;
-                    a32[p] = fmaf(r.y, rcp_approx(fmaf(e, e, r.z)), a32[p]);
-                }
-            }
-        }
-        flush<P>(a32, a64);
-    }
-}
-
-// far path: window covers the span, Gaussian term negligible.  Two lines share one reciprocal.
-template <int P>
-__device__ __forceinline__ void path_far(const float4 *s4, int js, int je, float fi0, float (&a32)[P],
-                                         double (&a64)[P]) {
-    for (int jb = js; jb < je; jb += K2_FLUSH) {
-        const int jend = min(jb + K2_FLUSH, je);
-        int j = jb;
-        for (; j + 1 < jend; j += 2) {
-            const float4 r1 = s4[j];
-            const float4 r2 = s4[j + 1];
-            const float d1 = fi0 - r1.x;
-            const float d2 = fi0 - r2.x;
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const float e1 = p ? d1 + (float)(32 * p) : d1;
-                const float e2 = p ? d2 + (float)(32 * p) : d2;
-                const float q1 = fmaf(e1, e1, r1.z);
-                const float q2 = fmaf(e2, e2, r2.z);
-                const float num = fmaf(r2.y, q1, r1.y * q2);
-                a32[p] = fmaf(num, rcp_approx(q1 * q2), a32[p]);
-            }
-        }
-        if (j < jend) {
-            const float4 r = s4[j];
-            const float d0 = fi0 - r.x;
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const float e = p ? d0 + (float)(32 * p) : d0;
-                a32[p] = fmaf(r.y, rcp_approx(fmaf(e, e, r.z)), a32[p]);
-            }
-        }
-        flush<P>(a32, a64);
-    }
-}
-
-// Warp-specialised persistent kernel: warps 0..7 consume (math), warp 8 produces (tile scheduling,
-// line-range search, TMA issue).  Slots of the ring are handed over with mbarriers only -- there is
-// no CTA-wide barrier in the steady state, so a warp that is in its slow near-zone does not hold up
-// the other seven (each warp's near-zone sits at a different place in the line stream).
-template <int P>
-__global__ void __launch_bounds__(K2_THREADS, 2) k2_line_sum(const K2Args a) {
+__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2Args a) {
+    static_assert(P >= 2 && P % 2 == 0, "points per thread must be even (packed FP32x2)");
+    constexpr int H = P / 2;
     constexpr int TILE = K2_CONSUMERS * 32 * P;
     constexpr int SPAN = 32 * P;                      // points per consumer warp
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -277,7 +301,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_line_sum(const K2Args a) {
             const long long k_hi = a.i_begin + tile0 + TILE - 1 + a.wm + 1;
             int lo = warp_lower_bound(a.idx, a.l_begin, a.l_end, k_lo);
             const int hi = warp_lower_bound(a.idx, lo, a.l_end, k_hi);
-            lo &= ~1;                                  // 16-byte alignment of the float2 stream
+            lo &= ~3;                                  // 16-byte alignment of the float stream
             const int nch = hi > lo ? (hi - lo + K2_CHUNK - 1) / K2_CHUNK : 1;   // empty tile: one empty chunk
             for (int c = 0; c < nch; ++c, ++it) {
                 uint32_t stage;
@@ -287,10 +311,11 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_line_sum(const K2Args a) {
                     const int cnt = max(min(K2_CHUNK, hi - first), 0);
                     sm.desc[stage] = K2Desc{tile0, cnt, (c == 0 ? K2_FIRST : 0) | (c == nch - 1 ? K2_LAST : 0), 0};
                     if (cnt > 0) {
-                        const uint32_t ce = (uint32_t)((cnt + 1) & ~1);   // padding records exist past l_end
-                        mbar_expect_tx(&sm.full[stage], ce * 24u);
-                        tma_bulk_g2s(sm.r4[stage], a.rec4 + first, ce * 16u, &sm.full[stage]);
-                        tma_bulk_g2s(sm.r2[stage], a.rec2 + first, ce * 8u, &sm.full[stage]);
+                        const uint32_t ce = (uint32_t)((cnt + 3) & ~3);   // padding records exist past l_end
+                        mbar_expect_tx(&sm.full[stage], ce * 36u);
+                        tma_bulk_g2s(sm.rA[stage], a.recA + first, ce * 16u, &sm.full[stage]);
+                        tma_bulk_g2s(sm.rB[stage], a.recB + first, ce * 16u, &sm.full[stage]);
+                        tma_bulk_g2s(sm.rD[stage], a.recD + first, ce * 4u, &sm.full[stage]);
                     } else {
                         mbar_arrive(&sm.full[stage]);
                     }
@@ -309,12 +334,13 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_line_sum(const K2Args a) {
 
     // ---------------------------------------------------------------------- consumer warps
     const float wmf = (float)a.wm;
-    float a32[P];
-    double a64[P];
+    Acc<H> s;
 #pragma unroll
-    for (int p = 0; p < P; ++p) { a32[p] = 0.f; a64[p] = 0.0; }
+    for (int h = 0; h < H; ++h) { s.a32[h] = make_float2(0.f, 0.f); s.fi[h] = make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int p = 0; p < P; ++p) s.a64[p] = 0.0;
     int wb = 0;
-    float wbf = 0.f, we1f = 0.f, fi0 = 0.f;
+    float wbf = 0.f, we1f = 0.f;
 
     for (uint32_t it = 0;; ++it) {
         const uint32_t stage = it % K2_STAGES;
@@ -322,53 +348,52 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_line_sum(const K2Args a) {
         const K2Desc d = sm.desc[stage];
         if (d.flags & K2_END) break;
         if (d.flags & K2_FIRST) {
-#pragma unroll
-            for (int p = 0; p < P; ++p) { a32[p] = 0.f; a64[p] = 0.0; }
             wb = d.tile0 + warp * SPAN;                // first point of this warp's span
             wbf = (float)wb;
             we1f = (float)(wb + SPAN - 1);
-            fi0 = (float)(wb + lane);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                s.a32[h] = make_float2(0.f, 0.f);
+                s.fi[h] = make_float2((float)(wb + lane + 64 * h), (float)(wb + lane + 64 * h + 32));
+            }
+#pragma unroll
+            for (int p = 0; p < P; ++p) s.a64[p] = 0.0;
         }
         const int cnt = d.cnt;
-        const float4 *s4 = sm.r4[stage];
-        const float2 *s2 = sm.r2[stage];
+        const float4 *sA = sm.rA[stage];
+        const float4 *sB = sm.rB[stage];
+        const float *sD = sm.rD[stage];
 
         if (a.variant == 0) {
-            path_general<P>(s4, s2, 0, cnt, fi0, wbf, we1f, wmf, a32, a64);
+            general_all<H>(sA, sB, cnt, wmf, s);
         } else if (cnt > 0) {
-            // near-zone radius of THIS staged chunk (max over its lines): a function of the tile
-            // geometry only, so the classes -- and the FP32 rounding -- do not depend on the sharding.
+            // near-zone radius of THIS staged chunk (max over its lines): a function of the tile geometry
+            // only, so the classes -- and the FP32 rounding -- do not depend on the sharding.
             float dgl = 0.f;
-            for (int j = lane; j < cnt; j += 32) dgl = fmaxf(dgl, s2[j].y);
+            for (int j = lane; j < cnt; j += 32) dgl = fmaxf(dgl, sD[j]);
             const float dgmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(dgl)));
             // class boundaries of the sorted staged lines relative to this warp's span, by counting
-            const float t0 = wbf - wmf;                       // idx <  t0 : window ends before the span
-            const float t5 = we1f + 1.f + wmf;                // idx >= t5 : window starts after the span
-            const float fl = we1f - wmf, fr1 = wbf + wmf + 1.f;   // full cover: fl <= idx < fr1
-            float t1, t2, t3, t4;
-            if (fl >= fr1) { t1 = t2 = t3 = t4 = t5; }       // window narrower than the span
-            else {
-                t1 = fl;
-                t4 = fr1;
-                t2 = fminf(fmaxf(wbf - dgmax, fl), fr1);
-                t3 = fminf(fmaxf(we1f + 1.f + dgmax, t2), fr1);
-            }
-            int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+            const float t0 = wbf - wmf;                        // idx <  t0 : window ends before the span
+            const float t5 = we1f + 1.f + wmf;                 // idx >= t5 : window starts after the span
+            float t1 = we1f - wmf, t4 = wbf + wmf + 1.f;       // full cover: t1 <= idx < t4
+            if (t1 >= t4) { t1 = t5; t4 = t5; }                // window narrower than the span: all masked
+            const float g0 = fmaxf(wbf - dgmax, t0);           // Gaussian cores can only come from [g0, g1)
+            const float g1 = fminf(we1f + 1.f + dgmax, t5);
+            int c0 = 0, c1 = 0, c4 = 0, c5 = 0, cg0 = 0, cg1 = 0;
             for (int j = lane; j < cnt; j += 32) {
-                const float f = s4[j].x;
-                c0 += f < t0; c1 += f < t1; c2 += f < t2; c3 += f < t3; c4 += f < t4; c5 += f < t5;
+                const float f = -sA[j].x;
+                c0 += f < t0; c1 += f < t1; c4 += f < t4; c5 += f < t5; cg0 += f < g0; cg1 += f < g1;
             }
             const int b0 = __reduce_add_sync(0xffffffffu, c0);
             const int b1 = __reduce_add_sync(0xffffffffu, c1);
-            const int b2 = __reduce_add_sync(0xffffffffu, c2);
-            const int b3 = __reduce_add_sync(0xffffffffu, c3);
             const int b4 = __reduce_add_sync(0xffffffffu, c4);
             const int b5 = __reduce_add_sync(0xffffffffu, c5);
-            path_general<P>(s4, s2, b0, b1, fi0, wbf, we1f, wmf, a32, a64);
-            path_far<P>(s4, b1, b2, fi0, a32, a64);
-            path_near<P>(s4, s2, b2, b3, fi0, wbf, we1f, a32, a64);
-            path_far<P>(s4, b3, b4, fi0, a32, a64);
-            path_general<P>(s4, s2, b4, b5, fi0, wbf, we1f, wmf, a32, a64);
+            const int bg0 = __reduce_add_sync(0xffffffffu, cg0);
+            const int bg1 = __reduce_add_sync(0xffffffffu, cg1);
+            lorentz_paired<H, true>(sA, sB, b0, b1, wmf, s);
+            lorentz_paired<H, false>(sA, sB, b1, b4, wmf, s);
+            lorentz_paired<H, true>(sA, sB, b4, b5, wmf, s);
+            if (dgmax > 0.f) gauss_pass<H>(sA, sB, sD, bg0, bg1, wbf, we1f, wmf, s);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[stage]);  // slot may be refilled
@@ -379,7 +404,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_line_sum(const K2Args a) {
             for (int p = 0; p < P; ++p) {
                 const int i = wb + 32 * p + lane;
                 if (i < a.n_chunk) {
-                    const double v = a64[p] * a.inv_scale;
+                    const double v = s.a64[p] * a.inv_scale;
                     if (a.out_mode == 0) reinterpret_cast<double *>(a.out)[i] = v;
                     else reinterpret_cast<float *>(a.out)[i] = (float)v;
                 }

@@ -1,0 +1,106 @@
+// k2_narrow.cuh -- K2 for NARROW cutoff windows (upper-atmosphere layers: W-2 of a few to ~200 points).
+//
+// Same sum as k2_line_sum (pyradClasses.py:371-400 in gather form), different mapping: when the window is
+// narrower than a warp's span, broadcasting every staged line to all lanes wastes most lanes, so here each
+// THREAD owns grid points and walks only the lines inside its own window.  A CTA owns 1024 consecutive
+// points; the sorted lines reaching the tile are staged in shared memory with TMA bulk copies (chunks of
+// 2048 records); per point the first line of the window is found by binary search over the staged (sorted)
+// indices and the walk stops at the first line past the window -- the window IS the loop range, so there
+// are no masks.  FP32 terms, flushed into an FP64 accumulator every 64 lines; fixed ascending line order per
+// point (deterministic, independent of sharding).
+//
+// Compact records written by K1 for this kernel:  recA = {-fidx, A, B, G},  recD = C.
+#pragma once
+#include "common.cuh"
+#include "k2_line_sum.cuh"
+
+namespace prb {
+
+constexpr int KN_THREADS = 256;
+constexpr int KN_ROUNDS = 4;                          // points per thread (strided by 256)
+constexpr int KN_TILE = KN_THREADS * KN_ROUNDS;       // 1024 points per CTA
+constexpr int KN_CHUNK = 2048;                        // staged records per pass
+
+struct KNSmem {
+    float4 rec[KN_CHUNK];
+    float cc[KN_CHUNK];
+    uint64_t bar;
+    int lo, hi;
+};
+
+__global__ void __launch_bounds__(KN_THREADS, 4) k2_narrow(const K2Args a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    KNSmem &sm = *reinterpret_cast<KNSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile0 = blockIdx.x * KN_TILE;           // shard-local index of the tile's first point
+
+    if (tid == 0) {
+        mbar_init(&sm.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        const long long k_lo = a.i_begin + tile0 - a.wm;
+        const long long k_hi = a.i_begin + tile0 + KN_TILE - 1 + a.wm + 1;
+        const int lo = warp_lower_bound(a.idx, a.l_begin, a.l_end, k_lo);
+        const int hi = warp_lower_bound(a.idx, lo, a.l_end, k_hi);
+        if (lane == 0) { sm.lo = lo & ~3; sm.hi = hi; }
+    }
+    __syncthreads();
+    const int lo = sm.lo, hi = sm.hi;
+    const int nch = hi > lo ? (hi - lo + KN_CHUNK - 1) / KN_CHUNK : 0;
+    const float wmf = (float)a.wm;
+
+    float fi[KN_ROUNDS];
+    double acc[KN_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < KN_ROUNDS; ++r) { fi[r] = (float)(tile0 + r * KN_THREADS + tid); acc[r] = 0.0; }
+
+    for (int c = 0; c < nch; ++c) {
+        const int first = lo + c * KN_CHUNK;
+        const int cnt = min(KN_CHUNK, hi - first);
+        if (tid == 0) {
+            const uint32_t ce = (uint32_t)((cnt + 3) & ~3);
+            mbar_expect_tx(&sm.bar, ce * 20u);
+            tma_bulk_g2s(sm.rec, a.recA + first, ce * 16u, &sm.bar);
+            tma_bulk_g2s(sm.cc, a.recD + first, ce * 4u, &sm.bar);
+        }
+        mbar_wait(&sm.bar, c & 1);
+#pragma unroll
+        for (int r = 0; r < KN_ROUNDS; ++r) {
+            // first staged line with fidx >= fi - wm  (rec[].x = -fidx, ascending in fidx)
+            const float key = fi[r] - wmf, last = fi[r] + wmf;
+            int jl = 0, jh = cnt;
+            while (jl < jh) {
+                const int m = (jl + jh) >> 1;
+                if (-sm.rec[m].x < key) jl = m + 1; else jh = m;
+            }
+            float s32 = 0.f;
+            int since = 0;
+            for (int j = jl; j < cnt; ++j) {
+                const float4 q4 = sm.rec[j];
+                if (-q4.x > last) break;
+                const float d = fi[r] + q4.x;
+                const float d2 = d * d;
+                float t = q4.y * rcp_approx(d2 + q4.z);
+                if (q4.w != 0.f) t = fmaf(q4.w, ex2_approx(sm.cc[j] * d2), t);
+                s32 += t;
+                if (++since == K2_FLUSH) { acc[r] += (double)s32; s32 = 0.f; since = 0; }
+            }
+            acc[r] += (double)s32;
+        }
+        __syncthreads();                              // the single staging buffer is refilled next pass
+    }
+
+#pragma unroll
+    for (int r = 0; r < KN_ROUNDS; ++r) {
+        const int i = tile0 + r * KN_THREADS + tid;
+        if (i < a.n_chunk) {
+            const double v = acc[r] * a.inv_scale;
+            if (a.out_mode == 0) reinterpret_cast<double *>(a.out)[i] = v;
+            else reinterpret_cast<float *>(a.out)[i] = (float)v;
+        }
+    }
+}
+
+}  // namespace prb

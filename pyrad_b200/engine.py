@@ -85,6 +85,9 @@ class Engine:
     def set_k2_variant(self, variant=K2_CLASSED, points_per_thread=0):
         _lib.check(self._lib.prb_set_k2_variant(self._h, int(variant), int(points_per_thread)))
 
+    def set_narrow_threshold(self, wm_below=-1):
+        _lib.check(self._lib.prb_set_narrow_threshold(self._h, int(wm_below)))
+
     # -- data
     def upload_lines(self, lines, n_groups=1):
         """lines: dict with nu, sw, gamma_air, gamma_self, elower, n_air, delta_air (+ optional int32 group),
@@ -215,6 +218,13 @@ class Engine:
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         _lib.check(self._lib.prb_atmosphere_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"k1_ms": a.value, "k2_ms": b.value, "k3_ms": c.value}
+
+    def atmosphere_layer_timing(self, n_layers):
+        a = np.zeros(n_layers, dtype=np.float32)
+        b = np.zeros(n_layers, dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        _lib.check(self._lib.prb_atmosphere_layer_timing(self._h, int(n_layers), a.ctypes.data_as(fp), b.ctypes.data_as(fp)))
+        return a, b
 
     def atmosphere_result_dev(self):
         a, b = C.c_void_p(), C.c_void_p()

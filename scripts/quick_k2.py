@@ -9,6 +9,10 @@ def main():
     n_lines = int(os.environ.get("QK_LINES", 500000))
     rmax = float(os.environ.get("QK_RMAX", 3000.0))
     w = workloads.cfg2(n_lines, rmax)
+    if os.environ.get("QK_P"):
+        w["P"] = float(os.environ["QK_P"])
+        w["T"] = int(os.environ.get("QK_T", 250))
+        w["cutoff"] = w["P"] / 1013.25 * 5
     e = eng.Engine(0)
     n = eng.grid_len(w["range_min"], w["range_max"], w["res"])
     t0 = time.time()
@@ -29,7 +33,10 @@ def main():
         combos = [tuple(int(x) for x in c.split(":")) for c in only.split(",")]
     for variant, ppt in combos:
         if True:
-            e.set_k2_variant(variant, ppt)
+            if ppt < 0:
+                e.set_k2_variant(variant, 0); e.set_narrow_threshold(1 << 20)
+            else:
+                e.set_k2_variant(variant, ppt); e.set_narrow_threshold(0)
             t0 = time.time()
             e.layer_prepass(T, P, w["conc"], [s.molmass for s in sp], [s.q(T) for s in sp], [s.q296 for s in sp], win, wts)
             e.synchronize()

@@ -1,0 +1,78 @@
+"""GPU parity at BASELINE.json's full sizes: the oracle cannot scatter 5e9+ pairs on a CPU in seconds, so
+full-size runs are checked (a) against the oracle's gather form at sampled grid points, and (b) through
+size-independent properties: linearity in S, additivity over line subsets, shard invariance."""
+import numpy as np
+import pytest
+
+from oracle import physics as ph
+from pyrad_b200 import engine as eng
+from pyrad_b200 import workloads
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def sample_points(n, k, seed):
+    rng = np.random.default_rng(seed)
+    edge = np.array([0, 1, 2, n // 2, n - 3, n - 2, n - 1])
+    return np.unique(np.concatenate([edge, rng.integers(0, n, k)]))
+
+
+def check_sampled(engine, w, weights_mode, P=None, T=None, n_pts=48, seed=0):
+    P = w["P"] if P is None else P
+    T = w["T"] if T is None else T
+    cutoff = P / 1013.25 * 5 if P != w["P"] else w["cutoff"]
+    n = H.engine_setup(engine, w)
+    wts = [eng.number_density_weight(c, P, T) for c in w["conc"]] if weights_mode else None
+    H.engine_prepass(engine, w, weights=wts, T=T, P=P, cutoff=cutoff)
+    out = engine.line_sum()
+    pts = sample_points(n, n_pts, seed)
+    sig = H.oracle_sigma_groups(w, T=T, P=P, cutoff=cutoff, points=pts)
+    if weights_mode:
+        ref = sum(ph.abs_coef(sig[g], w["conc"][g], P, T) for g in range(len(w["species"])))
+    else:
+        ref = sig.sum(axis=0)
+    floor = H.K_FLOOR_REL * np.abs(out).max()
+    err = np.abs(out[pts] - ref) / np.maximum(np.abs(ref), floor)
+    assert err.max() <= H.K_REL_TOL, (err.max(), pts[err.argmax()])
+    return out
+
+
+def test_cfg2_full_size_sampled_against_oracle(engine):
+    """cfg2: 3.0M points, 500k lines, W = 5000 (the bench workload)."""
+    w = workloads.cfg2()
+    out = check_sampled(engine, w, weights_mode=True)
+    assert engine.pair_count() > 4.9e9
+    assert np.all(np.isfinite(out)) and np.all(out >= 0)
+
+
+@pytest.mark.parametrize("P,T", [(353.4, 250), (44.28, 230), (5.315, 260)])
+def test_atmosphere_layer_shapes_full_size_sampled(engine, P, T):
+    """cfg4-sized line list (5M lines, 5M points) at three layer pressures: wide, mid and narrow windows."""
+    w = workloads.cfg5(cutoff=5.0)
+    check_sampled(engine, w, weights_mode=True, P=P, T=T, n_pts=24, seed=int(P))
+
+
+def test_cfg1_size_properties(engine):
+    """cfg1 (30 000 points, 50k lines): linearity in S, additivity over a line split, T=296 identity."""
+    w = workloads.cfg1()
+    n = H.engine_setup(engine, w)
+    H.engine_prepass(engine, w)
+    base = engine.line_sum()
+    ref_pts = sample_points(n, 40, 3)
+    sig = H.oracle_sigma_groups(w, points=ref_pts)[0]
+    assert H.k_rel_err(base[ref_pts], sig).max() <= H.K_REL_TOL
+    # linearity: S -> 4 S (a power of two: bitwise equal thanks to the power-of-two scaling)
+    L = dict(w["lines"]); L["sw"] = w["lines"]["sw"] * 4.0
+    w4 = dict(w); w4["lines"] = L
+    H.engine_setup(engine, w4)
+    H.engine_prepass(engine, w4)
+    assert np.array_equal(engine.line_sum(), 4.0 * base)
+    # additivity over odd/even line subsets
+    parts = []
+    for sel in (slice(0, None, 2), slice(1, None, 2)):
+        ws = dict(w); ws["lines"] = {k: np.ascontiguousarray(v[sel]) for k, v in w["lines"].items()}
+        H.engine_setup(engine, ws)
+        H.engine_prepass(engine, ws)
+        parts.append(engine.line_sum())
+    assert H.k_rel_err(parts[0] + parts[1], base).max() <= 2e-6
