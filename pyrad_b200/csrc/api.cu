@@ -301,11 +301,11 @@ static int build_group_params(int n_groups, double T, const double *conc, const 
 }
 
 static double pick_scale(double s_max, double w_max) {
-    // Power of two that puts the strongest possible S296*weight near 2^20: typical A = S*eta*h/pi/res^2
-    // then sits around 2^35..2^45, leaving > 2^80 of headroom for A*(d^2+B) and ~2^-126 as the floor.
+    // Power of two that puts the strongest possible S296*weight near 2^10: typical A = S*eta*h/pi/res^2
+    // then sits around 2^25..2^35, leaving headroom for A*q^2 (q = d^2+B up to ~2^30) and ~2^-126 as the floor.
     const double m = s_max * w_max;
     if (!(m > 0) || !std::isfinite(m)) return 1.0;
-    return std::ldexp(1.0, 20 - std::ilogb(m));
+    return std::ldexp(1.0, 10 - std::ilogb(m));
 }
 
 static LayerConsts layer_consts(double T, double res) {

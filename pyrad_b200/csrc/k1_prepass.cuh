@@ -139,7 +139,8 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__res
             // FP32 range guards: the paired far path forms A*(d^2+B) with |d| <= wm.
             const double qmax = (wm + 4096.0) * (wm + 4096.0) + B;   // partial lines reach one warp span past the window
             if (!(isfinite(A) && isfinite(G) && isfinite(B) && isfinite(C))) flags |= FLAG_NONFINITE;
-            else if (A * qmax > 8.0e37 || G > 8.0e37 || B > 1.0e18 || qmax * qmax > 8.0e37) flags |= FLAG_OVERFLOW;
+            // the triple-reciprocal path forms |A| q^2 and q^3
+            else if (fabs(A) * qmax * qmax > 8.0e37 || fabs(G) > 8.0e37 || qmax * qmax * qmax > 8.0e37) flags |= FLAG_OVERFLOW;
             const double fi = (double)((int64_t)idx[l] - i_base);
             const float nf = -(float)fi, Af = (float)A, Bf = (float)B;
             if (narrow) {                                         // compact layout of k2_narrow

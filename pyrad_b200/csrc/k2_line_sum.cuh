@@ -158,26 +158,35 @@ __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 __device__ __forceinline__ float2 lo2(const float4 &v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4 &v) { return make_float2(v.z, v.w); }
 
-// One paired-reciprocal step: lines 1 and 2 at the thread's 2*H points.
+// One triple-reciprocal step: lines 1, 2, 3 at the thread's 2*H points,
+//   A1/q1 + A2/q2 + A3/q3 = (A1 q2 q3 + q1 (A2 q3 + A3 q2)) * rcp(q1 q2 q3)
+// -- one MUFU per THREE (line, point) pairs and 13 packed FP32x2 instructions per six pairs, which balances
+// the XU pipe (8 cycles per MUFU) against the FP32 pipe (~1.3 cycles per packed instruction, measured).
 template <int H, bool MASKED>
-__device__ __forceinline__ void pair_step(const float4 &a1, const float4 &a2, const float2 &B1, const float2 &B2,
-                                          float wmf, Acc<H> &s) {
-    const float2 nf1 = lo2(a1), nf2 = lo2(a2);
+__device__ __forceinline__ void triple_step(const float4 &a1, const float4 &a2, const float4 &a3, const float2 &B1,
+                                            const float2 &B2, const float2 &B3, float wmf, Acc<H> &s) {
+    const float2 nf1 = lo2(a1), nf2 = lo2(a2), nf3 = lo2(a3);
 #pragma unroll
     for (int h = 0; h < H; ++h) {
         const float2 e1 = __fadd2_rn(s.fi[h], nf1);
         const float2 e2 = __fadd2_rn(s.fi[h], nf2);
+        const float2 e3 = __fadd2_rn(s.fi[h], nf3);
         const float2 q1 = __ffma2_rn(e1, e1, B1);
         const float2 q2 = __ffma2_rn(e2, e2, B2);
-        float2 A1 = hi2(a1), A2 = hi2(a2);
+        const float2 q3 = __ffma2_rn(e3, e3, B3);
+        float2 A1 = hi2(a1), A2 = hi2(a2), A3 = hi2(a3);
         if (MASKED) {
             A1.x = fabsf(e1.x) <= wmf ? A1.x : 0.f;
             A1.y = fabsf(e1.y) <= wmf ? A1.y : 0.f;
             A2.x = fabsf(e2.x) <= wmf ? A2.x : 0.f;
             A2.y = fabsf(e2.y) <= wmf ? A2.y : 0.f;
+            A3.x = fabsf(e3.x) <= wmf ? A3.x : 0.f;
+            A3.y = fabsf(e3.y) <= wmf ? A3.y : 0.f;
         }
-        const float2 num = __ffma2_rn(A2, q1, __fmul2_rn(A1, q2));
-        const float2 den = __fmul2_rn(q1, q2);
+        const float2 p23 = __fmul2_rn(q2, q3);
+        const float2 t = __ffma2_rn(A3, q2, __fmul2_rn(A2, q3));
+        const float2 num = __ffma2_rn(q1, t, __fmul2_rn(A1, p23));
+        const float2 den = __fmul2_rn(q1, p23);
         const float2 r = make_float2(rcp_approx(den.x), rcp_approx(den.y));
         s.a32[h] = __ffma2_rn(num, r, s.a32[h]);
     }
@@ -185,33 +194,42 @@ __device__ __forceinline__ void pair_step(const float4 &a1, const float4 &a2, co
 
 __device__ __forceinline__ float2 ldB(const float4 *sB, int j) { return *reinterpret_cast<const float2 *>(sB + j); }
 
-// Lorentz terms of lines [js, je), two lines per reciprocal, two points per instruction.  The record
-// loads of pair k+1 are issued before the math of pair k (register double buffering), so the LDS latency
-// is not exposed with only ~4 warps per scheduler.
+// Lorentz terms of lines [js, je), three lines per reciprocal, two points per instruction.  Two triples are
+// kept in flight (X and Y): the records of the next X triple are requested before the math of Y and vice
+// versa, so the shared-memory latency hides behind FP32 work without any register rotation.
 // MASKED: the window |d| <= wm may cover only part of the span -> zero A per point outside it.
 template <int H, bool MASKED>
 __device__ __forceinline__ void lorentz_paired(const float4 *sA, const float4 *sB, int js, int je, float wmf,
                                                Acc<H> &s) {
     const int n = je - js;
     if (n <= 0) return;
-    const int npairs = n >> 1;
-    if (npairs) {
-        float4 a1 = sA[js], a2 = sA[js + 1];
-        float2 B1 = ldB(sB, js), B2 = ldB(sB, js + 1);
+    int j = js;
+    const int n6 = (n / 6) * 6;
+    const int jq = js + n6;                                         // lines handled six at a time
+    if (n6) {
+        float4 xa1 = sA[j], xa2 = sA[j + 1], xa3 = sA[j + 2], ya1 = sA[j + 3], ya2 = sA[j + 4], ya3 = sA[j + 5];
+        float2 xb1 = ldB(sB, j), xb2 = ldB(sB, j + 1), xb3 = ldB(sB, j + 2);
+        float2 yb1 = ldB(sB, j + 3), yb2 = ldB(sB, j + 4), yb3 = ldB(sB, j + 5);
         int since = 0;
-        for (int k = 0; k < npairs; ++k) {
-            const int jn = js + 2 * min(k + 1, npairs - 1);        // last step re-reads itself (harmless)
-            const float4 na1 = sA[jn], na2 = sA[jn + 1];
-            const float2 nB1 = ldB(sB, jn), nB2 = ldB(sB, jn + 1);
-            pair_step<H, MASKED>(a1, a2, B1, B2, wmf, s);
-            a1 = na1; a2 = na2; B1 = nB1; B2 = nB2;
-            if (++since == K2_FLUSH / 2) { s.flush(); since = 0; }
+        for (j += 6; j < jq; j += 6) {
+            triple_step<H, MASKED>(xa1, xa2, xa3, xb1, xb2, xb3, wmf, s);
+            xa1 = sA[j]; xa2 = sA[j + 1]; xa3 = sA[j + 2];
+            xb1 = ldB(sB, j); xb2 = ldB(sB, j + 1); xb3 = ldB(sB, j + 2);
+            triple_step<H, MASKED>(ya1, ya2, ya3, yb1, yb2, yb3, wmf, s);
+            ya1 = sA[j + 3]; ya2 = sA[j + 4]; ya3 = sA[j + 5];
+            yb1 = ldB(sB, j + 3); yb2 = ldB(sB, j + 4); yb3 = ldB(sB, j + 5);
+            if (++since == K2_FLUSH / 6) { s.flush(); since = 0; }
         }
+        triple_step<H, MASKED>(xa1, xa2, xa3, xb1, xb2, xb3, wmf, s);
+        triple_step<H, MASKED>(ya1, ya2, ya3, yb1, yb2, yb3, wmf, s);
     }
-    if (n & 1) {                                                    // odd line: partner with the same q and zero weight
-        const float4 a1 = sA[je - 1];
-        const float2 B1 = ldB(sB, je - 1);
-        pair_step<H, MASKED>(a1, make_float4(a1.x, a1.y, 0.f, 0.f), B1, B1, wmf, s);
+    for (j = jq; j < je; j += 3) {                                  // tail: pad the triple with zero-weight copies
+        const float4 a1 = sA[j];
+        const float2 B1 = ldB(sB, j);
+        const float4 z = make_float4(a1.x, a1.y, 0.f, 0.f);
+        const bool h2 = j + 1 < je, h3 = j + 2 < je;
+        triple_step<H, MASKED>(a1, h2 ? sA[j + 1] : z, h3 ? sA[j + 2] : z, B1, h2 ? ldB(sB, j + 1) : B1,
+                               h3 ? ldB(sB, j + 2) : B1, wmf, s);
     }
     s.flush();
 }
