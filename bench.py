@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -192,8 +192,8 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-atmosphere", action="store_true", help="skip the secondary 100-layer atmosphere object")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -266,14 +266,13 @@ def main():
         dist.all_reduce(t)
         pairs_all = int(t.item())
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                 # sampled from warm-up through the timed region to the K2-only loop
     for _ in range(args.warmup):
         flush_buf.zero_()
         step_device()
     sync_all()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     # ---- timed region: K steps, CUDA events on the launching stream around every step, L2 flushed between steps
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
@@ -359,11 +358,14 @@ def main():
     if rank == 0:
         sm_max = float(peaks.get("sm_max_mhz", SM_MAX_MHZ_DEFAULT))
         f_hz = sm_max * 1e6
-        # FP32-pipe roofline of K2 (the binding pipe of the paired-reciprocal formulation): the far path needs
-        # 8 FP32-pipe instructions per TWO (line, point) pairs = 4 lane-slots = 8 flop-slots per pair.
+        # FP32-pipe roofline of K2, the pipe that binds the triple-reciprocal formulation (ncu: math_pipe_throttle is
+        # the top stall, pipe_fma_cycles_active ~70 %): 13 packed FP32x2 instructions per six (line, point) pairs =
+        # 4.33 FP32 lane-slots per pair; a lane-slot is what the nominal "2 flop" FMA peak counts, so achieved
+        # TFLOP/s-equivalent = pairs/s x 4.33 x 2 against 148 SM x 128 lanes x 2 x f_max.
         fp32_peak = SM_COUNT * 128 * 2 * f_hz / 1e12
         k2_pairs_s = pairs_rank / k2_t
-        fp32_ach = k2_pairs_s * 8 / 1e12
+        slots_per_pair = 13.0 / 3.0
+        fp32_ach = k2_pairs_s * slots_per_pair * 2 / 1e12
         mufu_naive_peak = SM_COUNT * 16 * f_hz / 2.0          # 2 MUFU per Voigt pair
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -379,11 +381,12 @@ def main():
                          "k2_ms": k2_t * 1e3, "k2_pairs_per_s": k2_pairs_s,
                          "peak_source": "nominal: 148 SM x 128 FP32 lanes x 2 x %.0f MHz (MEASURED_PEAKS.json has no FP32 "
                                         "figure; %s file used for the clock)" % (sm_max, peaks_kind),
-                         "algorithmic": "8 FP32 flop-slots per (line, gridpoint) pair (paired-reciprocal far path, DESIGN.md)"},
+                         "algorithmic": "4.33 FP32 lane-slots (x2 flop) per (line, gridpoint) pair: 13 packed FP32x2 instr per 6 pairs in "
+                                        "the triple-reciprocal path (DESIGN.md section 4); real flops are 6.33 per pair"},
             "roofline_sfu": {"bound": "sfu", "achieved": k2_pairs_s / 1e9, "peak": mufu_naive_peak / 1e9, "unit": "Gpair/s",
                              "frac": k2_pairs_s / mufu_naive_peak,
                              "note": "SURVEY 8(d) naive bound (2 MUFU per Voigt pair, 16 MUFU/clk/SM); the kernel issues "
-                                     "0.5 MUFU per far pair, hence > 1"},
+                                     "1/3 MUFU per Lorentz pair (triple reciprocal), hence > 1"},
             "wall_s_timed_region": wall,
         }
         if atm:

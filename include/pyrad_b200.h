@@ -66,7 +66,7 @@ int         prb_synchronize(prb_engine *e);             /* stream sync + deferre
 int         prb_device_info(prb_engine *e, int *sm_count, int *cc_major, int *cc_minor,
                             int *sm_clock_khz, size_t *free_bytes, size_t *total_bytes);
 int         prb_set_k2_variant(prb_engine *e, int variant, int points_per_thread /* 0 = auto */);
-/* windows with W-2 < wm_below use the thread-per-point kernel k2_narrow (0 = never, <0 = default 128) */
+/* windows with W-2 < wm_below use the thread-per-point kernel k2_narrow (0 = never, <0 = default 100) */
 int         prb_set_narrow_threshold(prb_engine *e, int64_t wm_below);
 
 /* ---- line list (a1): SoA float64, ascending nu0; group[i] in [0, n_groups) or NULL (all 0) - */

@@ -90,7 +90,7 @@ struct prb_engine {
     DevBuf<DevState> st;          // one per layer
     PrepassArgs last;
     int k2_variant = PRB_K2_CLASSED, k2_ppt = 0;
-    int64_t narrow_wm = 128;     // windows with W-2 below this use k2_narrow
+    int64_t narrow_wm = 100;     // windows with W-2 below this use k2_narrow
 
     // outputs / scratch
     DevBuf<double> out64;
@@ -223,13 +223,6 @@ extern "C" int prb_upload_lines(prb_engine *e, int64_t n, const double *nu0, con
     if (n_groups < 1) return fail(PRB_ERR_ARG, "prb_upload_lines: n_groups must be >= 1");
     if (n > 0 && (!nu0 || !s296 || !gamma_air || !gamma_self || !elower || !n_air || !delta_air))
         return fail(PRB_ERR_ARG, "prb_upload_lines: NULL column");
-    for (int64_t i = 1; i < n; ++i)
-        if (!(nu0[i] >= nu0[i - 1])) return fail(PRB_ERR_ARG, "prb_upload_lines: nu0 must be ascending");
-    double smax = 0;
-    for (int64_t i = 0; i < n; ++i) smax = std::max(smax, std::fabs(s296[i]));
-    if (group)
-        for (int64_t i = 0; i < n; ++i)
-            if (group[i] < 0 || group[i] >= n_groups) return fail(PRB_ERR_ARG, "prb_upload_lines: group id out of range");
     CK(cudaSetDevice(e->device));
     const int64_t na = n + 16;                                  // padding records: TMA copies are 16-byte granular
     DevBuf<double> *cols[7] = {&e->nu0, &e->s296, &e->gair, &e->gself, &e->elower, &e->nair, &e->delta};
@@ -243,11 +236,24 @@ extern "C" int prb_upload_lines(prb_engine *e, int64_t n, const double *nu0, con
         CK(e->group.ensure(na));
         if (n) CK(cudaMemcpyAsync(e->group.p, group, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
     }
+    // (the H2D copies above are in flight from pinned memory while the host validates)
+    // one validation pass over the host columns: ascending nu0, max |S296|, group ids in range
+    double smax = 0;
+    bool sorted = true, group_ok = true;
+    for (int64_t i = 0; i < n; ++i) {
+        const double sa = std::fabs(s296[i]);
+        smax = sa > smax ? sa : smax;
+        if (i && !(nu0[i] >= nu0[i - 1])) sorted = false;
+        if (group && (group[i] < 0 || group[i] >= n_groups)) group_ok = false;
+    }
     CK(e->idx.ensure(na));
     CK(e->recA.ensure(na));
     CK(e->recB.ensure(na));
     CK(e->recD.ensure(na));
     CK(cudaStreamSynchronize(e->stream));
+    e->lines_set = false;
+    if (!sorted) return fail(PRB_ERR_ARG, "prb_upload_lines: nu0 must be ascending");
+    if (!group_ok) return fail(PRB_ERR_ARG, "prb_upload_lines: group id out of range");
     e->n_lines = n;
     e->n_alloc = na;
     e->n_groups = n_groups;
@@ -308,11 +314,16 @@ static double pick_scale(double s_max, double w_max) {
     return std::ldexp(1.0, 10 - std::ilogb(m));
 }
 
-static LayerConsts layer_consts(double T, double res) {
+static LayerConsts layer_consts(double T, double P, double res) {
     LayerConsts lc;
     lc.log_t0_over_t = std::log(kT0 / T);
     lc.inv_t_minus_inv_t0 = 1.0 / T - 1.0 / kT0;
     lc.inv_res2 = 1.0 / (res * res);
+    lc.res2 = res * res;
+    lc.p_over_p0 = P / kP0;
+    const double c2 = cLight * hPlanck * 100 / kBoltz;
+    lc.neg_c2_over_t = -c2 / T;
+    lc.neg_c2_over_t0 = -c2 / kT0;
     return lc;
 }
 
@@ -334,7 +345,7 @@ static int launch_prepass(prb_engine *e, double T, double P, int64_t W, const Gr
     const int64_t cnt = ke - kb;
     if (cnt > 0) {
         k1_prepass<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(
-            L, e->idx.p, gp_dev, kb, ke, n, T, P, layer_consts(T, e->res), scale, e->i_begin, (double)wm, narrow, e->recA.p, e->recB.p,
+            L, e->idx.p, gp_dev, kb, ke, n, T, P, layer_consts(T, P, e->res), scale, e->i_begin, (double)wm, narrow, e->recA.p, e->recB.p,
             e->recD.p, st_dev, dbg);
         CK(cudaGetLastError());
     }
@@ -409,7 +420,7 @@ extern "C" int prb_debug_line_params(prb_engine *e, double *nu_shift, double *ga
     DevBuf<float4> r4, r5; DevBuf<float> r2;
     CK(r4.ensure(na)); CK(r5.ensure(na)); CK(r2.ensure(na));
     k1_prepass<<<(unsigned)((na + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, e->gp.p, 0, na, n, e->last.T, e->last.P,
-                                                                   layer_consts(e->last.T, e->res), e->last.scale, save_b, (double)e->last.wm, 0,
+                                                                   layer_consts(e->last.T, e->last.P, e->res), e->last.scale, save_b, (double)e->last.wm, 0,
                                                                    r4.p, r5.p, r2.p, st.p, dbg);
     e->i_begin = save_b; e->i_end = save_e;
     CK(cudaGetLastError());
@@ -761,7 +772,7 @@ extern "C" int prb_atmosphere_layer_timing(prb_engine *e, int32_t n_layers, floa
 
 extern "C" int prb_set_narrow_threshold(prb_engine *e, int64_t wm_below) {
     if (!e) return fail(PRB_ERR_ARG, "null engine");
-    e->narrow_wm = wm_below < 0 ? 128 : wm_below;
+    e->narrow_wm = wm_below < 0 ? 100 : wm_below;
     e->last.valid = false;                                      // record layout may change: redo the prepass
     return PRB_OK;
 }

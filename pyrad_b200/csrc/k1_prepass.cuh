@@ -30,6 +30,10 @@ struct LayerConsts {
     double log_t0_over_t;          // log(296 / T)
     double inv_t_minus_inv_t0;     // 1/T - 1/296
     double inv_res2;               // 1 / res^2
+    double res2;                   // res^2
+    double p_over_p0;              // P / 1013.25
+    double neg_c2_over_t;          // -c2 / T
+    double neg_c2_over_t0;         // -c2 / 296
 };
 
 struct DebugOut {
@@ -74,13 +78,16 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__res
             const int g = L.group ? L.group[l] : 0;
             const GroupParams p = gp[g];
             const double nu = L.nu0[l];
-            const double nus = nu + L.delta[l] * P / kP0;
-            // (t0/T)^n = exp(n * log(t0/T)): the log is a per-layer constant (lc.log_t0_over_t)
-            const double gl = ((1 - p.conc) * L.gair[l] + p.conc * L.gself[l]) * (P / kP0) *
+            // Divisions are the expensive FP64 operation here (K1 is FP64-pipe bound, not HBM bound), so
+            // per-layer reciprocals come from the host (lc.*) and each regime needs a single 1/h.  This
+            // changes roundings by an ulp relative to the reference's operation order (1e-16), nothing more.
+            const double nus = nu + L.delta[l] * lc.p_over_p0;
+            // (t0/T)^n = exp(n * log(t0/T)): the log is a per-layer constant
+            const double gl = ((1 - p.conc) * L.gair[l] + p.conc * L.gself[l]) * lc.p_over_p0 *
                               exp(L.nair[l] * lc.log_t0_over_t);
             const double gd = nus * p.dopp;
             const double ratio = gl / gd;                         // gd == 0 -> inf -> Lorentz, as numpy
-            const double stim = (1 - exp(-c2 * nus / T)) / (1 - exp(-c2 * nus / kT0));
+            const double stim = (1 - exp(lc.neg_c2_over_t * nus)) / (1 - exp(lc.neg_c2_over_t0 * nus));
             // exp(-c2 E/T) / exp(-c2 E/t0) evaluated as one exponential (same value to ~1e-16)
             const double boltz = exp(-c2 * L.elower[l] * lc.inv_t_minus_inv_t0);
             const double S = L.s296[l] * p.qratio * stim * boltz;
@@ -93,10 +100,11 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__res
             float dg = -1.0f;
             if (ratio < .01) {
                 regime = REGIME_GAUSS;
+                const double inv_gd = 1.0 / gd;
                 A = 0.0; B = 1.0;
-                G = sw / gd * inv_sqrtpi;
+                G = sw * inv_gd * inv_sqrtpi;
                 bg = gd * gd * inv_res2;
-                C = -log2e / bg;
+                C = -log2e * lc.res2 * inv_gd * inv_gd;
             } else if (ratio > 100) {
                 regime = REGIME_LORENTZ;
                 A = sw * gl * (inv_res2 / kPi);
@@ -109,14 +117,15 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__res
                 const double f5 = pow5(gFW) + 2.69269 * g2 * g2 * lFW + 2.42843 * g2 * gFW * l2 +
                                   4.47163 * g2 * l2 * lFW + .07842 * gFW * l2 * l2 + pow5(lFW);
                 const double f = exp(.2 * log(f5));               // f5 ** .2
-                const double rho = lFW / f;
-                const double eta = 1.36603 * rho - .47719 * rho * rho + .11116 * rho * rho * rho;
                 const double hh = f / 2;
+                const double inv_hh = 1.0 / hh;
+                const double rho = gl * inv_hh;                   // lFW / f
+                const double eta = 1.36603 * rho - .47719 * rho * rho + .11116 * rho * rho * rho;
                 A = sw * eta * hh * (inv_res2 / kPi);
                 B = hh * hh * inv_res2;
-                G = sw * (1 - eta) / hh * inv_sqrtpi;
+                G = sw * (1 - eta) * inv_hh * inv_sqrtpi;
                 bg = B;
-                C = -log2e / B;
+                C = -log2e * lc.res2 * inv_hh * inv_hh;
             }
             // near-zone radius: beyond it the Gaussian term is < 1e-9 of the same line's Lorentz term
             // (or below the scaled FP32 floor for Gaussian-only lines), so K2 may skip it.  FP32 is

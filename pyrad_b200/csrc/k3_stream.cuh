@@ -86,9 +86,14 @@ struct FoldLayer {
     float c2_over_t;         // 100 h c / kB / T_layer
 };
 
+__device__ __forceinline__ float k3_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float k3_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 __device__ __forceinline__ float planck_f32(float a_nu3, float x) {
-    // a nu^3 / (e^x - 1); expm1f keeps the small-x end (first few hundred grid points) accurate.
-    return a_nu3 / expm1f(x);
+    // a nu^3 / (e^x - 1).  For x >= 0.25 two MUFUs (ex2, rcp) are accurate to ~1e-6 relative; below that the
+    // subtraction cancels, so the first few hundred grid points (nu < ~40 cm^-1) take expm1f instead.
+    if (x < 0.25f) return a_nu3 / expm1f(x);
+    return a_nu3 * k3_rcp(k3_ex2(x * 1.4426950408889634f) - 1.0f);
 }
 
 __global__ void __launch_bounds__(256)
@@ -115,7 +120,7 @@ k3_fold_f32(const float *__restrict__ kmat, int64_t ld, int n_layers, const Fold
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float e = kk[q] * fl.neg_depth_log2e;       // -tau_l * log2(e)
-                const float t = exp2f(e);
+                const float t = k3_ex2(e);
                 const float b = planck_f32(a3[q], fl.c2_over_t * nu[q]);
                 rad[q] = fmaf(t, rad[q] - b, b);                  // T*I + (1-T)*B
                 tau[q] += e;
