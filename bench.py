@@ -195,6 +195,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the finished spectra are all-gathered -- 'peer' = stores into every rank's buffer "
+                         "over NVLink from inside the compute kernel (default), 'nccl' = a separate NCCL all-gather")
     ap.add_argument("--no-atmosphere", action="store_true", help="skip the secondary 100-layer atmosphere object")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--atm-layers", type=int, default=100)
@@ -241,15 +244,20 @@ def main():
     flush_buf = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # 512 MiB > 126 MB L2
     hold = {"gather": None}
 
+    use_peer = world > 1 and args.gather == "peer"
+    if use_peer:
+        pd.connect_peers(e, rank, world, n_chunk, dist)
+
     def step_device():
-        """K1 -> K2 -> K3 on resident inputs (+ the all-gather of the finished transmittance spectrum)."""
+        """K1 -> K2 (layer physics fused into its epilogue) on resident inputs, and the all-gather of the finished
+        radiance + transmittance spectra: peer stores from inside K2 + one flag barrier, or a separate NCCL call."""
         e.atmosphere([w["depth_cm"]], [T], [P], conc, molmass, qt, q296, [win], w["t_surface"], w["range_max"])
-        if world > 1:
-            _, tr_ptr = e.atmosphere_result_dev()
-            tr = pd.device_tensor(tr_ptr, n_chunk)
+        if world > 1 and not use_peer:
+            rad_ptr, tr_ptr = e.atmosphere_result_dev()
             if hold["gather"] is None:
-                hold["gather"] = torch.empty(world * n_chunk, dtype=torch.float32, device="cuda")
-            dist.all_gather_into_tensor(hold["gather"], tr)
+                hold["gather"] = [torch.empty(world * n_chunk, dtype=torch.float32, device="cuda") for _ in range(2)]
+            dist.all_gather_into_tensor(hold["gather"][0], pd.device_tensor(rad_ptr, n_chunk))
+            dist.all_gather_into_tensor(hold["gather"][1], pd.device_tensor(tr_ptr, n_chunk))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -285,6 +293,7 @@ def main():
     sync_all()
     wall = time.perf_counter() - wall0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches_per_step = e.atmosphere_launches()
     tm = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -348,7 +357,7 @@ def main():
     # ---- secondary object: the 100-layer atmosphere (cfg4), strong-sharded by wavenumber chunk
     atm = None
     if not args.no_atmosphere:
-        atm = run_atmosphere(e, args, rank, world, ext, peaks)
+        atm = run_atmosphere(e, args, rank, world, ext, peaks, use_peer)
 
     # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample of the same workload
     cpu = None
@@ -371,11 +380,13 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": "wavenumber chunks x%d, one all-gather" % world,
+            "config": {"workload": WORKLOAD, "parallelism": "wavenumber chunks x%d, %s" % (
+                           world, "no collective" if world == 1 else
+                           ("all-gather fused into K2 (NVLink peer stores + flag barrier)" if use_peer else "NCCL all-gather")),
                        "pairs_per_step": pairs_all, "lines_per_gpu": n_l, "points_per_gpu": n_chunk,
                        "l2": "flushed between timed steps (512 MiB write)",
                        "numerics": "FP64 prepass, FP32 lineshape evaluation, FP64 accumulation; k stored FP32"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * args.steps,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": fp32_ach / fp32_peak, "traffic": None, "kernel": "k2_line_sum<8>",
                          "k2_ms": k2_t * 1e3, "k2_pairs_per_s": k2_pairs_s,
@@ -400,7 +411,7 @@ def main():
     return 0
 
 
-def run_atmosphere(e, args, rank, world, ext, peaks):
+def run_atmosphere(e, args, rank, world, ext, peaks, use_peer):
     """100-layer standard atmosphere, 0-5000 cm-1 @ 0.001 cm-1, ~5M lines: K1+K2 per layer, one K3 fold, one
     all-gather.  Strong scaling: the N ranks split ONE spectrum by pair-count-balanced wavenumber chunks."""
     import torch
@@ -421,9 +432,14 @@ def run_atmosphere(e, args, rank, world, ext, peaks):
     molmass = [s.molmass for s in sp]
     q296 = [s.q296 for s in sp]
     nc = plan.i_end - plan.i_begin
+    if use_peer:
+        e.peer_disconnect()
+        pd.connect_peers(e, rank, world, plan.max_chunk, dist)
 
     def run():
         e.atmosphere(w["depth_cm"], w["T"], w["P"], w["conc"], molmass, qt, q296, win, w["t_surface"], w["range_max"])
+        if use_peer:
+            return pd.gathered_spectra(e)           # [world, ld] views of the gather buffer the kernels filled
         rad_p, tr_p = e.atmosphere_result_dev()
         rad = pd.device_tensor(rad_p, nc)
         tr = pd.device_tensor(tr_p, nc)
@@ -461,7 +477,8 @@ def run_atmosphere(e, args, rank, world, ext, peaks):
     return {"workload": "cfg4: %d-layer US-std atmosphere 0-70 km, 0-5000 cm-1 @ 0.001 cm-1 (%d points, %d lines), "
                         "reference cutoff 5*P/p0 per layer" % (len(win), n_total, len(w["lines"]["nu"])),
             "spectra_per_s": 1e3 / ms, "ms_per_spectrum": ms, "pairs": pairs, "pairs_per_s": pairs / (ms * 1e-3),
-            "scaling": "strong", "n_gpus": world, "chunk_points_rank0": nc,
+            "scaling": "strong", "n_gpus": world, "chunk_points_rank0": nc, "launches": e.atmosphere_launches(),
+            "gather": "none" if world == 1 else ("peer stores fused into K3" if use_peer else "nccl"),
             "rank0_stage_ms": tim,
             "roofline_k3": {"bound": "hbm", "achieved": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                             "frac": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9 / hbm, "traffic": None,

@@ -43,8 +43,9 @@ extern "C" {
 #define PRB_ERR_STATE       -3   /* call order violated (e.g. line_sum before prepass) */
 #define PRB_ERR_RANGE       -4   /* grid segment too large for exact FP32 offsets, or coefficient overflow */
 #define PRB_ERR_NODEVICE    -5   /* no usable CUDA device: there is no CPU fallback */
+#define PRB_ERR_PEER        -6   /* peer-memory gather: IPC mapping failed or a rank did not arrive */
 
-#define PRB_ABI_VERSION      1
+#define PRB_ABI_VERSION      2
 
 /* prb_line_sum output modes */
 #define PRB_OUT_F64          0   /* double per grid point */
@@ -53,6 +54,13 @@ extern "C" {
 /* K2 kernel variants (for A/B parity tests and profiling) */
 #define PRB_K2_GENERAL       0   /* every staged line through the predicated two-term path */
 #define PRB_K2_CLASSED       1   /* per-warp window classes + paired-reciprocal far path (default) */
+
+/* prb_set_option */
+#define PRB_OPT_BATCH_LAYERS        1   /* prb_atmosphere: one K1 + one K2 launch per kernel class (default 1) */
+#define PRB_OPT_FUSE_SINGLE_LAYER   2   /* single-layer prb_atmosphere: layer physics in K2's epilogue (default 1) */
+#define PRB_OPT_RECORD_BUDGET_MB    3   /* device memory for resident per-layer line records; 0 = auto */
+
+#define PRB_PEER_HANDLE_BYTES      64   /* sizeof(cudaIpcMemHandle_t) */
 
 typedef struct prb_engine prb_engine;
 
@@ -139,6 +147,24 @@ int prb_set_timing(prb_engine *e, int enabled);
 int prb_atmosphere_timing(prb_engine *e, float *k1_ms, float *k2_ms, float *k3_ms);
 int prb_atmosphere_layer_timing(prb_engine *e, int32_t n_layers, float *k1_ms, float *k2_ms);   /* per layer */
 int prb_atmosphere_kmatrix_dev(prb_engine *e, void **kmat_dev, int64_t *ld);                 /* float[L][ld] */
+int prb_atmosphere_launches(prb_engine *e);              /* kernels launched by the last prb_atmosphere */
+int prb_set_option(prb_engine *e, int option, int64_t value);
+
+/* ---- multi-GPU (section 8(e)): wavenumber chunks, one process per GPU on one NVLink/NVSwitch node.
+ * The path has no exchange step; the only collective is the all-gather of the finished spectra, and it is
+ * fused into the compute step: after prb_peer_connect, prb_atmosphere stores this rank's radiance and
+ * transmittance straight into every rank's gather buffer (peer memory, from inside its last kernel) and
+ * finishes with a cross-GPU flag barrier.  All ranks must call prb_atmosphere the same number of times.
+ *   prb_peer_alloc     allocate this rank's gather buffer (world slots of max_chunk_points floats, two
+ *                      fields, double buffered) and export it: handle_out receives PRB_PEER_HANDLE_BYTES
+ *   (host side)        exchange the handles between the ranks (any transport; rank order)
+ *   prb_peer_connect   handles = world * PRB_PEER_HANDLE_BYTES bytes, rank order
+ *   prb_peer_gathered_dev  float[world][ld] radiance / transmittance of the last step, valid on this device
+ *                      once the engine's stream has passed the step */
+int prb_peer_alloc(prb_engine *e, int rank, int world, int64_t max_chunk_points, void *handle_out);
+int prb_peer_connect(prb_engine *e, const void *handles);
+int prb_peer_disconnect(prb_engine *e);
+int prb_peer_gathered_dev(prb_engine *e, void **radiance_dev, void **transmittance_dev, int64_t *ld);
 
 #ifdef __cplusplus
 }

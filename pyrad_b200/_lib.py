@@ -59,6 +59,12 @@ PROTOTYPES = {
     "prb_atmosphere_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "prb_atmosphere_layer_timing": (C.c_int, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "prb_atmosphere_kmatrix_dev": (C.c_int, [_vp, C.POINTER(_vp), _lp]),
+    "prb_atmosphere_launches": (C.c_int, [_vp]),
+    "prb_set_option": (C.c_int, [_vp, C.c_int, _i64]),
+    "prb_peer_alloc": (C.c_int, [_vp, C.c_int, C.c_int, _i64, _vp]),
+    "prb_peer_connect": (C.c_int, [_vp, _vp]),
+    "prb_peer_disconnect": (C.c_int, [_vp]),
+    "prb_peer_gathered_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _lp]),
 }
 
 _lib = None

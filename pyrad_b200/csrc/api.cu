@@ -55,12 +55,31 @@ struct DevBuf {
     }
 };
 
-struct PrepassArgs {
+// Host-side description of one layer of a launch sequence (one K1 table row + one K2 table row).
+struct LayerJob {
     double T = 0, P = 0, scale = 1;
-    int64_t W = 0, wm = 0, l0 = 0, l1 = 0, k1_begin = 0, k1_end = 0;
+    int64_t W = 0, wm = 0, l0 = 0, l1 = 0;   // window, K2 line range [l0, l1)
     int narrow = 0;              // record layout / kernel: 1 = k2_narrow (thread-per-point gather)
+    int ppt = 8;                 // points per thread of k2_line_sum for this window
+    int slot = 0;                // which slice of the record arrays holds this layer
+    const GroupParams *gp_dev = nullptr;
+    DevState *st_dev = nullptr;
+    void *out_dev = nullptr;
     bool valid = false;
 };
+
+// Peer-memory gather buffers (multi-GPU, one process per GPU on one NVLink/NVSwitch node).
+struct PeerState {
+    int rank = 0, world = 0;
+    int64_t ld = 0;                          // floats per rank slot
+    unsigned char *local = nullptr;          // this rank's allocation (exported over CUDA IPC)
+    unsigned char *base[K2_MAX_PEERS] = {};  // every rank's allocation as mapped here (base[rank] == local)
+    bool connected = false;
+    unsigned int epoch = 0;                  // collective step counter (all ranks advance together)
+    size_t bytes = 0;
+};
+constexpr int RING = 16;
+constexpr size_t PEER_HEADER = 4096;         // flags[2][K2_MAX_PEERS] + error word, then the float buffers
 
 struct prb_engine {
     int device = 0;
@@ -86,17 +105,32 @@ struct prb_engine {
     // per-layer
     DevBuf<float4> recA, recB;
     DevBuf<float> recD;
+    int64_t rec_slots = 0;        // the record arrays hold rec_slots layers of n_alloc records each
     DevBuf<GroupParams> gp;       // n_layers * n_groups
     DevBuf<DevState> st;          // one per layer
-    PrepassArgs last;
+    DevBuf<K1Layer> k1tab;        // device tables of the batched launches
+    DevBuf<K2Layer> k2tab;
+    LayerJob last;
     int k2_variant = PRB_K2_CLASSED, k2_ppt = 0;
     int64_t narrow_wm = 100;     // windows with W-2 below this use k2_narrow
+    bool batch_layers = true;    // prb_atmosphere: one K1 launch + one K2 launch per kernel class
+    bool fuse_single = true;     // single wide layer: layer physics + peer stores in K2's epilogue
+    int64_t rec_budget_mb = 0;   // 0 = auto (a quarter of the free memory)
+    PeerState peer;
+    DevBuf<unsigned int> peer_err;
+    // pinned ring of single-layer K2 table rows (prb_line_sum_dev is enqueue-only)
+    K2Layer *ring_h = nullptr;
+    DevBuf<K2Layer> ring_d;
+    cudaEvent_t ring_ev[RING] = {};
+    int ring_next = 0;
 
     // outputs / scratch
     DevBuf<double> out64;
     DevBuf<double> scratch_a, scratch_b, scratch_c, scratch_d, scratch_w;
     // atmosphere
     DevBuf<float> kmat, rad, trans;
+    float *res_rad = nullptr, *res_trans = nullptr;   // where the last prb_atmosphere left its spectra
+    int last_launches = 0;                            // kernels launched by the last prb_atmosphere
     DevBuf<FoldLayer> fold;
     int64_t kmat_ld = 0;
     int atm_layers = 0;
@@ -143,6 +177,14 @@ extern "C" int prb_create(int device, prb_engine **out) {
     return PRB_OK;
 }
 
+static void peer_release(prb_engine *e) {
+    PeerState &ps = e->peer;
+    for (int r = 0; r < ps.world; ++r)
+        if (ps.connected && r != ps.rank && ps.base[r]) cudaIpcCloseMemHandle(ps.base[r]);
+    if (ps.local) cudaFree(ps.local);
+    ps = PeerState{};
+}
+
 extern "C" int prb_destroy(prb_engine *e) {
     if (!e) return PRB_OK;
     cudaSetDevice(e->device);
@@ -153,6 +195,9 @@ extern "C" int prb_destroy(prb_engine *e) {
     e->out64.release(); e->scratch_a.release(); e->scratch_b.release(); e->scratch_c.release();
     e->scratch_d.release(); e->scratch_w.release();
     e->kmat.release(); e->rad.release(); e->trans.release(); e->fold.release();
+    e->k1tab.release(); e->k2tab.release(); e->ring_d.release(); e->peer_err.release();
+    if (e->ring_h) { cudaFreeHost(e->ring_h); for (auto x : e->ring_ev) if (x) cudaEventDestroy(x); }
+    peer_release(e);
     for (auto x : e->ev) cudaEventDestroy(x);
     cudaStreamDestroy(e->stream);
     delete e;
@@ -224,7 +269,9 @@ extern "C" int prb_upload_lines(prb_engine *e, int64_t n, const double *nu0, con
     if (n > 0 && (!nu0 || !s296 || !gamma_air || !gamma_self || !elower || !n_air || !delta_air))
         return fail(PRB_ERR_ARG, "prb_upload_lines: NULL column");
     CK(cudaSetDevice(e->device));
-    const int64_t na = n + 16;                                  // padding records: TMA copies are 16-byte granular
+    // padding records (TMA copies are 16-byte granular); a multiple of 4 so that every per-layer slice of the
+    // record arrays starts 16-byte aligned
+    const int64_t na = (n + 16 + 3) & ~int64_t(3);
     DevBuf<double> *cols[7] = {&e->nu0, &e->s296, &e->gair, &e->gself, &e->elower, &e->nair, &e->delta};
     const double *src[7] = {nu0, s296, gamma_air, gamma_self, elower, n_air, delta_air};
     for (int c = 0; c < 7; ++c) {
@@ -250,6 +297,7 @@ extern "C" int prb_upload_lines(prb_engine *e, int64_t n, const double *nu0, con
     CK(e->recA.ensure(na));
     CK(e->recB.ensure(na));
     CK(e->recD.ensure(na));
+    e->rec_slots = (int64_t)(std::min(e->recA.n, std::min(e->recB.n, e->recD.n)) / (size_t)na);
     CK(cudaStreamSynchronize(e->stream));
     e->lines_set = false;
     if (!sorted) return fail(PRB_ERR_ARG, "prb_upload_lines: nu0 must be ascending");
@@ -327,40 +375,85 @@ static LayerConsts layer_consts(double T, double P, double res) {
     return lc;
 }
 
-static int launch_prepass(prb_engine *e, double T, double P, int64_t W, const GroupParams *gp_dev, double scale,
-                          DevState *st_dev, DebugOut dbg, PrepassArgs *pa) {
-    const int64_t wm = std::max<int64_t>(W - 2, 0);
-    const int64_t n = e->n_lines;
-    // lines that can reach the owned chunk: idx in [i_begin - wm, i_end - 1 + wm]
-    const int32_t *hb = e->h_idx.data();
-    const int64_t klo = e->i_begin - wm, khi = e->i_end - 1 + wm;
-    int64_t l0 = std::lower_bound(hb, hb + n, klo, [](int32_t a, int64_t k) { return (int64_t)a < k; }) - hb;
-    int64_t l1 = std::upper_bound(hb, hb + n, khi, [](int64_t k, int32_t a) { return k < (int64_t)a; }) - hb;
-    if (l1 < l0) l1 = l0;
-    const int narrow = (e->k2_variant == PRB_K2_CLASSED && wm < e->narrow_wm) ? 1 : 0;
-    const int64_t kb = l0 & ~int64_t(3);
-    const int64_t ke = std::min<int64_t>(l1 + 8, e->n_alloc);
-    LinesSoA L{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
-               e->has_group ? e->group.p : nullptr};
-    const int64_t cnt = ke - kb;
-    if (cnt > 0) {
-        k1_prepass<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(
-            L, e->idx.p, gp_dev, kb, ke, n, T, P, layer_consts(T, P, e->res), scale, e->i_begin, (double)wm, narrow, e->recA.p, e->recB.p,
-            e->recD.p, st_dev, dbg);
-        CK(cudaGetLastError());
-    }
-    pa->T = T; pa->P = P; pa->scale = scale; pa->W = W; pa->wm = wm;
-    pa->l0 = l0; pa->l1 = l1; pa->k1_begin = kb; pa->k1_end = ke;
-    pa->narrow = narrow;
-    pa->valid = true;
-    return PRB_OK;
-}
-
 static int check_segment(prb_engine *e, int64_t wm) {
     // FP32 offsets must be exact integers: chunk + tile rounding + both windows below 2^24.
     if (chunk_len(e) + 2 * wm + 8192 >= (int64_t(1) << 24))
         return fail(PRB_ERR_RANGE, "owned grid chunk plus cutoff windows exceeds 2^24 points; shard the grid "
                                    "(prb_set_grid i_begin/i_end) into smaller chunks");
+    return PRB_OK;
+}
+
+static int pick_ppt(const prb_engine *e, int64_t wm) {
+    if (e->k2_ppt) return e->k2_ppt;
+    // a warp spans 32*P points: keep the span well inside the window so most lines cover it fully
+    if (wm >= 1024) return 8;
+    if (wm >= 256) return 4;
+    return 2;
+}
+
+// Window, kernel class and K2 line range of one layer on the owned chunk.
+static LayerJob plan_job(const prb_engine *e, double T, double P, int64_t W, double scale) {
+    LayerJob j;
+    j.T = T; j.P = P; j.W = W; j.scale = scale;
+    j.wm = std::max<int64_t>(W - 2, 0);
+    const int64_t n = e->n_lines;
+    // lines that can reach the owned chunk: idx in [i_begin - wm, i_end - 1 + wm]
+    const int32_t *hb = e->h_idx.data();
+    const int64_t klo = e->i_begin - j.wm, khi = e->i_end - 1 + j.wm;
+    j.l0 = std::lower_bound(hb, hb + n, klo, [](int32_t a, int64_t k) { return (int64_t)a < k; }) - hb;
+    j.l1 = std::upper_bound(hb, hb + n, khi, [](int64_t k, int32_t a) { return k < (int64_t)a; }) - hb;
+    if (j.l1 < j.l0) j.l1 = j.l0;
+    j.narrow = (e->k2_variant == PRB_K2_CLASSED && j.wm < e->narrow_wm) ? 1 : 0;
+    j.ppt = pick_ppt(e, j.wm);
+    j.valid = true;
+    return j;
+}
+
+static int ensure_records(prb_engine *e, int64_t slots) {
+    if (slots <= e->rec_slots) return PRB_OK;
+    const size_t na = (size_t)e->n_alloc;
+    CK(e->recA.ensure(na * slots));
+    CK(e->recB.ensure(na * slots));
+    CK(e->recD.ensure(na * slots));
+    e->rec_slots = slots;
+    return PRB_OK;
+}
+
+// ONE K1 launch for jobs[0..n): the union of their line ranges, every thread walking the n layers.
+// `tab_host`/`tab_dev` are caller-provided table rows (the host rows must outlive the copy).
+static int launch_prepass(prb_engine *e, const LayerJob *jobs, int n, K1Layer *tab_host, K1Layer *tab_dev,
+                          DebugOut dbg) {
+    if (n <= 0) return PRB_OK;
+    int64_t l0 = jobs[0].l0, l1 = jobs[0].l1;
+    const size_t na = (size_t)e->n_alloc;
+    for (int k = 0; k < n; ++k) {
+        const LayerJob &j = jobs[k];
+        l0 = std::min(l0, j.l0);
+        l1 = std::max(l1, j.l1);
+        K1Layer &t = tab_host[k];
+        t.T = j.T; t.P = j.P;
+        t.lc = layer_consts(j.T, j.P, e->res);
+        t.scale = j.scale;
+        t.wm = (double)j.wm;
+        t.gp = j.gp_dev;
+        t.recA = e->recA.p + na * j.slot;
+        t.recB = e->recB.p + na * j.slot;
+        t.recD = e->recD.p + na * j.slot;
+        t.st = j.st_dev;
+        t.narrow = j.narrow;
+        t.pad = 0;
+    }
+    CK(cudaMemcpyAsync(tab_dev, tab_host, sizeof(K1Layer) * n, cudaMemcpyHostToDevice, e->stream));
+    const int64_t kb = l0 & ~int64_t(3);
+    const int64_t ke = std::min<int64_t>(l1 + 8, e->n_alloc);
+    const int64_t cnt = ke - kb;
+    if (cnt > 0) {
+        LinesSoA L{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
+                   e->has_group ? e->group.p : nullptr};
+        k1_prepass<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, tab_dev, n, kb, ke, e->n_lines,
+                                                                        e->i_begin, dbg);
+        CK(cudaGetLastError());
+    }
     return PRB_OK;
 }
 
@@ -381,12 +474,19 @@ extern "C" int prb_layer_prepass(prb_engine *e, double T, double P, int32_t n_gr
     build_group_params(n_groups, T, conc, molmass, q_t, q_296, weight, h.data(), &w_max);
     CK(e->gp.ensure(n_groups));
     CK(e->st.ensure(1));
+    CK(e->k1tab.ensure(1));
+    CK(e->k2tab.ensure(1));
+    if ((rc = ensure_records(e, 1))) return rc;
     CK(cudaMemcpyAsync(e->gp.p, h.data(), sizeof(GroupParams) * n_groups, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemsetAsync(e->st.p, 0, sizeof(DevState), e->stream));
-    const double scale = pick_scale(e->s_max, w_max);
-    rc = launch_prepass(e, T, P, window_len, e->gp.p, scale, e->st.p, DebugOut{}, &e->last);
+    LayerJob j = plan_job(e, T, P, window_len, pick_scale(e->s_max, w_max));
+    j.gp_dev = e->gp.p;
+    j.st_dev = e->st.p;
+    K1Layer row;
+    rc = launch_prepass(e, &j, 1, &row, e->k1tab.p, DebugOut{});
     if (rc) return rc;
-    CK(cudaStreamSynchronize(e->stream));                       // h (pageable) must outlive the copy
+    CK(cudaStreamSynchronize(e->stream));                       // h, row (pageable) must outlive the copies
+    e->last = j;
     return PRB_OK;
 }
 
@@ -405,24 +505,28 @@ extern "C" int prb_debug_line_params(prb_engine *e, double *nu_shift, double *ga
     CK(cudaMemsetAsync(e->scratch_d.p, 0, sizeof(double) * na, e->stream));
     CK(cudaMemsetAsync(reg.p, 0xff, sizeof(int32_t) * na, e->stream));
     DebugOut dbg{e->scratch_a.p, e->scratch_b.p, e->scratch_c.p, e->scratch_d.p, reg.p};
-    PrepassArgs pa;
     DevBuf<DevState> st;
+    DevBuf<K1Layer> tab;
     CK(st.ensure(1));
+    CK(tab.ensure(1));
     CK(cudaMemsetAsync(st.p, 0, sizeof(DevState), e->stream));
-    // whole list, so every line gets a value irrespective of the owned chunk
-    const int64_t save_b = e->i_begin, save_e = e->i_end;
-    e->i_begin = 0; e->i_end = e->n_total;
-    const int64_t huge_w = std::max<int64_t>(e->last.W, 2) ;
-    (void)huge_w;
-    LinesSoA L{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
-               e->has_group ? e->group.p : nullptr};
-    // records are scratch here: use temporaries so the live prepass is not disturbed
+    // whole list, so every line gets a value irrespective of the owned chunk; the records are scratch here
+    // (temporaries, so the live prepass is not disturbed)
     DevBuf<float4> r4, r5; DevBuf<float> r2;
     CK(r4.ensure(na)); CK(r5.ensure(na)); CK(r2.ensure(na));
-    k1_prepass<<<(unsigned)((na + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, e->gp.p, 0, na, n, e->last.T, e->last.P,
-                                                                   layer_consts(e->last.T, e->last.P, e->res), e->last.scale, save_b, (double)e->last.wm, 0,
-                                                                   r4.p, r5.p, r2.p, st.p, dbg);
-    e->i_begin = save_b; e->i_end = save_e;
+    K1Layer row;
+    row.T = e->last.T; row.P = e->last.P;
+    row.lc = layer_consts(e->last.T, e->last.P, e->res);
+    row.scale = e->last.scale;
+    row.wm = (double)e->last.wm;
+    row.gp = e->gp.p;
+    row.recA = r4.p; row.recB = r5.p; row.recD = r2.p;
+    row.st = st.p;
+    row.narrow = 0; row.pad = 0;
+    CK(cudaMemcpyAsync(tab.p, &row, sizeof(K1Layer), cudaMemcpyHostToDevice, e->stream));
+    LinesSoA L{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
+               e->has_group ? e->group.p : nullptr};
+    k1_prepass<<<(unsigned)((na + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, tab.p, 1, 0, na, n, e->i_begin, dbg);
     CK(cudaGetLastError());
     if (nu_shift) CK(cudaMemcpyAsync(nu_shift, e->scratch_a.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
     if (gamma_l) CK(cudaMemcpyAsync(gamma_l, e->scratch_b.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
@@ -431,19 +535,11 @@ extern "C" int prb_debug_line_params(prb_engine *e, double *nu_shift, double *ga
     if (regime) CK(cudaMemcpyAsync(regime, reg.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (index) for (int64_t i = 0; i < n; ++i) index[i] = e->h_idx[i];
-    r4.release(); r5.release(); r2.release(); reg.release(); st.release();
+    r4.release(); r5.release(); r2.release(); reg.release(); st.release(); tab.release();
     return PRB_OK;
 }
 
 // ------------------------------------------------------------------------------------ K2
-static int pick_ppt(const prb_engine *e, int64_t wm) {
-    if (e->k2_ppt) return e->k2_ppt;
-    // a warp spans 32*P points: keep the span well inside the window so most lines cover it fully
-    if (wm >= 1024) return 8;
-    if (wm >= 256) return 4;
-    return 2;
-}
-
 template <int P>
 static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
     const int tile = K2_CONSUMERS * 32 * P;
@@ -456,36 +552,57 @@ static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
         if (ce != cudaSuccess) return ce;
         attr_set = true;
     }
-    const int grid = std::min(a.n_tiles, K2_MIN_CTAS * e->prop.multiProcessorCount);
+    const int64_t items = (int64_t)a.n_tiles * a.n_layers;
+    const int grid = (int)std::min<int64_t>(items, (int64_t)K2_MIN_CTAS * e->prop.multiProcessorCount);
     k2_line_sum<P><<<grid, K2_THREADS, smem, e->stream>>>(a);
     return cudaGetLastError();
 }
 
-static int launch_line_sum(prb_engine *e, const PrepassArgs &pa, DevState *st_dev, void *out_dev, int out_mode) {
+// ONE K2 launch for jobs[0..n), which must share a kernel class (all narrow, or all the same ppt) and be sorted
+// widest window first.  The launch's tile counter lives in jobs[0]'s state block and is reset here.
+static int launch_line_sum(prb_engine *e, const LayerJob *jobs, int n, K2Layer *tab_host, K2Layer *tab_dev,
+                           int out_mode, const K2Fuse *fuse) {
+    if (n <= 0) return PRB_OK;
+    const size_t na = (size_t)e->n_alloc;
+    for (int k = 0; k < n; ++k) {
+        const LayerJob &j = jobs[k];
+        K2Layer &t = tab_host[k];
+        t.recA = e->recA.p + na * j.slot;
+        t.recB = e->recB.p + na * j.slot;
+        t.recD = e->recD.p + na * j.slot;
+        t.out = j.out_dev;
+        t.inv_scale = 1.0 / j.scale;
+        t.l_begin = (int)j.l0;
+        t.l_end = (int)j.l1;
+        t.wm = (int)j.wm;
+        t.pad = 0;
+    }
+    CK(cudaMemcpyAsync(tab_dev, tab_host, sizeof(K2Layer) * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(&jobs[0].st_dev->tile_counter, 0, sizeof(unsigned int), e->stream));
     K2Args a{};
-    a.recA = e->recA.p;
-    a.recB = e->recB.p;
-    a.recD = e->recD.p;
+    a.layers = tab_dev;
+    a.n_layers = n;
     a.idx = e->idx.p;
-    a.l_begin = (int)pa.l0;
-    a.l_end = (int)pa.l1;
     a.i_begin = e->i_begin;
     a.n_chunk = (int)chunk_len(e);
-    a.wm = (int)pa.wm;
     a.variant = e->k2_variant;
     a.out_mode = out_mode;
-    a.inv_scale = 1.0 / pa.scale;
-    a.out = out_dev;
-    a.st = st_dev;
+    a.st = jobs[0].st_dev;
+    if (fuse) a.fuse = *fuse;
     cudaError_t ce;
-    if (pa.narrow) {
+    if (jobs[0].narrow) {
         a.n_tiles = (a.n_chunk + KN_TILE - 1) / KN_TILE;
-        if (a.n_tiles > 0) k2_narrow<<<a.n_tiles, KN_THREADS, sizeof(KNSmem), e->stream>>>(a);
+        for (int k0 = 0; k0 < n && a.n_tiles > 0; k0 += 65535) {        // grid.y limit
+            K2Args b = a;
+            b.layers = tab_dev + k0;
+            b.n_layers = std::min(n - k0, 65535);
+            k2_narrow<<<dim3((unsigned)a.n_tiles, (unsigned)b.n_layers), KN_THREADS, sizeof(KNSmem), e->stream>>>(b);
+        }
         ce = cudaGetLastError();
         if (ce != cudaSuccess) return fail(PRB_ERR_CUDA, std::string("k2_narrow launch failed: ") + cudaGetErrorString(ce));
         return PRB_OK;
     }
-    switch (pick_ppt(e, pa.wm)) {
+    switch (jobs[0].ppt) {
         case 2: ce = launch_k2_t<2>(e, a); break;
         case 4: ce = launch_k2_t<4>(e, a); break;
         case 16: ce = launch_k2_t<16>(e, a); break;
@@ -501,9 +618,21 @@ extern "C" int prb_line_sum_dev(prb_engine *e, void *out_dev, int out_mode) {
     if (!out_dev) return fail(PRB_ERR_ARG, "prb_line_sum_dev: NULL output");
     if (out_mode != PRB_OUT_F64 && out_mode != PRB_OUT_F32) return fail(PRB_ERR_ARG, "prb_line_sum_dev: bad out_mode");
     CK(cudaSetDevice(e->device));
-    // the tile scheduler counter is consumed by a launch: reset it (the status flags must survive)
-    CK(cudaMemsetAsync(&e->st.p->tile_counter, 0, sizeof(unsigned int), e->stream));
-    return launch_line_sum(e, e->last, e->st.p, out_dev, out_mode);
+    LayerJob j = e->last;
+    j.out_dev = out_dev;
+    // enqueue-only entry point: the table row travels through a small pinned ring (a slot is reused only after
+    // the copy that read it has completed), so no host synchronisation is needed here
+    if (!e->ring_h) {
+        CK(cudaMallocHost((void **)&e->ring_h, sizeof(K2Layer) * RING));
+        CK(e->ring_d.ensure(RING));
+        for (int k = 0; k < RING; ++k) CK(cudaEventCreateWithFlags(&e->ring_ev[k], cudaEventDisableTiming));
+    }
+    const int slot = e->ring_next++ % RING;
+    CK(cudaEventSynchronize(e->ring_ev[slot]));
+    int rc = launch_line_sum(e, &j, 1, e->ring_h + slot, e->ring_d.p + slot, out_mode, nullptr);
+    if (rc) return rc;
+    CK(cudaEventRecord(e->ring_ev[slot], e->stream));
+    return PRB_OK;
 }
 
 extern "C" int prb_line_sum(prb_engine *e, double *out_host) {
@@ -609,6 +738,12 @@ extern "C" int prb_xsc_place(prb_engine *e, int64_t n_out, int64_t dst0, int64_t
 }
 
 // ------------------------------------------------------------------------------------ atmosphere
+static float *peer_slot(const prb_engine *e, int dst, int parity, int field, int src_rank) {
+    const PeerState &ps = e->peer;
+    return reinterpret_cast<float *>(ps.base[dst] + PEER_HEADER) +
+           ((size_t)(parity * 2 + field) * ps.world + src_rank) * (size_t)ps.ld;
+}
+
 extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups, const double *depth_cm,
                               const double *t_layer, const double *p_layer, const double *conc, const double *molmass,
                               const double *q_t, const double *q_296, const int64_t *window_len, double t_surface,
@@ -627,12 +762,23 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
     }
     int rc = check_segment(e, wmax);
     if (rc) return rc;
+    PeerState &ps = e->peer;
+    if (ps.connected && nc > ps.ld) return fail(PRB_ERR_ARG, "prb_atmosphere: owned chunk exceeds the peer gather slot");
 
     // per-(layer, group) params: weight = conc * P / 1e4 / kB / T  (absCoef, pyradClasses.py:581-583)
     std::vector<GroupParams> h((size_t)n_layers * n_groups);
-    std::vector<double> scale(n_layers);
     std::vector<FoldLayer> hf(n_layers);
+    std::vector<LayerJob> jobs(n_layers);
     const double c2 = 100 * hPlanck * cLight / kBoltz;
+    e->kmat_ld = (nc + 3) & ~int64_t(3);
+    CK(e->gp.ensure(h.size()));
+    CK(e->st.ensure(n_layers));
+    CK(e->fold.ensure(n_layers));
+    CK(e->k1tab.ensure(n_layers));
+    CK(e->k2tab.ensure(n_layers));
+    CK(e->kmat.ensure((size_t)e->kmat_ld * n_layers));
+    CK(e->rad.ensure(e->kmat_ld));
+    CK(e->trans.ensure(e->kmat_ld));
     for (int l = 0; l < n_layers; ++l) {
         std::vector<double> w(n_groups);
         for (int g = 0; g < n_groups; ++g)
@@ -640,17 +786,13 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
         double w_max = 0;
         build_group_params(n_groups, t_layer[l], conc + (size_t)l * n_groups, molmass, q_t + (size_t)l * n_groups,
                            q_296, w.data(), h.data() + (size_t)l * n_groups, &w_max);
-        scale[l] = pick_scale(e->s_max, w_max);
         hf[l].neg_depth_log2e = (float)(-depth_cm[l] * 1.4426950408889634);
         hf[l].c2_over_t = (float)(c2 / t_layer[l]);
+        jobs[l] = plan_job(e, t_layer[l], p_layer[l], window_len[l], pick_scale(e->s_max, w_max));
+        jobs[l].gp_dev = e->gp.p + (size_t)l * n_groups;
+        jobs[l].st_dev = e->st.p + l;
+        jobs[l].out_dev = e->kmat.p + (size_t)l * e->kmat_ld;
     }
-    e->kmat_ld = (nc + 3) & ~int64_t(3);
-    CK(e->gp.ensure(h.size()));
-    CK(e->st.ensure(n_layers));
-    CK(e->fold.ensure(n_layers));
-    CK(e->kmat.ensure((size_t)e->kmat_ld * n_layers));
-    CK(e->rad.ensure(e->kmat_ld));
-    CK(e->trans.ensure(e->kmat_ld));
     CK(cudaMemcpyAsync(e->gp.p, h.data(), sizeof(GroupParams) * h.size(), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->fold.p, hf.data(), sizeof(FoldLayer) * n_layers, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemsetAsync(e->st.p, 0, sizeof(DevState) * n_layers, e->stream));
@@ -658,7 +800,58 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
         CK(cudaMemsetAsync(e->kmat.p, 0, sizeof(float) * e->kmat_ld * n_layers, e->stream));
         e->atm_layers = n_layers;
     }
-    const size_t n_ev = (size_t)2 * n_layers + 2;
+
+    // Launch plan.  Layers are processed widest window first, in batches of `slots` layers whose records are
+    // resident together (36 B per line per layer): ONE K1 launch per batch, then ONE K2 launch per kernel class
+    // of the batch, each walking all its (layer, tile) items from one dynamic counter -- a handful of launch
+    // tails per atmosphere instead of one per layer, which is what strong scaling over small chunks needs.
+    std::stable_sort(jobs.begin(), jobs.end(), [](const LayerJob &x, const LayerJob &y) { return x.wm > y.wm; });
+    int64_t slots = 1;
+    if (e->batch_layers && n_layers > 1) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_layer = (size_t)36 * (size_t)std::max<int64_t>(e->n_alloc, 1);
+        const size_t have = (size_t)e->rec_slots * per_layer;               // already allocated records count as free
+        const size_t budget = e->rec_budget_mb > 0 ? (size_t)e->rec_budget_mb << 20 : (free_b + have) / 4;
+        slots = std::max<int64_t>(1, std::min<int64_t>(n_layers, (int64_t)(budget / per_layer)));
+    }
+    if ((rc = ensure_records(e, slots))) return rc;
+
+    // destinations of the finished spectra
+    unsigned int epoch = 0;
+    K3Dst dst{};
+    if (ps.connected) {
+        epoch = ++ps.epoch;
+        dst.n = ps.world;
+        for (int d = 0; d < ps.world; ++d) {
+            dst.rad[d] = peer_slot(e, d, epoch & 1, 0, ps.rank);
+            dst.trans[d] = peer_slot(e, d, epoch & 1, 1, ps.rank);
+        }
+        e->res_rad = dst.rad[ps.rank];
+        e->res_trans = dst.trans[ps.rank];
+    } else {
+        dst.n = 1;
+        dst.rad[0] = e->rad.p;
+        dst.trans[0] = e->trans.p;
+        e->res_rad = e->rad.p;
+        e->res_trans = e->trans.p;
+    }
+    const double dx = e->n_total > 1 ? (range_max - e->range_min) / (double)(e->n_total - 1) : 0.0;
+    const bool fused = n_layers == 1 && e->fuse_single && !jobs[0].narrow && e->k2_variant == PRB_K2_CLASSED;
+    K2Fuse fuse{};
+    if (fused) {
+        fuse.enabled = 1;
+        fuse.n_dst = dst.n;
+        fuse.neg_depth_log2e = hf[0].neg_depth_log2e;
+        fuse.c2_over_t = hf[0].c2_over_t;
+        fuse.c2_over_tsurf = (float)(c2 / t_surface);
+        fuse.n_total = e->n_total;
+        fuse.x0 = e->range_min; fuse.dx = dx; fuse.x_last = range_max;
+        for (int d = 0; d < dst.n; ++d) { fuse.rad[d] = dst.rad[d]; fuse.trans[d] = dst.trans[d]; }
+    }
+
+    const int n_batches = (int)((n_layers + slots - 1) / slots);
+    const size_t n_ev = (size_t)3 * n_batches + 2;
     if (e->timing) {
         while (e->ev.size() < n_ev) {
             cudaEvent_t x;
@@ -666,49 +859,87 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
             e->ev.push_back(x);
         }
     }
-    for (int l = 0; l < n_layers; ++l) {
-        PrepassArgs pa;
-        if (e->timing) CK(cudaEventRecord(e->ev[2 * l], e->stream));
-        rc = launch_prepass(e, t_layer[l], p_layer[l], window_len[l], e->gp.p + (size_t)l * n_groups, scale[l],
-                            e->st.p + l, DebugOut{}, &pa);
+    std::vector<K1Layer> k1rows(n_layers);
+    std::vector<K2Layer> k2rows(n_layers);
+    int launches = 0;
+    for (int bi = 0; bi < n_batches; ++bi) {
+        const int b0 = (int)(bi * slots), b1 = (int)std::min<int64_t>(n_layers, b0 + slots);
+        for (int k = b0; k < b1; ++k) jobs[k].slot = k - b0;
+        if (e->timing) CK(cudaEventRecord(e->ev[3 * bi], e->stream));
+        rc = launch_prepass(e, jobs.data() + b0, b1 - b0, k1rows.data() + b0, e->k1tab.p + b0, DebugOut{});
         if (rc) return rc;
-        if (e->timing) CK(cudaEventRecord(e->ev[2 * l + 1], e->stream));
-        rc = launch_line_sum(e, pa, e->st.p + l, e->kmat.p + (size_t)l * e->kmat_ld, PRB_OUT_F32);
-        if (rc) return rc;
+        ++launches;
+        if (e->timing) CK(cudaEventRecord(e->ev[3 * bi + 1], e->stream));
+        for (int c0 = b0; c0 < b1;) {                            // runs of one kernel class (sorted by window)
+            int c1 = c0 + 1;
+            while (c1 < b1 && jobs[c1].narrow == jobs[c0].narrow && (jobs[c0].narrow || jobs[c1].ppt == jobs[c0].ppt)) ++c1;
+            rc = launch_line_sum(e, jobs.data() + c0, c1 - c0, k2rows.data() + c0, e->k2tab.p + c0, PRB_OUT_F32,
+                                 fused ? &fuse : nullptr);
+            if (rc) return rc;
+            ++launches;
+            c0 = c1;
+        }
+        if (e->timing) CK(cudaEventRecord(e->ev[3 * bi + 2], e->stream));
     }
-    if (e->timing) CK(cudaEventRecord(e->ev[2 * n_layers], e->stream));
-    if (nc > 0) {
-        const double dx = e->n_total > 1 ? (range_max - e->range_min) / (double)(e->n_total - 1) : 0.0;
+    if (e->timing) CK(cudaEventRecord(e->ev[3 * n_batches], e->stream));
+    if (nc > 0 && !fused) {
         k3_fold_f32<<<stream_grid(e, nc, 4), 256, 0, e->stream>>>(e->kmat.p, e->kmat_ld, n_layers, e->fold.p, nc,
                                                                  e->i_begin, e->n_total, e->range_min, dx, range_max,
-                                                                 (float)(c2 / t_surface), e->rad.p, e->trans.p);
+                                                                 (float)(c2 / t_surface), dst);
         CK(cudaGetLastError());
+        ++launches;
     }
-    if (e->timing) CK(cudaEventRecord(e->ev[2 * n_layers + 1], e->stream));
+    if (e->timing) CK(cudaEventRecord(e->ev[3 * n_batches + 1], e->stream));
+    if (ps.connected) {
+        PeerSignal sg{};
+        for (int d = 0; d < ps.world; ++d) sg.flags[d] = reinterpret_cast<unsigned int *>(ps.base[d]);
+        sg.rank = ps.rank; sg.world = ps.world; sg.epoch = epoch;
+        sg.err = e->peer_err.p;
+        sg.timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
+        k_peer_signal_wait<<<1, 32, 0, e->stream>>>(sg);
+        CK(cudaGetLastError());
+        ++launches;
+    }
+    e->last_launches = launches;
     CK(cudaStreamSynchronize(e->stream));                       // pageable staging vectors go out of scope
     if (e->timing) {
         e->t_k1 = e->t_k2 = e->t_k3 = 0;
         e->t_layer_k1.assign(n_layers, 0.f);
         e->t_layer_k2.assign(n_layers, 0.f);
-        for (int l = 0; l < n_layers; ++l) {
+        for (int bi = 0; bi < n_batches; ++bi) {
+            const int b0 = (int)(bi * slots), b1 = (int)std::min<int64_t>(n_layers, b0 + slots);
             float a = 0, b = 0;
-            CK(cudaEventElapsedTime(&a, e->ev[2 * l], e->ev[2 * l + 1]));
-            CK(cudaEventElapsedTime(&b, e->ev[2 * l + 1], e->ev[2 * l + 2]));
+            CK(cudaEventElapsedTime(&a, e->ev[3 * bi], e->ev[3 * bi + 1]));
+            CK(cudaEventElapsedTime(&b, e->ev[3 * bi + 1], e->ev[3 * bi + 2]));
             e->t_k1 += a;
             e->t_k2 += b;
-            e->t_layer_k1[l] = a;
-            e->t_layer_k2[l] = b;
+            // per-layer figures are exact with one layer per batch (prb_set_option PRB_OPT_BATCH_LAYERS 0), else
+            // the batch time spread evenly; reported in the caller's layer order
+            for (int k = b0; k < b1; ++k) {
+                const int l = (int)(jobs[k].st_dev - e->st.p);
+                e->t_layer_k1[l] = a / (b1 - b0);
+                e->t_layer_k2[l] = b / (b1 - b0);
+            }
         }
-        CK(cudaEventElapsedTime(&e->t_k3, e->ev[2 * n_layers], e->ev[2 * n_layers + 1]));
+        CK(cudaEventElapsedTime(&e->t_k3, e->ev[3 * n_batches], e->ev[3 * n_batches + 1]));
     }
     e->last.valid = false;
+    if (ps.connected) {
+        unsigned int perr = 0;
+        CK(cudaMemcpy(&perr, e->peer_err.p, sizeof perr, cudaMemcpyDeviceToHost));
+        if (perr) {
+            CK(cudaMemset(e->peer_err.p, 0, sizeof perr));
+            return fail(PRB_ERR_PEER, "peer gather timed out: a rank did not finish the step (ranks must call "
+                                      "prb_atmosphere the same number of times)");
+        }
+    }
     return check_flags(e, n_layers);
 }
 
 extern "C" int prb_atmosphere_result_dev(prb_engine *e, void **radiance_dev, void **transmittance_dev) {
     if (!e || !e->atm_layers) return fail(PRB_ERR_STATE, "prb_atmosphere_result_dev: run prb_atmosphere first");
-    if (radiance_dev) *radiance_dev = e->rad.p;
-    if (transmittance_dev) *transmittance_dev = e->trans.p;
+    if (radiance_dev) *radiance_dev = e->res_rad;
+    if (transmittance_dev) *transmittance_dev = e->res_trans;
     return PRB_OK;
 }
 
@@ -724,7 +955,7 @@ extern "C" int prb_atmosphere_read(prb_engine *e, double *radiance_host, double 
     CK(cudaSetDevice(e->device));
     const int64_t nc = chunk_len(e);
     std::vector<float> tmp(nc);
-    const float *src[2] = {e->rad.p, e->trans.p};
+    const float *src[2] = {e->res_rad, e->res_trans};
     double *dst[2] = {radiance_host, transmittance_host};
     for (int k = 0; k < 2; ++k) {
         if (!dst[k]) continue;
@@ -739,9 +970,9 @@ extern "C" int prb_atmosphere_read_f32(prb_engine *e, float *radiance_host, floa
     if (!e || !e->atm_layers) return fail(PRB_ERR_STATE, "prb_atmosphere_read_f32: run prb_atmosphere first");
     CK(cudaSetDevice(e->device));
     const int64_t nc = chunk_len(e);
-    if (radiance_host) CK(cudaMemcpyAsync(radiance_host, e->rad.p, sizeof(float) * nc, cudaMemcpyDeviceToHost, e->stream));
+    if (radiance_host) CK(cudaMemcpyAsync(radiance_host, e->res_rad, sizeof(float) * nc, cudaMemcpyDeviceToHost, e->stream));
     if (transmittance_host)
-        CK(cudaMemcpyAsync(transmittance_host, e->trans.p, sizeof(float) * nc, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(transmittance_host, e->res_trans, sizeof(float) * nc, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return PRB_OK;
 }
@@ -774,5 +1005,90 @@ extern "C" int prb_set_narrow_threshold(prb_engine *e, int64_t wm_below) {
     if (!e) return fail(PRB_ERR_ARG, "null engine");
     e->narrow_wm = wm_below < 0 ? 100 : wm_below;
     e->last.valid = false;                                      // record layout may change: redo the prepass
+    return PRB_OK;
+}
+
+extern "C" int prb_set_option(prb_engine *e, int option, int64_t value) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    switch (option) {
+        case PRB_OPT_BATCH_LAYERS: e->batch_layers = value != 0; return PRB_OK;
+        case PRB_OPT_FUSE_SINGLE_LAYER: e->fuse_single = value != 0; return PRB_OK;
+        case PRB_OPT_RECORD_BUDGET_MB: e->rec_budget_mb = value < 0 ? 0 : value; return PRB_OK;
+        default: return fail(PRB_ERR_ARG, "prb_set_option: unknown option");
+    }
+}
+
+extern "C" int prb_atmosphere_launches(prb_engine *e) { return e ? e->last_launches : 0; }
+
+// ------------------------------------------------------------------------------------ peer gather (multi-GPU)
+// One process per GPU on one NVLink / NVSwitch node.  Each rank allocates a gather buffer, exports it as a CUDA
+// IPC handle; the host side exchanges the 64-byte handles by whatever transport it has (torch.distributed in
+// pyrad_b200/distributed.py, MPI, a file) and hands all of them back.  From then on prb_atmosphere stores this
+// rank's finished spectra straight into every rank's buffer from inside its last kernel and ends with a cross-GPU
+// flag barrier, so the all-gather of the spectra is part of the compute step (no separate collective).
+extern "C" int prb_peer_alloc(prb_engine *e, int rank, int world, int64_t max_chunk_points, void *handle_out) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (world < 1 || world > K2_MAX_PEERS || rank < 0 || rank >= world)
+        return fail(PRB_ERR_ARG, "prb_peer_alloc: world must be 1..8 and 0 <= rank < world");
+    if (max_chunk_points < 1 || !handle_out) return fail(PRB_ERR_ARG, "prb_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PRB_PEER_HANDLE_BYTES, "handle size");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    peer_release(e);
+    PeerState &ps = e->peer;
+    ps.rank = rank; ps.world = world;
+    ps.ld = (max_chunk_points + 63) & ~int64_t(63);
+    ps.bytes = PEER_HEADER + (size_t)2 * 2 * world * (size_t)ps.ld * sizeof(float);
+    CK(cudaMalloc((void **)&ps.local, ps.bytes));
+    CK(cudaMemset(ps.local, 0, ps.bytes));
+    CK(e->peer_err.ensure(1));
+    CK(cudaMemset(e->peer_err.p, 0, sizeof(unsigned int)));
+    cudaIpcMemHandle_t hd;
+    CK(cudaIpcGetMemHandle(&hd, ps.local));
+    memcpy(handle_out, &hd, sizeof hd);
+    return PRB_OK;
+}
+
+extern "C" int prb_peer_connect(prb_engine *e, const void *handles) {
+    if (!e || !handles) return fail(PRB_ERR_ARG, "prb_peer_connect: bad arguments");
+    PeerState &ps = e->peer;
+    if (!ps.local) return fail(PRB_ERR_STATE, "prb_peer_connect: call prb_peer_alloc first");
+    if (ps.connected) return fail(PRB_ERR_STATE, "prb_peer_connect: already connected");
+    CK(cudaSetDevice(e->device));
+    for (int r = 0; r < ps.world; ++r) {
+        if (r == ps.rank) { ps.base[r] = ps.local; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const unsigned char *)handles + (size_t)r * sizeof hd, sizeof hd);
+        void *ptr = nullptr;
+        cudaError_t ce = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) {
+            for (int q = 0; q < r; ++q) if (q != ps.rank && ps.base[q]) { cudaIpcCloseMemHandle(ps.base[q]); ps.base[q] = nullptr; }
+            return fail(PRB_ERR_PEER, std::string("prb_peer_connect: cudaIpcOpenMemHandle failed for rank ") +
+                                          std::to_string(r) + ": " + cudaGetErrorString(ce));
+        }
+        ps.base[r] = (unsigned char *)ptr;
+    }
+    ps.connected = true;
+    ps.epoch = 0;
+    return PRB_OK;
+}
+
+extern "C" int prb_peer_disconnect(prb_engine *e) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    peer_release(e);
+    e->res_rad = e->res_trans = nullptr;
+    e->atm_layers = 0;
+    return PRB_OK;
+}
+
+extern "C" int prb_peer_gathered_dev(prb_engine *e, void **radiance_dev, void **transmittance_dev, int64_t *ld) {
+    if (!e || !e->peer.connected || !e->peer.epoch)
+        return fail(PRB_ERR_STATE, "prb_peer_gathered_dev: connect the peers and run prb_atmosphere first");
+    const int par = e->peer.epoch & 1;
+    if (radiance_dev) *radiance_dev = peer_slot(e, e->peer.rank, par, 0, 0);
+    if (transmittance_dev) *transmittance_dev = peer_slot(e, e->peer.rank, par, 1, 0);
+    if (ld) *ld = e->peer.ld;
     return PRB_OK;
 }

@@ -56,17 +56,49 @@ __global__ void k0_line_index(const double *__restrict__ nu0, int64_t n, int64_t
 
 __device__ __forceinline__ double pow5(double x) { double x2 = x * x; return x2 * x2 * x; }
 
+// One layer of a (possibly multi-layer) prepass launch.
+struct K1Layer {
+    double T, P;
+    LayerConsts lc;
+    double scale;                  // power-of-two scale of this layer's FP32 coefficients
+    double wm;                     // W-2 clamped at 0 (FP32 range guard)
+    const GroupParams *gp;         // n_groups entries for this layer
+    float4 *recA, *recB;           // this layer's record arrays (indexed by line)
+    float *recD;
+    DevState *st;                  // this layer's status flags
+    int narrow;                    // 1: compact records for k2_narrow
+    int pad;
+};
+
+// One thread per line; the thread keeps the line's seven constants in registers and walks the layers of the
+// batch, so the SoA columns are read once per launch instead of once per layer.
 __global__ void __launch_bounds__(256)
-k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__restrict__ gp,
-           int64_t l_begin, int64_t l_end, int64_t n_lines,
-           double T, double P, LayerConsts lc, double scale, int64_t i_base, double wm, int narrow,
-           float4 *__restrict__ recA, float4 *__restrict__ recB, float *__restrict__ recD, DevState *st,
-           DebugOut dbg) {
+k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const K1Layer *__restrict__ layers, int n_layers,
+           int64_t l_begin, int64_t l_end, int64_t n_lines, int64_t i_base, DebugOut dbg) {
     const double c2 = cLight * hPlanck * 100 / kBoltz;          // pyradIntensity.py:13
-    int64_t l = l_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t l = l_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = l < l_end;
+    const bool real = in_range && l < n_lines;
+    double nu = 0, delta = 0, gair = 0, gself = 0, nair = 0, elower = 0, s296 = 0, fi = 0;
+    int g = 0;
+    if (real) {
+        nu = L.nu0[l]; delta = L.delta[l]; gair = L.gair[l]; gself = L.gself[l];
+        nair = L.nair[l]; elower = L.elower[l]; s296 = L.s296[l];
+        g = L.group ? L.group[l] : 0;
+        fi = (double)((int64_t)idx[l] - i_base);
+    }
+#pragma unroll 1
+    for (int ly = 0; ly < n_layers; ++ly) {
+    const K1Layer &K = layers[ly];
+    const LayerConsts lc = K.lc;
+    const double scale = K.scale, wm = K.wm;
+    const int narrow = K.narrow;
+    float4 *__restrict__ recA = K.recA;
+    float4 *__restrict__ recB = K.recB;
+    float *__restrict__ recD = K.recD;
     unsigned int flags = 0;
-    if (l < l_end) {
-        if (l >= n_lines) {                                       // padding record: never in a window
+    if (in_range) {
+        if (!real) {                                              // padding record: never in a window
             if (narrow) {
                 recA[l] = make_float4(-K2_SENTINEL, 0.f, 1.f, 0.f);
             } else {
@@ -75,22 +107,20 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__res
             }
             recD[l] = -1.f;
         } else {
-            const int g = L.group ? L.group[l] : 0;
-            const GroupParams p = gp[g];
-            const double nu = L.nu0[l];
+            const GroupParams p = K.gp[g];
             // Divisions are the expensive FP64 operation here (K1 is FP64-pipe bound, not HBM bound), so
             // per-layer reciprocals come from the host (lc.*) and each regime needs a single 1/h.  This
             // changes roundings by an ulp relative to the reference's operation order (1e-16), nothing more.
-            const double nus = nu + L.delta[l] * lc.p_over_p0;
+            const double nus = nu + delta * lc.p_over_p0;
             // (t0/T)^n = exp(n * log(t0/T)): the log is a per-layer constant
-            const double gl = ((1 - p.conc) * L.gair[l] + p.conc * L.gself[l]) * lc.p_over_p0 *
-                              exp(L.nair[l] * lc.log_t0_over_t);
+            const double gl = ((1 - p.conc) * gair + p.conc * gself) * lc.p_over_p0 *
+                              exp(nair * lc.log_t0_over_t);
             const double gd = nus * p.dopp;
             const double ratio = gl / gd;                         // gd == 0 -> inf -> Lorentz, as numpy
             const double stim = (1 - exp(lc.neg_c2_over_t * nus)) / (1 - exp(lc.neg_c2_over_t0 * nus));
             // exp(-c2 E/T) / exp(-c2 E/t0) evaluated as one exponential (same value to ~1e-16)
-            const double boltz = exp(-c2 * L.elower[l] * lc.inv_t_minus_inv_t0);
-            const double S = L.s296[l] * p.qratio * stim * boltz;
+            const double boltz = exp(-c2 * elower * lc.inv_t_minus_inv_t0);
+            const double S = s296 * p.qratio * stim * boltz;
             const double sw = S * p.weight * scale;
             const double inv_res2 = lc.inv_res2;
             const double log2e = 1.4426950408889634;
@@ -150,7 +180,6 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__res
             if (!(isfinite(A) && isfinite(G) && isfinite(B) && isfinite(C))) flags |= FLAG_NONFINITE;
             // the triple-reciprocal path forms |A| q^2 and q^3
             else if (fabs(A) * qmax * qmax > 8.0e37 || fabs(G) > 8.0e37 || qmax * qmax * qmax > 8.0e37) flags |= FLAG_OVERFLOW;
-            const double fi = (double)((int64_t)idx[l] - i_base);
             const float nf = -(float)fi, Af = (float)A, Bf = (float)B;
             if (narrow) {                                         // compact layout of k2_narrow
                 recA[l] = make_float4(nf, Af, Bf, (float)G);
@@ -169,7 +198,8 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const GroupParams *__res
     }
     // OR of the status flags, one atomic per warp that has something to report (order independent).
     flags = __reduce_or_sync(0xffffffffu, flags);
-    if ((threadIdx.x & 31) == 0 && flags) atomicOr(&st->flags, flags);
+    if ((threadIdx.x & 31) == 0 && flags) atomicOr(&K.st->flags, flags);
+    }
 }
 
 }  // namespace prb

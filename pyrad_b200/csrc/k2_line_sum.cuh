@@ -28,6 +28,7 @@
 //   * tensor cores are deliberately unused: this is not a dense contraction.
 #pragma once
 #include "common.cuh"
+#include "k3_stream.cuh"
 
 namespace prb {
 
@@ -103,21 +104,46 @@ __device__ __forceinline__ int warp_lower_bound(const int32_t *__restrict__ idx,
 //   recA = {-fidx, -fidx, A, A}      fidx = line index relative to the shard's first point (exact integer)
 //   recB = {B, B, G, C}
 //   recD = Dg                         near-zone radius in grid points (-1: no Gaussian term)
-struct K2Args {
+// One layer of a (possibly multi-layer) launch.  A launch walks work items (layer, tile) handed out by one
+// dynamic counter, layers in table order (the host sorts them widest window first, so the expensive items
+// start first and the tail of the launch is made of cheap ones).
+struct K2Layer {
     const float4 *recA;
     const float4 *recB;
     const float *recD;
+    void *out;                 // this layer's output row (chunk-local index 0)
+    double inv_scale;          // undoes K1's power-of-two scale, exactly
+    int l_begin, l_end;        // line range prepared by K1 for this shard and window
+    int wm;                    // W-2 clamped at 0: max |d| that still accumulates
+    int pad;
+};
+
+// Optional fused single-layer epilogue (gas cell): the pointwise layer physics of K3 applied to the finished
+// tile -- k -> T = exp(-k u), I = B_l + T (B_surface - B_l) -- and the finished spectra stored straight into
+// every rank's gather buffer over NVLink peer memory (tile by tile, overlapping the remaining line sums).
+constexpr int K2_MAX_PEERS = 8;
+struct K2Fuse {
+    int enabled;
+    int n_dst;                           // 1 (local only) .. K2_MAX_PEERS
+    float neg_depth_log2e;               // -depth * log2(e)
+    float c2_over_t, c2_over_tsurf;      // 100 h c / kB / T
+    long long n_total;                   // points of the FULL grid (np.linspace axis)
+    double x0, dx, x_last;
+    float *rad[K2_MAX_PEERS];            // per destination: this rank's slot of the radiance gather buffer
+    float *trans[K2_MAX_PEERS];
+};
+
+struct K2Args {
+    const K2Layer *layers;     // device table, n_layers entries
+    int n_layers;
     const int32_t *idx;        // sorted absolute grid index per line
-    int l_begin, l_end;        // line range prepared by K1 for this shard
     long long i_begin;         // absolute index of the shard's first grid point
     int n_chunk;               // grid points owned
-    int wm;                    // W-2 clamped at 0: max |d| that still accumulates
-    int n_tiles;
+    int n_tiles;               // tiles per layer
     int variant;               // PRB_K2_GENERAL / PRB_K2_CLASSED
     int out_mode;              // PRB_OUT_F64 / PRB_OUT_F32
-    double inv_scale;
-    void *out;
-    DevState *st;
+    DevState *st;              // tile_counter of this launch
+    K2Fuse fuse;
 };
 
 // One ring slot: a chunk of staged line records plus its descriptor.
@@ -125,7 +151,7 @@ struct K2Desc {
     int tile0;      // shard-local index of the first point of the tile this chunk belongs to
     int cnt;        // staged lines to process (padding excluded)
     int flags;      // K2_FIRST | K2_LAST | K2_END
-    int pad;
+    int layer;      // index into K2Args::layers
 };
 constexpr int K2_FIRST = 1, K2_LAST = 2, K2_END = 4;
 
@@ -309,16 +335,24 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             stage = it % K2_STAGES;
             mbar_wait(&sm.empty[stage], ((it / K2_STAGES) & 1) ^ 1);   // fresh barrier: passes at once
         };
+        const int n_items = a.n_layers * a.n_tiles;
         while (true) {
-            int tile = 0;
-            if (lane == 0) tile = (int)atomicAdd(&a.st->tile_counter, 1u);
-            tile = __shfl_sync(0xffffffffu, tile, 0);
-            if (tile >= a.n_tiles) break;
+            int item = 0;
+            if (lane == 0) item = (int)atomicAdd(&a.st->tile_counter, 1u);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= n_items) break;
+            const int layer = item / a.n_tiles;
+            const int tile = item - layer * a.n_tiles;
+            const K2Layer *L = a.layers + layer;
+            const int wm = __ldg(&L->wm), l_begin = __ldg(&L->l_begin), l_end = __ldg(&L->l_end);
+            const float4 *recA = L->recA;
+            const float4 *recB = L->recB;
+            const float *recD = L->recD;
             const int tile0 = tile * TILE;
-            const long long k_lo = a.i_begin + tile0 - a.wm;
-            const long long k_hi = a.i_begin + tile0 + TILE - 1 + a.wm + 1;
-            int lo = warp_lower_bound(a.idx, a.l_begin, a.l_end, k_lo);
-            const int hi = warp_lower_bound(a.idx, lo, a.l_end, k_hi);
+            const long long k_lo = a.i_begin + tile0 - wm;
+            const long long k_hi = a.i_begin + tile0 + TILE - 1 + wm + 1;
+            int lo = warp_lower_bound(a.idx, l_begin, l_end, k_lo);
+            const int hi = warp_lower_bound(a.idx, lo, l_end, k_hi);
             lo &= ~3;                                  // 16-byte alignment of the float stream
             const int nch = hi > lo ? (hi - lo + K2_CHUNK - 1) / K2_CHUNK : 1;   // empty tile: one empty chunk
             for (int c = 0; c < nch; ++c, ++it) {
@@ -327,13 +361,13 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
                 if (lane == 0) {
                     const int first = lo + c * K2_CHUNK;
                     const int cnt = max(min(K2_CHUNK, hi - first), 0);
-                    sm.desc[stage] = K2Desc{tile0, cnt, (c == 0 ? K2_FIRST : 0) | (c == nch - 1 ? K2_LAST : 0), 0};
+                    sm.desc[stage] = K2Desc{tile0, cnt, (c == 0 ? K2_FIRST : 0) | (c == nch - 1 ? K2_LAST : 0), layer};
                     if (cnt > 0) {
                         const uint32_t ce = (uint32_t)((cnt + 3) & ~3);   // padding records exist past l_end
                         mbar_expect_tx(&sm.full[stage], ce * 36u);
-                        tma_bulk_g2s(sm.rA[stage], a.recA + first, ce * 16u, &sm.full[stage]);
-                        tma_bulk_g2s(sm.rB[stage], a.recB + first, ce * 16u, &sm.full[stage]);
-                        tma_bulk_g2s(sm.rD[stage], a.recD + first, ce * 4u, &sm.full[stage]);
+                        tma_bulk_g2s(sm.rA[stage], recA + first, ce * 16u, &sm.full[stage]);
+                        tma_bulk_g2s(sm.rB[stage], recB + first, ce * 16u, &sm.full[stage]);
+                        tma_bulk_g2s(sm.rD[stage], recD + first, ce * 4u, &sm.full[stage]);
                     } else {
                         mbar_arrive(&sm.full[stage]);
                     }
@@ -351,7 +385,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
     }
 
     // ---------------------------------------------------------------------- consumer warps
-    const float wmf = (float)a.wm;
+    float wmf = 0.f;
     Acc<H> s;
 #pragma unroll
     for (int h = 0; h < H; ++h) { s.a32[h] = make_float2(0.f, 0.f); s.fi[h] = make_float2(0.f, 0.f); }
@@ -366,6 +400,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
         const K2Desc d = sm.desc[stage];
         if (d.flags & K2_END) break;
         if (d.flags & K2_FIRST) {
+            wmf = (float)__ldg(&a.layers[d.layer].wm);
             wb = d.tile0 + warp * SPAN;                // first point of this warp's span
             wbf = (float)wb;
             we1f = (float)(wb + SPAN - 1);
@@ -418,13 +453,32 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
 
         if (d.flags & K2_LAST) {
             // epilogue: undo the power-of-two scale exactly and store (coalesced 32-point rows)
+            const K2Layer *L = a.layers + d.layer;
+            const double inv_scale = __ldg(&L->inv_scale);
+            void *out = L->out;
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const int i = wb + 32 * p + lane;
                 if (i < a.n_chunk) {
-                    const double v = s.a64[p] * a.inv_scale;
-                    if (a.out_mode == 0) reinterpret_cast<double *>(a.out)[i] = v;
-                    else reinterpret_cast<float *>(a.out)[i] = (float)v;
+                    const double v = s.a64[p] * inv_scale;
+                    if (a.out_mode == 0) reinterpret_cast<double *>(out)[i] = v;
+                    else reinterpret_cast<float *>(out)[i] = (float)v;
+                    if (a.fuse.enabled) {
+                        // same operations, in the same order, as k3_fold_f32 with one layer
+                        const double x = axis_value(a.i_begin + i, a.fuse.n_total, a.fuse.x0, a.fuse.dx, a.fuse.x_last);
+                        const float nu = (float)x;
+                        const float a3 = (float)(2E8 * hPlanck * (cLight * cLight) * (x * x * x));
+                        const float e = (float)v * a.fuse.neg_depth_log2e;
+                        const float t = k3_ex2(e);
+                        const float b = planck_f32(a3, a.fuse.c2_over_t * nu);
+                        const float rad = fmaf(t, planck_f32(a3, a.fuse.c2_over_tsurf * nu) - b, b);
+                        const float tr = exp2f(0.f + e);
+#pragma unroll 1
+                        for (int dst = 0; dst < a.fuse.n_dst; ++dst) {
+                            a.fuse.rad[dst][i] = rad;          // own slot of every rank's gather buffer (peer
+                            a.fuse.trans[dst][i] = tr;         // stores over NVLink are fire-and-forget)
+                        }
+                    }
                 }
             }
         }

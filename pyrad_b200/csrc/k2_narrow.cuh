@@ -33,6 +33,10 @@ __global__ void __launch_bounds__(KN_THREADS, 4) k2_narrow(const K2Args a) {
     KNSmem &sm = *reinterpret_cast<KNSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile0 = blockIdx.x * KN_TILE;           // shard-local index of the tile's first point
+    const K2Layer *L = a.layers + blockIdx.y;         // one grid row per layer of the batch
+    const int wm = __ldg(&L->wm);
+    const float4 *recA = L->recA;
+    const float *recD = L->recD;
 
     if (tid == 0) {
         mbar_init(&sm.bar, 1);
@@ -40,16 +44,17 @@ __global__ void __launch_bounds__(KN_THREADS, 4) k2_narrow(const K2Args a) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 0) {
-        const long long k_lo = a.i_begin + tile0 - a.wm;
-        const long long k_hi = a.i_begin + tile0 + KN_TILE - 1 + a.wm + 1;
-        const int lo = warp_lower_bound(a.idx, a.l_begin, a.l_end, k_lo);
-        const int hi = warp_lower_bound(a.idx, lo, a.l_end, k_hi);
+        const long long k_lo = a.i_begin + tile0 - wm;
+        const long long k_hi = a.i_begin + tile0 + KN_TILE - 1 + wm + 1;
+        const int l_end = __ldg(&L->l_end);
+        const int lo = warp_lower_bound(a.idx, __ldg(&L->l_begin), l_end, k_lo);
+        const int hi = warp_lower_bound(a.idx, lo, l_end, k_hi);
         if (lane == 0) { sm.lo = lo & ~3; sm.hi = hi; }
     }
     __syncthreads();
     const int lo = sm.lo, hi = sm.hi;
     const int nch = hi > lo ? (hi - lo + KN_CHUNK - 1) / KN_CHUNK : 0;
-    const float wmf = (float)a.wm;
+    const float wmf = (float)wm;
 
     float fi[KN_ROUNDS];
     double acc[KN_ROUNDS];
@@ -62,8 +67,8 @@ __global__ void __launch_bounds__(KN_THREADS, 4) k2_narrow(const K2Args a) {
         if (tid == 0) {
             const uint32_t ce = (uint32_t)((cnt + 3) & ~3);
             mbar_expect_tx(&sm.bar, ce * 20u);
-            tma_bulk_g2s(sm.rec, a.recA + first, ce * 16u, &sm.bar);
-            tma_bulk_g2s(sm.cc, a.recD + first, ce * 4u, &sm.bar);
+            tma_bulk_g2s(sm.rec, recA + first, ce * 16u, &sm.bar);
+            tma_bulk_g2s(sm.cc, recD + first, ce * 4u, &sm.bar);
         }
         mbar_wait(&sm.bar, c & 1);
 #pragma unroll
@@ -92,13 +97,15 @@ __global__ void __launch_bounds__(KN_THREADS, 4) k2_narrow(const K2Args a) {
         __syncthreads();                              // the single staging buffer is refilled next pass
     }
 
+    const double inv_scale = __ldg(&L->inv_scale);
+    void *out = L->out;
 #pragma unroll
     for (int r = 0; r < KN_ROUNDS; ++r) {
         const int i = tile0 + r * KN_THREADS + tid;
         if (i < a.n_chunk) {
-            const double v = acc[r] * a.inv_scale;
-            if (a.out_mode == 0) reinterpret_cast<double *>(a.out)[i] = v;
-            else reinterpret_cast<float *>(a.out)[i] = (float)v;
+            const double v = acc[r] * inv_scale;
+            if (a.out_mode == 0) reinterpret_cast<double *>(out)[i] = v;
+            else reinterpret_cast<float *>(out)[i] = (float)v;
         }
     }
 }

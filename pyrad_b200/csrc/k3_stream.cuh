@@ -96,10 +96,19 @@ __device__ __forceinline__ float planck_f32(float a_nu3, float x) {
     return a_nu3 * k3_rcp(k3_ex2(x * 1.4426950408889634f) - 1.0f);
 }
 
+// Destinations of the finished spectra: this rank's slot in every rank's gather buffer (peer memory over
+// NVLink; stores are fire-and-forget), or just the local result arrays when no peers are connected.
+constexpr int K3_MAX_DST = 8;
+struct K3Dst {
+    int n;
+    float *rad[K3_MAX_DST];
+    float *trans[K3_MAX_DST];
+};
+
 __global__ void __launch_bounds__(256)
 k3_fold_f32(const float *__restrict__ kmat, int64_t ld, int n_layers, const FoldLayer *__restrict__ layers,
             int64_t n_chunk, int64_t i_begin, int64_t n_total, double x0, double dx, double x_last,
-            float c2_over_tsurf, float *__restrict__ rad_out, float *__restrict__ trans_out) {
+            float c2_over_tsurf, const K3Dst dst) {
     const int64_t nvec = (n_chunk + 3) >> 2;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i0 = v << 2;
@@ -126,16 +135,56 @@ k3_fold_f32(const float *__restrict__ kmat, int64_t ld, int n_layers, const Fold
                 tau[q] += e;
             }
         }
-        if (i0 + 3 < n_chunk) {
-            *reinterpret_cast<float4 *>(rad_out + i0) = make_float4(rad[0], rad[1], rad[2], rad[3]);
-            *reinterpret_cast<float4 *>(trans_out + i0) =
-                make_float4(exp2f(tau[0]), exp2f(tau[1]), exp2f(tau[2]), exp2f(tau[3]));
-        } else {
-            for (int q = 0; q < 4 && i0 + q < n_chunk; ++q) {
-                rad_out[i0 + q] = rad[q];
-                trans_out[i0 + q] = exp2f(tau[q]);
+        const float4 r4 = make_float4(rad[0], rad[1], rad[2], rad[3]);
+        const float4 t4 = make_float4(exp2f(tau[0]), exp2f(tau[1]), exp2f(tau[2]), exp2f(tau[3]));
+        const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll 1
+        for (int d = 0; d < dst.n; ++d) {
+            if (i0 + 3 < n_chunk) {
+                *reinterpret_cast<float4 *>(dst.rad[d] + i0) = r4;
+                *reinterpret_cast<float4 *>(dst.trans[d] + i0) = t4;
+            } else {
+                for (int q = 0; q < 4 && i0 + q < n_chunk; ++q) {
+                    dst.rad[d][i0 + q] = rr[q];
+                    dst.trans[d][i0 + q] = tt[q];
+                }
             }
         }
+    }
+}
+
+// ---- cross-GPU completion barrier of one gather step ------------------------------------------------
+// Launched (one warp) after the kernel that stored this rank's spectra into every peer's gather buffer.
+// Lane p publishes "rank r finished epoch E" into peer p's flag block with a system-scope release, then
+// waits until peer p's flag for E has arrived here: when the kernel retires, every rank's slot of the LOCAL
+// gather buffer is complete.  A peer that never arrives trips the timeout and sets *err (reported by the host
+// as PRB_ERR_PEER) instead of hanging the GPU.
+struct PeerSignal {
+    unsigned int *flags[K3_MAX_DST];   // every rank's flag block (own one included), [2][K3_MAX_DST] words each
+    int rank, world;
+    unsigned int epoch;
+    unsigned int *err;
+    unsigned long long timeout_ns;
+};
+
+__global__ void k_peer_signal_wait(const PeerSignal s) {
+    const int p = threadIdx.x;
+    if (p >= s.world) return;
+    const int par = s.epoch & 1u;
+    __threadfence_system();
+    unsigned int *remote = s.flags[p] + par * K3_MAX_DST + s.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(s.epoch) : "memory");
+    const unsigned int *mine = s.flags[s.rank] + par * K3_MAX_DST + p;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (true) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int)(v - s.epoch) >= 0) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > s.timeout_ns) { atomicOr(s.err, 1u); break; }
+        __nanosleep(200);
     }
 }
 

@@ -55,6 +55,31 @@ def assemble(gathered, plan):
     return torch.cat(parts) if parts else gathered.new_zeros(0)
 
 
+def connect_peers(engine, rank, world, max_chunk_points, dist):
+    """Set up the engine's peer-memory gather: allocate this rank's buffer, exchange the CUDA IPC handles
+    with ONE all_gather of 64 bytes per rank (torch.distributed: plumbing), map every peer.  After this,
+    engine.atmosphere() leaves the gathered spectra of all ranks in engine.peer_gathered_dev() -- the
+    all-gather is fused into the compute step (stores over NVLink from inside the kernel)."""
+    import torch
+    handle = engine.peer_alloc(rank, world, max_chunk_points)
+    if world == 1:
+        engine.peer_connect([handle])
+        return
+    mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).cuda()
+    allh = torch.empty(world * len(handle), dtype=torch.uint8, device="cuda")
+    dist.all_gather_into_tensor(allh, mine)
+    blob = bytes(allh.cpu().numpy().tobytes())
+    engine.peer_connect(blob)
+    dist.barrier()
+
+
+def gathered_spectra(engine, plan_or_chunks=None):
+    """(radiance, transmittance) as torch views [world, ld] of the engine's gather buffer (no copy)."""
+    rp, tp, ld = engine.peer_gathered_dev()
+    world = engine._peer_world
+    return (device_tensor(rp, world * ld).view(world, ld), device_tensor(tp, world * ld).view(world, ld))
+
+
 class CudaArrayView:
     """Zero-copy view of engine-owned device memory for torch (``torch.as_tensor(view, device='cuda')``)."""
 

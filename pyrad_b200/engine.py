@@ -10,6 +10,8 @@ P0 = 1013.25
 
 OUT_F64, OUT_F32 = 0, 1
 K2_GENERAL, K2_CLASSED = 0, 1
+OPT_BATCH_LAYERS, OPT_FUSE_SINGLE_LAYER, OPT_RECORD_BUDGET_MB = 1, 2, 3
+PEER_HANDLE_BYTES = 64
 
 
 def _f64(a):
@@ -84,6 +86,9 @@ class Engine:
 
     def set_k2_variant(self, variant=K2_CLASSED, points_per_thread=0):
         _lib.check(self._lib.prb_set_k2_variant(self._h, int(variant), int(points_per_thread)))
+
+    def set_option(self, option, value):
+        _lib.check(self._lib.prb_set_option(self._h, int(option), int(value)))
 
     def set_narrow_threshold(self, wm_below=-1):
         _lib.check(self._lib.prb_set_narrow_threshold(self._h, int(wm_below)))
@@ -230,6 +235,33 @@ class Engine:
         a, b = C.c_void_p(), C.c_void_p()
         _lib.check(self._lib.prb_atmosphere_result_dev(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def atmosphere_launches(self):
+        """Kernels launched by the last atmosphere() call."""
+        return int(self._lib.prb_atmosphere_launches(self._h))
+
+    # -- multi-GPU: peer-memory gather of the finished spectra (include/pyrad_b200.h, "multi-GPU")
+    def peer_alloc(self, rank, world, max_chunk_points):
+        """Allocate this rank's gather buffer; returns its 64-byte CUDA IPC handle (bytes)."""
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        _lib.check(self._lib.prb_peer_alloc(self._h, int(rank), int(world), int(max_chunk_points), buf))
+        self._peer_world = int(world)
+        return buf.raw
+
+    def peer_connect(self, handles):
+        """handles: the world handles in rank order (list of bytes or one bytes object)."""
+        blob = b"".join(handles) if not isinstance(handles, (bytes, bytearray)) else bytes(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        _lib.check(self._lib.prb_peer_connect(self._h, buf))
+
+    def peer_disconnect(self):
+        _lib.check(self._lib.prb_peer_disconnect(self._h))
+
+    def peer_gathered_dev(self):
+        """(radiance_ptr, transmittance_ptr, ld): float[world][ld] arrays of the last step on this device."""
+        a, b, ld = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(self._lib.prb_peer_gathered_dev(self._h, C.byref(a), C.byref(b), C.byref(ld)))
+        return a.value, b.value, ld.value
 
     def atmosphere_kmatrix_dev(self):
         p, ld = C.c_void_p(), C.c_int64()

@@ -16,6 +16,8 @@ def main():
     win = [eng.window_len(c, w["res"]) for c in w["cutoff"]]
     qt = np.array([[s.q(T) for s in sp] for T in w["T"]])
     e.set_timing(True)
+    if os.environ.get("QA_NOBATCH"):
+        e.set_option(eng.OPT_BATCH_LAYERS, 0)      # per-layer launches: exact per-layer timings
     args = (w["depth_cm"], w["T"], w["P"], w["conc"], [s.molmass for s in sp], qt, [s.q296 for s in sp], win, w["t_surface"], w["range_max"])
     e.atmosphere(*args)
     cs = ClockSampler(0); cs.start()

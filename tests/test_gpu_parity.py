@@ -226,3 +226,84 @@ def test_lines_next_to_zero_wavenumber_with_negative_shift(engine, narrow):
     floor = H.K_FLOOR_REL * np.abs(ref).max()
     err = np.abs(out - ref) / np.maximum(np.abs(ref), floor)
     assert err.max() <= H.K_REL_TOL, (err.max(), int(err.argmax()))
+
+
+def _run_atm(engine, w, win=None):
+    sp = w["species"]
+    win = [eng.window_len(c, w["res"]) for c in w["cutoff"]] if win is None else win
+    qt = np.array([[s.q(T) for s in sp] for T in w["T"]])
+    engine.atmosphere(w["depth_cm"], w["T"], w["P"], w["conc"], [s.molmass for s in sp], qt, [s.q296 for s in sp],
+                      win, w["t_surface"], w["range_max"])
+    rad = np.empty(engine.n_chunk, dtype=np.float32)
+    tr = np.empty(engine.n_chunk, dtype=np.float32)
+    engine.atmosphere_read_f32(rad, tr)
+    return rad, tr
+
+
+def test_atmosphere_batched_launches_are_bitwise_equal_to_per_layer_launches(engine):
+    """The multi-layer launches (one K1 + one K2 per kernel class, layers sorted by window) only change WHEN a
+    (layer, tile) item runs, never its arithmetic: spectra must be identical to the layer-at-a-time schedule,
+    also when the record budget forces several batches."""
+    w = workloads.atmosphere(n_layers=24, n_lines=8000, rmin=600.0, rmax=660.0, res=0.001, top_km=60.0)
+    w["lines"] = {k: v[:-1] for k, v in w["lines"].items()}
+    H.engine_setup(engine, w)
+    assert engine.n_lines % 4 != 0                                  # per-layer record slices must stay TMA aligned
+    try:
+        engine.set_option(eng.OPT_BATCH_LAYERS, 0)
+        rad0, tr0 = _run_atm(engine, w)
+        n0 = engine.atmosphere_launches()
+        engine.set_option(eng.OPT_BATCH_LAYERS, 1)
+        rad1, tr1 = _run_atm(engine, w)
+        n1 = engine.atmosphere_launches()
+        engine.set_option(eng.OPT_RECORD_BUDGET_MB, 2)          # 8000 lines x 36 B -> 7 layers per batch
+        rad2, tr2 = _run_atm(engine, w)
+        n2 = engine.atmosphere_launches()
+    finally:
+        engine.set_option(eng.OPT_BATCH_LAYERS, 1)
+        engine.set_option(eng.OPT_RECORD_BUDGET_MB, 0)
+    assert np.array_equal(rad0, rad1) and np.array_equal(tr0, tr1)
+    assert np.array_equal(rad0, rad2) and np.array_equal(tr0, tr2)
+    assert n0 == 2 * 24 + 1 and n1 <= 1 + 4 + 1 and n1 < n2 < n0
+
+
+def test_single_layer_fused_epilogue_equals_k3_fold(engine):
+    """Gas cell (one layer): K2's fused epilogue (k -> T, Planck, transmission) is the same arithmetic as the
+    separate K3 fold -- bitwise -- and one launch fewer."""
+    w = workloads.atmosphere(n_layers=1, n_lines=5000, rmin=600.0, rmax=650.0, res=0.001, top_km=2.0)
+    H.engine_setup(engine, w)
+    try:
+        engine.set_option(eng.OPT_FUSE_SINGLE_LAYER, 0)
+        rad0, tr0 = _run_atm(engine, w)
+        n0 = engine.atmosphere_launches()
+        engine.set_option(eng.OPT_FUSE_SINGLE_LAYER, 1)
+        rad1, tr1 = _run_atm(engine, w)
+        n1 = engine.atmosphere_launches()
+    finally:
+        engine.set_option(eng.OPT_FUSE_SINGLE_LAYER, 1)
+    assert (n0, n1) == (3, 2)
+    assert np.array_equal(rad0, rad1) and np.array_equal(tr0, tr1)
+    assert 0 <= tr1.min() < tr1.max() <= 1 and np.isfinite(rad1[1:]).all()
+
+
+def test_peer_gather_single_rank_roundtrip(engine):
+    """world = 1 exercises the whole peer path on one GPU: IPC export, slot addressing, double buffering by
+    epoch, the signal/wait kernel -- the gathered row must equal the rank's own spectra, step after step."""
+    w = workloads.atmosphere(n_layers=3, n_lines=4000, rmin=600.0, rmax=630.0, res=0.001, top_km=30.0)
+    H.engine_setup(engine, w)
+    rad_ref, tr_ref = _run_atm(engine, w)
+    import ctypes as C
+    try:
+        h = engine.peer_alloc(0, 1, engine.n_chunk)
+        assert len(h) == eng.PEER_HANDLE_BYTES
+        engine.peer_connect([h])
+        for step in range(3):
+            rad, tr = _run_atm(engine, w)
+            assert np.array_equal(rad, rad_ref) and np.array_equal(tr, tr_ref)
+            rp, tp, ld = engine.peer_gathered_dev()
+            assert ld >= engine.n_chunk and rp and tp
+            own_r, own_t = engine.atmosphere_result_dev()
+            assert (own_r, own_t) == (rp, tp)                       # rank 0's slot is row 0 of the gather buffer
+    finally:
+        engine.peer_disconnect()
+    rad, tr = _run_atm(engine, w)                                   # back to the local result arrays
+    assert np.array_equal(rad, rad_ref)
