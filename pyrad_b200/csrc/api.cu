@@ -108,7 +108,7 @@ struct prb_engine {
     int64_t rec_slots = 0;        // the record arrays hold rec_slots layers of n_alloc records each
     DevBuf<GroupParams> gp;       // n_layers * n_groups
     DevBuf<DevState> st;          // one per layer
-    DevBuf<K1Layer> k1tab;        // device tables of the batched launches
+    K1Table k1_host;              // K1's layer table (passed by value as a kernel parameter)
     DevBuf<K2Layer> k2tab;
     LayerJob last;
     int k2_variant = PRB_K2_CLASSED, k2_ppt = 0;
@@ -119,6 +119,9 @@ struct prb_engine {
     PeerState peer;
     DevBuf<unsigned int> peer_err;
     // pinned ring of single-layer K2 table rows (prb_line_sum_dev is enqueue-only)
+    unsigned char *blk_h = nullptr;                   // pinned staging of prb_atmosphere's small tables
+    size_t blk_cap = 0;
+    DevBuf<unsigned char> blk_d;
     K2Layer *ring_h = nullptr;
     DevBuf<K2Layer> ring_d;
     cudaEvent_t ring_ev[RING] = {};
@@ -195,7 +198,9 @@ extern "C" int prb_destroy(prb_engine *e) {
     e->out64.release(); e->scratch_a.release(); e->scratch_b.release(); e->scratch_c.release();
     e->scratch_d.release(); e->scratch_w.release();
     e->kmat.release(); e->rad.release(); e->trans.release(); e->fold.release();
-    e->k1tab.release(); e->k2tab.release(); e->ring_d.release(); e->peer_err.release();
+    e->k2tab.release(); e->ring_d.release(); e->peer_err.release();
+    if (e->blk_h) cudaFreeHost(e->blk_h);
+    e->blk_d.release();
     if (e->ring_h) { cudaFreeHost(e->ring_h); for (auto x : e->ring_ev) if (x) cudaEventDestroy(x); }
     peer_release(e);
     for (auto x : e->ev) cudaEventDestroy(x);
@@ -206,17 +211,21 @@ extern "C" int prb_destroy(prb_engine *e) {
 
 extern "C" void *prb_stream(prb_engine *e) { return e ? (void *)e->stream : nullptr; }
 
-static int check_flags(prb_engine *e, int n_states) {
-    std::vector<DevState> h(n_states);
-    CK(cudaMemcpyAsync(h.data(), e->st.p, sizeof(DevState) * n_states, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+static int report_flags(const DevState *h, int n_states) {
     unsigned int f = 0;
-    for (auto &s : h) f |= s.flags;
+    for (int k = 0; k < n_states; ++k) f |= h[k].flags;
     if (f & FLAG_NONFINITE)
         return fail(PRB_ERR_RANGE, "line prepass produced a non-finite coefficient (bad line data or T/P/Q inputs)");
     if (f & FLAG_OVERFLOW)
         return fail(PRB_ERR_RANGE, "line coefficient exceeds the scaled FP32 range (window too wide or S(T)/S296 too large)");
     return PRB_OK;
+}
+
+static int check_flags(prb_engine *e, int n_states) {
+    std::vector<DevState> h(n_states);
+    CK(cudaMemcpyAsync(h.data(), e->st.p, sizeof(DevState) * n_states, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return report_flags(h.data(), n_states);
 }
 
 extern "C" int prb_synchronize(prb_engine *e) {
@@ -419,40 +428,46 @@ static int ensure_records(prb_engine *e, int64_t slots) {
     return PRB_OK;
 }
 
-// ONE K1 launch for jobs[0..n): the union of their line ranges, every thread walking the n layers.
-// `tab_host`/`tab_dev` are caller-provided table rows (the host rows must outlive the copy).
-static int launch_prepass(prb_engine *e, const LayerJob *jobs, int n, K1Layer *tab_host, K1Layer *tab_dev,
-                          DebugOut dbg) {
-    if (n <= 0) return PRB_OK;
-    int64_t l0 = jobs[0].l0, l1 = jobs[0].l1;
+static void fill_k1_row(const prb_engine *e, const LayerJob &j, K1Layer &t) {
     const size_t na = (size_t)e->n_alloc;
-    for (int k = 0; k < n; ++k) {
-        const LayerJob &j = jobs[k];
-        l0 = std::min(l0, j.l0);
-        l1 = std::max(l1, j.l1);
-        K1Layer &t = tab_host[k];
-        t.T = j.T; t.P = j.P;
-        t.lc = layer_consts(j.T, j.P, e->res);
-        t.scale = j.scale;
-        t.wm = (double)j.wm;
-        t.gp = j.gp_dev;
-        t.recA = e->recA.p + na * j.slot;
-        t.recB = e->recB.p + na * j.slot;
-        t.recD = e->recD.p + na * j.slot;
-        t.st = j.st_dev;
-        t.narrow = j.narrow;
-        t.pad = 0;
-    }
-    CK(cudaMemcpyAsync(tab_dev, tab_host, sizeof(K1Layer) * n, cudaMemcpyHostToDevice, e->stream));
-    const int64_t kb = l0 & ~int64_t(3);
-    const int64_t ke = std::min<int64_t>(l1 + 8, e->n_alloc);
-    const int64_t cnt = ke - kb;
-    if (cnt > 0) {
-        LinesSoA L{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
-                   e->has_group ? e->group.p : nullptr};
-        k1_prepass<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, tab_dev, n, kb, ke, e->n_lines,
-                                                                        e->i_begin, dbg);
-        CK(cudaGetLastError());
+    t.T = j.T; t.P = j.P;
+    t.lc = layer_consts(j.T, j.P, e->res);
+    t.scale = j.scale;
+    t.wm = (double)j.wm;
+    t.gp = j.gp_dev;
+    t.recA = e->recA.p + na * j.slot;
+    t.recB = e->recB.p + na * j.slot;
+    t.recD = e->recD.p + na * j.slot;
+    t.st = j.st_dev;
+    t.narrow = j.narrow;
+    t.pad = 0;
+}
+
+// K1 for jobs[0..n): ONE launch per K1_MAX_LAYERS layers over the union of their line ranges, every thread walking
+// the layers.  The layer table is a kernel parameter (constant bank), so nothing has to be uploaded first.
+static int run_prepass(prb_engine *e, const LayerJob *jobs, int n, DebugOut dbg, int *launches = nullptr) {
+    for (int k0 = 0; k0 < n; k0 += K1_MAX_LAYERS) {
+        const int m = std::min(n - k0, K1_MAX_LAYERS);
+        K1Table &tab = e->k1_host;
+        tab.n = m;
+        tab.pad = 0;
+        int64_t l0 = jobs[k0].l0, l1 = jobs[k0].l1;
+        for (int k = 0; k < m; ++k) {
+            fill_k1_row(e, jobs[k0 + k], tab.rows[k]);
+            l0 = std::min(l0, jobs[k0 + k].l0);
+            l1 = std::max(l1, jobs[k0 + k].l1);
+        }
+        const int64_t kb = l0 & ~int64_t(3);
+        const int64_t ke = std::min<int64_t>(l1 + 8, e->n_alloc);
+        const int64_t cnt = ke - kb;
+        if (cnt > 0) {
+            LinesSoA L{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
+                       e->has_group ? e->group.p : nullptr};
+            k1_prepass<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, tab, kb, ke, e->n_lines,
+                                                                            e->i_begin, dbg);
+            CK(cudaGetLastError());
+            if (launches) ++*launches;
+        }
     }
     return PRB_OK;
 }
@@ -474,7 +489,6 @@ extern "C" int prb_layer_prepass(prb_engine *e, double T, double P, int32_t n_gr
     build_group_params(n_groups, T, conc, molmass, q_t, q_296, weight, h.data(), &w_max);
     CK(e->gp.ensure(n_groups));
     CK(e->st.ensure(1));
-    CK(e->k1tab.ensure(1));
     CK(e->k2tab.ensure(1));
     if ((rc = ensure_records(e, 1))) return rc;
     CK(cudaMemcpyAsync(e->gp.p, h.data(), sizeof(GroupParams) * n_groups, cudaMemcpyHostToDevice, e->stream));
@@ -482,8 +496,7 @@ extern "C" int prb_layer_prepass(prb_engine *e, double T, double P, int32_t n_gr
     LayerJob j = plan_job(e, T, P, window_len, pick_scale(e->s_max, w_max));
     j.gp_dev = e->gp.p;
     j.st_dev = e->st.p;
-    K1Layer row;
-    rc = launch_prepass(e, &j, 1, &row, e->k1tab.p, DebugOut{});
+    rc = run_prepass(e, &j, 1, DebugOut{});
     if (rc) return rc;
     CK(cudaStreamSynchronize(e->stream));                       // h, row (pageable) must outlive the copies
     e->last = j;
@@ -506,15 +519,15 @@ extern "C" int prb_debug_line_params(prb_engine *e, double *nu_shift, double *ga
     CK(cudaMemsetAsync(reg.p, 0xff, sizeof(int32_t) * na, e->stream));
     DebugOut dbg{e->scratch_a.p, e->scratch_b.p, e->scratch_c.p, e->scratch_d.p, reg.p};
     DevBuf<DevState> st;
-    DevBuf<K1Layer> tab;
     CK(st.ensure(1));
-    CK(tab.ensure(1));
     CK(cudaMemsetAsync(st.p, 0, sizeof(DevState), e->stream));
     // whole list, so every line gets a value irrespective of the owned chunk; the records are scratch here
     // (temporaries, so the live prepass is not disturbed)
     DevBuf<float4> r4, r5; DevBuf<float> r2;
     CK(r4.ensure(na)); CK(r5.ensure(na)); CK(r2.ensure(na));
-    K1Layer row;
+    K1Table &tab = e->k1_host;
+    tab.n = 1;
+    K1Layer &row = tab.rows[0];
     row.T = e->last.T; row.P = e->last.P;
     row.lc = layer_consts(e->last.T, e->last.P, e->res);
     row.scale = e->last.scale;
@@ -523,10 +536,9 @@ extern "C" int prb_debug_line_params(prb_engine *e, double *nu_shift, double *ga
     row.recA = r4.p; row.recB = r5.p; row.recD = r2.p;
     row.st = st.p;
     row.narrow = 0; row.pad = 0;
-    CK(cudaMemcpyAsync(tab.p, &row, sizeof(K1Layer), cudaMemcpyHostToDevice, e->stream));
     LinesSoA L{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
                e->has_group ? e->group.p : nullptr};
-    k1_prepass<<<(unsigned)((na + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, tab.p, 1, 0, na, n, e->i_begin, dbg);
+    k1_prepass<<<(unsigned)((na + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, tab, 0, na, n, e->i_begin, dbg);
     CK(cudaGetLastError());
     if (nu_shift) CK(cudaMemcpyAsync(nu_shift, e->scratch_a.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
     if (gamma_l) CK(cudaMemcpyAsync(gamma_l, e->scratch_b.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
@@ -535,7 +547,7 @@ extern "C" int prb_debug_line_params(prb_engine *e, double *nu_shift, double *ga
     if (regime) CK(cudaMemcpyAsync(regime, reg.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (index) for (int64_t i = 0; i < n; ++i) index[i] = e->h_idx[i];
-    r4.release(); r5.release(); r2.release(); reg.release(); st.release(); tab.release();
+    r4.release(); r5.release(); r2.release(); reg.release(); st.release();
     return PRB_OK;
 }
 
@@ -558,27 +570,25 @@ static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
     return cudaGetLastError();
 }
 
-// ONE K2 launch for jobs[0..n), which must share a kernel class (all narrow, or all the same ppt) and be sorted
-// widest window first.  The launch's tile counter lives in jobs[0]'s state block and is reset here.
-static int launch_line_sum(prb_engine *e, const LayerJob *jobs, int n, K2Layer *tab_host, K2Layer *tab_dev,
-                           int out_mode, const K2Fuse *fuse) {
-    if (n <= 0) return PRB_OK;
+static void fill_k2_row(const prb_engine *e, const LayerJob &j, K2Layer &t) {
     const size_t na = (size_t)e->n_alloc;
-    for (int k = 0; k < n; ++k) {
-        const LayerJob &j = jobs[k];
-        K2Layer &t = tab_host[k];
-        t.recA = e->recA.p + na * j.slot;
-        t.recB = e->recB.p + na * j.slot;
-        t.recD = e->recD.p + na * j.slot;
-        t.out = j.out_dev;
-        t.inv_scale = 1.0 / j.scale;
-        t.l_begin = (int)j.l0;
-        t.l_end = (int)j.l1;
-        t.wm = (int)j.wm;
-        t.pad = 0;
-    }
-    CK(cudaMemcpyAsync(tab_dev, tab_host, sizeof(K2Layer) * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemsetAsync(&jobs[0].st_dev->tile_counter, 0, sizeof(unsigned int), e->stream));
+    t.recA = e->recA.p + na * j.slot;
+    t.recB = e->recB.p + na * j.slot;
+    t.recD = e->recD.p + na * j.slot;
+    t.out = j.out_dev;
+    t.inv_scale = 1.0 / j.scale;
+    t.l_begin = (int)j.l0;
+    t.l_end = (int)j.l1;
+    t.wm = (int)j.wm;
+    t.pad = 0;
+}
+
+// ONE K2 launch for jobs[0..n), which must share a kernel class (all narrow, or all the same ppt) and be sorted
+// widest window first.  tab_dev holds the n table rows (fill_k2_row); the launch's tile counter lives in jobs[0]'s
+// state block and must be zero (stream-ordered) when the kernel starts.
+static int run_line_sum(prb_engine *e, const LayerJob *jobs, int n, const K2Layer *tab_dev, int out_mode,
+                        const K2Fuse *fuse) {
+    if (n <= 0) return PRB_OK;
     K2Args a{};
     a.layers = tab_dev;
     a.n_layers = n;
@@ -629,7 +639,10 @@ extern "C" int prb_line_sum_dev(prb_engine *e, void *out_dev, int out_mode) {
     }
     const int slot = e->ring_next++ % RING;
     CK(cudaEventSynchronize(e->ring_ev[slot]));
-    int rc = launch_line_sum(e, &j, 1, e->ring_h + slot, e->ring_d.p + slot, out_mode, nullptr);
+    fill_k2_row(e, j, e->ring_h[slot]);
+    CK(cudaMemcpyAsync(e->ring_d.p + slot, e->ring_h + slot, sizeof(K2Layer), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(&j.st_dev->tile_counter, 0, sizeof(unsigned int), e->stream));
+    int rc = run_line_sum(e, &j, 1, e->ring_d.p + slot, out_mode, nullptr);
     if (rc) return rc;
     CK(cudaEventRecord(e->ring_ev[slot], e->stream));
     return PRB_OK;
@@ -765,37 +778,52 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
     PeerState &ps = e->peer;
     if (ps.connected && nc > ps.ld) return fail(PRB_ERR_ARG, "prb_atmosphere: owned chunk exceeds the peer gather slot");
 
+    // Everything small the kernels of this call read -- status blocks (zeroed: flags + tile counters), per-(layer,
+    // group) params, fold constants, the K2 launch table (K1's is a kernel parameter) -- is built in ONE pinned block and uploaded with
+    // ONE copy, so a step is a copy plus its kernel launches.
+    const size_t off_st = 0;
+    const size_t off_gp = off_st + sizeof(DevState) * n_layers;
+    const size_t off_fold = off_gp + sizeof(GroupParams) * (size_t)n_layers * n_groups;
+    const size_t off_k2 = (off_fold + sizeof(FoldLayer) * n_layers + 15) & ~size_t(15);
+    const size_t blk_bytes = off_k2 + sizeof(K2Layer) * n_layers;
+    if (blk_bytes > e->blk_cap) {
+        if (e->blk_h) cudaFreeHost(e->blk_h);
+        e->blk_h = nullptr;
+        e->blk_cap = 0;
+        CK(cudaMallocHost((void **)&e->blk_h, blk_bytes));
+        e->blk_cap = blk_bytes;
+    }
+    CK(e->blk_d.ensure(blk_bytes));
+    memset(e->blk_h, 0, blk_bytes);
+    DevState *st_dev = reinterpret_cast<DevState *>(e->blk_d.p + off_st);
+    GroupParams *gp_dev = reinterpret_cast<GroupParams *>(e->blk_d.p + off_gp);
+    FoldLayer *fold_dev = reinterpret_cast<FoldLayer *>(e->blk_d.p + off_fold);
+    K2Layer *k2_dev = reinterpret_cast<K2Layer *>(e->blk_d.p + off_k2);
+    GroupParams *h = reinterpret_cast<GroupParams *>(e->blk_h + off_gp);
+    FoldLayer *hf = reinterpret_cast<FoldLayer *>(e->blk_h + off_fold);
+    K2Layer *k2rows = reinterpret_cast<K2Layer *>(e->blk_h + off_k2);
+
     // per-(layer, group) params: weight = conc * P / 1e4 / kB / T  (absCoef, pyradClasses.py:581-583)
-    std::vector<GroupParams> h((size_t)n_layers * n_groups);
-    std::vector<FoldLayer> hf(n_layers);
     std::vector<LayerJob> jobs(n_layers);
     const double c2 = 100 * hPlanck * cLight / kBoltz;
     e->kmat_ld = (nc + 3) & ~int64_t(3);
-    CK(e->gp.ensure(h.size()));
-    CK(e->st.ensure(n_layers));
-    CK(e->fold.ensure(n_layers));
-    CK(e->k1tab.ensure(n_layers));
-    CK(e->k2tab.ensure(n_layers));
     CK(e->kmat.ensure((size_t)e->kmat_ld * n_layers));
     CK(e->rad.ensure(e->kmat_ld));
     CK(e->trans.ensure(e->kmat_ld));
+    std::vector<double> w(n_groups);
     for (int l = 0; l < n_layers; ++l) {
-        std::vector<double> w(n_groups);
         for (int g = 0; g < n_groups; ++g)
             w[g] = conc[(size_t)l * n_groups + g] * p_layer[l] / 1E4 / kBoltz / t_layer[l];
         double w_max = 0;
         build_group_params(n_groups, t_layer[l], conc + (size_t)l * n_groups, molmass, q_t + (size_t)l * n_groups,
-                           q_296, w.data(), h.data() + (size_t)l * n_groups, &w_max);
+                           q_296, w.data(), h + (size_t)l * n_groups, &w_max);
         hf[l].neg_depth_log2e = (float)(-depth_cm[l] * 1.4426950408889634);
         hf[l].c2_over_t = (float)(c2 / t_layer[l]);
         jobs[l] = plan_job(e, t_layer[l], p_layer[l], window_len[l], pick_scale(e->s_max, w_max));
-        jobs[l].gp_dev = e->gp.p + (size_t)l * n_groups;
-        jobs[l].st_dev = e->st.p + l;
+        jobs[l].gp_dev = gp_dev + (size_t)l * n_groups;
+        jobs[l].st_dev = st_dev + l;
         jobs[l].out_dev = e->kmat.p + (size_t)l * e->kmat_ld;
     }
-    CK(cudaMemcpyAsync(e->gp.p, h.data(), sizeof(GroupParams) * h.size(), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->fold.p, hf.data(), sizeof(FoldLayer) * n_layers, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemsetAsync(e->st.p, 0, sizeof(DevState) * n_layers, e->stream));
     if (e->atm_layers != n_layers) {
         CK(cudaMemsetAsync(e->kmat.p, 0, sizeof(float) * e->kmat_ld * n_layers, e->stream));
         e->atm_layers = n_layers;
@@ -842,8 +870,8 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
     if (fused) {
         fuse.enabled = 1;
         fuse.n_dst = dst.n;
-        fuse.neg_depth_log2e = hf[0].neg_depth_log2e;
-        fuse.c2_over_t = hf[0].c2_over_t;
+        fuse.neg_depth_log2e = (float)(-depth_cm[0] * 1.4426950408889634);
+        fuse.c2_over_t = (float)(c2 / t_layer[0]);
         fuse.c2_over_tsurf = (float)(c2 / t_surface);
         fuse.n_total = e->n_total;
         fuse.x0 = e->range_min; fuse.dx = dx; fuse.x_last = range_max;
@@ -859,22 +887,22 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
             e->ev.push_back(x);
         }
     }
-    std::vector<K1Layer> k1rows(n_layers);
-    std::vector<K2Layer> k2rows(n_layers);
+    for (int k = 0; k < n_layers; ++k) {
+        jobs[k].slot = (int)(k % slots);
+        fill_k2_row(e, jobs[k], k2rows[k]);
+    }
+    CK(cudaMemcpyAsync(e->blk_d.p, e->blk_h, blk_bytes, cudaMemcpyHostToDevice, e->stream));
     int launches = 0;
     for (int bi = 0; bi < n_batches; ++bi) {
         const int b0 = (int)(bi * slots), b1 = (int)std::min<int64_t>(n_layers, b0 + slots);
-        for (int k = b0; k < b1; ++k) jobs[k].slot = k - b0;
         if (e->timing) CK(cudaEventRecord(e->ev[3 * bi], e->stream));
-        rc = launch_prepass(e, jobs.data() + b0, b1 - b0, k1rows.data() + b0, e->k1tab.p + b0, DebugOut{});
+        rc = run_prepass(e, jobs.data() + b0, b1 - b0, DebugOut{}, &launches);
         if (rc) return rc;
-        ++launches;
         if (e->timing) CK(cudaEventRecord(e->ev[3 * bi + 1], e->stream));
         for (int c0 = b0; c0 < b1;) {                            // runs of one kernel class (sorted by window)
             int c1 = c0 + 1;
             while (c1 < b1 && jobs[c1].narrow == jobs[c0].narrow && (jobs[c0].narrow || jobs[c1].ppt == jobs[c0].ppt)) ++c1;
-            rc = launch_line_sum(e, jobs.data() + c0, c1 - c0, k2rows.data() + c0, e->k2tab.p + c0, PRB_OUT_F32,
-                                 fused ? &fuse : nullptr);
+            rc = run_line_sum(e, jobs.data() + c0, c1 - c0, k2_dev + c0, PRB_OUT_F32, fused ? &fuse : nullptr);
             if (rc) return rc;
             ++launches;
             c0 = c1;
@@ -883,7 +911,7 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
     }
     if (e->timing) CK(cudaEventRecord(e->ev[3 * n_batches], e->stream));
     if (nc > 0 && !fused) {
-        k3_fold_f32<<<stream_grid(e, nc, 4), 256, 0, e->stream>>>(e->kmat.p, e->kmat_ld, n_layers, e->fold.p, nc,
+        k3_fold_f32<<<stream_grid(e, nc, 4), 256, 0, e->stream>>>(e->kmat.p, e->kmat_ld, n_layers, fold_dev, nc,
                                                                  e->i_begin, e->n_total, e->range_min, dx, range_max,
                                                                  (float)(c2 / t_surface), dst);
         CK(cudaGetLastError());
@@ -901,7 +929,10 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
         ++launches;
     }
     e->last_launches = launches;
-    CK(cudaStreamSynchronize(e->stream));                       // pageable staging vectors go out of scope
+    // status blocks back in the same breath; the synchronisation also keeps the pinned block ours until the next call
+    std::vector<DevState> hst(n_layers);
+    CK(cudaMemcpyAsync(hst.data(), st_dev, sizeof(DevState) * n_layers, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     if (e->timing) {
         e->t_k1 = e->t_k2 = e->t_k3 = 0;
         e->t_layer_k1.assign(n_layers, 0.f);
@@ -916,7 +947,7 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
             // per-layer figures are exact with one layer per batch (prb_set_option PRB_OPT_BATCH_LAYERS 0), else
             // the batch time spread evenly; reported in the caller's layer order
             for (int k = b0; k < b1; ++k) {
-                const int l = (int)(jobs[k].st_dev - e->st.p);
+                const int l = (int)(jobs[k].st_dev - st_dev);
                 e->t_layer_k1[l] = a / (b1 - b0);
                 e->t_layer_k2[l] = b / (b1 - b0);
             }
@@ -933,7 +964,7 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
                                       "prb_atmosphere the same number of times)");
         }
     }
-    return check_flags(e, n_layers);
+    return report_flags(hst.data(), n_layers);
 }
 
 extern "C" int prb_atmosphere_result_dev(prb_engine *e, void **radiance_dev, void **transmittance_dev) {

@@ -70,92 +70,144 @@ struct K1Layer {
     int pad;
 };
 
+// The layer table travels as a kernel parameter: per-layer constants are then constant-bank operands of the
+// FP64 instructions (no registers, no loads), which is what lets the register budget hold the line's own data.
+constexpr int K1_MAX_LAYERS = 128;
+struct K1Table {
+    int n;
+    int pad;
+    K1Layer rows[K1_MAX_LAYERS];
+};
+
+// f5^(-1/5) without log/exp/division: FP32 seed (two MUFU) and two Newton steps on g(r) = r^-5 - f5,
+//   r <- r (1 + (1 - f5 r^5)/5)   (quadratic: 1e-6 -> ~3e-12 -> below FP64 resolution).
+__device__ __forceinline__ double inv_fifth_root(double f5) {
+    double r = (double)__powf((float)f5, -0.2f);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double r2 = r * r;
+        const double r5 = r2 * r2 * r;
+        r = fma(r, fma(-f5, r5, 1.0) * 0.2, r);
+    }
+    return r;
+}
+
+// exp(x) for |x| <= 0.02 (degree-7 Taylor, truncation < 1e-18)
+__device__ __forceinline__ double exp_tiny(double x) {
+    double p = 1.0 / 5040;
+    p = fma(p, x, 1.0 / 720);
+    p = fma(p, x, 1.0 / 120);
+    p = fma(p, x, 1.0 / 24);
+    p = fma(p, x, 1.0 / 6);
+    p = fma(p, x, 0.5);
+    p = fma(p, x, 1.0);
+    return fma(p, x, 1.0);
+}
+
 // One thread per line; the thread keeps the line's seven constants in registers and walks the layers of the
 // batch, so the SoA columns are read once per launch instead of once per layer.
-__global__ void __launch_bounds__(256)
-k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const K1Layer *__restrict__ layers, int n_layers,
+__global__ void __launch_bounds__(256, 3)
+k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ K1Table tab,
            int64_t l_begin, int64_t l_end, int64_t n_lines, int64_t i_base, DebugOut dbg) {
     const double c2 = cLight * hPlanck * 100 / kBoltz;          // pyradIntensity.py:13
     const int64_t l = l_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = l < l_end;
     const bool real = in_range && l < n_lines;
-    double nu = 0, delta = 0, gair = 0, gself = 0, nair = 0, elower = 0, s296 = 0, fi = 0;
+    double nu = 0, delta = 0, gair = 0, gself = 0, nair = 0, elower = 0, s296 = 0;
+    float nf = 0.f;
     int g = 0;
     if (real) {
         nu = L.nu0[l]; delta = L.delta[l]; gair = L.gair[l]; gself = L.gself[l];
         nair = L.nair[l]; elower = L.elower[l]; s296 = L.s296[l];
         g = L.group ? L.group[l] : 0;
-        fi = (double)((int64_t)idx[l] - i_base);
+        nf = -(float)((double)((int64_t)idx[l] - i_base));
     }
+    // exp(-c2 nu0 / t0): the layer-independent factor of the stimulated-emission denominator
+    const double e296 = exp(-c2 / kT0 * nu);
+    const double neg_c2_e = -c2 * elower;
+    const int n_layers = tab.n;
 #pragma unroll 1
     for (int ly = 0; ly < n_layers; ++ly) {
-    const K1Layer &K = layers[ly];
-    const LayerConsts lc = K.lc;
-    const double scale = K.scale, wm = K.wm;
-    const int narrow = K.narrow;
-    float4 *__restrict__ recA = K.recA;
-    float4 *__restrict__ recB = K.recB;
-    float *__restrict__ recD = K.recD;
-    unsigned int flags = 0;
-    if (in_range) {
-        if (!real) {                                              // padding record: never in a window
-            if (narrow) {
-                recA[l] = make_float4(-K2_SENTINEL, 0.f, 1.f, 0.f);
+        const K1Layer &K = tab.rows[ly];
+        unsigned int flags = 0;
+        if (in_range && !real) {                                  // padding record: never in a window
+            if (K.narrow) {
+                K.recA[l] = make_float4(-K2_SENTINEL, 0.f, 1.f, 0.f);
             } else {
-                recA[l] = make_float4(-K2_SENTINEL, -K2_SENTINEL, 0.f, 0.f);
-                recB[l] = make_float4(1.f, 1.f, 0.f, -1.f);
+                K.recA[l] = make_float4(-K2_SENTINEL, -K2_SENTINEL, 0.f, 0.f);
+                K.recB[l] = make_float4(1.f, 1.f, 0.f, -1.f);
             }
-            recD[l] = -1.f;
-        } else {
+            K.recD[l] = -1.f;
+        } else if (real) {
             const GroupParams p = K.gp[g];
-            // Divisions are the expensive FP64 operation here (K1 is FP64-pipe bound, not HBM bound), so
-            // per-layer reciprocals come from the host (lc.*) and each regime needs a single 1/h.  This
-            // changes roundings by an ulp relative to the reference's operation order (1e-16), nothing more.
-            const double nus = nu + delta * lc.p_over_p0;
+            // FP64 divisions and transcendentals are what this kernel costs, so: per-layer reciprocals come from
+            // the host (K.lc), each regime needs a single 1/h, the 5th root is a Newton iteration, and the
+            // layer-independent exponential is hoisted.  This moves roundings by an ulp or two relative to the
+            // reference's operation order (1e-16); the parity tests hold the per-line values to 1e-12.
+            const double pp0 = K.lc.p_over_p0;
+            const double dshift = delta * pp0;
+            const double nus = nu + dshift;
             // (t0/T)^n = exp(n * log(t0/T)): the log is a per-layer constant
-            const double gl = ((1 - p.conc) * gair + p.conc * gself) * lc.p_over_p0 *
-                              exp(nair * lc.log_t0_over_t);
+            const double gl = ((1 - p.conc) * gair + p.conc * gself) * pp0 * exp(nair * K.lc.log_t0_over_t);
             const double gd = nus * p.dopp;
-            const double ratio = gl / gd;                         // gd == 0 -> inf -> Lorentz, as numpy
-            const double stim = (1 - exp(lc.neg_c2_over_t * nus)) / (1 - exp(lc.neg_c2_over_t0 * nus));
+            // regime (pyradClasses.py:378-387): ratio = gl / gd compared with .01 and 100.  Away from the two
+            // thresholds products decide; within 1e-14 of one (or for gd <= 0: inf / negative ratios, as numpy)
+            // the division itself does, so the tag is exactly the reference's.
+            int regime;
+            {
+                const double lo = .01 * gd, hi = 100 * gd;
+                const double eps = 1e-14;
+                if (gd > 0 && gl < lo * (1 - eps)) regime = REGIME_GAUSS;
+                else if (gd > 0 && gl > hi * (1 + eps)) regime = REGIME_LORENTZ;
+                else if (gd > 0 && gl > lo * (1 + eps) && gl < hi * (1 - eps)) regime = REGIME_VOIGT;
+                else {
+                    const double ratio = gl / gd;                 // gd == 0 -> inf -> Lorentz, as numpy
+                    regime = ratio < .01 ? REGIME_GAUSS : (ratio > 100 ? REGIME_LORENTZ : REGIME_VOIGT);
+                }
+            }
+            // stimulated emission (1 - e^{-c2 nu*/T}) / (1 - e^{-c2 nu*/t0}); e^{-c2 nu*/t0} = e296 * e^{-c2 dshift/t0}
+            const double x0 = K.lc.neg_c2_over_t0 * dshift;
+            // (next to 0 cm^-1 the denominator cancels: keep the reference's own single exponential there)
+            const double e_t0 = (fabs(x0) <= 0.02 && nu > 1.0) ? e296 * exp_tiny(x0) : exp(K.lc.neg_c2_over_t0 * nus);
+            const double stim = (1 - exp(K.lc.neg_c2_over_t * nus)) / (1 - e_t0);
             // exp(-c2 E/T) / exp(-c2 E/t0) evaluated as one exponential (same value to ~1e-16)
-            const double boltz = exp(-c2 * elower * lc.inv_t_minus_inv_t0);
+            const double boltz = exp(neg_c2_e * K.lc.inv_t_minus_inv_t0);
             const double S = s296 * p.qratio * stim * boltz;
-            const double sw = S * p.weight * scale;
-            const double inv_res2 = lc.inv_res2;
+            const double sw = S * p.weight * K.scale;
+            const double inv_res2 = K.lc.inv_res2;
             const double log2e = 1.4426950408889634;
             const double inv_sqrtpi = 0.5641895835477563;         // 1/sqrt(pi)
             double A, B, G, C, bg;                                // bg: Gaussian (h/res)^2
-            int regime;
             float dg = -1.0f;
-            if (ratio < .01) {
-                regime = REGIME_GAUSS;
+            if (regime == REGIME_GAUSS) {
                 const double inv_gd = 1.0 / gd;
                 A = 0.0; B = 1.0;
                 G = sw * inv_gd * inv_sqrtpi;
                 bg = gd * gd * inv_res2;
-                C = -log2e * lc.res2 * inv_gd * inv_gd;
-            } else if (ratio > 100) {
-                regime = REGIME_LORENTZ;
+                C = -log2e * K.lc.res2 * inv_gd * inv_gd;
+            } else if (regime == REGIME_LORENTZ) {
                 A = sw * gl * (inv_res2 / kPi);
                 B = gl * gl * inv_res2;
                 G = 0.0; C = -1.0; bg = 0.0;
             } else {
-                regime = REGIME_VOIGT;
                 const double gFW = 2 * gd, lFW = 2 * gl;
                 const double g2 = gFW * gFW, l2 = lFW * lFW;
                 const double f5 = pow5(gFW) + 2.69269 * g2 * g2 * lFW + 2.42843 * g2 * gFW * l2 +
                                   4.47163 * g2 * l2 * lFW + .07842 * gFW * l2 * l2 + pow5(lFW);
-                const double f = exp(.2 * log(f5));               // f5 ** .2
-                const double hh = f / 2;
-                const double inv_hh = 1.0 / hh;
+                // f = f5 ** .2 (pyradLineshape.py:66): 1/f by Newton when f5 sits in the FP32 seed's range
+                double inv_f;
+                if (f5 > 1e-30 && f5 < 1e30) inv_f = inv_fifth_root(f5);
+                else inv_f = 1.0 / exp(.2 * log(f5));
+                const double r2 = inv_f * inv_f;
+                const double hh = 0.5 * (f5 * (r2 * r2));         // f / 2, f = f5 * f5^(-4/5)
+                const double inv_hh = 2 * inv_f;
                 const double rho = gl * inv_hh;                   // lFW / f
                 const double eta = 1.36603 * rho - .47719 * rho * rho + .11116 * rho * rho * rho;
                 A = sw * eta * hh * (inv_res2 / kPi);
                 B = hh * hh * inv_res2;
                 G = sw * (1 - eta) * inv_hh * inv_sqrtpi;
                 bg = B;
-                C = -log2e * lc.res2 * inv_hh * inv_hh;
+                C = -log2e * K.lc.res2 * inv_hh * inv_hh;
             }
             // near-zone radius: beyond it the Gaussian term is < 1e-9 of the same line's Lorentz term
             // (or below the scaled FP32 floor for Gaussian-only lines), so K2 may skip it.  FP32 is
@@ -176,18 +228,19 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const K1Layer *__restric
                 if (t2 > 0.f) dg = fminf(ceilf(sqrtf(t2 * (float)bg)) + 2.f, 3.0e7f);
             }
             // FP32 range guards: the paired far path forms A*(d^2+B) with |d| <= wm.
-            const double qmax = (wm + 4096.0) * (wm + 4096.0) + B;   // partial lines reach one warp span past the window
+            const double wq = K.wm + 4096.0;                      // partial lines reach one warp span past the window
+            const double qmax = wq * wq + B;
             if (!(isfinite(A) && isfinite(G) && isfinite(B) && isfinite(C))) flags |= FLAG_NONFINITE;
             // the triple-reciprocal path forms |A| q^2 and q^3
             else if (fabs(A) * qmax * qmax > 8.0e37 || fabs(G) > 8.0e37 || qmax * qmax * qmax > 8.0e37) flags |= FLAG_OVERFLOW;
-            const float nf = -(float)fi, Af = (float)A, Bf = (float)B;
-            if (narrow) {                                         // compact layout of k2_narrow
-                recA[l] = make_float4(nf, Af, Bf, (float)G);
-                recD[l] = (float)C;
+            const float Af = (float)A, Bf = (float)B;
+            if (K.narrow) {                                       // compact layout of k2_narrow
+                K.recA[l] = make_float4(nf, Af, Bf, (float)G);
+                K.recD[l] = (float)C;
             } else {
-                recA[l] = make_float4(nf, nf, Af, Af);
-                recB[l] = make_float4(Bf, Bf, (float)G, (float)C);
-                recD[l] = dg;
+                K.recA[l] = make_float4(nf, nf, Af, Af);
+                K.recB[l] = make_float4(Bf, Bf, (float)G, (float)C);
+                K.recD[l] = dg;
             }
             if (dbg.nu_shift) dbg.nu_shift[l] = nus;
             if (dbg.gl) dbg.gl[l] = gl;
@@ -195,10 +248,9 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const K1Layer *__restric
             if (dbg.st) dbg.st[l] = S;
             if (dbg.regime) dbg.regime[l] = regime;
         }
-    }
-    // OR of the status flags, one atomic per warp that has something to report (order independent).
-    flags = __reduce_or_sync(0xffffffffu, flags);
-    if ((threadIdx.x & 31) == 0 && flags) atomicOr(&K.st->flags, flags);
+        // OR of the status flags, one atomic per warp that has something to report (order independent).
+        flags = __reduce_or_sync(0xffffffffu, flags);
+        if ((threadIdx.x & 31) == 0 && flags) atomicOr(&K.st->flags, flags);
     }
 }
 

@@ -80,6 +80,8 @@ k3_xsc_place(int64_t n_out, int64_t dst0, int64_t src0, int64_t count, int inter
     }
 }
 
+constexpr int K3_UNROLL = 8;
+
 // ---- atmosphere fold, FP32 storage, float4 per thread --------------------------------------------
 struct FoldLayer {
     float neg_depth_log2e;   // -depth * log2(e): T = exp2(k * this)
@@ -90,8 +92,14 @@ __device__ __forceinline__ float k3_rcp(float x) { float r; asm("rcp.approx.ftz.
 __device__ __forceinline__ float k3_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 __device__ __forceinline__ float planck_f32(float a_nu3, float x) {
-    // a nu^3 / (e^x - 1).  For x >= 0.25 two MUFUs (ex2, rcp) are accurate to ~1e-6 relative; below that the
-    // subtraction cancels, so the first few hundred grid points (nu < ~40 cm^-1) take expm1f instead.
+    // a nu^3 / (e^x - 1), x = c2 nu / T, to ~1e-7 relative with as few MUFU operations as the range allows:
+    //   x >  8.5 : y = e^-x < 2.1e-4, 1/(e^x - 1) = y/(1 - y) = y + y^2 + O(y^3)       -- one MUFU (ex2)
+    //   x >= .25 : rcp(e^x - 1)                                                        -- two MUFU (ex2, rcp)
+    //   x <  .25 : the subtraction cancels, so the first few hundred grid points (nu < ~40 cm^-1) take expm1f.
+    if (x > 8.5f) {
+        const float y = k3_ex2(x * -1.4426950408889634f);
+        return a_nu3 * fmaf(y, y, y);
+    }
     if (x < 0.25f) return a_nu3 / expm1f(x);
     return a_nu3 * k3_rcp(k3_ex2(x * 1.4426950408889634f) - 1.0f);
 }
@@ -121,18 +129,30 @@ k3_fold_f32(const float *__restrict__ kmat, int64_t ld, int n_layers, const Fold
             rad[q] = planck_f32(a3[q], c2_over_tsurf * nu[q]);   // I_0 = B(nu, T_surface)
             tau[q] = 0.f;
         }
-#pragma unroll 4
-        for (int l = 0; l < n_layers; ++l) {
-            const float4 k4 = __ldg(reinterpret_cast<const float4 *>(kmat + (int64_t)l * ld + i0));
-            const FoldLayer fl = layers[l];
-            const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+        // layers in groups of K3_UNROLL: all of a group's loads are issued before its math, so every thread keeps
+        // K3_UNROLL x 16 B in flight (the kernel is latency bound otherwise); the k matrix is read exactly once,
+        // hence the streaming (evict-first) loads.
+        const float *col = kmat + i0;
+        for (int l0 = 0; l0 < n_layers; l0 += K3_UNROLL) {
+            float4 k4[K3_UNROLL];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float e = kk[q] * fl.neg_depth_log2e;       // -tau_l * log2(e)
-                const float t = k3_ex2(e);
-                const float b = planck_f32(a3[q], fl.c2_over_t * nu[q]);
-                rad[q] = fmaf(t, rad[q] - b, b);                  // T*I + (1-T)*B
-                tau[q] += e;
+            for (int j = 0; j < K3_UNROLL; ++j)
+                k4[j] = (l0 + j < n_layers) ? __ldcs(reinterpret_cast<const float4 *>(col + (int64_t)(l0 + j) * ld))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < K3_UNROLL; ++j) {
+                if (l0 + j < n_layers) {
+                    const FoldLayer fl = layers[l0 + j];
+                    const float kk[4] = {k4[j].x, k4[j].y, k4[j].z, k4[j].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float e = kk[q] * fl.neg_depth_log2e;       // -tau_l * log2(e)
+                        const float t = k3_ex2(e);
+                        const float b = planck_f32(a3[q], fl.c2_over_t * nu[q]);
+                        rad[q] = fmaf(t, rad[q] - b, b);                  // T*I + (1-T)*B
+                        tau[q] += e;
+                    }
+                }
             }
         }
         const float4 r4 = make_float4(rad[0], rad[1], rad[2], rad[3]);
