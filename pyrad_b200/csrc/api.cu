@@ -557,7 +557,7 @@ static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
     const int tile = K2_CONSUMERS * 32 * P;
     a.n_tiles = (int)((a.n_chunk + tile - 1) / tile);
     if (a.n_tiles == 0) return cudaSuccess;
-    const size_t smem = sizeof(K2Smem);
+    const size_t smem = sizeof(K2Smem) + (PRB_K2_ACC_SMEM ? sizeof(double) * P * K2_CONSUMERS * 32 : 0);
     static bool attr_set = false;                               // per template instance
     if (!attr_set) {
         cudaError_t ce = cudaFuncSetAttribute(k2_line_sum<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -37,7 +37,13 @@ struct DevState {
 constexpr unsigned int FLAG_OVERFLOW = 1u, FLAG_NONFINITE = 2u;
 
 // K2 geometry
-constexpr int K2_CONSUMERS = 8;          // math warps per CTA
+#ifndef PRB_K2_CONSUMERS
+#define PRB_K2_CONSUMERS 8
+#endif
+#ifndef PRB_K2_ACC_SMEM
+#define PRB_K2_ACC_SMEM 0
+#endif
+constexpr int K2_CONSUMERS = PRB_K2_CONSUMERS;        // math warps per CTA
 constexpr int K2_THREADS = 32 * (K2_CONSUMERS + 1);   // + one TMA producer warp
 #ifndef PRB_K2_CHUNK
 #define PRB_K2_CHUNK 256

@@ -169,12 +169,20 @@ template <int H>
 struct Acc {
     float2 fi[H];       // grid coordinates of the thread's points: (p even, p odd) = (fi0+64j, fi0+64j+32)
     float2 a32[H];      // FP32 partial sums
+#if PRB_K2_ACC_SMEM
+    // FP64 accumulators in shared memory (touched once per K2_FLUSH lines): 16 registers per thread traded for
+    // more resident warps.  Point p of the thread sits at a64[p * K2_ACC_STRIDE] (conflict-free: lanes are adjacent).
+    double *a64;
+    __device__ __forceinline__ double &acc(int p) { return a64[p * (K2_CONSUMERS * 32)]; }
+#else
     double a64[2 * H];  // FP64 accumulators
+    __device__ __forceinline__ double &acc(int p) { return a64[p]; }
+#endif
     __device__ __forceinline__ void flush() {
 #pragma unroll
         for (int j = 0; j < H; ++j) {
-            a64[2 * j] += (double)a32[j].x;
-            a64[2 * j + 1] += (double)a32[j].y;
+            acc(2 * j) += (double)a32[j].x;
+            acc(2 * j + 1) += (double)a32[j].y;
             a32[j] = make_float2(0.f, 0.f);
         }
     }
@@ -389,8 +397,11 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
     Acc<H> s;
 #pragma unroll
     for (int h = 0; h < H; ++h) { s.a32[h] = make_float2(0.f, 0.f); s.fi[h] = make_float2(0.f, 0.f); }
+#if PRB_K2_ACC_SMEM
+    s.a64 = reinterpret_cast<double *>(smem_raw + sizeof(K2Smem)) + tid;
+#endif
 #pragma unroll
-    for (int p = 0; p < P; ++p) s.a64[p] = 0.0;
+    for (int p = 0; p < P; ++p) s.acc(p) = 0.0;
     int wb = 0;
     float wbf = 0.f, we1f = 0.f;
 
@@ -410,7 +421,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
                 s.fi[h] = make_float2((float)(wb + lane + 64 * h), (float)(wb + lane + 64 * h + 32));
             }
 #pragma unroll
-            for (int p = 0; p < P; ++p) s.a64[p] = 0.0;
+            for (int p = 0; p < P; ++p) s.acc(p) = 0.0;
         }
         const int cnt = d.cnt;
         const float4 *sA = sm.rA[stage];
@@ -460,7 +471,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             for (int p = 0; p < P; ++p) {
                 const int i = wb + 32 * p + lane;
                 if (i < a.n_chunk) {
-                    const double v = s.a64[p] * inv_scale;
+                    const double v = s.acc(p) * inv_scale;
                     if (a.out_mode == 0) reinterpret_cast<double *>(out)[i] = v;
                     else reinterpret_cast<float *>(out)[i] = (float)v;
                     if (a.fuse.enabled) {
