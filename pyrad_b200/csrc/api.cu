@@ -557,12 +557,13 @@ static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
     const int tile = K2_CONSUMERS * 32 * P;
     a.n_tiles = (int)((a.n_chunk + tile - 1) / tile);
     if (a.n_tiles == 0) return cudaSuccess;
-    const size_t smem = sizeof(K2Smem) + (PRB_K2_ACC_SMEM ? sizeof(double) * P * K2_CONSUMERS * 32 : 0);
-    static bool attr_set = false;                               // per template instance
-    if (!attr_set) {
+    const bool staging = a.fuse.enabled && a.fuse.n_dst > 1;
+    const size_t smem = K2_SMEM_BYTES<P>(staging);
+    static size_t attr_bytes = 0;                               // per template instance
+    if (smem > attr_bytes) {
         cudaError_t ce = cudaFuncSetAttribute(k2_line_sum<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;
-        attr_set = true;
+        attr_bytes = smem;
     }
     const int64_t items = (int64_t)a.n_tiles * a.n_layers;
     const int grid = (int)std::min<int64_t>(items, (int64_t)K2_MIN_CTAS * e->prop.multiProcessorCount);

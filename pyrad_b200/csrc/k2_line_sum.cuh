@@ -78,6 +78,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
         : "memory");
 }
 
+// TMA 1-D bulk copy shared -> global (SASS: UBLKCP); the destination may be peer memory over NVLink.  Completion
+// is tracked per thread in bulk async-groups.
+__device__ __forceinline__ void tma_bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_barrier() {          // the math warps only (the producer never joins)
+    asm volatile("bar.sync 1, %0;" ::"n"(K2_CONSUMERS * 32) : "memory");
+}
+
 // First position in idx[lo, hi) whose value is >= key, found by the whole warp: every round each
 // lane probes one of 32 evenly spaced positions and a ballot narrows the interval 32-fold.
 __device__ __forceinline__ int warp_lower_bound(const int32_t *__restrict__ idx, int lo, int hi, long long key) {
@@ -163,6 +173,16 @@ struct K2Smem {
     uint64_t full[K2_STAGES];      // producer -> consumers: TMA bytes landed (+ descriptor written)
     uint64_t empty[K2_STAGES];     // consumers -> producer: all consumer warps are done with the slot
 };
+
+// Dynamic shared memory of k2_line_sum<P>: K2Smem | FP64 accumulators (PRB_K2_ACC_SMEM) | peer staging (2 x TILE floats).
+template <int P>
+__host__ __device__ constexpr size_t K2_SMEM_BASE() {
+    return ((sizeof(K2Smem) + (PRB_K2_ACC_SMEM ? sizeof(double) * P * K2_CONSUMERS * 32 : 0)) + 127) & ~size_t(127);
+}
+template <int P>
+__host__ __device__ constexpr size_t K2_SMEM_BYTES(bool peer_staging) {
+    return K2_SMEM_BASE<P>() + (peer_staging ? sizeof(float) * 2 * K2_CONSUMERS * 32 * P : 0);
+}
 
 // Per-thread state of a consumer: H = P/2 packed point pairs.
 template <int H>
@@ -409,7 +429,11 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
         const uint32_t stage = it % K2_STAGES;
         mbar_wait(&sm.full[stage], (it / K2_STAGES) & 1);
         const K2Desc d = sm.desc[stage];
-        if (d.flags & K2_END) break;
+        if (d.flags & K2_END) {
+            // the peer stores of the last tile must have left shared memory before the CTA retires
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            break;
+        }
         if (d.flags & K2_FIRST) {
             wmf = (float)__ldg(&a.layers[d.layer].wm);
             wb = d.tile0 + warp * SPAN;                // first point of this warp's span
@@ -467,6 +491,16 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             const K2Layer *L = a.layers + d.layer;
             const double inv_scale = __ldg(&L->inv_scale);
             void *out = L->out;
+            // Multi-GPU: a full tile's finished spectra are staged in shared memory and pushed to every rank's
+            // gather buffer with TMA bulk stores (asynchronous: no thread waits on NVLink, the next tile's line sum
+            // starts at once).  Ragged last tiles and single-destination runs store directly.
+            const bool bulk = a.fuse.enabled && a.fuse.n_dst > 1 && d.tile0 + TILE <= a.n_chunk;
+            float *stage_rad = reinterpret_cast<float *>(smem_raw + K2_SMEM_BASE<P>());
+            float *stage_tr = stage_rad + TILE;
+            if (bulk) {
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free again
+                consumer_barrier();
+            }
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const int i = wb + 32 * p + lane;
@@ -484,12 +518,29 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
                         const float b = planck_f32(a3, a.fuse.c2_over_t * nu);
                         const float rad = fmaf(t, planck_f32(a3, a.fuse.c2_over_tsurf * nu) - b, b);
                         const float tr = exp2f(0.f + e);
+                        if (bulk) {
+                            stage_rad[i - d.tile0] = rad;
+                            stage_tr[i - d.tile0] = tr;
+                        } else {
 #pragma unroll 1
-                        for (int dst = 0; dst < a.fuse.n_dst; ++dst) {
-                            a.fuse.rad[dst][i] = rad;          // own slot of every rank's gather buffer (peer
-                            a.fuse.trans[dst][i] = tr;         // stores over NVLink are fire-and-forget)
+                            for (int dst = 0; dst < a.fuse.n_dst; ++dst) {
+                                a.fuse.rad[dst][i] = rad;      // own slot of every rank's gather buffer
+                                a.fuse.trans[dst][i] = tr;
+                            }
                         }
                     }
+                }
+            }
+            if (bulk) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                consumer_barrier();
+                if (tid == 0) {
+#pragma unroll 1
+                    for (int dst = 0; dst < a.fuse.n_dst; ++dst) {
+                        tma_bulk_s2g(a.fuse.rad[dst] + d.tile0, stage_rad, TILE * 4u);
+                        tma_bulk_s2g(a.fuse.trans[dst] + d.tile0, stage_tr, TILE * 4u);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         }
