@@ -441,11 +441,11 @@ def run_atmosphere(e, args, rank, world, ext, peaks, use_peer):
         if use_peer:
             return pd.gathered_spectra(e)           # [world, ld] views of the gather buffer the kernels filled
         rad_p, tr_p = e.atmosphere_result_dev()
+        if world == 1:
+            return rad_p, tr_p                      # one rank: the finished spectra are already where they belong
         rad = pd.device_tensor(rad_p, nc)
         tr = pd.device_tensor(tr_p, nc)
-        g1 = pd.all_gather_spectra(rad, plan, dist if world > 1 else None)
-        g2 = pd.all_gather_spectra(tr, plan, dist if world > 1 else None)
-        return g1, g2
+        return pd.all_gather_spectra(rad, plan, dist), pd.all_gather_spectra(tr, plan, dist)
 
     run()
     torch.cuda.synchronize()

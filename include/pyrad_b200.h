@@ -150,6 +150,23 @@ int prb_atmosphere_kmatrix_dev(prb_engine *e, void **kmat_dev, int64_t *ld);    
 int prb_atmosphere_launches(prb_engine *e);              /* kernels launched by the last prb_atmosphere */
 int prb_set_option(prb_engine *e, int option, int64_t value);
 
+/* ---- section 8(f) rows beside the hot path -------------------------------------------------------
+ * prb_line_survey: Isotope.createLineSurvey (pyradClasses.py:409-428) for the uploaded lines on the current
+ *   grid: out[int((nu0 - rangeMin)/res)] += S296 in line order, bins outside [0, n_out-1] dropped.  Bit-exact.
+ * prb_integrate_spectrum: integrateSpectrum (pyradClasses.py:26-29) = sum(nan_to_num(spectrum)) * unitAngle * res
+ *   (deterministic pairwise device reduction).
+ * prb_atmosphere_integrate: the same integral of the device-resident radiance of the last prb_atmosphere (owned
+ *   chunk), plus the plain sum of the total transmittance; either pointer may be NULL.
+ * prb_derived_spectra: emissivity 1-T, optical depth -ln T, absorbance log10(1/T) (pyradClasses.py:73-88,
+ *   330-340, 596-606) from a transmittance array; any output may be NULL. */
+int prb_line_survey(prb_engine *e, int64_t n_out, double *out_host);
+int prb_integrate_spectrum(prb_engine *e, int64_t n, const double *spectrum, double unit_angle, double res,
+                           double *value);
+int prb_atmosphere_integrate(prb_engine *e, double unit_angle, double res, double *radiance_integral,
+                             double *transmittance_sum);
+int prb_derived_spectra(prb_engine *e, int64_t n, const double *transmittance, double *emissivity,
+                        double *optical_depth, double *absorbance);
+
 /* ---- multi-GPU (section 8(e)): wavenumber chunks, one process per GPU on one NVLink/NVSwitch node.
  * The path has no exchange step; the only collective is the all-gather of the finished spectra, and it is
  * fused into the compute step: after prb_peer_connect, prb_atmosphere stores this rank's radiance and

@@ -61,6 +61,10 @@ PROTOTYPES = {
     "prb_atmosphere_kmatrix_dev": (C.c_int, [_vp, C.POINTER(_vp), _lp]),
     "prb_atmosphere_launches": (C.c_int, [_vp]),
     "prb_set_option": (C.c_int, [_vp, C.c_int, _i64]),
+    "prb_line_survey": (C.c_int, [_vp, _i64, _dp]),
+    "prb_integrate_spectrum": (C.c_int, [_vp, _i64, _dp, _d, _d, _dp]),
+    "prb_atmosphere_integrate": (C.c_int, [_vp, _d, _d, _dp, _dp]),
+    "prb_derived_spectra": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp]),
     "prb_peer_alloc": (C.c_int, [_vp, C.c_int, C.c_int, _i64, _vp]),
     "prb_peer_connect": (C.c_int, [_vp, _vp]),
     "prb_peer_disconnect": (C.c_int, [_vp]),

@@ -62,7 +62,7 @@ def _n_base(obj):
 # ---------------------------------------------------------------------------------- module-level getters
 def integrateSpectrum(spectrum, unitAngle=pi, res=None):
     res = BASE_RESOLUTION if res is None else res
-    return np.sum(np.nan_to_num(spectrum)) * unitAngle * res
+    return engine().integrate_spectrum(spectrum, unitAngle, res)          # device reduction (K4)
 
 
 def getCrossSection(obj):
@@ -86,7 +86,7 @@ def getTransmittance(obj):
 def getOpticalDepth(obj):
     if not obj.progressCrossSection:
         obj.createCrossSection()
-    return -np.log(obj.transmittance)
+    return engine().derived_spectra(obj.transmittance, want=("optical_depth",))["optical_depth"]
 
 
 def getAbsorbance(obj):
@@ -269,7 +269,7 @@ class _Spectral:
 
     @property
     def emissivity(self):
-        return 1 - self.transmittance
+        return engine().derived_spectra(self.transmittance, want=("emissivity",))["emissivity"]
 
     @property
     def emittance(self):
@@ -277,7 +277,7 @@ class _Spectral:
 
     @property
     def absorbance(self):
-        return np.log10(1 / self.transmittance)
+        return engine().derived_spectra(self.transmittance, want=("absorbance",))["absorbance"]
 
     def transmission(self, surfaceSpectrum):
         return self._stream(("radiance",), np.asarray(surfaceSpectrum, dtype=np.float64))[2]
@@ -367,12 +367,16 @@ class Isotope(list, _Spectral):
         self.progressCrossSection = True
 
     def createLineSurvey(self):
-        survey = np.zeros(_n_base(self))
+        """pyradClasses.py:409-428 on the device (K4): S296 summed per grid bin in line order, bit-exact."""
+        n_out = _n_base(self)
         nu = self._cols["nu"]
         if nu.size:
-            idx = np.trunc((nu - self.layer.rangeMin) / self.layer.resolution).astype(np.int64)
-            ok = (idx >= 0) & (idx <= len(survey) - 1)
-            np.add.at(survey, idx[ok], self._cols["sw"][ok])
+            e = engine()
+            e.upload_lines(self._cols, 1)
+            e.set_grid(self.layer.rangeMin, self.layer.resolution, max(n_out, 1))
+            survey = e.line_survey(n_out)
+        else:
+            survey = np.zeros(n_out)
         self.lineSurvey = survey
         return survey
 

@@ -14,6 +14,7 @@
 #include "k2_line_sum.cuh"
 #include "k2_narrow.cuh"
 #include "k3_stream.cuh"
+#include "k4_derived.cuh"
 
 using namespace prb;
 
@@ -1122,5 +1123,90 @@ extern "C" int prb_peer_gathered_dev(prb_engine *e, void **radiance_dev, void **
     if (radiance_dev) *radiance_dev = peer_slot(e, e->peer.rank, par, 0, 0);
     if (transmittance_dev) *transmittance_dev = peer_slot(e, e->peer.rank, par, 1, 0);
     if (ld) *ld = e->peer.ld;
+    return PRB_OK;
+}
+
+// ------------------------------------------------------------------------------------ K4: survey, integrals, derived
+extern "C" int prb_line_survey(prb_engine *e, int64_t n_out, double *out_host) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (!e->grid_set) return fail(PRB_ERR_STATE, "prb_line_survey: upload lines and set the grid first");
+    if (n_out < 0 || (n_out > 0 && !out_host)) return fail(PRB_ERR_ARG, "prb_line_survey: bad arguments");
+    if (n_out == 0) return PRB_OK;
+    CK(cudaSetDevice(e->device));
+    CK(e->scratch_b.ensure(n_out));
+    CK(cudaMemsetAsync(e->scratch_b.p, 0, sizeof(double) * n_out, e->stream));
+    if (e->n_lines > 0) {
+        k4_line_survey<<<(unsigned)((e->n_lines + 255) / 256), 256, 0, e->stream>>>(e->idx.p, e->s296.p, e->n_lines, n_out,
+                                                                                  e->scratch_b.p);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(out_host, e->scratch_b.p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PRB_OK;
+}
+
+template <typename T>
+static int device_sum(prb_engine *e, const T *x_dev, int64_t n, double scale, double *out_host) {
+    const int64_t per_block = (int64_t)K4_BLOCK * K4_PER_THREAD;
+    const int64_t nb = std::max<int64_t>(1, (n + per_block - 1) / per_block);
+    CK(e->scratch_w.ensure(nb + 1));
+    k4_sum_partial<T><<<(unsigned)nb, K4_BLOCK, 0, e->stream>>>(x_dev, n, e->scratch_w.p);
+    CK(cudaGetLastError());
+    k4_sum_final<<<1, K4_BLOCK, 0, e->stream>>>(e->scratch_w.p, nb, scale, e->scratch_w.p + nb);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_host, e->scratch_w.p + nb, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PRB_OK;
+}
+
+extern "C" int prb_integrate_spectrum(prb_engine *e, int64_t n, const double *spectrum, double unit_angle, double res,
+                                      double *value) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (n < 0 || (n > 0 && !spectrum) || !value) return fail(PRB_ERR_ARG, "prb_integrate_spectrum: bad arguments");
+    CK(cudaSetDevice(e->device));
+    CK(e->scratch_a.ensure(std::max<int64_t>(n, 1)));
+    if (n) CK(cudaMemcpyAsync(e->scratch_a.p, spectrum, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    // value = sum * unitAngle * res, left to right as the reference (pyradClasses.py:27-28)
+    double sum = 0;
+    int rc = device_sum<double>(e, e->scratch_a.p, n, 1.0, &sum);
+    if (rc) return rc;
+    *value = sum * unit_angle * res;
+    return PRB_OK;
+}
+
+extern "C" int prb_atmosphere_integrate(prb_engine *e, double unit_angle, double res, double *radiance_integral,
+                                        double *transmittance_sum) {
+    if (!e || !e->atm_layers || !e->res_rad)
+        return fail(PRB_ERR_STATE, "prb_atmosphere_integrate: run prb_atmosphere first");
+    CK(cudaSetDevice(e->device));
+    const int64_t nc = chunk_len(e);
+    int rc;
+    if (radiance_integral) {
+        double s = 0;
+        if ((rc = device_sum<float>(e, e->res_rad, nc, 1.0, &s))) return rc;
+        *radiance_integral = s * unit_angle * res;
+    }
+    if (transmittance_sum) {
+        if ((rc = device_sum<float>(e, e->res_trans, nc, 1.0, transmittance_sum))) return rc;
+    }
+    return PRB_OK;
+}
+
+extern "C" int prb_derived_spectra(prb_engine *e, int64_t n, const double *transmittance, double *emissivity,
+                                   double *optical_depth, double *absorbance) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (n < 0 || (n > 0 && !transmittance)) return fail(PRB_ERR_ARG, "prb_derived_spectra: bad arguments");
+    if (n == 0) return PRB_OK;
+    CK(cudaSetDevice(e->device));
+    CK(e->scratch_a.ensure(n)); CK(e->scratch_b.ensure(n)); CK(e->scratch_c.ensure(n)); CK(e->scratch_d.ensure(n));
+    CK(cudaMemcpyAsync(e->scratch_a.p, transmittance, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    k4_derived_f64<<<stream_grid(e, n), 256, 0, e->stream>>>(n, e->scratch_a.p, emissivity ? e->scratch_b.p : nullptr,
+                                                            optical_depth ? e->scratch_c.p : nullptr,
+                                                            absorbance ? e->scratch_d.p : nullptr);
+    CK(cudaGetLastError());
+    if (emissivity) CK(cudaMemcpyAsync(emissivity, e->scratch_b.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
+    if (optical_depth) CK(cudaMemcpyAsync(optical_depth, e->scratch_c.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
+    if (absorbance) CK(cudaMemcpyAsync(absorbance, e->scratch_d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     return PRB_OK;
 }

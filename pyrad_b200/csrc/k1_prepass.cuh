@@ -209,16 +209,16 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
                 bg = B;
                 C = -log2e * K.lc.res2 * inv_hh * inv_hh;
             }
-            // near-zone radius: beyond it the Gaussian term is < 1e-9 of the same line's Lorentz term
+            // near-zone radius: beyond it the Gaussian term is < 2e-7 of the same line's Lorentz term
             // (or below the scaled FP32 floor for Gaussian-only lines), so K2 may skip it.  FP32 is
-            // plenty here (the radius is rounded up and padded): solve e^{-t2}(1+t2) <= rho9 with one
+            // plenty here (the radius is rounded up and padded): solve e^{-t2}(1+t2) <= rho9 (the 2e-7 ratio) with one
             // fixed-point step from t2 = -ln(rho9) plus a margin of 1 (the step undershoots by < 1).
             // (G can be negative: a line whose pressure-shifted wavenumber is < 0 gets a negative Doppler width
             // in the reference, pyradClasses.py:261-263 -- reproduced, so the test is on |G|.)
             if (G != 0.0) {
                 float t2 = 160.f;
                 if (A != 0.0) {
-                    const float rho9 = (float)fabs(1e-9 * A / (B * G));
+                    const float rho9 = (float)fabs(2e-7 * A / (B * G));
                     if (rho9 >= 1.f) t2 = -1.f;
                     else {
                         const float ln = -__logf(fmaxf(rho9, 1e-37f));

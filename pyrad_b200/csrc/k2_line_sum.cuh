@@ -69,6 +69,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Producer-side wait: the producer runs ahead of the math warps and spends most of its life here, so it asks the
+// hardware to park the warp (suspend-time hint) instead of burning issue slots the math warps could use.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITP_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONEP_%=;\n"
+        "bra WAITP_%=;\n"
+        "DONEP_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(4000u)
+        : "memory");
+}
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile(
@@ -289,7 +304,8 @@ __device__ __forceinline__ void lorentz_paired(const float4 *sA, const float4 *s
 }
 
 // Gaussian cores of lines [js, je): only lines whose near zone meets the span (warp-uniform test).
-template <int H>
+// MASKED: the window |d| <= wm may cover only part of the span -> zero G per point outside it.
+template <int H, bool MASKED>
 __device__ __forceinline__ void gauss_pass(const float4 *sA, const float4 *sB, const float *sD, int js, int je,
                                            float wbf, float we1f, float wmf, Acc<H> &s) {
     int since = 0;
@@ -303,9 +319,11 @@ __device__ __forceinline__ void gauss_pass(const float4 *sA, const float4 *sB, c
         for (int h = 0; h < H; ++h) {
             const float2 e = __fadd2_rn(s.fi[h], nf);
             const float2 arg = __fmul2_rn(C2, __fmul2_rn(e, e));
-            float2 g;
-            g.x = fabsf(e.x) <= wmf ? b.z : 0.f;
-            g.y = fabsf(e.y) <= wmf ? b.z : 0.f;
+            float2 g = splat(b.z);
+            if (MASKED) {
+                g.x = fabsf(e.x) <= wmf ? b.z : 0.f;
+                g.y = fabsf(e.y) <= wmf ? b.z : 0.f;
+            }
             s.a32[h] = __ffma2_rn(g, make_float2(ex2_approx(arg.x), ex2_approx(arg.y)), s.a32[h]);
         }
         if (++since == K2_FLUSH) { s.flush(); since = 0; }
@@ -361,7 +379,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
         uint32_t it = 0;
         auto slot_acquire = [&](uint32_t &stage) {
             stage = it % K2_STAGES;
-            mbar_wait(&sm.empty[stage], ((it / K2_STAGES) & 1) ^ 1);   // fresh barrier: passes at once
+            mbar_wait_parked(&sm.empty[stage], ((it / K2_STAGES) & 1) ^ 1);   // fresh barrier: passes at once
         };
         const int n_items = a.n_layers * a.n_tiles;
         while (true) {
@@ -481,7 +499,11 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             lorentz_paired<H, true>(sA, sB, b0, b1, wmf, s);
             lorentz_paired<H, false>(sA, sB, b1, b4, wmf, s);
             lorentz_paired<H, true>(sA, sB, b4, b5, wmf, s);
-            if (dgmax > 0.f) gauss_pass<H>(sA, sB, sD, bg0, bg1, wbf, we1f, wmf, s);
+            if (dgmax > 0.f) {                                  // [bg0, bg1) lies inside [b0, b5)
+                gauss_pass<H, true>(sA, sB, sD, bg0, min(bg1, b1), wbf, we1f, wmf, s);
+                gauss_pass<H, false>(sA, sB, sD, max(bg0, b1), min(bg1, b4), wbf, we1f, wmf, s);
+                gauss_pass<H, true>(sA, sB, sD, max(bg0, b4), bg1, wbf, we1f, wmf, s);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[stage]);  // slot may be refilled

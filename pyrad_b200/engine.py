@@ -236,6 +236,33 @@ class Engine:
         _lib.check(self._lib.prb_atmosphere_result_dev(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    # -- section 8(f) rows: survey, integrals, derived spectra
+    def line_survey(self, n_out):
+        """Isotope.createLineSurvey (pyradClasses.py:409-428) of the uploaded lines on the current grid."""
+        out = np.empty(int(n_out))
+        _lib.check(self._lib.prb_line_survey(self._h, int(n_out), _dp(out)))
+        return out
+
+    def integrate_spectrum(self, spectrum, unit_angle, res):
+        """integrateSpectrum (pyradClasses.py:26-29)."""
+        x = _f64(spectrum)
+        v = C.c_double()
+        _lib.check(self._lib.prb_integrate_spectrum(self._h, x.size, _dp(x), float(unit_angle), float(res), C.byref(v)))
+        return v.value
+
+    def atmosphere_integrate(self, unit_angle, res):
+        """(integral of the device-resident radiance, sum of the total transmittance) over the owned chunk."""
+        a, b = C.c_double(), C.c_double()
+        _lib.check(self._lib.prb_atmosphere_integrate(self._h, float(unit_angle), float(res), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def derived_spectra(self, transmittance, want=("emissivity", "optical_depth", "absorbance")):
+        t = _f64(transmittance)
+        out = {k: (np.empty(t.size) if k in want else None) for k in ("emissivity", "optical_depth", "absorbance")}
+        _lib.check(self._lib.prb_derived_spectra(self._h, t.size, _dp(t), _dp(out["emissivity"]),
+                                                 _dp(out["optical_depth"]), _dp(out["absorbance"])))
+        return out
+
     def atmosphere_launches(self):
         """Kernels launched by the last atmosphere() call."""
         return int(self._lib.prb_atmosphere_launches(self._h))

@@ -73,6 +73,16 @@ def case_gas_cell(name, species_names, conc, n_lines, rmin, rmax, T, P, depth, s
         out["surface"] = np.asarray(surf)
         out["layer_transmission"] = np.asarray(layer.transmission(surf))
         out["layer_planck"] = np.asarray(layer.planck(layer.T))
+        # section 8(f) rows: line survey, derived spectra, integrated radiance
+        for g, m in enumerate(mols):
+            out["survey_%d" % g] = np.asarray(m[0].createLineSurvey())
+        out["layer_survey"] = np.asarray(layer.lineSurvey)
+        with np.errstate(all="ignore"):
+            out["layer_optical_depth"] = np.asarray(C.getOpticalDepth(layer))
+            out["layer_absorbance"] = np.asarray(C.getAbsorbance(layer))
+            out["layer_emissivity"] = np.asarray(C.getEmissivity(layer))
+        out["integrated_transmission"] = float(C.integrateSpectrum(out["layer_transmission"], res=ref.utils.BASE_RESOLUTION))
+        out["integrated_surface"] = float(C.integrateSpectrum(out["surface"], res=ref.utils.BASE_RESOLUTION))
     for g, ln in enumerate(all_lines):
         out.update(pack_lines("lines%d" % g, ln))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)

@@ -57,6 +57,39 @@ def test_mirror_matches_reference_gas_cell(name, data_root):
     np.testing.assert_allclose(out, g["layer_transmission"], rtol=2e-5)
 
 
+@pytest.mark.parametrize("name", G.CELL_CASES)
+def test_mirror_survey_derived_and_integral_match_reference(name, data_root, engine):
+    """SURVEY section 8(f) rows through the mirror (device kernels k4_*): the line survey is bit-exact; derived
+    spectra follow the transmittance's own tolerance; the integral is a pairwise device reduction."""
+    g = G.load(name)
+    species = [str(s) for s in g["species"]]
+    for i, s in enumerate(species):
+        seed(data_root, g, i, s)
+    C.BASE_RESOLUTION = float(g["base"])
+    layer = C.Layer(float(g["depth"]), int(g["T"]), float(g["P"]), float(g["range_min"]), float(g["range_max"]),
+                    dynamicResolution=bool(g["dynamic"]))
+    mols = [layer.addMolecule(s, concentration=float(c)) for s, c in zip(species, g["conc"])]
+    for i, m in enumerate(mols):
+        np.testing.assert_array_equal(m[0].createLineSurvey(), g["survey_%d" % i])
+    np.testing.assert_array_equal(layer.lineSurvey, g["layer_survey"])
+    with np.errstate(all="ignore"):
+        tau, tau_ref = C.getOpticalDepth(layer), g["layer_optical_depth"]
+        ab, ab_ref = C.getAbsorbance(layer), g["layer_absorbance"]
+    fin = np.isfinite(tau_ref) & (g["layer_transmittance"] > 1e-300)
+    np.testing.assert_allclose(tau[fin], tau_ref[fin], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(ab[fin], ab_ref[fin], rtol=2e-5, atol=1e-6)
+    assert np.abs(C.getEmissivity(layer) - g["layer_emissivity"]).max() <= H.T_ABS_TOL
+    # the kernels themselves on the reference's own arrays: numpy-level agreement
+    d = engine.derived_spectra(g["layer_transmittance"])
+    np.testing.assert_array_equal(d["emissivity"], g["layer_emissivity"])
+    np.testing.assert_allclose(d["optical_depth"][fin], tau_ref[fin], rtol=1e-14, atol=1e-300)
+    np.testing.assert_allclose(d["absorbance"][fin], ab_ref[fin], rtol=1e-14, atol=1e-300)
+    for key, ref in (("layer_transmission", "integrated_transmission"), ("surface", "integrated_surface")):
+        v = C.integrateSpectrum(g[key], res=float(g["base"]))
+        assert v == pytest.approx(float(g[ref]), rel=1e-13)
+    assert C.integrateSpectrum(np.array([1.0, np.nan, 2.0, 1e300]), res=1.0) == pytest.approx((3.0 + 1e300) * np.pi, rel=1e-15)
+
+
 @pytest.mark.parametrize("name", G.XSC_CASES)
 def test_mirror_matches_reference_xsc(name, data_root):
     g = G.load(name)

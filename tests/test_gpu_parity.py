@@ -307,3 +307,13 @@ def test_peer_gather_single_rank_roundtrip(engine):
         engine.peer_disconnect()
     rad, tr = _run_atm(engine, w)                                   # back to the local result arrays
     assert np.array_equal(rad, rad_ref)
+
+
+def test_atmosphere_integrals_on_device(engine):
+    """integrateSpectrum of the device-resident radiance (K4 reduction) versus numpy on the read-back arrays."""
+    w = workloads.atmosphere(n_layers=4, n_lines=4000, rmin=600.0, rmax=640.0, res=0.001, top_km=20.0)
+    H.engine_setup(engine, w)
+    rad, tr = _run_atm(engine, w)
+    integ, tsum = engine.atmosphere_integrate(np.pi, w["res"])
+    assert integ == pytest.approx(float(np.sum(np.nan_to_num(rad.astype(np.float64))) * np.pi * w["res"]), rel=1e-12)
+    assert tsum == pytest.approx(float(np.sum(tr.astype(np.float64))), rel=1e-12)

@@ -80,6 +80,28 @@ def test_oracle_reproduces_reference_gas_cell(name):
     np.testing.assert_allclose(ph.transmission(t, g["surface"], g["layer_planck"]), g["layer_transmission"], rtol=1e-12)
 
 
+@pytest.mark.parametrize("name", G.CELL_CASES)
+def test_oracle_reproduces_reference_survey_and_derived_spectra(name):
+    """line survey, optical depth / absorbance / emissivity, integrateSpectrum."""
+    g = G.load(name)
+    rmin, rmax, base, res = float(g["range_min"]), float(g["range_max"]), float(g["base"]), float(g["res"])
+    cutoff = ph.layer_cutoff(float(g["P"]))
+    n_out = ph.grid_len(rmin, rmax, base)
+    total = np.zeros(n_out)
+    for i in range(len(g["conc"])):
+        ln = G.lines_of(g, i, cutoff, rmin, rmax)
+        sv = ph.line_survey(ln["nu"], ln["sw"], rmin, res, n_out)
+        np.testing.assert_array_equal(sv, g["survey_%d" % i])                 # same adds in the same order
+        total += sv
+    np.testing.assert_array_equal(total, g["layer_survey"])
+    t = g["layer_transmittance"]
+    np.testing.assert_array_equal(ph.optical_depth(t), g["layer_optical_depth"])
+    np.testing.assert_array_equal(ph.absorbance(t), g["layer_absorbance"])
+    np.testing.assert_array_equal(ph.emissivity(t), g["layer_emissivity"])
+    assert ph.integrate_spectrum(g["layer_transmission"], res=base) == float(g["integrated_transmission"])
+    assert ph.integrate_spectrum(g["surface"], res=base) == float(g["integrated_surface"])
+
+
 @pytest.mark.parametrize("name", G.XSC_CASES)
 def test_oracle_reproduces_reference_xsc(name):
     g = G.load(name)
