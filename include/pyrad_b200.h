@@ -44,6 +44,7 @@ extern "C" {
 #define PRB_ERR_RANGE       -4   /* grid segment too large for exact FP32 offsets, or coefficient overflow */
 #define PRB_ERR_NODEVICE    -5   /* no usable CUDA device: there is no CPU fallback */
 #define PRB_ERR_PEER        -6   /* peer-memory gather: IPC mapping failed or a rank did not arrive */
+#define PRB_ERR_PARSE       -7   /* text ingestion: a row or number is not in the expected format */
 
 #define PRB_ABI_VERSION      2
 
@@ -83,6 +84,19 @@ int prb_upload_lines(prb_engine *e, int64_t n,
                      const double *gamma_air, const double *gamma_self,
                      const double *elower, const double *n_air, const double *delta_air,
                      const int32_t *group, int32_t n_groups);
+
+/* Line list straight from HITRAN-online CSV text (section 8(f) row 1; pyradUtilities.py:173-189, 421-448): `text`
+ * is the concatenation of the segment files (host memory; rows molec,iso,nu,sw,a,elower,gamma_air,gamma_self,
+ * delta_air,n_air; rows starting with '#' are skipped).  Parsed ON THE DEVICE with exact decimal->double
+ * conversion (the value float() returns), kept when wave_min < nu < wave_max (strict), duplicate wavenumbers
+ * collapse to the last row, file order preserved.  Replaces prb_upload_lines (single group).  prb_download_lines
+ * copies the resulting columns to host buffers (n = prb_line_count entries each; any may be NULL). */
+int     prb_ingest_hitran_csv(prb_engine *e, const char *text, int64_t n_bytes, double wave_min, double wave_max,
+                              int64_t *n_lines_out);
+int     prb_download_lines(prb_engine *e, double *nu0, double *s296, double *einstein_a, double *elower,
+                           double *gamma_air, double *gamma_self, double *delta_air, double *n_air);
+int64_t prb_line_count(prb_engine *e);                  /* lines on the device; < 0 when none */
+int     prb_debug_parse_double(const char *text, int64_t n_bytes, double *value);   /* host-side run of the device parser */
 
 /* ---- grid (a10/a11): point i of the FULL grid sits at range_min + i*res, i in [0, n_total).
  * This engine (rank) owns the contiguous chunk [i_begin, i_end).  Computes every line's

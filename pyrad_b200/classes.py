@@ -337,7 +337,7 @@ class Isotope(list, _Spectral):
 
     def getData(self):
         cols = _io.gather_lines(self.globalIsoNumber, self.layer.effectiveRangeMin, self.layer.effectiveRangeMax,
-                                DATA_ROOT)
+                                DATA_ROOT, engine())
         self.setLines(cols, _io.read_q_table(self.globalIsoNumber, DATA_ROOT))
         self.createLineSurvey()
 

@@ -15,6 +15,8 @@
 #include "k2_narrow.cuh"
 #include "k3_stream.cuh"
 #include "k4_derived.cuh"
+#include "k5_ingest.cuh"
+#include <thrust/iterator/counting_iterator.h>
 
 using namespace prb;
 
@@ -90,7 +92,7 @@ struct prb_engine {
     // line list
     int64_t n_lines = 0, n_alloc = 0;
     int n_groups = 0;
-    DevBuf<double> nu0, s296, gair, gself, elower, nair, delta;
+    DevBuf<double> nu0, s296, gair, gself, elower, nair, delta, einstein_a;
     DevBuf<int32_t> group;
     bool has_group = false;
     double s_max = 0;
@@ -194,7 +196,7 @@ extern "C" int prb_destroy(prb_engine *e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     e->nu0.release(); e->s296.release(); e->gair.release(); e->gself.release();
-    e->elower.release(); e->nair.release(); e->delta.release(); e->group.release();
+    e->elower.release(); e->nair.release(); e->delta.release(); e->group.release(); e->einstein_a.release();
     e->idx.release(); e->recA.release(); e->recB.release(); e->recD.release(); e->gp.release(); e->st.release();
     e->out64.release(); e->scratch_a.release(); e->scratch_b.release(); e->scratch_c.release();
     e->scratch_d.release(); e->scratch_w.release();
@@ -269,6 +271,22 @@ extern "C" int prb_set_k2_variant(prb_engine *e, int variant, int ppt) {
 }
 
 // ------------------------------------------------------------------------------------ lines
+// Device storage for n lines: SoA columns, grid indices and one layer of K2 records, all with padding records
+// (TMA copies are 16-byte granular) and a length that is a multiple of 4 so every per-layer slice of the record
+// arrays starts 16-byte aligned.
+static int alloc_line_storage(prb_engine *e, int64_t n) {
+    const int64_t na = (n + 16 + 3) & ~int64_t(3);
+    DevBuf<double> *cols[8] = {&e->nu0, &e->s296, &e->gair, &e->gself, &e->elower, &e->nair, &e->delta, &e->einstein_a};
+    for (int c = 0; c < 8; ++c) CK(cols[c]->ensure(na));
+    CK(e->idx.ensure(na));
+    CK(e->recA.ensure(na));
+    CK(e->recB.ensure(na));
+    CK(e->recD.ensure(na));
+    e->rec_slots = (int64_t)(std::min(e->recA.n, std::min(e->recB.n, e->recD.n)) / (size_t)na);
+    e->n_alloc = na;
+    return PRB_OK;
+}
+
 extern "C" int prb_upload_lines(prb_engine *e, int64_t n, const double *nu0, const double *s296,
                                 const double *gamma_air, const double *gamma_self, const double *elower,
                                 const double *n_air, const double *delta_air, const int32_t *group,
@@ -279,15 +297,13 @@ extern "C" int prb_upload_lines(prb_engine *e, int64_t n, const double *nu0, con
     if (n > 0 && (!nu0 || !s296 || !gamma_air || !gamma_self || !elower || !n_air || !delta_air))
         return fail(PRB_ERR_ARG, "prb_upload_lines: NULL column");
     CK(cudaSetDevice(e->device));
-    // padding records (TMA copies are 16-byte granular); a multiple of 4 so that every per-layer slice of the
-    // record arrays starts 16-byte aligned
-    const int64_t na = (n + 16 + 3) & ~int64_t(3);
+    int rc = alloc_line_storage(e, n);
+    if (rc) return rc;
+    const int64_t na = e->n_alloc;
     DevBuf<double> *cols[7] = {&e->nu0, &e->s296, &e->gair, &e->gself, &e->elower, &e->nair, &e->delta};
     const double *src[7] = {nu0, s296, gamma_air, gamma_self, elower, n_air, delta_air};
-    for (int c = 0; c < 7; ++c) {
-        CK(cols[c]->ensure(na));
+    for (int c = 0; c < 7; ++c)
         if (n) CK(cudaMemcpyAsync(cols[c]->p, src[c], sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
-    }
     e->has_group = group != nullptr;
     if (group) {
         CK(e->group.ensure(na));
@@ -303,17 +319,11 @@ extern "C" int prb_upload_lines(prb_engine *e, int64_t n, const double *nu0, con
         if (i && !(nu0[i] >= nu0[i - 1])) sorted = false;
         if (group && (group[i] < 0 || group[i] >= n_groups)) group_ok = false;
     }
-    CK(e->idx.ensure(na));
-    CK(e->recA.ensure(na));
-    CK(e->recB.ensure(na));
-    CK(e->recD.ensure(na));
-    e->rec_slots = (int64_t)(std::min(e->recA.n, std::min(e->recB.n, e->recD.n)) / (size_t)na);
     CK(cudaStreamSynchronize(e->stream));
     e->lines_set = false;
     if (!sorted) return fail(PRB_ERR_ARG, "prb_upload_lines: nu0 must be ascending");
     if (!group_ok) return fail(PRB_ERR_ARG, "prb_upload_lines: group id out of range");
     e->n_lines = n;
-    e->n_alloc = na;
     e->n_groups = n_groups;
     e->s_max = smax;
     e->lines_set = true;
@@ -1209,4 +1219,131 @@ extern "C" int prb_derived_spectra(prb_engine *e, int64_t n, const double *trans
     if (absorbance) CK(cudaMemcpyAsync(absorbance, e->scratch_d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return PRB_OK;
+}
+
+// ------------------------------------------------------------------------------------ K5: HITRAN CSV ingestion
+extern "C" int prb_ingest_hitran_csv(prb_engine *e, const char *text, int64_t n_bytes, double wave_min, double wave_max,
+                                     int64_t *n_lines_out) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (n_bytes < 0 || (n_bytes > 0 && !text)) return fail(PRB_ERR_ARG, "prb_ingest_hitran_csv: bad arguments");
+    if (n_bytes > (int64_t(1) << 36)) return fail(PRB_ERR_ARG, "prb_ingest_hitran_csv: more than 64 GiB of text; ingest in pieces");
+    CK(cudaSetDevice(e->device));
+    const int64_t n_pad = std::max<int64_t>((n_bytes + 15) & ~int64_t(15), 16);
+    DevBuf<char> d_text;
+    DevBuf<unsigned char> d_nl, d_state;
+    DevBuf<int32_t> d_keep, d_pos;
+    DevBuf<int64_t> d_nlpos;
+    DevBuf<unsigned long long> d_scal;          // [0] newline count, [1] first bad row, [2] smax bits, [3] unsorted flag, [4] selected
+    DevBuf<unsigned char> d_tmp;
+    DevBuf<double> t[8];
+    auto cleanup = [&]() {
+        d_text.release(); d_nl.release(); d_state.release(); d_keep.release(); d_pos.release(); d_nlpos.release();
+        d_scal.release(); d_tmp.release();
+        for (auto &x : t) x.release();
+    };
+#define CKI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); char b_[512]; \
+        snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        return fail(PRB_ERR_CUDA, b_); } } while (0)
+    CKI(d_text.ensure(n_pad));
+    CKI(d_nl.ensure(n_pad));
+    CKI(d_scal.ensure(8));
+    CKI(cudaMemsetAsync(d_text.p + (n_pad - 16), 0, 16, e->stream));
+    if (n_bytes) CKI(cudaMemcpyAsync(d_text.p, text, n_bytes, cudaMemcpyHostToDevice, e->stream));
+    unsigned long long h_scal[8] = {0, ~0ull, 0, 0, 0, 0, 0, 0};
+    CKI(cudaMemcpyAsync(d_scal.p, h_scal, sizeof h_scal, cudaMemcpyHostToDevice, e->stream));
+    k5_mark_newlines<<<(unsigned)((n_pad / 16 + 255) / 256), 256, 0, e->stream>>>(d_text.p, n_bytes, d_nl.p, d_scal.p);
+    CKI(cudaGetLastError());
+    CKI(cudaMemcpyAsync(h_scal, d_scal.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CKI(cudaStreamSynchronize(e->stream));
+    const int64_t n_nl = (int64_t)h_scal[0];
+    const int64_t n_rows = n_nl + ((n_bytes > 0 && text[n_bytes - 1] != '\n') ? 1 : 0);
+    int64_t n_kept = 0;
+    if (n_rows > 0) {
+        // newline positions (CUB stream compaction of a counting sequence)
+        CKI(d_nlpos.ensure(n_nl + 1));
+        size_t tmp_bytes = 0;
+        thrust::counting_iterator<int64_t> counting(0);
+        long long *d_selected = reinterpret_cast<long long *>(d_scal.p + 4);
+        CKI(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, counting, d_nl.p, d_nlpos.p, d_selected, n_bytes, e->stream));
+        CKI(d_tmp.ensure(tmp_bytes));
+        CKI(cub::DeviceSelect::Flagged(d_tmp.p, tmp_bytes, counting, d_nl.p, d_nlpos.p, d_selected, n_bytes, e->stream));
+        for (auto &x : t) CKI(x.ensure(n_rows));
+        CKI(d_state.ensure(n_rows));
+        CKI(d_keep.ensure(n_rows));
+        CKI(d_pos.ensure(n_rows + 1));
+        IngestCols tc{t[0].p, t[1].p, t[2].p, t[3].p, t[4].p, t[5].p, t[6].p, t[7].p};
+        k5_parse_rows<<<(unsigned)((n_rows + 127) / 128), 128, 0, e->stream>>>(d_text.p, n_bytes, d_nlpos.p, n_nl, n_rows, wave_min,
+                                                                             wave_max, tc, d_state.p, d_scal.p + 1);
+        CKI(cudaGetLastError());
+        k5_resolve_duplicates<<<(unsigned)((n_rows + 255) / 256), 256, 0, e->stream>>>(t[0].p, d_state.p, n_rows, d_keep.p);
+        CKI(cudaGetLastError());
+        // exclusive scan of the keep flags -> output slots
+        size_t tmp2 = 0;
+        CKI(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, d_keep.p, d_pos.p, n_rows, e->stream));
+        CKI(d_tmp.ensure(tmp2));
+        CKI(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp2, d_keep.p, d_pos.p, n_rows, e->stream));
+        int32_t last_pos = 0, last_keep = 0;
+        CKI(cudaMemcpyAsync(&last_pos, d_pos.p + (n_rows - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        CKI(cudaMemcpyAsync(&last_keep, d_keep.p + (n_rows - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        CKI(cudaMemcpyAsync(h_scal, d_scal.p, sizeof h_scal, cudaMemcpyDeviceToHost, e->stream));
+        CKI(cudaStreamSynchronize(e->stream));
+        if (h_scal[1] != ~0ull) {
+            cleanup();
+            return fail(PRB_ERR_PARSE, "prb_ingest_hitran_csv: row " + std::to_string(h_scal[1]) +
+                                           " is not a HITRAN-online CSV row (10 comma-separated fields, plain decimal numbers)");
+        }
+        n_kept = (int64_t)last_pos + last_keep;
+        e->lines_set = false;
+        int rc = alloc_line_storage(e, n_kept);
+        if (rc) { cleanup(); return rc; }
+        IngestCols dst{e->nu0.p, e->s296.p, e->einstein_a.p, e->elower.p, e->gair.p, e->gself.p, e->delta.p, e->nair.p};
+        k5_scatter_kept<<<(unsigned)((n_rows + 255) / 256), 256, 0, e->stream>>>(tc, d_keep.p, d_pos.p, n_rows, dst);
+        CKI(cudaGetLastError());
+        if (n_kept > 0) {
+            k5_finalize<<<(unsigned)((n_kept + 255) / 256), 256, 0, e->stream>>>(e->nu0.p, e->s296.p, n_kept, d_scal.p + 2,
+                                                                               reinterpret_cast<unsigned int *>(d_scal.p + 3));
+            CKI(cudaGetLastError());
+        }
+        CKI(cudaMemcpyAsync(h_scal, d_scal.p, sizeof h_scal, cudaMemcpyDeviceToHost, e->stream));
+        CKI(cudaStreamSynchronize(e->stream));
+    } else {
+        e->lines_set = false;
+        int rc = alloc_line_storage(e, 0);
+        if (rc) { cleanup(); return rc; }
+    }
+#undef CKI
+    cleanup();
+    if (h_scal[3] & 0xffffffffull) return fail(PRB_ERR_ARG, "prb_ingest_hitran_csv: wavenumbers are not ascending");
+    double smax;
+    memcpy(&smax, &h_scal[2], sizeof smax);
+    e->n_lines = n_kept;
+    e->n_groups = 1;
+    e->has_group = false;
+    e->s_max = smax;
+    e->lines_set = true;
+    e->grid_set = false;
+    e->last.valid = false;
+    if (n_lines_out) *n_lines_out = n_kept;
+    return PRB_OK;
+}
+
+extern "C" int prb_download_lines(prb_engine *e, double *nu0, double *s296, double *einstein_a, double *elower,
+                                  double *gamma_air, double *gamma_self, double *delta_air, double *n_air) {
+    if (!e || !e->lines_set) return fail(PRB_ERR_STATE, "prb_download_lines: no line list on the device");
+    CK(cudaSetDevice(e->device));
+    const int64_t n = e->n_lines;
+    double *dst[8] = {nu0, s296, einstein_a, elower, gamma_air, gamma_self, delta_air, n_air};
+    const double *src[8] = {e->nu0.p, e->s296.p, e->einstein_a.p, e->elower.p, e->gair.p, e->gself.p, e->delta.p, e->nair.p};
+    for (int c = 0; c < 8; ++c)
+        if (dst[c] && n) CK(cudaMemcpyAsync(dst[c], src[c], sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PRB_OK;
+}
+
+extern "C" int64_t prb_line_count(prb_engine *e) { return (e && e->lines_set) ? e->n_lines : -1; }
+
+// The number parser on the host (same source as the device kernel) for the CPU test suite.
+extern "C" int prb_debug_parse_double(const char *text, int64_t n_bytes, double *value) {
+    if (!text || !value || n_bytes < 0) return PRB_ERR_ARG;
+    return parse_double(text, text + n_bytes, value) ? PRB_OK : PRB_ERR_PARSE;
 }

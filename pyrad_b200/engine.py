@@ -108,6 +108,26 @@ class Engine:
         self.n_lines = n
         self.n_groups = int(n_groups)
 
+    def ingest_csv(self, text, wave_min, wave_max):
+        """HITRAN-online CSV bytes -> the engine's line list, parsed on the device (K5).  Returns the line count."""
+        blob = bytes(text)
+        n = C.c_int64()
+        _lib.check(self._lib.prb_ingest_hitran_csv(self._h, blob, len(blob), float(wave_min), float(wave_max),
+                                                   C.byref(n)))
+        self.n_lines = n.value
+        self.n_groups = 1
+        return n.value
+
+    def download_lines(self):
+        """The device-resident line list as SoA float64 columns (hitran_io.LINE_COLUMNS)."""
+        n = int(self._lib.prb_line_count(self._h))
+        if n < 0:
+            raise _lib.EngineError(-3, "no line list on the device")
+        names = ("nu", "sw", "a", "elower", "gamma_air", "gamma_self", "delta_air", "n_air")
+        cols = {k: np.empty(n) for k in names}
+        _lib.check(self._lib.prb_download_lines(self._h, *[_dp(cols[k]) for k in names]))
+        return cols
+
     def set_grid(self, range_min, res, n_total, i_begin=0, i_end=None):
         i_end = n_total if i_end is None else i_end
         _lib.check(self._lib.prb_set_grid(self._h, float(range_min), float(res), int(n_total), int(i_begin),

@@ -35,31 +35,44 @@ def _rows(path):
     return rows
 
 
-def gather_lines(global_iso, wave_min, wave_max, root=None):
-    """All lines with wave_min < nu < wave_max (strict, as the reference) from the 100 cm-1 segment files,
-    as SoA float64 arrays ascending in nu.  Duplicate wavenumbers collapse, last one wins (the reference
-    keys a dict by nu)."""
+def segment_paths(global_iso, wave_min, wave_max, root=None):
+    """The 100 cm-1 segment files gatherData walks (pyradUtilities.py:173-187): int(min/100)*100, +100, ... < max."""
     seg = int(wave_min / 100) * 100
-    found = {}
+    out = []
     while seg < wave_max:
-        path = os.path.join(data_dir(root), str(global_iso), "%d.pyr" % seg)
+        out.append(os.path.join(data_dir(root), str(global_iso), "%d.pyr" % seg))
+        seg += 100
+    return out
+
+
+def gather_text(global_iso, wave_min, wave_max, root=None):
+    """Raw bytes of the segment files, concatenated in segment order, for the device parser
+    (prb_ingest_hitran_csv).  A file that is absent is an error (pyrad_b200 never downloads); a file tagged
+    empty by the reference (NULL_TAG in its first row, openReturnLines :98) contributes nothing."""
+    parts = []
+    for path in segment_paths(global_iso, wave_min, wave_max, root):
         if not os.path.isfile(path):
             raise FileNotFoundError("%s is missing (pyrad_b200 never downloads; seed the data tree first)" % path)
-        rows = _rows(path)
-        for row in rows or ():
-            c = row.split(",")
-            if len(c) < 10 or row.startswith("#"):
-                continue
-            nu = float(c[2])
-            if wave_min < nu < wave_max:
-                found[nu] = (float(c[3]), float(c[4]), float(c[5]), float(c[6]), float(c[7]), float(c[8]), float(c[9]))
-        seg += 100
-    nus = list(found.keys())                      # insertion order == file order (ascending), like the reference
-    vals = np.array([found[n] for n in nus], dtype=np.float64).reshape(len(nus), 7)
-    out = {"nu": np.array(nus, dtype=np.float64)}
-    for j, k in enumerate(LINE_COLUMNS[1:]):
-        out[k] = np.ascontiguousarray(vals[:, j]) if len(nus) else np.zeros(0)
-    return out
+        with open(path, "rb") as f:
+            blob = f.read()
+        head = blob.split(b"\n", 1)[0]
+        if not blob or NULL_TAG.encode() in head:
+            continue
+        if not blob.endswith(b"\n"):
+            blob += b"\n"
+        parts.append(blob)
+    return b"".join(parts)
+
+
+def gather_lines(global_iso, wave_min, wave_max, root=None, engine=None):
+    """All lines with wave_min < nu < wave_max (strict, as the reference) from the 100 cm-1 segment files, as SoA
+    float64 arrays in file order; duplicate wavenumbers collapse, last one wins (the reference keys a dict by nu).
+    The text is parsed ON THE DEVICE (K5, exact decimal -> double conversion); the columns come back for the
+    host-side Line objects and stay resident as the engine's line list."""
+    if engine is None:
+        raise ValueError("gather_lines needs the CUDA engine (there is no host parser in this package)")
+    engine.ingest_csv(gather_text(global_iso, wave_min, wave_max, root), wave_min, wave_max)
+    return engine.download_lines()
 
 
 def read_q_table(global_iso, root=None):
