@@ -156,6 +156,10 @@ int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
 int prb_atmosphere_result_dev(prb_engine *e, void **radiance_dev, void **transmittance_dev); /* float[chunk] each */
 int prb_atmosphere_read(prb_engine *e, double *radiance_host, double *transmittance_host);
 int prb_atmosphere_read_f32(prb_engine *e, float *radiance_host, float *transmittance_host);   /* no widening */
+/* Zero-copy delivery: register PINNED, 16-byte aligned host buffers (n_points floats each); every following
+ * prb_atmosphere also stores its finished spectra there from inside the kernels (tile by tile over PCIe while the
+ * line sum is still running), so no read call is needed.  Pass NULL, NULL, 0 to switch it off. */
+int prb_set_result_host(prb_engine *e, float *radiance_host, float *transmittance_host, int64_t n_points);
 /* stage timing: CUDA events on the engine stream, summed over layers, of the last prb_atmosphere */
 int prb_set_timing(prb_engine *e, int enabled);
 int prb_atmosphere_timing(prb_engine *e, float *k1_ms, float *k2_ms, float *k3_ms);

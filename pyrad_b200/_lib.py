@@ -59,6 +59,7 @@ PROTOTYPES = {
     "prb_atmosphere_result_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "prb_atmosphere_read": (C.c_int, [_vp, _dp, _dp]),
     "prb_atmosphere_read_f32": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "prb_set_result_host": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _i64]),
     "prb_set_timing": (C.c_int, [_vp, C.c_int]),
     "prb_atmosphere_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "prb_atmosphere_layer_timing": (C.c_int, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

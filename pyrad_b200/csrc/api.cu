@@ -3,6 +3,7 @@
 #include "../../include/pyrad_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -84,6 +85,20 @@ struct PeerState {
 constexpr int RING = 16;
 constexpr size_t PEER_HEADER = 4096;         // flags[2][K2_MAX_PEERS] + error word, then the float buffers
 
+struct IngestScratch {
+    DevBuf<char> text;
+    DevBuf<unsigned char> nl, state, tmp;
+    DevBuf<int32_t> keep, pos;
+    DevBuf<int64_t> nlpos;
+    DevBuf<unsigned long long> scal;
+    DevBuf<double> cols[8];
+    void release() {
+        text.release(); nl.release(); state.release(); tmp.release(); keep.release(); pos.release(); nlpos.release();
+        scal.release();
+        for (auto &c : cols) c.release();
+    }
+};
+
 struct prb_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -121,6 +136,7 @@ struct prb_engine {
     int64_t rec_budget_mb = 0;   // 0 = auto (a quarter of the free memory)
     PeerState peer;
     DevBuf<unsigned int> peer_err;
+    IngestScratch ingest;
     // pinned ring of single-layer K2 table rows (prb_line_sum_dev is enqueue-only)
     unsigned char *blk_h = nullptr;                   // pinned staging of prb_atmosphere's small tables
     size_t blk_cap = 0;
@@ -136,6 +152,8 @@ struct prb_engine {
     // atmosphere
     DevBuf<float> kmat, rad, trans;
     float *res_rad = nullptr, *res_trans = nullptr;   // where the last prb_atmosphere left its spectra
+    float *host_rad_dev = nullptr, *host_trans_dev = nullptr;   // device views of the caller's pinned result buffers
+    int64_t host_result_len = 0;
     int last_launches = 0;                            // kernels launched by the last prb_atmosphere
     DevBuf<FoldLayer> fold;
     int64_t kmat_ld = 0;
@@ -204,6 +222,7 @@ extern "C" int prb_destroy(prb_engine *e) {
     e->k2tab.release(); e->ring_d.release(); e->peer_err.release();
     if (e->blk_h) cudaFreeHost(e->blk_h);
     e->blk_d.release();
+    e->ingest.release();
     if (e->ring_h) { cudaFreeHost(e->ring_h); for (auto x : e->ring_ev) if (x) cudaEventDestroy(x); }
     peer_release(e);
     for (auto x : e->ev) cudaEventDestroy(x);
@@ -789,6 +808,8 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
     if (rc) return rc;
     PeerState &ps = e->peer;
     if (ps.connected && nc > ps.ld) return fail(PRB_ERR_ARG, "prb_atmosphere: owned chunk exceeds the peer gather slot");
+    if (e->host_rad_dev && nc > e->host_result_len)
+        return fail(PRB_ERR_ARG, "prb_atmosphere: owned chunk exceeds the host result buffers (prb_set_result_host)");
 
     // Everything small the kernels of this call read -- status blocks (zeroed: flags + tile counters), per-(layer,
     // group) params, fold constants, the K2 launch table (K1's is a kernel parameter) -- is built in ONE pinned block and uploaded with
@@ -875,6 +896,11 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
         dst.trans[0] = e->trans.p;
         e->res_rad = e->rad.p;
         e->res_trans = e->trans.p;
+    }
+    if (e->host_rad_dev) {                                      // zero-copy result delivery (prb_set_result_host)
+        dst.rad[dst.n] = e->host_rad_dev;
+        dst.trans[dst.n] = e->host_trans_dev;
+        ++dst.n;
     }
     const double dx = e->n_total > 1 ? (range_max - e->range_min) / (double)(e->n_total - 1) : 0.0;
     const bool fused = n_layers == 1 && e->fuse_single && !jobs[0].narrow && e->k2_variant == PRB_K2_CLASSED;
@@ -1228,19 +1254,26 @@ extern "C" int prb_ingest_hitran_csv(prb_engine *e, const char *text, int64_t n_
     if (n_bytes < 0 || (n_bytes > 0 && !text)) return fail(PRB_ERR_ARG, "prb_ingest_hitran_csv: bad arguments");
     if (n_bytes > (int64_t(1) << 36)) return fail(PRB_ERR_ARG, "prb_ingest_hitran_csv: more than 64 GiB of text; ingest in pieces");
     CK(cudaSetDevice(e->device));
-    const int64_t n_pad = std::max<int64_t>((n_bytes + 15) & ~int64_t(15), 16);
-    DevBuf<char> d_text;
-    DevBuf<unsigned char> d_nl, d_state;
-    DevBuf<int32_t> d_keep, d_pos;
-    DevBuf<int64_t> d_nlpos;
-    DevBuf<unsigned long long> d_scal;          // [0] newline count, [1] first bad row, [2] smax bits, [3] unsorted flag, [4] selected
-    DevBuf<unsigned char> d_tmp;
-    DevBuf<double> t[8];
-    auto cleanup = [&]() {
-        d_text.release(); d_nl.release(); d_state.release(); d_keep.release(); d_pos.release(); d_nlpos.release();
-        d_scal.release(); d_tmp.release();
-        for (auto &x : t) x.release();
+    const bool trace = getenv("PRB_INGEST_TIMING") != nullptr;           // development aid: phase times on stderr
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prev = now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(e->stream);
+        const double t = now();
+        fprintf(stderr, "[ingest] %-28s %8.3f ms\n", what, t - t_prev);
+        t_prev = t;
     };
+    const int64_t n_pad = std::max<int64_t>((n_bytes + 15) & ~int64_t(15), 16);
+    // scratch lives in the engine and only grows (device allocation is far slower than the parse itself)
+    IngestScratch &g = e->ingest;
+    DevBuf<char> &d_text = g.text;
+    DevBuf<unsigned char> &d_nl = g.nl, &d_state = g.state, &d_tmp = g.tmp;
+    DevBuf<int32_t> &d_keep = g.keep, &d_pos = g.pos;
+    DevBuf<int64_t> &d_nlpos = g.nlpos;
+    DevBuf<unsigned long long> &d_scal = g.scal;   // [0] newline count, [1] first bad row, [2] smax bits, [3] unsorted flag, [4] selected
+    DevBuf<double> *t = g.cols;
+    auto cleanup = [&]() {};
 #define CKI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); char b_[512]; \
         snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
         return fail(PRB_ERR_CUDA, b_); } } while (0)
@@ -1251,10 +1284,12 @@ extern "C" int prb_ingest_hitran_csv(prb_engine *e, const char *text, int64_t n_
     if (n_bytes) CKI(cudaMemcpyAsync(d_text.p, text, n_bytes, cudaMemcpyHostToDevice, e->stream));
     unsigned long long h_scal[8] = {0, ~0ull, 0, 0, 0, 0, 0, 0};
     CKI(cudaMemcpyAsync(d_scal.p, h_scal, sizeof h_scal, cudaMemcpyHostToDevice, e->stream));
+    lap("alloc + H2D text");
     k5_mark_newlines<<<(unsigned)((n_pad / 16 + 255) / 256), 256, 0, e->stream>>>(d_text.p, n_bytes, d_nl.p, d_scal.p);
     CKI(cudaGetLastError());
     CKI(cudaMemcpyAsync(h_scal, d_scal.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     CKI(cudaStreamSynchronize(e->stream));
+    lap("mark newlines");
     const int64_t n_nl = (int64_t)h_scal[0];
     const int64_t n_rows = n_nl + ((n_bytes > 0 && text[n_bytes - 1] != '\n') ? 1 : 0);
     int64_t n_kept = 0;
@@ -1267,14 +1302,16 @@ extern "C" int prb_ingest_hitran_csv(prb_engine *e, const char *text, int64_t n_
         CKI(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, counting, d_nl.p, d_nlpos.p, d_selected, n_bytes, e->stream));
         CKI(d_tmp.ensure(tmp_bytes));
         CKI(cub::DeviceSelect::Flagged(d_tmp.p, tmp_bytes, counting, d_nl.p, d_nlpos.p, d_selected, n_bytes, e->stream));
-        for (auto &x : t) CKI(x.ensure(n_rows));
+        lap("newline positions (CUB)");
+        for (int c = 0; c < 8; ++c) CKI(t[c].ensure(n_rows));
         CKI(d_state.ensure(n_rows));
         CKI(d_keep.ensure(n_rows));
         CKI(d_pos.ensure(n_rows + 1));
         IngestCols tc{t[0].p, t[1].p, t[2].p, t[3].p, t[4].p, t[5].p, t[6].p, t[7].p};
-        k5_parse_rows<<<(unsigned)((n_rows + 127) / 128), 128, 0, e->stream>>>(d_text.p, n_bytes, d_nlpos.p, n_nl, n_rows, wave_min,
+        k5_parse_rows<<<(unsigned)((n_rows + K5_ROWS - 1) / K5_ROWS), K5_ROWS, 0, e->stream>>>(d_text.p, n_bytes, d_nlpos.p, n_nl, n_rows, wave_min,
                                                                              wave_max, tc, d_state.p, d_scal.p + 1);
         CKI(cudaGetLastError());
+        lap("alloc rows + parse");
         k5_resolve_duplicates<<<(unsigned)((n_rows + 255) / 256), 256, 0, e->stream>>>(t[0].p, d_state.p, n_rows, d_keep.p);
         CKI(cudaGetLastError());
         // exclusive scan of the keep flags -> output slots
@@ -1292,6 +1329,7 @@ extern "C" int prb_ingest_hitran_csv(prb_engine *e, const char *text, int64_t n_
             return fail(PRB_ERR_PARSE, "prb_ingest_hitran_csv: row " + std::to_string(h_scal[1]) +
                                            " is not a HITRAN-online CSV row (10 comma-separated fields, plain decimal numbers)");
         }
+        lap("duplicates + scan");
         n_kept = (int64_t)last_pos + last_keep;
         e->lines_set = false;
         int rc = alloc_line_storage(e, n_kept);
@@ -1311,8 +1349,10 @@ extern "C" int prb_ingest_hitran_csv(prb_engine *e, const char *text, int64_t n_
         int rc = alloc_line_storage(e, 0);
         if (rc) { cleanup(); return rc; }
     }
+        lap("scatter + finalize");
 #undef CKI
     cleanup();
+    lap("free");
     if (h_scal[3] & 0xffffffffull) return fail(PRB_ERR_ARG, "prb_ingest_hitran_csv: wavenumbers are not ascending");
     double smax;
     memcpy(&smax, &h_scal[2], sizeof smax);
@@ -1346,4 +1386,32 @@ extern "C" int64_t prb_line_count(prb_engine *e) { return (e && e->lines_set) ? 
 extern "C" int prb_debug_parse_double(const char *text, int64_t n_bytes, double *value) {
     if (!text || !value || n_bytes < 0) return PRB_ERR_ARG;
     return parse_double(text, text + n_bytes, value) ? PRB_OK : PRB_ERR_PARSE;
+}
+
+// Zero-copy result delivery: the kernels that finish the spectra (K2's fused epilogue / K3) also store them into
+// the caller's PINNED host buffers (TMA bulk stores over PCIe, tile by tile while the rest of the line sum runs),
+// so when prb_atmosphere returns the results are already in host memory -- no separate device-to-host copy.
+extern "C" int prb_set_result_host(prb_engine *e, float *radiance_host, float *transmittance_host, int64_t n_points) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (!radiance_host && !transmittance_host) {                  // switch off
+        e->host_rad_dev = e->host_trans_dev = nullptr;
+        e->host_result_len = 0;
+        return PRB_OK;
+    }
+    if (!radiance_host || !transmittance_host || n_points < 1)
+        return fail(PRB_ERR_ARG, "prb_set_result_host: both buffers and their length are required");
+    if (((uintptr_t)radiance_host | (uintptr_t)transmittance_host) & 15)
+        return fail(PRB_ERR_ARG, "prb_set_result_host: buffers must be 16-byte aligned");
+    CK(cudaSetDevice(e->device));
+    void *dr = nullptr, *dt = nullptr;
+    if (cudaHostGetDevicePointer(&dr, radiance_host, 0) != cudaSuccess ||
+        cudaHostGetDevicePointer(&dt, transmittance_host, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PRB_ERR_ARG, "prb_set_result_host: buffers must be pinned host memory (cudaHostAlloc / cudaHostRegister / "
+                                 "torch pin_memory); pageable memory cannot be written from the device");
+    }
+    e->host_rad_dev = (float *)dr;
+    e->host_trans_dev = (float *)dt;
+    e->host_result_len = n_points;
+    return PRB_OK;
 }

@@ -147,15 +147,16 @@ struct K2Layer {
 // tile -- k -> T = exp(-k u), I = B_l + T (B_surface - B_l) -- and the finished spectra stored straight into
 // every rank's gather buffer over NVLink peer memory (tile by tile, overlapping the remaining line sums).
 constexpr int K2_MAX_PEERS = 8;
+constexpr int K2_MAX_DST = K2_MAX_PEERS + 1;   // every rank's gather buffer + the caller's pinned host result buffers
 struct K2Fuse {
     int enabled;
-    int n_dst;                           // 1 (local only) .. K2_MAX_PEERS
+    int n_dst;                           // 1 (local only) .. K2_MAX_DST
     float neg_depth_log2e;               // -depth * log2(e)
     float c2_over_t, c2_over_tsurf;      // 100 h c / kB / T
     long long n_total;                   // points of the FULL grid (np.linspace axis)
     double x0, dx, x_last;
-    float *rad[K2_MAX_PEERS];            // per destination: this rank's slot of the radiance gather buffer
-    float *trans[K2_MAX_PEERS];
+    float *rad[K2_MAX_DST];              // per destination: this rank's slot of the radiance gather buffer
+    float *trans[K2_MAX_DST];
 };
 
 struct K2Args {

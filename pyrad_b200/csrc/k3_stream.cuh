@@ -106,7 +106,8 @@ __device__ __forceinline__ float planck_f32(float a_nu3, float x) {
 
 // Destinations of the finished spectra: this rank's slot in every rank's gather buffer (peer memory over
 // NVLink; stores are fire-and-forget), or just the local result arrays when no peers are connected.
-constexpr int K3_MAX_DST = 8;
+constexpr int K3_MAX_PEERS = 8;
+constexpr int K3_MAX_DST = K3_MAX_PEERS + 1;          // + the caller's pinned host result buffers (zero-copy)
 struct K3Dst {
     int n;
     float *rad[K3_MAX_DST];
@@ -180,7 +181,7 @@ k3_fold_f32(const float *__restrict__ kmat, int64_t ld, int n_layers, const Fold
 // gather buffer is complete.  A peer that never arrives trips the timeout and sets *err (reported by the host
 // as PRB_ERR_PEER) instead of hanging the GPU.
 struct PeerSignal {
-    unsigned int *flags[K3_MAX_DST];   // every rank's flag block (own one included), [2][K3_MAX_DST] words each
+    unsigned int *flags[K3_MAX_PEERS]; // every rank's flag block (own one included), [2][K3_MAX_PEERS] words each
     int rank, world;
     unsigned int epoch;
     unsigned int *err;
@@ -192,9 +193,9 @@ __global__ void k_peer_signal_wait(const PeerSignal s) {
     if (p >= s.world) return;
     const int par = s.epoch & 1u;
     __threadfence_system();
-    unsigned int *remote = s.flags[p] + par * K3_MAX_DST + s.rank;
+    unsigned int *remote = s.flags[p] + par * K3_MAX_PEERS + s.rank;
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(s.epoch) : "memory");
-    const unsigned int *mine = s.flags[s.rank] + par * K3_MAX_DST + p;
+    const unsigned int *mine = s.flags[s.rank] + par * K3_MAX_PEERS + p;
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (true) {

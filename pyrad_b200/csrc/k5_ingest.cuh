@@ -52,15 +52,34 @@ k5_mark_newlines(const char *__restrict__ text, int64_t n, unsigned char *__rest
 
 // Row r spans [start_r, end_r): start_0 = 0, start_r = nl_pos[r-1] + 1; end_r = nl_pos[r] (or n for a last row
 // without a trailing newline).
-__global__ void __launch_bounds__(128)
+constexpr int K5_ROWS = 128;            // rows (threads) per block
+constexpr int K5_STAGE = 24 * 1024;     // shared-memory staging of the block's rows (they are contiguous in the text)
+
+__global__ void __launch_bounds__(K5_ROWS)
 k5_parse_rows(const char *__restrict__ text, int64_t n, const int64_t *__restrict__ nl_pos, int64_t n_nl, int64_t n_rows,
               double wave_min, double wave_max, IngestCols tmp, unsigned char *__restrict__ state,
               unsigned long long *__restrict__ first_bad) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(16) char stage[K5_STAGE];
+    // the block's rows [r0, r1) are one contiguous byte range: pull it into shared memory with coalesced 16-byte
+    // loads, then every thread walks its own row there (byte-wise walks of global memory do not coalesce)
+    const int64_t r0 = (int64_t)blockIdx.x * K5_ROWS;
+    const int64_t r1 = min(r0 + (int64_t)K5_ROWS, n_rows);
+    const int64_t blk_b = r0 == 0 ? 0 : nl_pos[r0 - 1] + 1;
+    const int64_t blk_e = (r1 - 1) < n_nl ? nl_pos[r1 - 1] : n;
+    const int64_t a0 = blk_b & ~int64_t(15);
+    const bool staged = blk_e - a0 <= K5_STAGE;
+    if (staged) {
+        const int64_t span = (blk_e - a0 + 15) & ~int64_t(15);              // the text buffer is padded to 16 bytes
+        for (int64_t i = (int64_t)threadIdx.x * 16; i < span; i += (int64_t)K5_ROWS * 16)
+            *reinterpret_cast<uint4 *>(stage + i) = *reinterpret_cast<const uint4 *>(text + a0 + i);
+    }
+    __syncthreads();
+    const int64_t r = r0 + threadIdx.x;
     if (r >= n_rows) return;
     const int64_t b = r == 0 ? 0 : nl_pos[r - 1] + 1;
     const int64_t e = r < n_nl ? nl_pos[r] : n;
-    const char *p = text + b, *end = text + e;
+    const char *base = staged ? stage - a0 : text;
+    const char *p = base + b, *end = base + e;
     unsigned char st = ROW_BAD;
     if (p < end && *p == '#') {
         st = ROW_SKIP;                                            // comment row

@@ -236,6 +236,16 @@ class Engine:
             self._h, rad.ctypes.data_as(fp) if rad is not None else None,
             tr.ctypes.data_as(fp) if tr is not None else None))
 
+    def set_result_host(self, rad=None, tr=None):
+        """Register pinned float32 host arrays that every following atmosphere() fills directly from the device
+        kernels (zero-copy); call with no arguments to switch it off."""
+        fp = C.POINTER(C.c_float)
+        if rad is None and tr is None:
+            _lib.check(self._lib.prb_set_result_host(self._h, None, None, 0))
+            return
+        assert rad.dtype == np.float32 and tr.dtype == np.float32 and rad.size == tr.size
+        _lib.check(self._lib.prb_set_result_host(self._h, rad.ctypes.data_as(fp), tr.ctypes.data_as(fp), rad.size))
+
     def set_timing(self, enabled=True):
         _lib.check(self._lib.prb_set_timing(self._h, int(bool(enabled))))
 

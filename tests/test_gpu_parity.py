@@ -317,3 +317,24 @@ def test_atmosphere_integrals_on_device(engine):
     integ, tsum = engine.atmosphere_integrate(np.pi, w["res"])
     assert integ == pytest.approx(float(np.sum(np.nan_to_num(rad.astype(np.float64))) * np.pi * w["res"]), rel=1e-12)
     assert tsum == pytest.approx(float(np.sum(tr.astype(np.float64))), rel=1e-12)
+
+
+@pytest.mark.parametrize("n_layers,top", [(1, 2.0), (5, 40.0)])
+def test_zero_copy_host_results_equal_read_back(engine, n_layers, top):
+    """prb_set_result_host: the kernels store the finished spectra into pinned host memory themselves (K2's fused
+    epilogue for one layer, K3 otherwise); the bytes must equal an explicit read-back."""
+    import torch
+    w = workloads.atmosphere(n_layers=n_layers, n_lines=6000, rmin=600.0, rmax=650.0, res=0.001, top_km=top)
+    H.engine_setup(engine, w)
+    rad_ref, tr_ref = _run_atm(engine, w)
+    h_rad = torch.zeros(engine.n_chunk, dtype=torch.float32).pin_memory()
+    h_tr = torch.zeros(engine.n_chunk, dtype=torch.float32).pin_memory()
+    engine.set_result_host(h_rad.numpy(), h_tr.numpy())
+    try:
+        rad, tr = _run_atm(engine, w)
+        assert np.array_equal(h_rad.numpy(), rad_ref) and np.array_equal(h_tr.numpy(), tr_ref)
+        assert np.array_equal(rad, rad_ref) and np.array_equal(tr, tr_ref)      # the device copy is still there
+        with pytest.raises(Exception):
+            engine.set_result_host(np.zeros(engine.n_chunk, dtype=np.float32), np.zeros(engine.n_chunk, dtype=np.float32))
+    finally:
+        engine.set_result_host()
