@@ -14,6 +14,7 @@
 #include "k1_prepass.cuh"
 #include "k2_line_sum.cuh"
 #include "k2_narrow.cuh"
+#include "k2_point.cuh"
 #include "k3_stream.cuh"
 #include "k4_derived.cuh"
 #include "k5_ingest.cuh"
@@ -132,6 +133,7 @@ struct prb_engine {
     int k2_variant = PRB_K2_CLASSED, k2_ppt = 0;
     int64_t narrow_wm = 100;     // windows with W-2 below this use k2_narrow
     bool batch_layers = true;    // prb_atmosphere: one K1 launch + one K2 launch per kernel class
+    bool point_kernel = true;    // windows up to 511 points: k2_point instead of k2_narrow
     bool fuse_single = true;     // single wide layer: layer physics + peer stores in K2's epilogue
     int64_t rec_budget_mb = 0;   // 0 = auto (a quarter of the free memory)
     PeerState peer;
@@ -442,7 +444,12 @@ static LayerJob plan_job(const prb_engine *e, double T, double P, int64_t W, dou
     j.l0 = std::lower_bound(hb, hb + n, klo, [](int32_t a, int64_t k) { return (int64_t)a < k; }) - hb;
     j.l1 = std::upper_bound(hb, hb + n, khi, [](int64_t k, int32_t a) { return k < (int64_t)a; }) - hb;
     if (j.l1 < j.l0) j.l1 = j.l0;
-    j.narrow = (e->k2_variant == PRB_K2_CLASSED && j.wm < e->narrow_wm) ? 1 : 0;
+    // kernel kind: 0 = k2_line_sum (wide), 2 = k2_point (table-driven thread-per-point, 16 <= W-2 <= 511),
+    // 1 = k2_narrow (binary-search thread-per-point: windows of a few points, where building the table costs more
+    //     than it saves -- measured on B200 -- and forced thresholds above 511)
+    j.narrow = 0;
+    if (e->k2_variant == PRB_K2_CLASSED && j.wm < e->narrow_wm)
+        j.narrow = (e->point_kernel && j.wm >= KP_MIN_WM && j.wm <= KP_MAX_WM) ? 2 : 1;
     j.ppt = pick_ppt(e, j.wm);
     j.valid = true;
     return j;
@@ -631,6 +638,23 @@ static int run_line_sum(prb_engine *e, const LayerJob *jobs, int n, const K2Laye
     a.st = jobs[0].st_dev;
     if (fuse) a.fuse = *fuse;
     cudaError_t ce;
+    if (jobs[0].narrow == 2) {
+        static bool kp_attr = false;
+        if (!kp_attr) {
+            CK(cudaFuncSetAttribute(k2_point, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KPSmem)));
+            kp_attr = true;
+        }
+        a.n_tiles = (a.n_chunk + KP_TILE - 1) / KP_TILE;
+        for (int k0 = 0; k0 < n && a.n_tiles > 0; k0 += 65535) {        // grid.y limit
+            K2Args b = a;
+            b.layers = tab_dev + k0;
+            b.n_layers = std::min(n - k0, 65535);
+            k2_point<<<dim3((unsigned)a.n_tiles, (unsigned)b.n_layers), KP_THREADS, sizeof(KPSmem), e->stream>>>(b);
+        }
+        ce = cudaGetLastError();
+        if (ce != cudaSuccess) return fail(PRB_ERR_CUDA, std::string("k2_point launch failed: ") + cudaGetErrorString(ce));
+        return PRB_OK;
+    }
     if (jobs[0].narrow) {
         a.n_tiles = (a.n_chunk + KN_TILE - 1) / KN_TILE;
         for (int k0 = 0; k0 < n && a.n_tiles > 0; k0 += 65535) {        // grid.y limit
@@ -1082,6 +1106,7 @@ extern "C" int prb_set_option(prb_engine *e, int option, int64_t value) {
     switch (option) {
         case PRB_OPT_BATCH_LAYERS: e->batch_layers = value != 0; return PRB_OK;
         case PRB_OPT_FUSE_SINGLE_LAYER: e->fuse_single = value != 0; return PRB_OK;
+        case PRB_OPT_POINT_KERNEL: e->point_kernel = value != 0; e->last.valid = false; return PRB_OK;
         case PRB_OPT_RECORD_BUDGET_MB: e->rec_budget_mb = value < 0 ? 0 : value; return PRB_OK;
         default: return fail(PRB_ERR_ARG, "prb_set_option: unknown option");
     }

@@ -133,6 +133,7 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
         if (in_range && !real) {                                  // padding record: never in a window
             if (K.narrow) {
                 K.recA[l] = make_float4(-K2_SENTINEL, 0.f, 1.f, 0.f);
+                reinterpret_cast<float2 *>(K.recB)[l] = make_float2(-1.f, -1.f);
             } else {
                 K.recA[l] = make_float4(-K2_SENTINEL, -K2_SENTINEL, 0.f, 0.f);
                 K.recB[l] = make_float4(1.f, 1.f, 0.f, -1.f);
@@ -234,8 +235,9 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
             // the triple-reciprocal path forms |A| q^2 and q^3
             else if (fabs(A) * qmax * qmax > 8.0e37 || fabs(G) > 8.0e37 || qmax * qmax * qmax > 8.0e37) flags |= FLAG_OVERFLOW;
             const float Af = (float)A, Bf = (float)B;
-            if (K.narrow) {                                       // compact layout of k2_narrow
+            if (K.narrow) {                                       // compact layout of k2_point / k2_narrow
                 K.recA[l] = make_float4(nf, Af, Bf, (float)G);
+                reinterpret_cast<float2 *>(K.recB)[l] = make_float2((float)C, dg);
                 K.recD[l] = (float)C;
             } else {
                 K.recA[l] = make_float4(nf, nf, Af, Af);

@@ -16,6 +16,10 @@ def main():
     win = [eng.window_len(c, w["res"]) for c in w["cutoff"]]
     qt = np.array([[s.q(T) for s in sp] for T in w["T"]])
     e.set_timing(True)
+    if os.environ.get("QA_OLDNARROW"):
+        e.set_option(eng.OPT_POINT_KERNEL, 0)
+    if os.environ.get("QA_NARROW"):
+        e.set_narrow_threshold(int(os.environ["QA_NARROW"]))
     if os.environ.get("QA_NOBATCH"):
         e.set_option(eng.OPT_BATCH_LAYERS, 0)      # per-layer launches: exact per-layer timings
     args = (w["depth_cm"], w["T"], w["P"], w["conc"], [s.molmass for s in sp], qt, [s.q296 for s in sp], win, w["t_surface"], w["range_max"])
@@ -27,7 +31,7 @@ def main():
     idx = pt.line_index(w["lines"]["nu"], w["range_min"], w["res"])
     print("total %.1f ms  %s  clocks %s" % (dt * 1e3, e.atmosphere_timing(), clocks))
     for l in range(L):
-        if l < 12 or l % 10 == 0:
+        if l < 12 or l % 10 == 0 or os.environ.get("QA_ALL"):
             pairs = pt.block_pair_cost(idx, n, [win[l]]).sum()
             print("layer %3d P=%8.3f W=%5d k1 %.3f ms k2 %.3f ms pairs %.3e  %.3e pairs/s" % (l, w["P"][l], win[l], k1[l], k2[l], pairs, pairs / (k2[l] * 1e-3)))
 

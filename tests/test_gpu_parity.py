@@ -165,10 +165,12 @@ def test_atmosphere_small(engine):
     np.testing.assert_allclose(rad, I, rtol=2e-5)
 
 
-@pytest.mark.parametrize("P", [150.0, 30.0, 2.0])
+@pytest.mark.parametrize("P", [300.0, 150.0, 30.0, 2.0])
 def test_k2_narrow_kernel_matches_wide_kernel_and_oracle(engine, P):
-    """Upper-atmosphere windows take the thread-per-point kernel (k2_narrow); forcing the wide kernel on the
-    same inputs must agree, and both must match the oracle.  Shard invariance holds for it as well."""
+    """Upper-atmosphere windows take the thread-per-point kernels (k2_point with table-driven line ranges up to
+    W-2 = 511, here P <= 150; k2_narrow with binary searches above that, here P = 300 with the threshold forced);
+    forcing the wide kernel on the same inputs must agree, and both must match the oracle.  Shard invariance holds
+    for them as well."""
     w = workloads.gas_cell(["co2", "h2o"], 6000, 600.0, 660.0, 0.0025, 240, P, [400e-6, 0.01], 10.0, 31)
     n = H.engine_setup(engine, w)
     ref = H.oracle_sigma_groups(w).sum(axis=0)
