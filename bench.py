@@ -32,6 +32,15 @@ SM_COUNT = 148
 SM_MAX_MHZ_DEFAULT = 1965.0
 
 
+def load_traffic(key):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/traffic.json)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
+        return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -395,7 +404,10 @@ def main():
                        "numerics": "FP64 prepass, FP32 lineshape evaluation, FP64 accumulation; k stored FP32"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": fp32_ach / fp32_peak, "traffic": None, "kernel": "k2_line_sum<8>",
+                         "frac": fp32_ach / fp32_peak, "traffic": load_traffic("k2_line_sum<8>@cfg2"),
+                         "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/traffic.json); the kernel is FP32-pipe "
+                                         "bound, its algorithmic DRAM traffic is the 18 MB of line records",
+                         "kernel": "k2_line_sum<8>",
                          "k2_ms": k2_t * 1e3, "k2_pairs_per_s": k2_pairs_s,
                          "peak_source": "nominal: 148 SM x 128 FP32 lanes x 2 x %.0f MHz (MEASURED_PEAKS.json has no FP32 "
                                         "figure; %s file used for the clock)" % (sm_max, peaks_kind),
@@ -522,7 +534,8 @@ def run_atmosphere(e, args, rank, world, ext, peaks, use_peer):
             "gather": "none" if world == 1 else ("peer stores fused into K3" if use_peer else "nccl"),
             "rank0_stage_ms": tim,
             "roofline_k3": {"bound": "hbm", "achieved": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                            "frac": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9 / hbm, "traffic": None,
+                            "frac": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9 / hbm,
+                            "traffic": load_traffic("k3_fold_f32@cfg4") if world == 1 and len(win) == 100 else None,
                             "algorithmic_bytes": k3_bytes}}
 
 

@@ -79,6 +79,31 @@ struct K1Table {
     K1Layer rows[K1_MAX_LAYERS];
 };
 
+// exp(x) for the arguments this kernel meets (|x| <= 700), coefficients in constant memory so that every DFMA takes
+// its constant straight from the constant bank (the profile of the library exp showed 28 % of K1's instructions
+// moving 64-bit immediates into registers).  x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor (remainder 4e-18),
+// result scaled by adding k to the exponent field.  ~2 ulp; the parity tests hold K1's outputs to 1e-12.
+__constant__ double K1_EXP[18] = {
+    1.4426950408889634,            // [0] log2(e)
+    6755399441055744.0,            // [1] 1.5 * 2^52: rounds to the nearest integer in the low word
+    -6.93147180369123816490e-01,   // [2] -ln2 (high part)
+    -1.90821492927058770002e-10,   // [3] -ln2 (low part)
+    1.0 / 6227020800.0,            // [4] 1/13!
+    1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
+    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+__device__ __forceinline__ double exp_k1(double x) {
+    if (!(fabs(x) <= 700.0)) return exp(x);                       // out of range / NaN: the library routine
+    const double t = fma(x, K1_EXP[0], K1_EXP[1]);
+    const int k = __double2loint(t);
+    const double kf = t - K1_EXP[1];
+    double r = fma(kf, K1_EXP[2], x);
+    r = fma(kf, K1_EXP[3], r);
+    double p = K1_EXP[4];
+#pragma unroll
+    for (int i = 5; i < 18; ++i) p = fma(p, r, K1_EXP[i]);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
 // f5^(-1/5) without log/exp/division: FP32 seed (two MUFU) and two Newton steps on g(r) = r^-5 - f5,
 //   r <- r (1 + (1 - f5 r^5)/5)   (quadratic: 1e-6 -> ~3e-12 -> below FP64 resolution).
 __device__ __forceinline__ double inv_fifth_root(double f5) {
@@ -123,7 +148,7 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
         nf = -(float)((double)((int64_t)idx[l] - i_base));
     }
     // exp(-c2 nu0 / t0): the layer-independent factor of the stimulated-emission denominator
-    const double e296 = exp(-c2 / kT0 * nu);
+    const double e296 = exp_k1(-c2 / kT0 * nu);
     const double neg_c2_e = -c2 * elower;
     const int n_layers = tab.n;
 #pragma unroll 1
@@ -149,7 +174,7 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
             const double dshift = delta * pp0;
             const double nus = nu + dshift;
             // (t0/T)^n = exp(n * log(t0/T)): the log is a per-layer constant
-            const double gl = ((1 - p.conc) * gair + p.conc * gself) * pp0 * exp(nair * K.lc.log_t0_over_t);
+            const double gl = ((1 - p.conc) * gair + p.conc * gself) * pp0 * exp_k1(nair * K.lc.log_t0_over_t);
             const double gd = nus * p.dopp;
             // regime (pyradClasses.py:378-387): ratio = gl / gd compared with .01 and 100.  Away from the two
             // thresholds products decide; within 1e-14 of one (or for gd <= 0: inf / negative ratios, as numpy)
@@ -169,10 +194,10 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
             // stimulated emission (1 - e^{-c2 nu*/T}) / (1 - e^{-c2 nu*/t0}); e^{-c2 nu*/t0} = e296 * e^{-c2 dshift/t0}
             const double x0 = K.lc.neg_c2_over_t0 * dshift;
             // (next to 0 cm^-1 the denominator cancels: keep the reference's own single exponential there)
-            const double e_t0 = (fabs(x0) <= 0.02 && nu > 1.0) ? e296 * exp_tiny(x0) : exp(K.lc.neg_c2_over_t0 * nus);
-            const double stim = (1 - exp(K.lc.neg_c2_over_t * nus)) / (1 - e_t0);
+            const double e_t0 = (fabs(x0) <= 0.02 && nu > 1.0) ? e296 * exp_tiny(x0) : exp_k1(K.lc.neg_c2_over_t0 * nus);
+            const double stim = (1 - exp_k1(K.lc.neg_c2_over_t * nus)) / (1 - e_t0);
             // exp(-c2 E/T) / exp(-c2 E/t0) evaluated as one exponential (same value to ~1e-16)
-            const double boltz = exp(neg_c2_e * K.lc.inv_t_minus_inv_t0);
+            const double boltz = exp_k1(neg_c2_e * K.lc.inv_t_minus_inv_t0);
             const double S = s296 * p.qratio * stim * boltz;
             const double sw = S * p.weight * K.scale;
             const double inv_res2 = K.lc.inv_res2;
