@@ -681,6 +681,45 @@ class Atmosphere(list):
             spectrum = layer.transmission(spectrum)
         return spectrum
 
+    def columnSpectrum(self, surfaceTemperature):
+        """The whole column on the device in ONE engine call (prb_atmosphere): K1 for every layer, the batched line
+        sums, and the fold  I <- T_l I + (1 - T_l) B(nu, T_l)  starting from I_0 = B(nu, surfaceTemperature).
+        Returns (radiance, total transmittance) on the layers' common grid.  Same physics as ``transmission`` above,
+        without one host round trip per layer and isotope; needs layers that share range and base resolution, carry
+        the same line-by-line molecules in the same order, and no xsc molecules."""
+        layers = list(self)
+        if not layers:
+            raise ValueError("atmosphere has no layers")
+        ref = layers[0]
+        for l in layers:
+            if (l.rangeMin, l.rangeMax) != (ref.rangeMin, ref.rangeMax) or l.resolution != BASE_RESOLUTION:
+                raise ValueError("columnSpectrum needs layers on one grid at the base resolution "
+                                 "(build them with dynamicResolution=False)")
+            if [iso.globalIsoNumber for m in l for iso in m if not m.exotic] != \
+                    [iso.globalIsoNumber for m in ref for iso in m if not m.exotic] or any(m.exotic for m in l):
+                raise ValueError("columnSpectrum needs the same line-by-line isotopologues in every layer and no xsc molecules")
+        # line source: the layer with the widest cutoff read the widest wavenumber range from the data tree
+        widest = max(layers, key=lambda l: l.distanceFromCenter)
+        isos = [iso for m in widest for iso in m]
+        cols = {k: np.concatenate([iso._cols[k] for iso in isos]) if isos else np.zeros(0)
+                for k in ("nu", "sw", "gamma_air", "gamma_self", "elower", "n_air", "delta_air")}
+        group = np.concatenate([np.full(len(iso._cols["nu"]), g, dtype=np.int32) for g, iso in enumerate(isos)]) \
+            if isos else np.zeros(0, dtype=np.int32)
+        order = np.argsort(cols["nu"], kind="stable")
+        lines = {k: np.ascontiguousarray(v[order]) for k, v in cols.items()}
+        lines["group"] = np.ascontiguousarray(group[order])
+        n = _n_base(ref)
+        e = engine()
+        e.upload_lines(lines, n_groups=max(len(isos), 1))
+        e.set_grid(ref.rangeMin, BASE_RESOLUTION, n)
+        conc = [[m.concentration for m in l for _ in m] for l in layers]
+        q_t = [[iso.q[l.T] for m in l for iso in m] for l in layers]          # KeyError on a non-tabulated T
+        window = [_eng.window_len(l.distanceFromCenter, BASE_RESOLUTION) for l in layers]
+        e.atmosphere([l.depth for l in layers], [l.T for l in layers], [l.P for l in layers], conc,
+                     [iso.molmass for iso in isos], q_t, [iso.q296 for iso in isos], window, surfaceTemperature,
+                     ref.rangeMax)
+        return e.atmosphere_read()
+
 
 def getGlobalIsotope(ID, isotopeDepth):
     return [HITRAN_GLOBAL_ISO[ID][i] for i in range(1, isotopeDepth + 1)]

@@ -117,3 +117,27 @@ def test_mirror_error_behaviour(data_root):
     assert H.k_rel_err(C.getCrossSection(m[0]), g["sigma_0"]).max() <= H.K_REL_TOL
     layer.changePressure(500.0)                                    # invalidates and recomputes (lazy cache)
     assert not m[0].progressCrossSection
+
+
+def test_mirror_column_spectrum_equals_layer_by_layer_transmission(data_root):
+    """Atmosphere.columnSpectrum (one prb_atmosphere call: batched K1/K2 + FP32 fold on the device) against the fold of
+    Layer.transmission through the host-buffer FP64 path, on the same data tree."""
+    g = G.load("cell_fine_grid")
+    species = [str(s) for s in g["species"]]
+    for i, s in enumerate(species):
+        seed(data_root, g, i, s)
+    C.BASE_RESOLUTION = float(g["base"])
+    atm = C.Atmosphere("column")
+    rmin, rmax = float(g["range_min"]), float(g["range_max"])
+    for depth, T, P in ((2e4, 280, 800.0), (3e4, 250, 300.0), (5e4, 220, 40.0), (8e4, 230, 3.0)):
+        layer = atm.addLayer(depth, T, P, rmin, rmax, dynamicResolution=False)
+        for s, c in zip(species, g["conc"]):
+            layer.addMolecule(s, concentration=float(c))
+    rad, trans = atm.columnSpectrum(288)
+    surface = atm[0].planck(288)
+    ref = atm.transmission(surface)
+    t_ref = np.ones_like(ref)
+    for layer in atm:
+        t_ref = t_ref * C.getTransmittance(layer)
+    assert np.abs(trans - t_ref).max() <= H.T_ABS_TOL
+    np.testing.assert_allclose(rad, ref, rtol=3e-5)
