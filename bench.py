@@ -340,9 +340,14 @@ def main():
     e.set_result_host(h_rad.numpy(), h_tr.numpy())     # zero-copy delivery: K2's epilogue stores into these pinned buffers
 
     def step_e2e():
-        e.upload_lines(lines_view, n_groups=len(sp))                                  # H2D: the step's inputs
-        e.set_grid(w["range_min"], w["res"], w["n_total"], w["i_begin"], w["i_end"])
-        step_device()                                                                 # D2H: finished tiles land in h_rad / h_tr
+        # ONE call, host buffers in, host buffers out: the line columns cross PCIe in wavenumber pieces while the
+        # earlier pieces' prepass and line sums already run (H2D), finished tiles land in h_rad / h_tr (D2H)
+        e.gas_cell_host(lines_view, len(sp), w["range_min"], w["res"], w["n_total"], w["i_begin"], w["i_end"],
+                        w["depth_cm"], T, P, conc[0], molmass, qt[0], q296, win, w["t_surface"], w["range_max"])
+        if world > 1 and not use_peer:
+            rad_ptr, tr_ptr = e.atmosphere_result_dev()
+            dist.all_gather_into_tensor(hold["gather"][0], pd.device_tensor(rad_ptr, n_chunk))
+            dist.all_gather_into_tensor(hold["gather"][1], pd.device_tensor(tr_ptr, n_chunk))
 
     for _ in range(2):
         step_e2e()
@@ -360,10 +365,10 @@ def main():
     e2e_s = float(te.item())
     n_l = e.n_lines
     h2d = n_l * (7 * 8 + 4) + 4 * 32 * len(sp)
-    d2h = 4 * (n_l + 8) + 2 * 4 * n_chunk + 16
+    d2h = 4 * (n_l + 20) + 2 * 4 * n_chunk + 16 * 8
     e2e = {"value": pairs_all / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / e2e_steps * 1e3,
-           "api": "prb_upload_lines + prb_set_grid + prb_atmosphere(L=1) with prb_set_result_host (pinned host buffers; results stored into them tile by tile from inside K2)"}
+           "api": "prb_gas_cell_host with prb_set_result_host: pinned host buffers in and out, line columns uploaded in wavenumber pieces under the compute, results stored into host memory tile by tile from inside K2"}
 
     # ---- secondary object: the 100-layer atmosphere (cfg4), strong-sharded by wavenumber chunk
     atm = None

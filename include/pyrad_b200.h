@@ -154,6 +154,17 @@ int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
                    const double *depth_cm, const double *t_layer, const double *p_layer,
                    const double *conc, const double *molmass, const double *q_t, const double *q_296,
                    const int64_t *window_len, double t_surface, double range_max);
+/* One call from HOST line columns to the spectra of one gas cell, with the host->device copies overlapped with the
+ * compute: = prb_upload_lines + prb_set_grid + prb_atmosphere(1 layer), bit for bit, but the columns cross PCIe in
+ * wavenumber pieces and each piece's prepass and line sum (one wave of K2 tiles) start as soon as it has landed.
+ * Combine with prb_set_result_host for results that arrive in host memory the same way (pinned buffers recommended
+ * for the inputs too).  Leaves the line list, grid and results on the device like the three separate calls. */
+int prb_gas_cell_host(prb_engine *e, int64_t n, const double *nu0, const double *s296, const double *gamma_air,
+                      const double *gamma_self, const double *elower, const double *n_air, const double *delta_air,
+                      const int32_t *group, int32_t n_groups, double range_min, double res, int64_t n_total,
+                      int64_t i_begin, int64_t i_end, double depth_cm, double t_layer, double p_layer,
+                      const double *conc, const double *molmass, const double *q_t, const double *q_296,
+                      int64_t window_len, double t_surface, double range_max);
 int prb_atmosphere_result_dev(prb_engine *e, void **radiance_dev, void **transmittance_dev); /* float[chunk] each */
 int prb_atmosphere_read(prb_engine *e, double *radiance_host, double *transmittance_host);
 int prb_atmosphere_read_f32(prb_engine *e, float *radiance_host, float *transmittance_host);   /* no widening */

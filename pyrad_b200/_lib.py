@@ -56,6 +56,8 @@ PROTOTYPES = {
     "prb_planck": (C.c_int, [_vp, _i64, _d, _d, _d, _d, _dp]),
     "prb_xsc_place": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.c_int, _d, _d, _i64, _dp, _dp, _dp]),
     "prb_atmosphere": (C.c_int, [_vp, _i32, _i32, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _lp, _d, _d]),
+    "prb_gas_cell_host": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _i32, _d, _d, _i64, _i64, _i64,
+                                    _d, _d, _d, _dp, _dp, _dp, _dp, _i64, _d, _d]),
     "prb_atmosphere_result_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "prb_atmosphere_read": (C.c_int, [_vp, _dp, _dp]),
     "prb_atmosphere_read_f32": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -68,6 +69,7 @@ struct LayerJob {
     int ppt = 8;                 // points per thread of k2_line_sum for this window
     int slot = 0;                // which slice of the record arrays holds this layer
     const GroupParams *gp_dev = nullptr;
+    const double *scale_dev = nullptr;   // pipelined upload: the scale is computed on the device
     DevState *st_dev = nullptr;
     void *out_dev = nullptr;
     bool valid = false;
@@ -139,6 +141,11 @@ struct prb_engine {
     PeerState peer;
     DevBuf<unsigned int> peer_err;
     IngestScratch ingest;
+    // pipelined host upload (prb_gas_cell_host)
+    cudaStream_t copy_stream = nullptr, stream2 = nullptr;
+    std::vector<cudaEvent_t> pipe_ev;
+    unsigned long long *pin_scal = nullptr;           // pinned: [0] max|S296| bits, [1] validation flags
+    DevBuf<unsigned long long> dev_scal;
     // pinned ring of single-layer K2 table rows (prb_line_sum_dev is enqueue-only)
     unsigned char *blk_h = nullptr;                   // pinned staging of prb_atmosphere's small tables
     size_t blk_cap = 0;
@@ -225,6 +232,11 @@ extern "C" int prb_destroy(prb_engine *e) {
     if (e->blk_h) cudaFreeHost(e->blk_h);
     e->blk_d.release();
     e->ingest.release();
+    e->dev_scal.release();
+    if (e->pin_scal) cudaFreeHost(e->pin_scal);
+    for (auto x : e->pipe_ev) cudaEventDestroy(x);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->stream2) cudaStreamDestroy(e->stream2);
     if (e->ring_h) { cudaFreeHost(e->ring_h); for (auto x : e->ring_ev) if (x) cudaEventDestroy(x); }
     peer_release(e);
     for (auto x : e->ev) cudaEventDestroy(x);
@@ -363,7 +375,7 @@ extern "C" int prb_set_grid(prb_engine *e, double range_min, double res, int64_t
     if (n_total > 2000000000LL) return fail(PRB_ERR_ARG, "prb_set_grid: n_total too large");
     CK(cudaSetDevice(e->device));
     const int64_t na = e->n_alloc;
-    k0_line_index<<<(unsigned)((na + 255) / 256), 256, 0, e->stream>>>(e->nu0.p, e->n_lines, na, range_min, res,
+    k0_line_index<<<(unsigned)((na + 255) / 256), 256, 0, e->stream>>>(e->nu0.p, e->n_lines, 0, na, range_min, res,
                                                                       e->idx.p);
     CK(cudaGetLastError());
     e->h_idx.resize(na);
@@ -470,6 +482,7 @@ static void fill_k1_row(const prb_engine *e, const LayerJob &j, K1Layer &t) {
     t.T = j.T; t.P = j.P;
     t.lc = layer_consts(j.T, j.P, e->res);
     t.scale = j.scale;
+    t.scale_dev = j.scale_dev;
     t.wm = (double)j.wm;
     t.gp = j.gp_dev;
     t.recA = e->recA.p + na * j.slot;
@@ -568,6 +581,7 @@ extern "C" int prb_debug_line_params(prb_engine *e, double *nu_shift, double *ga
     row.T = e->last.T; row.P = e->last.P;
     row.lc = layer_consts(e->last.T, e->last.P, e->res);
     row.scale = e->last.scale;
+    row.scale_dev = nullptr;
     row.wm = (double)e->last.wm;
     row.gp = e->gp.p;
     row.recA = r4.p; row.recB = r5.p; row.recD = r2.p;
@@ -619,6 +633,20 @@ static void fill_k2_row(const prb_engine *e, const LayerJob &j, K2Layer &t) {
     t.l_end = (int)j.l1;
     t.wm = (int)j.wm;
     t.pad = 0;
+}
+
+// A sub-launch of k2_line_sum<P> over tiles [a.tile_base, a.tile_base + a.n_tiles) of one layer (pipelined upload).
+template <int P>
+static cudaError_t launch_k2_sub(prb_engine *e, K2Args a, cudaStream_t st) {
+    if (a.n_tiles <= 0) return cudaSuccess;
+    const bool staging = a.fuse.enabled && a.fuse.n_dst > 1;
+    const size_t smem = K2_SMEM_BYTES<P>(staging);
+    cudaError_t ce = cudaFuncSetAttribute(k2_line_sum<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)K2_SMEM_BYTES<P>(true));
+    if (ce != cudaSuccess) return ce;
+    const int grid = std::min(a.n_tiles, K2_MIN_CTAS * e->prop.multiProcessorCount);
+    k2_line_sum<P><<<grid, K2_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
 }
 
 // ONE K2 launch for jobs[0..n), which must share a kernel class (all narrow, or all the same ppt) and be sorted
@@ -812,12 +840,27 @@ static float *peer_slot(const prb_engine *e, int dst, int parity, int field, int
            ((size_t)(parity * 2 + field) * ps.world + src_rank) * (size_t)ps.ld;
 }
 
-extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups, const double *depth_cm,
-                              const double *t_layer, const double *p_layer, const double *conc, const double *molmass,
-                              const double *q_t, const double *q_296, const int64_t *window_len, double t_surface,
-                              double range_max) {
+// Pipelined upload of a gas cell (prb_gas_cell_host): the line columns arrive in S pieces on a copy stream, piece s
+// completes event ev[s]; sub-launch s of K2 covers tiles [tile_lo[s], tile_hi[s]) -- one full wave of CTAs -- and
+// needs lines [line_lo[s], line_hi[s]); K0/K1 for the lines of piece s = [line_hi[s-1], line_hi[s]).
+struct UploadPipe {
+    int S = 0;
+    std::vector<int64_t> line_lo, line_hi;
+    std::vector<int> tile_lo, tile_hi;
+    std::vector<cudaEvent_t> ev;                 // piece s has landed
+    std::vector<cudaEvent_t> ev_k1;              // K1 of piece s is done (the two compute streams alternate)
+    cudaStream_t stream2 = nullptr;
+    std::function<int(int)> enqueue_piece;       // puts the copies of piece s on the copy stream and records ev[s]
+    const unsigned long long *smax_bits_dev = nullptr;   // max|S296| as computed on the device
+    double *scale_dev = nullptr;
+};
+
+static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, const double *depth_cm,
+                           const double *t_layer, const double *p_layer, const double *conc, const double *molmass,
+                           const double *q_t, const double *q_296, const int64_t *window_len, double t_surface,
+                           double range_max, const UploadPipe *pipe) {
     if (!e) return fail(PRB_ERR_ARG, "null engine");
-    if (!e->grid_set) return fail(PRB_ERR_STATE, "prb_atmosphere: set the grid first");
+    if (!e->grid_set && !pipe) return fail(PRB_ERR_STATE, "prb_atmosphere: set the grid first");
     if (n_layers < 1 || n_groups != e->n_groups) return fail(PRB_ERR_ARG, "prb_atmosphere: bad n_layers / n_groups");
     if (!depth_cm || !t_layer || !p_layer || !conc || !molmass || !q_t || !q_296 || !window_len)
         return fail(PRB_ERR_ARG, "prb_atmosphere: NULL array");
@@ -838,11 +881,12 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
     // Everything small the kernels of this call read -- status blocks (zeroed: flags + tile counters), per-(layer,
     // group) params, fold constants, the K2 launch table (K1's is a kernel parameter) -- is built in ONE pinned block and uploaded with
     // ONE copy, so a step is a copy plus its kernel launches.
+    const int n_rows = pipe ? std::max(pipe->S, 1) : n_layers;      // status blocks / K2 table rows (one per launch item)
     const size_t off_st = 0;
-    const size_t off_gp = off_st + sizeof(DevState) * n_layers;
+    const size_t off_gp = off_st + sizeof(DevState) * n_rows;
     const size_t off_fold = off_gp + sizeof(GroupParams) * (size_t)n_layers * n_groups;
     const size_t off_k2 = (off_fold + sizeof(FoldLayer) * n_layers + 15) & ~size_t(15);
-    const size_t blk_bytes = off_k2 + sizeof(K2Layer) * n_layers;
+    const size_t blk_bytes = off_k2 + sizeof(K2Layer) * n_rows;
     if (blk_bytes > e->blk_cap) {
         if (e->blk_h) cudaFreeHost(e->blk_h);
         e->blk_h = nullptr;
@@ -868,6 +912,7 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
     CK(e->rad.ensure(e->kmat_ld));
     CK(e->trans.ensure(e->kmat_ld));
     std::vector<double> w(n_groups);
+    double pipe_w_max = 1.0;
     for (int l = 0; l < n_layers; ++l) {
         for (int g = 0; g < n_groups; ++g)
             w[g] = conc[(size_t)l * n_groups + g] * p_layer[l] / 1E4 / kBoltz / t_layer[l];
@@ -876,7 +921,20 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
                            q_296, w.data(), h + (size_t)l * n_groups, &w_max);
         hf[l].neg_depth_log2e = (float)(-depth_cm[l] * 1.4426950408889634);
         hf[l].c2_over_t = (float)(c2 / t_layer[l]);
-        jobs[l] = plan_job(e, t_layer[l], p_layer[l], window_len[l], pick_scale(e->s_max, w_max));
+        if (pipe) {                                             // the grid indices are not on the host yet
+            LayerJob &j = jobs[l];
+            j.T = t_layer[l]; j.P = p_layer[l]; j.W = window_len[l];
+            j.scale = 1.0;                                      // placeholder: the device computes it (k0_pick_scale)
+            j.scale_dev = pipe->scale_dev;
+            pipe_w_max = w_max;
+            j.wm = std::max<int64_t>(window_len[l] - 2, 0);
+            j.l0 = 0; j.l1 = e->n_lines;
+            j.narrow = 0;
+            j.ppt = pick_ppt(e, j.wm);
+            j.valid = true;
+        } else {
+            jobs[l] = plan_job(e, t_layer[l], p_layer[l], window_len[l], pick_scale(e->s_max, w_max));
+        }
         jobs[l].gp_dev = gp_dev + (size_t)l * n_groups;
         jobs[l].st_dev = st_dev + l;
         jobs[l].out_dev = e->kmat.p + (size_t)l * e->kmat_ld;
@@ -953,9 +1011,80 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
         jobs[k].slot = (int)(k % slots);
         fill_k2_row(e, jobs[k], k2rows[k]);
     }
+    if (pipe) {
+        for (int sidx = 0; sidx < pipe->S; ++sidx) {            // one K2 table row per sub-launch: its own line range
+            k2rows[sidx] = k2rows[0];
+            k2rows[sidx].l_begin = (int)pipe->line_lo[sidx];
+            k2rows[sidx].l_end = (int)pipe->line_hi[sidx];
+        }
+    }
     CK(cudaMemcpyAsync(e->blk_d.p, e->blk_h, blk_bytes, cudaMemcpyHostToDevice, e->stream));
     int launches = 0;
-    for (int bi = 0; bi < n_batches; ++bi) {
+    if (pipe) {
+        if (!fused) return fail(PRB_ERR_STATE, "pipelined upload needs the fused single-layer path");
+        const int64_t n = e->n_lines, na = e->n_alloc;
+        // the scale of the records, on the device: into K1's scale word and (inverted) the K2 table rows
+        static_assert(sizeof(K2Layer) % sizeof(double) == 0, "K2Layer rows are addressed in doubles");
+        k0_pick_scale<<<1, 32, 0, e->stream>>>(pipe->smax_bits_dev, pipe_w_max, pipe->scale_dev,
+                                              &k2_dev[0].inv_scale, pipe->S, (int)(sizeof(K2Layer) / sizeof(double)));
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(pipe->ev_k1[pipe->S], e->stream));     // "tables ready" for the second stream
+        CK(cudaStreamWaitEvent(pipe->stream2, pipe->ev_k1[pipe->S], 0));
+        // Sub-launches alternate between two streams: while the tail of wave s drains (its CTAs retire one by one, its
+        // bulk stores to the host / peers complete), K0/K1/K2 of wave s+1 already run on the freed SMs.
+        for (int sidx = 0; sidx < pipe->S; ++sidx) {
+            // keep the copy stream one piece ahead of the launches (the host enqueues both; neither should wait for it)
+            if (sidx + 1 < pipe->S && (rc = pipe->enqueue_piece(sidx + 1))) return rc;
+            cudaStream_t st = (sidx & 1) ? pipe->stream2 : e->stream;
+            CK(cudaStreamWaitEvent(st, pipe->ev[sidx], 0));
+            if (sidx) CK(cudaStreamWaitEvent(st, pipe->ev_k1[sidx - 1], 0));   // records of the earlier pieces
+            // K0 + K1 for the lines this piece brought (the last piece also writes the padding records)
+            const int64_t a = sidx ? pipe->line_hi[sidx - 1] : 0;
+            const int64_t b = sidx == pipe->S - 1 ? na : pipe->line_hi[sidx];
+            if (b > a) {
+                k0_line_index<<<(unsigned)((b - a + 255) / 256), 256, 0, st>>>(e->nu0.p, n, a, b, e->range_min, e->res, e->idx.p);
+                CK(cudaGetLastError());
+                LayerJob jj = jobs[0];
+                jj.l0 = a;
+                jj.l1 = std::min<int64_t>(b, n);
+                K1Table &tab = e->k1_host;
+                tab.n = 1;
+                tab.pad = 0;
+                fill_k1_row(e, jj, tab.rows[0]);
+                LinesSoA Ls{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
+                            e->has_group ? e->group.p : nullptr};
+                k1_prepass<<<(unsigned)((b - a + 255) / 256), 256, 0, st>>>(Ls, e->idx.p, tab, a, b, n, e->i_begin, DebugOut{});
+                CK(cudaGetLastError());
+                launches += 2;
+            }
+            CK(cudaEventRecord(pipe->ev_k1[sidx], st));
+            // K2 over this piece's wave of tiles
+            K2Args ka{};
+            ka.layers = k2_dev + sidx;
+            ka.n_layers = 1;
+            ka.idx = e->idx.p;
+            ka.i_begin = e->i_begin;
+            ka.n_chunk = (int)nc;
+            ka.variant = e->k2_variant;
+            ka.out_mode = PRB_OUT_F32;
+            ka.st = st_dev + sidx;
+            ka.fuse = fuse;
+            ka.tile_base = pipe->tile_lo[sidx];
+            ka.n_tiles = pipe->tile_hi[sidx] - pipe->tile_lo[sidx];
+            cudaError_t ce;
+            switch (jobs[0].ppt) {
+                case 2: ce = launch_k2_sub<2>(e, ka, st); break;
+                case 4: ce = launch_k2_sub<4>(e, ka, st); break;
+                case 16: ce = launch_k2_sub<16>(e, ka, st); break;
+                default: ce = launch_k2_sub<8>(e, ka, st); break;
+            }
+            if (ce != cudaSuccess) return fail(PRB_ERR_CUDA, std::string("k2_line_sum sub-launch failed: ") + cudaGetErrorString(ce));
+            ++launches;
+        }
+        CK(cudaEventRecord(pipe->ev_k1[pipe->S], pipe->stream2));  // join: everything after this sees both streams' work
+        CK(cudaStreamWaitEvent(e->stream, pipe->ev_k1[pipe->S], 0));
+    }
+    for (int bi = 0; bi < (pipe ? 0 : n_batches); ++bi) {
         const int b0 = (int)(bi * slots), b1 = (int)std::min<int64_t>(n_layers, b0 + slots);
         if (e->timing) CK(cudaEventRecord(e->ev[3 * bi], e->stream));
         rc = run_prepass(e, jobs.data() + b0, b1 - b0, DebugOut{}, &launches);
@@ -992,8 +1121,8 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
     }
     e->last_launches = launches;
     // status blocks back in the same breath; the synchronisation also keeps the pinned block ours until the next call
-    std::vector<DevState> hst(n_layers);
-    CK(cudaMemcpyAsync(hst.data(), st_dev, sizeof(DevState) * n_layers, cudaMemcpyDeviceToHost, e->stream));
+    std::vector<DevState> hst(n_rows);
+    CK(cudaMemcpyAsync(hst.data(), st_dev, sizeof(DevState) * n_rows, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (e->timing) {
         e->t_k1 = e->t_k2 = e->t_k3 = 0;
@@ -1009,7 +1138,7 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
             // per-layer figures are exact with one layer per batch (prb_set_option PRB_OPT_BATCH_LAYERS 0), else
             // the batch time spread evenly; reported in the caller's layer order
             for (int k = b0; k < b1; ++k) {
-                const int l = (int)(jobs[k].st_dev - st_dev);
+                const int l = pipe ? 0 : (int)(jobs[k].st_dev - st_dev);
                 e->t_layer_k1[l] = a / (b1 - b0);
                 e->t_layer_k2[l] = b / (b1 - b0);
             }
@@ -1026,7 +1155,15 @@ extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
                                       "prb_atmosphere the same number of times)");
         }
     }
-    return report_flags(hst.data(), n_layers);
+    return report_flags(hst.data(), n_rows);
+}
+
+extern "C" int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups, const double *depth_cm,
+                              const double *t_layer, const double *p_layer, const double *conc, const double *molmass,
+                              const double *q_t, const double *q_296, const int64_t *window_len, double t_surface,
+                              double range_max) {
+    return atmosphere_impl(e, n_layers, n_groups, depth_cm, t_layer, p_layer, conc, molmass, q_t, q_296, window_len,
+                           t_surface, range_max, nullptr);
 }
 
 extern "C" int prb_atmosphere_result_dev(prb_engine *e, void **radiance_dev, void **transmittance_dev) {
@@ -1438,5 +1575,142 @@ extern "C" int prb_set_result_host(prb_engine *e, float *radiance_host, float *t
     e->host_rad_dev = (float *)dr;
     e->host_trans_dev = (float *)dt;
     e->host_result_len = n_points;
+    return PRB_OK;
+}
+
+// ------------------------------------------------------------------------------------ gas cell, host to host, pipelined
+// One call from HOST line columns to HOST spectra with the copies overlapped with the compute in both directions:
+//   * the S296 column goes first (the FP32 scale of the records needs max|S|), then the other columns in S pieces,
+//     wavenumber ascending, on a copy stream;
+//   * the grid chunk is cut into S pieces of ONE WAVE of K2 tiles each (2 CTAs x SM count); piece s of the lines is
+//     what sub-launch s needs beyond the earlier pieces (its tiles' windows plus margin), so K0/K1/K2 of piece s start
+//     as soon as its lines have landed while the later pieces are still crossing PCIe;
+//   * finished tiles leave through K2's fused epilogue: into the device result arrays, every peer's gather buffer
+//     when connected, and the pinned host buffers registered with prb_set_result_host.
+// The arithmetic is that of prb_upload_lines + prb_set_grid + prb_atmosphere(1 layer), bit for bit (same tiles, same
+// records); narrow windows and tiny inputs simply take that sequence.
+extern "C" int prb_gas_cell_host(prb_engine *e, int64_t n, const double *nu0, const double *s296, const double *gamma_air,
+                                 const double *gamma_self, const double *elower, const double *n_air,
+                                 const double *delta_air, const int32_t *group, int32_t n_groups, double range_min,
+                                 double res, int64_t n_total, int64_t i_begin, int64_t i_end, double depth_cm,
+                                 double t_layer, double p_layer, const double *conc, const double *molmass,
+                                 const double *q_t, const double *q_296, int64_t window_len, double t_surface,
+                                 double range_max) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (n < 0 || n > 2000000000LL || n_groups < 1) return fail(PRB_ERR_ARG, "prb_gas_cell_host: bad line count / n_groups");
+    if (n > 0 && (!nu0 || !s296 || !gamma_air || !gamma_self || !elower || !n_air || !delta_air))
+        return fail(PRB_ERR_ARG, "prb_gas_cell_host: NULL column");
+    if (!(res > 0) || n_total < 0 || i_begin < 0 || i_end < i_begin || i_end > n_total || n_total > 2000000000LL)
+        return fail(PRB_ERR_ARG, "prb_gas_cell_host: bad grid");
+    if (!conc || !molmass || !q_t || !q_296 || window_len < 1) return fail(PRB_ERR_ARG, "prb_gas_cell_host: bad layer arguments");
+    CK(cudaSetDevice(e->device));
+    const int64_t nc = i_end - i_begin;
+    const int64_t wm = std::max<int64_t>(window_len - 2, 0);
+    const int ppt = pick_ppt(e, wm);
+    const int tile_pts = K2_CONSUMERS * 32 * ppt;
+    const int n_tiles = (int)((nc + tile_pts - 1) / tile_pts);
+    const int wave = K2_MIN_CTAS * e->prop.multiProcessorCount;
+    const int S = (n_tiles + wave - 1) / wave;
+    const bool pipelined = e->k2_variant == PRB_K2_CLASSED && e->fuse_single && wm >= e->narrow_wm && S >= 2 && n >= 4096;
+    if (!pipelined) {
+        int rc = prb_upload_lines(e, n, nu0, s296, gamma_air, gamma_self, elower, n_air, delta_air, group, n_groups);
+        if (rc) return rc;
+        if ((rc = prb_set_grid(e, range_min, res, n_total, i_begin, i_end))) return rc;
+        return prb_atmosphere(e, 1, n_groups, &depth_cm, &t_layer, &p_layer, conc, molmass, q_t, q_296, &window_len,
+                              t_surface, range_max);
+    }
+    if (nc + 2 * wm + 8192 >= (int64_t(1) << 24))
+        return fail(PRB_ERR_RANGE, "owned grid chunk plus cutoff windows exceeds 2^24 points; shard the grid");
+    if (!e->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+        CK(cudaMallocHost((void **)&e->pin_scal, 64));
+        CK(e->dev_scal.ensure(8));
+    }
+    while ((int)e->pipe_ev.size() < 2 * (S + 1)) {
+        cudaEvent_t x;
+        CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+        e->pipe_ev.push_back(x);
+    }
+    e->lines_set = false;
+    e->grid_set = false;
+    e->last.valid = false;
+    int rc = alloc_line_storage(e, n);
+    if (rc) return rc;
+    e->n_lines = n;
+    e->n_groups = n_groups;
+    e->has_group = group != nullptr;
+    if (group) CK(e->group.ensure(e->n_alloc));
+    e->range_min = range_min; e->res = res; e->n_total = n_total; e->i_begin = i_begin; e->i_end = i_end;
+
+    // S296 first: max|S| fixes the power-of-two scale of every record
+    CK(cudaMemsetAsync(e->dev_scal.p, 0, 64, e->stream));
+    CK(cudaEventRecord(e->pipe_ev[S], e->stream));
+    CK(cudaStreamWaitEvent(e->copy_stream, e->pipe_ev[S], 0));
+    CK(cudaMemcpyAsync(e->s296.p, s296, sizeof(double) * n, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaEventRecord(e->pipe_ev[S], e->copy_stream));
+    CK(cudaStreamWaitEvent(e->stream, e->pipe_ev[S], 0));
+    k0_absmax<<<e->prop.multiProcessorCount * 4, 256, 0, e->stream>>>(e->s296.p, n, e->dev_scal.p);
+    CK(cudaGetLastError());
+
+    // piece boundaries: sub-launch s owns tiles [s*wave, (s+1)*wave) and needs the lines whose grid index lies in
+    // [first point - wm, last point + wm]; two grid points of slack cover the truncation of the index
+    UploadPipe pipe;
+    pipe.S = S;
+    pipe.ev.assign(e->pipe_ev.begin(), e->pipe_ev.begin() + S);
+    pipe.ev_k1.assign(e->pipe_ev.begin() + S + 1, e->pipe_ev.begin() + 2 * (S + 1));
+    pipe.stream2 = e->stream2;
+    pipe.smax_bits_dev = e->dev_scal.p;
+    pipe.scale_dev = reinterpret_cast<double *>(e->dev_scal.p + 2);
+    for (int sidx = 0; sidx < S; ++sidx) {
+        const int t0 = sidx * wave, t1 = std::min(n_tiles, t0 + wave);
+        const int64_t p0 = (int64_t)t0 * tile_pts, p1 = std::min<int64_t>(nc, (int64_t)t1 * tile_pts);
+        const double nu_lo = range_min + (double)(i_begin + p0 - wm - 2) * res;
+        const double nu_hi = range_min + (double)(i_begin + p1 - 1 + wm + 3) * res;
+        int64_t lo = std::lower_bound(nu0, nu0 + n, nu_lo) - nu0;
+        int64_t hi = sidx == S - 1 ? n : std::upper_bound(nu0, nu0 + n, nu_hi) - nu0;
+        if (sidx && hi < pipe.line_hi[sidx - 1]) hi = pipe.line_hi[sidx - 1];
+        if (lo > hi) lo = hi;
+        pipe.tile_lo.push_back(t0);
+        pipe.tile_hi.push_back(t1);
+        pipe.line_lo.push_back(lo);
+        pipe.line_hi.push_back(hi);
+    }
+    // the other columns, piece by piece, on the copy stream (piece 0 now, piece s+1 while piece s is being launched)
+    DevBuf<double> *cols[6] = {&e->nu0, &e->gair, &e->gself, &e->elower, &e->nair, &e->delta};
+    const double *src[6] = {nu0, gamma_air, gamma_self, elower, n_air, delta_air};
+    pipe.enqueue_piece = [&](int sidx) -> int {
+        const int64_t a = sidx ? pipe.line_hi[sidx - 1] : 0, b = pipe.line_hi[sidx];
+        if (b > a) {
+            for (int c = 0; c < 6; ++c)
+                CK(cudaMemcpyAsync(cols[c]->p + a, src[c] + a, sizeof(double) * (b - a), cudaMemcpyHostToDevice, e->copy_stream));
+            if (group)
+                CK(cudaMemcpyAsync(e->group.p + a, group + a, sizeof(int32_t) * (b - a), cudaMemcpyHostToDevice, e->copy_stream));
+        }
+        CK(cudaEventRecord(e->pipe_ev[sidx], e->copy_stream));
+        return PRB_OK;
+    };
+    if ((rc = pipe.enqueue_piece(0))) return rc;
+
+    rc = atmosphere_impl(e, 1, n_groups, &depth_cm, &t_layer, &p_layer, conc, molmass, q_t, q_296, &window_len, t_surface,
+                         range_max, &pipe);
+    // what prb_upload_lines checks on the host, checked on the device after the fact; and the index array for the
+    // host-side planning of later calls
+    k0_validate_lines<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->nu0.p, group ? e->group.p : nullptr, n, n_groups,
+                                                                        reinterpret_cast<unsigned int *>(e->dev_scal.p + 1));
+    e->h_idx.resize(e->n_alloc);
+    cudaMemcpyAsync(e->h_idx.data(), e->idx.p, sizeof(int32_t) * e->n_alloc, cudaMemcpyDeviceToHost, e->stream);
+    cudaMemcpyAsync(e->pin_scal, e->dev_scal.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream);
+    CK(cudaStreamSynchronize(e->copy_stream));
+    CK(cudaStreamSynchronize(e->stream2));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    memcpy(&e->s_max, e->pin_scal, sizeof(double));             // max|S296|, for the planning of later calls
+    const unsigned int vf = (unsigned int)e->pin_scal[1];
+    if (vf & 1u) return fail(PRB_ERR_ARG, "prb_gas_cell_host: nu0 must be ascending");
+    if (vf & 2u) return fail(PRB_ERR_ARG, "prb_gas_cell_host: group id out of range");
+    if (rc) return rc;
+    e->lines_set = true;
+    e->grid_set = true;
     return PRB_OK;
 }

@@ -43,9 +43,9 @@ struct DebugOut {
 
 // K0: arrayIndex = int((nu0 - rangeMin) / res)   (pyradClasses.py:390; FP64 divide, truncation
 // toward zero, UN-shifted nu0).  Saturated to int32; padding entries get INT32_MAX.
-__global__ void k0_line_index(const double *__restrict__ nu0, int64_t n, int64_t n_alloc,
+__global__ void k0_line_index(const double *__restrict__ nu0, int64_t n, int64_t l_begin, int64_t n_alloc,
                               double range_min, double res, int32_t *__restrict__ idx) {
-    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t l = l_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_alloc) return;
     if (l >= n) { idx[l] = INT32_MAX; return; }
     double q = __ddiv_rn(__dsub_rn(nu0[l], range_min), res);
@@ -54,13 +54,53 @@ __global__ void k0_line_index(const double *__restrict__ nu0, int64_t n, int64_t
     idx[l] = (int32_t)t;
 }
 
+// max |x| of a column as its bit pattern (|x| >= 0: bit order == value order), and -- for the line list checks the
+// host does in prb_upload_lines -- "ascending nu0" / "group id in range" as device flags.
+__global__ void __launch_bounds__(256)
+k0_absmax(const double *__restrict__ x, int64_t n, unsigned long long *__restrict__ out_bits) {
+    unsigned long long b = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long v = (unsigned long long)__double_as_longlong(fabs(x[i]));
+        b = v > b ? v : b;
+    }
+    const unsigned int hi = __reduce_max_sync(0xffffffffu, (unsigned int)(b >> 32));
+    const unsigned int lo = __reduce_max_sync(0xffffffffu, (unsigned int)(b >> 32) == hi ? (unsigned int)b : 0u);
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, ((unsigned long long)hi << 32) | lo);
+}
+
+// The host's pick_scale (api.cu) on the device: scale = 2^(10 - ilogb(max|S| * max weight)), written where K1 reads
+// it and, inverted, into the K2 table rows of the launches that will undo it.
+__global__ void k0_pick_scale(const unsigned long long *__restrict__ smax_bits, double w_max, double *__restrict__ scale_out,
+                              double *__restrict__ inv_scale_rows, int n_rows, int row_stride_doubles) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double m = __longlong_as_double((long long)*smax_bits) * w_max;
+    double sc = 1.0;
+    if (m > 0 && isfinite(m)) sc = ldexp(1.0, 10 - ilogb(m));
+    *scale_out = sc;
+    for (int r = 0; r < n_rows; ++r) inv_scale_rows[(size_t)r * row_stride_doubles] = 1.0 / sc;
+}
+
+__global__ void __launch_bounds__(256)
+k0_validate_lines(const double *__restrict__ nu0, const int32_t *__restrict__ group, int64_t n, int n_groups,
+                  unsigned int *__restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int f = 0;
+    if (i < n) {
+        if (i + 1 < n && !(nu0[i + 1] >= nu0[i])) f |= 1u;
+        if (group && (group[i] < 0 || group[i] >= n_groups)) f |= 2u;
+    }
+    f = __reduce_or_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
 __device__ __forceinline__ double pow5(double x) { double x2 = x * x; return x2 * x2 * x; }
 
 // One layer of a (possibly multi-layer) prepass launch.
 struct K1Layer {
     double T, P;
     LayerConsts lc;
-    double scale;                  // power-of-two scale of this layer's FP32 coefficients
+    double scale;                  // power-of-two scale of this layer's FP32 coefficients ...
+    const double *scale_dev;       // ... or, when not NULL, where the device computed it (pipelined upload: no host sync)
     double wm;                     // W-2 clamped at 0 (FP32 range guard)
     const GroupParams *gp;         // n_groups entries for this layer
     float4 *recA, *recB;           // this layer's record arrays (indexed by line)
@@ -199,7 +239,7 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
             // exp(-c2 E/T) / exp(-c2 E/t0) evaluated as one exponential (same value to ~1e-16)
             const double boltz = exp_k1(neg_c2_e * K.lc.inv_t_minus_inv_t0);
             const double S = s296 * p.qratio * stim * boltz;
-            const double sw = S * p.weight * K.scale;
+            const double sw = S * p.weight * (K.scale_dev ? __ldg(K.scale_dev) : K.scale);
             const double inv_res2 = K.lc.inv_res2;
             const double log2e = 1.4426950408889634;
             const double inv_sqrtpi = 0.5641895835477563;         // 1/sqrt(pi)

@@ -165,7 +165,8 @@ struct K2Args {
     const int32_t *idx;        // sorted absolute grid index per line
     long long i_begin;         // absolute index of the shard's first grid point
     int n_chunk;               // grid points owned
-    int n_tiles;               // tiles per layer
+    int n_tiles;               // tiles per layer handled by this launch
+    int tile_base;             // first tile of this launch (sub-launches of a pipelined upload; 0 otherwise)
     int variant;               // PRB_K2_GENERAL / PRB_K2_CLASSED
     int out_mode;              // PRB_OUT_F64 / PRB_OUT_F32
     DevState *st;              // tile_counter of this launch
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             item = __shfl_sync(0xffffffffu, item, 0);
             if (item >= n_items) break;
             const int layer = item / a.n_tiles;
-            const int tile = item - layer * a.n_tiles;
+            const int tile = a.tile_base + item - layer * a.n_tiles;
             const K2Layer *L = a.layers + layer;
             const int wm = __ldg(&L->wm), l_begin = __ldg(&L->l_begin), l_end = __ldg(&L->l_end);
             const float4 *recA = L->recA;

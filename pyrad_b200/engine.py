@@ -223,6 +223,29 @@ class Engine:
                                             win.ctypes.data_as(C.POINTER(C.c_int64)), float(t_surface),
                                             float(range_max)))
 
+    def gas_cell_host(self, lines, n_groups, range_min, res, n_total, i_begin, i_end, depth_cm, T, P, conc, molmass,
+                      q_t, q_296, window, t_surface, range_max):
+        """upload_lines + set_grid + atmosphere(one layer) in ONE call with the host->device copies overlapped with
+        the compute (prb_gas_cell_host).  Results: atmosphere_read*(), or the buffers given to set_result_host()."""
+        cols = [_f64(lines[k]) for k in ("nu", "sw", "gamma_air", "gamma_self", "elower", "n_air", "delta_air")]
+        n = cols[0].size
+        grp = lines.get("group") if hasattr(lines, "get") else None
+        gp = None
+        if grp is not None:
+            grp = np.ascontiguousarray(grp, dtype=np.int32)
+            gp = grp.ctypes.data_as(C.POINTER(C.c_int32))
+        g = int(n_groups)
+        arrs = [_f64(np.broadcast_to(np.asarray(a, dtype=np.float64), (g,))) for a in (conc, molmass, q_t, q_296)]
+        _lib.check(self._lib.prb_gas_cell_host(self._h, n, *[_dp(c) for c in cols], gp, g, float(range_min), float(res),
+                                               int(n_total), int(i_begin), int(i_end), float(depth_cm), float(T), float(P),
+                                               *[_dp(a) for a in arrs], int(window), float(t_surface), float(range_max)))
+        self.n_lines, self.n_groups = n, g
+        self.n_chunk = int(i_end) - int(i_begin)
+        self.n_total = int(n_total)
+        self.i_begin, self.i_end = int(i_begin), int(i_end)
+        self._res = float(res)
+        self.range_min = float(range_min)
+
     def atmosphere_read(self):
         rad = np.empty(self.n_chunk)
         tr = np.empty(self.n_chunk)

@@ -340,3 +340,43 @@ def test_zero_copy_host_results_equal_read_back(engine, n_layers, top):
             engine.set_result_host(np.zeros(engine.n_chunk, dtype=np.float32), np.zeros(engine.n_chunk, dtype=np.float32))
     finally:
         engine.set_result_host()
+
+
+def test_pipelined_gas_cell_equals_separate_calls(engine):
+    """prb_gas_cell_host: line columns uploaded in wavenumber pieces on a copy stream, one wave of K2 tiles per piece,
+    results stored into pinned host buffers by K2 itself -- bitwise equal to upload_lines + set_grid + atmosphere."""
+    import torch
+    w = workloads.gas_cell(["h2o", "co2", "ch4", "o3"], 60000, 0.0, 1300.0, 0.001, 296, 1013.25,
+                           [0.01, 400e-6, 1.8e-6, 5e-8], 10.0, 77)
+    sp = w["species"]
+    n = eng.grid_len(w["range_min"], w["range_max"], w["res"])
+    assert n > 2 * 296 * 2048                                       # more than two waves of tiles: really pipelined
+    win = eng.window_len(w["cutoff"], w["res"])
+    mol, q296, qt = [s.molmass for s in sp], [s.q296 for s in sp], [s.q(w["T"]) for s in sp]
+    engine.upload_lines(w["lines"], n_groups=len(sp))
+    engine.set_grid(w["range_min"], w["res"], n)
+    engine.atmosphere([w["depth_cm"]], [w["T"]], [w["P"]], [w["conc"]], mol, [qt], q296, [win], 288.0, w["range_max"])
+    rad_ref = np.empty(n, dtype=np.float32); tr_ref = np.empty(n, dtype=np.float32)
+    engine.atmosphere_read_f32(rad_ref, tr_ref)
+    pairs_ref = None
+    h_rad = torch.zeros(n, dtype=torch.float32).pin_memory()
+    h_tr = torch.zeros(n, dtype=torch.float32).pin_memory()
+    engine.set_result_host(h_rad.numpy(), h_tr.numpy())
+    try:
+        for a, b in ((0, n), (4096 * 20, n - 4096 * 30)):           # the whole grid, then an interior chunk
+            h_rad.zero_(); h_tr.zero_()
+            engine.gas_cell_host(w["lines"], len(sp), w["range_min"], w["res"], n, a, b, w["depth_cm"], w["T"], w["P"],
+                                 w["conc"], mol, qt, q296, win, 288.0, w["range_max"])
+            assert np.array_equal(h_rad.numpy()[: b - a], rad_ref[a:b], equal_nan=True) and np.array_equal(h_tr.numpy()[: b - a], tr_ref[a:b])
+            rad = np.empty(b - a, dtype=np.float32); tr = np.empty(b - a, dtype=np.float32)
+            engine.atmosphere_read_f32(rad, tr)
+            assert np.array_equal(rad, rad_ref[a:b], equal_nan=True) and np.array_equal(tr, tr_ref[a:b])
+        # the engine is left as after the separate calls: the prepass / pair count work on the resident list
+        engine.layer_prepass(w["T"], w["P"], w["conc"], mol, qt, q296, win)
+        assert engine.pair_count() > 0
+        bad = dict(w["lines"]); bad["nu"] = bad["nu"][::-1].copy()
+        with pytest.raises(Exception):
+            engine.gas_cell_host(bad, len(sp), w["range_min"], w["res"], n, 0, n, w["depth_cm"], w["T"], w["P"],
+                                 w["conc"], mol, qt, q296, win, 288.0, w["range_max"])
+    finally:
+        engine.set_result_host()
