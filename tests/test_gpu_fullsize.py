@@ -53,6 +53,17 @@ def test_atmosphere_layer_shapes_full_size_sampled(engine, P, T):
     check_sampled(engine, w, weights_mode=True, P=P, T=T, n_pts=24, seed=int(P))
 
 
+def test_cfg5_stress_sweep_full_size_sampled(engine):
+    """cfg5: 5M lines, 5M points, 25 cm-1 cutoff (W = 25 000, ~2.5e11 accumulations) against the oracle's gather form
+    at sampled points, plus the exact accumulate count."""
+    w = workloads.cfg5()
+    out = check_sampled(engine, w, weights_mode=True, n_pts=16, seed=5)
+    n = eng.grid_len(w["range_min"], w["range_max"], w["res"])
+    idx = ph.line_index(w["lines"]["nu"], w["range_min"], w["res"])
+    assert engine.pair_count() == ph.pair_count(idx, n, eng.window_len(w["cutoff"], w["res"])) > 2.4e11
+    assert np.all(np.isfinite(out)) and np.all(out >= 0)
+
+
 def test_cfg1_size_properties(engine):
     """cfg1 (30 000 points, 50k lines): linearity in S, additivity over a line split, T=296 identity."""
     w = workloads.cfg1()
