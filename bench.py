@@ -530,6 +530,11 @@ def run_atmosphere(e, args, rank, world, ext, peaks, use_peer):
     pairs = float(pt.block_pair_cost(idx, n_total, win).sum())
     tim = e.atmosphere_timing()
     e.set_timing(False)
+    tim_max = dict(tim)
+    if world > 1:                                   # slowest rank per stage (the step ends when the slowest rank does)
+        tt = torch.tensor([tim["k1_ms"], tim["k2_ms"], tim["k3_ms"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tim_max = dict(zip(("k1_ms", "k2_ms", "k3_ms"), [float(x) for x in tt.tolist()]))
     k3_bytes = len(win) * nc * 4 + nc * 8
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     return {"workload": "cfg4: %d-layer US-std atmosphere 0-70 km, 0-5000 cm-1 @ 0.001 cm-1 (%d points, %d lines), "
@@ -537,7 +542,7 @@ def run_atmosphere(e, args, rank, world, ext, peaks, use_peer):
             "spectra_per_s": 1e3 / ms, "ms_per_spectrum": ms, "pairs": pairs, "pairs_per_s": pairs / (ms * 1e-3),
             "scaling": "strong", "n_gpus": world, "chunk_points_rank0": nc, "launches": e.atmosphere_launches(),
             "gather": "none" if world == 1 else ("peer stores fused into K3" if use_peer else "nccl"),
-            "rank0_stage_ms": tim,
+            "rank0_stage_ms": tim, "max_rank_stage_ms": tim_max,
             "roofline_k3": {"bound": "hbm", "achieved": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                             "frac": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9 / hbm,
                             "traffic": load_traffic("k3_fold_f32@cfg4") if world == 1 and len(win) == 100 else None,

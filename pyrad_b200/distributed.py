@@ -16,7 +16,7 @@ class ShardPlan:
     def __init__(self, nu0, range_min, res, n_total, windows, rank, world, balance=True):
         idx = pt.line_index(nu0, range_min, res)
         if balance and world > 1:
-            cost = pt.block_pair_cost(idx, n_total, windows)
+            cost = pt.block_time_cost(idx, n_total, windows)
             self.chunks = pt.balanced_chunks(cost, n_total, world)
         else:
             self.chunks = pt.equal_chunks(n_total, world)

@@ -53,6 +53,38 @@ def block_pair_cost(idx, n_total, windows, block=ALIGN):
     return cost
 
 
+#: Measured B200 cost model of K2 per kernel class (profiles/r01_k2_experiments.txt): seconds per (line, point)
+#: accumulation and per grid point of a layer, by window W-2.  Only the RATIOS matter for balancing.
+def _class_cost(wm):
+    if wm >= 1024:
+        return 1 / 4.9e12, 0.0            # k2_line_sum<8>
+    if wm >= 256:
+        return 1 / 3.1e12, 0.0            # k2_line_sum<4>
+    if wm >= 100:
+        return 1 / 1.7e12, 0.0            # k2_line_sum<2>
+    if wm >= 16:
+        return 1 / 1.5e12, 4e-12          # k2_point
+    return 1 / 1.5e12, 1.5e-11            # k2_narrow: a few lines per point, per-point overhead dominates
+
+
+def block_time_cost(idx, n_total, windows, block=ALIGN):
+    """Estimated K2 seconds per grid block over all layers: the pair counts of block_pair_cost weighted by the
+    measured cost of the kernel class each window runs on, plus the per-point overhead of the thread-per-point
+    kernels.  Balancing on this instead of the raw pair count evens out ranks whose chunks differ in width (edge
+    chunks see one-sided windows, so equal pair counts give them more points -- and more narrow-layer work)."""
+    windows = [int(w) for w in np.atleast_1d(windows)]
+    nb = (n_total + block - 1) // block
+    a = np.arange(nb, dtype=np.int64) * block
+    pts = (np.minimum(a + block, n_total) - a).astype(np.float64)
+    cost = np.zeros(nb, dtype=np.float64)
+    by_class = {}
+    for w in windows:
+        by_class.setdefault(_class_cost(max(w - 2, 0)), []).append(w)
+    for (c_pair, c_point), ws in by_class.items():
+        cost += c_pair * block_pair_cost(idx, n_total, ws, block) + c_point * len(ws) * pts
+    return cost
+
+
 def balanced_chunks(cost, n_total, nranks, block=ALIGN):
     """Contiguous, block-aligned chunks [(i_begin, i_end)] with near-equal cost.  A rank may get an
     empty chunk when there are fewer blocks than ranks."""

@@ -51,6 +51,20 @@ def test_chunks_are_aligned_contiguous_and_balanced():
         assert max(per) <= max(per_eq)
 
 
+def test_time_cost_weights_classes_and_points():
+    rng = np.random.default_rng(2)
+    n_total = 200_000
+    idx = np.sort(rng.integers(0, n_total, 50_000))
+    wide = pt.block_time_cost(idx, n_total, [5000])
+    assert np.allclose(wide, pt.block_pair_cost(idx, n_total, [5000]) / 4.9e12)
+    # a window of one sample: hardly any pairs, the per-point term carries the cost
+    tiny = pt.block_time_cost(idx, n_total, [1] * 10)
+    assert tiny.sum() > 10 * n_total * 1e-11 and tiny.min() > 0
+    mixed = pt.block_time_cost(idx, n_total, [5000, 300, 1])
+    assert np.allclose(mixed, pt.block_time_cost(idx, n_total, [5000]) + pt.block_time_cost(idx, n_total, [300]) +
+                       pt.block_time_cost(idx, n_total, [1]))
+
+
 def test_line_subset_reaches_every_window():
     ln = synth.make_lines(5000, 0.0, 100.0, 5)
     idx = pt.line_index(ln["nu"], 0.0, 0.01)
