@@ -46,10 +46,10 @@ constexpr unsigned int FLAG_OVERFLOW = 1u, FLAG_NONFINITE = 2u;
 constexpr int K2_CONSUMERS = PRB_K2_CONSUMERS;        // math warps per CTA
 constexpr int K2_THREADS = 32 * (K2_CONSUMERS + 1);   // + one TMA producer warp
 #ifndef PRB_K2_CHUNK
-#define PRB_K2_CHUNK 256
+#define PRB_K2_CHUNK 768
 #endif
 #ifndef PRB_K2_STAGES
-#define PRB_K2_STAGES 6
+#define PRB_K2_STAGES 3
 #endif
 #ifndef PRB_K2_MIN_CTAS
 #define PRB_K2_MIN_CTAS 2
