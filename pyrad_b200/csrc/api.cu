@@ -439,8 +439,10 @@ static int check_segment(prb_engine *e, int64_t wm) {
 static int pick_ppt(const prb_engine *e, int64_t wm) {
     if (e->k2_ppt) return e->k2_ppt;
     // a warp spans 32*P points: keep the span well inside the window so most lines cover it fully
-    if (wm >= 1024) return 8;
-    if (wm >= 256) return 4;
+    static const int64_t t8 = getenv("PRB_PPT8_MIN") ? atoll(getenv("PRB_PPT8_MIN")) : 1024;   // development overrides
+    static const int64_t t4 = getenv("PRB_PPT4_MIN") ? atoll(getenv("PRB_PPT4_MIN")) : 256;
+    if (wm >= t8) return 8;
+    if (wm >= t4) return 4;
     return 2;
 }
 

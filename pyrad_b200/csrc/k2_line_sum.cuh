@@ -311,24 +311,36 @@ template <int H, bool MASKED>
 __device__ __forceinline__ void gauss_pass(const float4 *sA, const float4 *sB, const float *sD, int js, int je,
                                            float wbf, float we1f, float wmf, Acc<H> &s) {
     int since = 0;
-    for (int j = js; j < je; ++j) {
-        const float dg = sD[j];
-        const float f = -sA[j].x;
-        if (!((dg >= 0.f) && (f + dg >= wbf) && (f - dg <= we1f))) continue;
-        const float4 b = sB[j];
-        const float2 nf = splat(-f), C2 = splat(b.w);
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-            const float2 e = __fadd2_rn(s.fi[h], nf);
-            const float2 arg = __fmul2_rn(C2, __fmul2_rn(e, e));
-            float2 g = splat(b.z);
-            if (MASKED) {
-                g.x = fabsf(e.x) <= wmf ? b.z : 0.f;
-                g.y = fabsf(e.y) <= wmf ? b.z : 0.f;
-            }
-            s.a32[h] = __ffma2_rn(g, make_float2(ex2_approx(arg.x), ex2_approx(arg.y)), s.a32[h]);
+    // 32 candidates per step: every lane tests one line's near zone against the span, a ballot collects the hits and
+    // the warp then walks the hits in ascending line order (the candidates come from the slot's LARGEST radius, so
+    // most of them miss: testing them one by one cost as much as evaluating the hits)
+    for (int jb = js; jb < je; jb += 32) {
+        const int jt = jb + (int)(threadIdx.x & 31);
+        bool hit = false;
+        if (jt < je) {
+            const float dg = sD[jt];
+            const float f = -sA[jt].x;
+            hit = (dg >= 0.f) && (f + dg >= wbf) && (f - dg <= we1f);
         }
-        if (++since == K2_FLUSH) { s.flush(); since = 0; }
+        unsigned int m = __ballot_sync(0xffffffffu, hit);
+        while (m) {
+            const int j = jb + __ffs(m) - 1;
+            m &= m - 1;
+            const float4 b = sB[j];
+            const float2 nf = splat(sA[j].x), C2 = splat(b.w);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float2 e = __fadd2_rn(s.fi[h], nf);
+                const float2 arg = __fmul2_rn(C2, __fmul2_rn(e, e));
+                float2 g = splat(b.z);
+                if (MASKED) {
+                    g.x = fabsf(e.x) <= wmf ? b.z : 0.f;
+                    g.y = fabsf(e.y) <= wmf ? b.z : 0.f;
+                }
+                s.a32[h] = __ffma2_rn(g, make_float2(ex2_approx(arg.x), ex2_approx(arg.y)), s.a32[h]);
+            }
+            if (++since == K2_FLUSH) { s.flush(); since = 0; }
+        }
     }
     if (since) s.flush();
 }
