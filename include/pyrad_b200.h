@@ -60,6 +60,7 @@ extern "C" {
 #define PRB_OPT_BATCH_LAYERS        1   /* prb_atmosphere: one K1 + one K2 launch per kernel class (default 1) */
 #define PRB_OPT_FUSE_SINGLE_LAYER   2   /* single-layer prb_atmosphere: layer physics in K2's epilogue (default 1) */
 #define PRB_OPT_RECORD_BUDGET_MB    3   /* device memory for resident per-layer line records; 0 = auto */
+#define PRB_OPT_FOLD_TMA            5   /* layer fold: k matrix staged through shared memory by TMA (default 1) or register-held loads (0) */
 #define PRB_OPT_POINT_KERNEL        4   /* narrow windows: table-driven k2_point (default 1) or binary-search k2_narrow (0) */
 
 #define PRB_PEER_HANDLE_BYTES      64   /* sizeof(cudaIpcMemHandle_t) */

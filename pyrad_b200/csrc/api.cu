@@ -135,6 +135,7 @@ struct prb_engine {
     int k2_variant = PRB_K2_CLASSED, k2_ppt = 0;
     int64_t narrow_wm = 100;     // windows with W-2 below this use k2_narrow
     bool batch_layers = true;    // prb_atmosphere: one K1 launch + one K2 launch per kernel class
+    bool k3_tma = true;          // layer fold: k matrix staged by TMA (k3_fold_tma) instead of register-held loads
     bool point_kernel = true;    // windows up to 511 points: k2_point instead of k2_narrow
     bool fuse_single = true;     // single wide layer: layer physics + peer stores in K2's epilogue
     int64_t rec_budget_mb = 0;   // 0 = auto (a quarter of the free memory)
@@ -1104,9 +1105,28 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
     }
     if (e->timing) CK(cudaEventRecord(e->ev[3 * n_batches], e->stream));
     if (nc > 0 && !fused) {
-        k3_fold_f32<<<stream_grid(e, nc, 4), 256, 0, e->stream>>>(e->kmat.p, e->kmat_ld, n_layers, fold_dev, nc,
-                                                                 e->i_begin, e->n_total, e->range_min, dx, range_max,
-                                                                 (float)(c2 / t_surface), dst);
+        if (e->k3_tma && n_layers >= K3T_LAYERS) {
+            static bool k3_attr = false;
+            if (!k3_attr) {
+                CK(cudaFuncSetAttribute(k3_fold_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3TSmem)));
+                k3_attr = true;
+            }
+            const int64_t n_strips = (nc + K3T_STRIP - 1) / K3T_STRIP;
+            const int grid = (int)std::min<int64_t>(n_strips, K3T_MINB * (int64_t)e->prop.multiProcessorCount);
+            // linear interpolation of B over 3 grid steps: relative error <= (3 dx)^2 / 8 * max(6 / nu^2, (c2/T)^2);
+            // keep it below 1e-7, and stay where x = c2 nu / T >= 0.25 for every layer (no expm1 branch)
+            double t_max = t_surface, t_min = t_surface;
+            for (int l = 0; l < n_layers; ++l) { t_max = std::max(t_max, t_layer[l]); t_min = std::min(t_min, t_layer[l]); }
+            double nu_min = std::max(3 * dx * std::sqrt(6.0 / 8e-7), 0.26 * t_max / c2);
+            if ((3 * dx) * (3 * dx) / 8 * (c2 / t_min) * (c2 / t_min) > 1e-7) nu_min = 1e30;      // grid too coarse: never
+            k3_fold_tma<<<grid, K3T_THREADS, sizeof(K3TSmem), e->stream>>>(e->kmat.p, e->kmat_ld, n_layers, fold_dev, nc,
+                                                                          e->i_begin, e->n_total, e->range_min, dx, range_max,
+                                                                          (float)(c2 / t_surface), (float)nu_min, dst);
+        } else {
+            k3_fold_f32<<<stream_grid(e, nc, 4), 256, 0, e->stream>>>(e->kmat.p, e->kmat_ld, n_layers, fold_dev, nc,
+                                                                     e->i_begin, e->n_total, e->range_min, dx, range_max,
+                                                                     (float)(c2 / t_surface), dst);
+        }
         CK(cudaGetLastError());
         ++launches;
     }
@@ -1246,6 +1266,7 @@ extern "C" int prb_set_option(prb_engine *e, int option, int64_t value) {
         case PRB_OPT_BATCH_LAYERS: e->batch_layers = value != 0; return PRB_OK;
         case PRB_OPT_FUSE_SINGLE_LAYER: e->fuse_single = value != 0; return PRB_OK;
         case PRB_OPT_POINT_KERNEL: e->point_kernel = value != 0; e->last.valid = false; return PRB_OK;
+        case PRB_OPT_FOLD_TMA: e->k3_tma = value != 0; return PRB_OK;
         case PRB_OPT_RECORD_BUDGET_MB: e->rec_budget_mb = value < 0 ? 0 : value; return PRB_OK;
         default: return fail(PRB_ERR_ARG, "prb_set_option: unknown option");
     }

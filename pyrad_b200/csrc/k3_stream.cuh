@@ -174,6 +174,149 @@ k3_fold_f32(const float *__restrict__ kmat, int64_t ld, int n_layers, const Fold
     }
 }
 
+// ---- the same fold with the k matrix staged through shared memory by TMA ----------------------------------------
+// A CTA owns strips of 1024 grid points (one float4 per thread) and walks the layers in groups of K3T_LAYERS rows:
+// one elected thread issues a bulk copy per row (4 KB each) into a small ring, one group ahead of the math, so the
+// loads in flight (5 CTAs x 16 KB per SM) are not held in registers; the math reads its float4 from shared memory
+// (conflict free).  Ring geometry measured on B200 (rows:slots:CTAs/SM -> ms at cfg4): 4:2:5 0.406, 4:3:4 0.424,
+// 6:3:3 0.459, 4:4:3 0.463, 2:4:6 0.535, 8:3:2 0.537.  The fold is instruction bound rather than memory bound (measured: staging alone
+// changes nothing), so above nu_interp_min the layer's Planck term is evaluated at the thread's first and last point
+// only and interpolated linearly for the two between -- half the instructions per point; k3_fold_f32 keeps the
+// per-point evaluation and is the reference the tests compare against.
+constexpr int K3T_THREADS = 256;
+constexpr int K3T_STRIP = K3T_THREADS * 4;             // points per strip
+#ifndef PRB_K3T_LAYERS
+#define PRB_K3T_LAYERS 4
+#endif
+#ifndef PRB_K3T_SLOTS
+#define PRB_K3T_SLOTS 2
+#endif
+#ifndef PRB_K3T_MINB
+#define PRB_K3T_MINB 5
+#endif
+constexpr int K3T_LAYERS = PRB_K3T_LAYERS;             // rows per ring slot
+constexpr int K3T_SLOTS = PRB_K3T_SLOTS;
+constexpr int K3T_MINB = PRB_K3T_MINB;                 // resident CTAs per SM the shared memory is sized for
+
+struct K3TSmem {
+    float k[K3T_SLOTS][K3T_LAYERS][K3T_STRIP];
+    uint64_t full[K3T_SLOTS];
+};
+
+__global__ void __launch_bounds__(K3T_THREADS, K3T_MINB)
+k3_fold_tma(const float *__restrict__ kmat, int64_t ld, int n_layers, const FoldLayer *__restrict__ layers,
+            int64_t n_chunk, int64_t i_begin, int64_t n_total, double x0, double dx, double x_last,
+            float c2_over_tsurf, float nu_interp_min, const K3Dst dst) {
+    extern __shared__ __align__(128) unsigned char k3_smem_raw[];
+    K3TSmem &sm = *reinterpret_cast<K3TSmem *>(k3_smem_raw);
+    const int tid = threadIdx.x;
+    const int64_t n_strips = (n_chunk + K3T_STRIP - 1) / K3T_STRIP;
+    const int groups = (n_layers + K3T_LAYERS - 1) / K3T_LAYERS;
+    // the CTA's work as one flat sequence of (strip, layer group) steps
+    const int64_t my_strips = blockIdx.x < n_strips ? (n_strips - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_steps = my_strips * groups;
+    if (tid == 0) {
+        for (int s = 0; s < K3T_SLOTS; ++s) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t step) {                   // thread 0 only
+        const int slot = (int)(step % K3T_SLOTS);
+        const int64_t strip = blockIdx.x + (step / groups) * gridDim.x;
+        const int g = (int)(step % groups);
+        const int64_t p0 = strip * K3T_STRIP;
+        const int64_t pts = min((int64_t)K3T_STRIP, ((n_chunk - p0) + 3) & ~int64_t(3));   // rows are padded to 4 floats
+        const int rows = min(K3T_LAYERS, n_layers - g * K3T_LAYERS);
+        mbar_expect_tx(&sm.full[slot], (uint32_t)(rows * pts * 4));
+        for (int r = 0; r < rows; ++r)
+            tma_bulk_g2s(sm.k[slot][r], kmat + (int64_t)(g * K3T_LAYERS + r) * ld + p0, (uint32_t)(pts * 4), &sm.full[slot]);
+    };
+    if (tid == 0)
+        for (int64_t s = 0; s < min(n_steps, (int64_t)(K3T_SLOTS - 1)); ++s) issue(s);
+
+    float nu[4], a3[4], rad[4], tau[4];
+    bool interp = false;
+    int64_t i0 = 0;
+    for (int64_t step = 0; step < n_steps; ++step) {
+        const int slot = (int)(step % K3T_SLOTS);
+        const int g = (int)(step % groups);
+        if (g == 0) {                                  // a new strip: surface radiance, zero optical depth
+            const int64_t strip = blockIdx.x + (step / groups) * gridDim.x;
+            i0 = strip * K3T_STRIP + 4 * tid;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double x = axis_value(i_begin + i0 + q, n_total, x0, dx, x_last);
+                nu[q] = (float)x;
+                a3[q] = (float)(2E8 * hPlanck * (cLight * cLight) * (x * x * x));
+                rad[q] = planck_f32(a3[q], c2_over_tsurf * nu[q]);
+                tau[q] = 0.f;
+            }
+            interp = nu[0] >= nu_interp_min;
+        }
+        // keep the ring two steps ahead: the slot being refilled was released by the barrier at the end of step-1
+        if (tid == 0 && step + K3T_SLOTS - 1 < n_steps) issue(step + K3T_SLOTS - 1);
+        mbar_wait(&sm.full[slot], (uint32_t)((step / K3T_SLOTS) & 1));
+        const int rows = min(K3T_LAYERS, n_layers - g * K3T_LAYERS);
+        if (i0 < n_chunk) {
+#pragma unroll
+            for (int r = 0; r < K3T_LAYERS; ++r) {
+                if (r < rows) {
+                    const float4 k4 = *reinterpret_cast<const float4 *>(&sm.k[slot][r][4 * tid]);
+                    const FoldLayer fl = layers[g * K3T_LAYERS + r];
+                    const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+                    float b[4];
+                    if (interp) {
+                        // B(nu, T_l) at the thread's first and last point, the two between by linear interpolation
+                        // (relative error < 1e-7 above nu_interp_min, chosen by the host from the grid spacing); one
+                        // path decision per thread instead of per point
+                        const float xa = fl.c2_over_t * nu[0], xb = fl.c2_over_t * nu[3];
+                        float ba, bb;
+                        if (xa > 8.5f) {
+                            const float ya = k3_ex2(xa * -1.4426950408889634f), yb = k3_ex2(xb * -1.4426950408889634f);
+                            ba = a3[0] * fmaf(ya, ya, ya);
+                            bb = a3[3] * fmaf(yb, yb, yb);
+                        } else {
+                            ba = a3[0] * k3_rcp(k3_ex2(xa * 1.4426950408889634f) - 1.0f);
+                            bb = a3[3] * k3_rcp(k3_ex2(xb * 1.4426950408889634f) - 1.0f);
+                        }
+                        const float db = bb - ba;
+                        b[0] = ba; b[1] = fmaf(db, 1.0f / 3.0f, ba); b[2] = fmaf(db, 2.0f / 3.0f, ba); b[3] = bb;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) b[q] = planck_f32(a3[q], fl.c2_over_t * nu[q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float e = kk[q] * fl.neg_depth_log2e;
+                        const float t = k3_ex2(e);
+                        rad[q] = fmaf(t, rad[q] - b[q], b[q]);
+                        tau[q] += e;
+                    }
+                }
+            }
+        }
+        __syncthreads();                               // every thread is done with this slot: it may be refilled
+        if (g == groups - 1 && i0 < n_chunk) {
+            const float4 r4 = make_float4(rad[0], rad[1], rad[2], rad[3]);
+            const float4 t4 = make_float4(exp2f(tau[0]), exp2f(tau[1]), exp2f(tau[2]), exp2f(tau[3]));
+            const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll 1
+            for (int d = 0; d < dst.n; ++d) {
+                if (i0 + 3 < n_chunk) {
+                    *reinterpret_cast<float4 *>(dst.rad[d] + i0) = r4;
+                    *reinterpret_cast<float4 *>(dst.trans[d] + i0) = t4;
+                } else {
+                    for (int q = 0; q < 4 && i0 + q < n_chunk; ++q) {
+                        dst.rad[d][i0 + q] = rr[q];
+                        dst.trans[d][i0 + q] = tt[q];
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ---- cross-GPU completion barrier of one gather step ------------------------------------------------
 // Launched (one warp) after the kernel that stored this rank's spectra into every peer's gather buffer.
 // Lane p publishes "rank r finished epoch E" into peer p's flag block with a system-scope release, then

@@ -16,6 +16,8 @@ def main():
     win = [eng.window_len(c, w["res"]) for c in w["cutoff"]]
     qt = np.array([[s.q(T) for s in sp] for T in w["T"]])
     e.set_timing(True)
+    if os.environ.get("QA_NOTMAFOLD"):
+        e.set_option(eng.OPT_FOLD_TMA, 0)
     if os.environ.get("QA_OLDNARROW"):
         e.set_option(eng.OPT_POINT_KERNEL, 0)
     if os.environ.get("QA_NARROW"):

@@ -380,3 +380,22 @@ def test_pipelined_gas_cell_equals_separate_calls(engine):
                                  w["conc"], mol, qt, q296, win, 288.0, w["range_max"])
     finally:
         engine.set_result_host()
+
+
+@pytest.mark.parametrize("n_layers,rmax", [(24, 660.0), (9, 607.777), (8, 601.003)])
+def test_tma_staged_fold_equals_register_fold(engine, n_layers, rmax):
+    """k3_fold_tma (k matrix through a shared-memory ring fed by TMA bulk copies, Planck term interpolated across each
+    thread's four points) against k3_fold_f32 (register-held loads, per-point Planck): the transmittance is the same
+    arithmetic (bitwise), the radiance agrees to FP32 rounding -- full strips, ragged last strips, ragged layer groups."""
+    w = workloads.atmosphere(n_layers=n_layers, n_lines=6000, rmin=600.0, rmax=rmax, res=0.001, top_km=50.0)
+    H.engine_setup(engine, w)
+    try:
+        engine.set_option(eng.OPT_FOLD_TMA, 0)
+        rad0, tr0 = _run_atm(engine, w)
+        engine.set_option(eng.OPT_FOLD_TMA, 1)
+        rad1, tr1 = _run_atm(engine, w)
+    finally:
+        engine.set_option(eng.OPT_FOLD_TMA, 1)
+    assert np.array_equal(tr0, tr1)
+    np.testing.assert_allclose(rad1, rad0, rtol=2e-6, atol=0)
+    assert np.isfinite(rad1).all() and 0 <= tr1.min() <= tr1.max() <= 1
