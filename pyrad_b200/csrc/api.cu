@@ -142,6 +142,9 @@ struct prb_engine {
     PeerState peer;
     DevBuf<unsigned int> peer_err;
     IngestScratch ingest;
+    DevBuf<int2> tile_bounds_buf[2];
+    int tile_bounds_next = 0;
+    int extra_launches = 0;                           // helper kernels launched inside run_line_sum (counted per call)
     // pipelined host upload (prb_gas_cell_host)
     cudaStream_t copy_stream = nullptr, stream2 = nullptr;
     std::vector<cudaEvent_t> pipe_ev;
@@ -233,6 +236,7 @@ extern "C" int prb_destroy(prb_engine *e) {
     if (e->blk_h) cudaFreeHost(e->blk_h);
     e->blk_d.release();
     e->ingest.release();
+    e->tile_bounds_buf[0].release(); e->tile_bounds_buf[1].release();
     e->dev_scal.release();
     if (e->pin_scal) cudaFreeHost(e->pin_scal);
     for (auto x : e->pipe_ev) cudaEventDestroy(x);
@@ -652,6 +656,22 @@ static cudaError_t launch_k2_sub(prb_engine *e, K2Args a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// Thread-per-point launches: the staged line range of every (layer, tile), precomputed in one parallel pass.
+static_assert(KP_TILE == KN_TILE, "k2_point and k2_narrow share the tile size of k2_tile_bounds");
+static int tile_bounds(prb_engine *e, K2Args &b) {
+    const size_t cnt = (size_t)b.n_layers * b.n_tiles;
+    if (e->tile_bounds_buf[e->tile_bounds_next].ensure(cnt) != cudaSuccess)
+        return fail(PRB_ERR_CUDA, "tile bounds allocation failed");
+    int2 *buf = e->tile_bounds_buf[e->tile_bounds_next].p;
+    e->tile_bounds_next ^= 1;                       // two buffers: consecutive launches of one call never share one
+    k2_tile_bounds<<<dim3((unsigned)((b.n_tiles + 255) / 256), (unsigned)b.n_layers), 256, 0, e->stream>>>(
+        b.layers, b.n_layers, b.idx, b.i_begin, b.n_tiles, KP_TILE, buf);
+    CK(cudaGetLastError());
+    ++e->extra_launches;
+    b.tile_bounds = buf;
+    return PRB_OK;
+}
+
 // ONE K2 launch for jobs[0..n), which must share a kernel class (all narrow, or all the same ppt) and be sorted
 // widest window first.  tab_dev holds the n table rows (fill_k2_row); the launch's tile counter lives in jobs[0]'s
 // state block and must be zero (stream-ordered) when the kernel starts.
@@ -680,6 +700,8 @@ static int run_line_sum(prb_engine *e, const LayerJob *jobs, int n, const K2Laye
             K2Args b = a;
             b.layers = tab_dev + k0;
             b.n_layers = std::min(n - k0, 65535);
+            int rc2 = tile_bounds(e, b);
+            if (rc2) return rc2;
             k2_point<<<dim3((unsigned)a.n_tiles, (unsigned)b.n_layers), KP_THREADS, sizeof(KPSmem), e->stream>>>(b);
         }
         ce = cudaGetLastError();
@@ -692,6 +714,8 @@ static int run_line_sum(prb_engine *e, const LayerJob *jobs, int n, const K2Laye
             K2Args b = a;
             b.layers = tab_dev + k0;
             b.n_layers = std::min(n - k0, 65535);
+            int rc2 = tile_bounds(e, b);
+            if (rc2) return rc2;
             k2_narrow<<<dim3((unsigned)a.n_tiles, (unsigned)b.n_layers), KN_THREADS, sizeof(KNSmem), e->stream>>>(b);
         }
         ce = cudaGetLastError();
@@ -1023,6 +1047,7 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
     }
     CK(cudaMemcpyAsync(e->blk_d.p, e->blk_h, blk_bytes, cudaMemcpyHostToDevice, e->stream));
     int launches = 0;
+    e->extra_launches = 0;
     if (pipe) {
         if (!fused) return fail(PRB_ERR_STATE, "pipelined upload needs the fused single-layer path");
         const int64_t n = e->n_lines, na = e->n_alloc;
@@ -1141,7 +1166,7 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
         CK(cudaGetLastError());
         ++launches;
     }
-    e->last_launches = launches;
+    e->last_launches = launches + e->extra_launches;
     // status blocks back in the same breath; the synchronisation also keeps the pinned block ours until the next call
     std::vector<DevState> hst(n_rows);
     CK(cudaMemcpyAsync(hst.data(), st_dev, sizeof(DevState) * n_rows, cudaMemcpyDeviceToHost, e->stream));

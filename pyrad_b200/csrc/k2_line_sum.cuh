@@ -117,6 +117,7 @@ struct K2Args {
     int n_chunk;               // grid points owned
     int n_tiles;               // tiles per layer handled by this launch
     int tile_base;             // first tile of this launch (sub-launches of a pipelined upload; 0 otherwise)
+    const int2 *tile_bounds;   // thread-per-point kernels: staged line range per (layer, tile), from k2_tile_bounds
     int variant;               // PRB_K2_GENERAL / PRB_K2_CLASSED
     int out_mode;              // PRB_OUT_F64 / PRB_OUT_F32
     DevState *st;              // tile_counter of this launch

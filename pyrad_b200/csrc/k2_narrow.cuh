@@ -16,6 +16,26 @@
 
 namespace prb {
 
+// Line range [lo, hi) of every (layer, tile) of a thread-per-point launch, one thread per tile: the two binary searches
+// over the global index array are a chain of dependent loads (~4 us) that used to sit at the head of every CTA's short
+// life; here they run massively parallel once per launch and the CTAs start with a single load.
+__global__ void __launch_bounds__(256)
+k2_tile_bounds(const K2Layer *__restrict__ layers, int n_layers, const int32_t *__restrict__ idx, long long i_begin,
+               int n_tiles, int tile_pts, int2 *__restrict__ bounds) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ly = blockIdx.y;
+    if (t >= n_tiles || ly >= n_layers) return;
+    const int wm = layers[ly].wm;
+    const long long k_lo = i_begin + (long long)t * tile_pts - wm;
+    const long long k_hi = i_begin + (long long)t * tile_pts + tile_pts - 1 + wm + 1;
+    int a = layers[ly].l_begin, b = layers[ly].l_end;
+    while (a < b) { const int m = (a + b) >> 1; if ((long long)idx[m] < k_lo) a = m + 1; else b = m; }
+    const int lo = a;
+    b = layers[ly].l_end;
+    while (a < b) { const int m = (a + b) >> 1; if ((long long)idx[m] < k_hi) a = m + 1; else b = m; }
+    bounds[(size_t)ly * n_tiles + t] = make_int2(lo, a);
+}
+
 constexpr int KN_THREADS = 256;
 constexpr int KN_ROUNDS = 4;                          // points per thread (strided by 256)
 constexpr int KN_TILE = KN_THREADS * KN_ROUNDS;       // 1024 points per CTA
@@ -44,11 +64,17 @@ __global__ void __launch_bounds__(KN_THREADS, 4) k2_narrow(const K2Args a) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 0) {
-        const long long k_lo = a.i_begin + tile0 - wm;
-        const long long k_hi = a.i_begin + tile0 + KN_TILE - 1 + wm + 1;
-        const int l_end = __ldg(&L->l_end);
-        const int lo = warp_lower_bound(a.idx, __ldg(&L->l_begin), l_end, k_lo);
-        const int hi = warp_lower_bound(a.idx, lo, l_end, k_hi);
+        int lo, hi;
+        if (a.tile_bounds) {
+            const int2 bd = __ldg(a.tile_bounds + (size_t)blockIdx.y * gridDim.x + blockIdx.x);
+            lo = bd.x; hi = bd.y;
+        } else {
+            const long long k_lo = a.i_begin + tile0 - wm;
+            const long long k_hi = a.i_begin + tile0 + KN_TILE - 1 + wm + 1;
+            const int l_end = __ldg(&L->l_end);
+            lo = warp_lower_bound(a.idx, __ldg(&L->l_begin), l_end, k_lo);
+            hi = warp_lower_bound(a.idx, lo, l_end, k_hi);
+        }
         if (lane == 0) { sm.lo = lo & ~3; sm.hi = hi; }
     }
     __syncthreads();

@@ -19,6 +19,7 @@
 #pragma once
 #include "common.cuh"
 #include "k2_line_sum.cuh"
+#include "k2_narrow.cuh"
 
 namespace prb {
 
@@ -55,11 +56,17 @@ __global__ void __launch_bounds__(KP_THREADS, 4) k2_point(const K2Args a) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 0) {
-        const long long k_lo = a.i_begin + tile0 - wm;
-        const long long k_hi = a.i_begin + tile0 + KP_TILE - 1 + wm + 1;
-        const int l_end = __ldg(&L->l_end);
-        const int lo = warp_lower_bound(a.idx, __ldg(&L->l_begin), l_end, k_lo);
-        const int hi = warp_lower_bound(a.idx, lo, l_end, k_hi);
+        int lo, hi;
+        if (a.tile_bounds) {
+            const int2 bd = __ldg(a.tile_bounds + (size_t)blockIdx.y * gridDim.x + blockIdx.x);
+            lo = bd.x; hi = bd.y;
+        } else {
+            const long long k_lo = a.i_begin + tile0 - wm;
+            const long long k_hi = a.i_begin + tile0 + KP_TILE - 1 + wm + 1;
+            const int l_end = __ldg(&L->l_end);
+            lo = warp_lower_bound(a.idx, __ldg(&L->l_begin), l_end, k_lo);
+            hi = warp_lower_bound(a.idx, lo, l_end, k_hi);
+        }
         if (lane == 0) { sm.lo = lo & ~3; sm.hi = hi; }
     }
     __syncthreads();

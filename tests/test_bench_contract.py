@@ -1,0 +1,29 @@
+"""The bench.py JSON contract on CPU: the reference arm (the oracle port on the host cores) prints ONE line with the
+keys the driver reads, on the same metric / unit / config as the GPU arm."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "line-gridpoint evals/s" and d["unit"] == "pairs/s"
+    assert d["higher_is_better"] is True and d["value"] > 1e6 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "cfg2" in d["config"]["workload"]
+
+
+def test_gpu_arm_declares_the_same_metric():
+    import bench
+    assert bench.METRIC == "line-gridpoint evals/s" and bench.UNIT == "pairs/s"
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert bench.METRIC.split()[0] in base["metric"]
