@@ -13,13 +13,17 @@ from . import partition as pt
 class ShardPlan:
     """Everything a rank needs to know about its chunk."""
 
-    def __init__(self, nu0, range_min, res, n_total, windows, rank, world, balance=True):
+    def __init__(self, nu0, range_min, res, n_total, windows, rank, world, balance=True, chunks=None, cost=None):
         idx = pt.line_index(nu0, range_min, res)
-        if balance and world > 1:
-            cost = pt.block_time_cost(idx, n_total, windows)
-            self.chunks = pt.balanced_chunks(cost, n_total, world)
+        self.cost = cost
+        if chunks is not None:
+            self.chunks = [tuple(c) for c in chunks]
+        elif balance and world > 1:
+            self.cost = pt.block_time_cost(idx, n_total, windows)
+            self.chunks = pt.balanced_chunks(self.cost, n_total, world)
         else:
             self.chunks = pt.equal_chunks(n_total, world)
+        self._args = (nu0, range_min, res, n_total, windows)
         self.rank, self.world = rank, world
         self.i_begin, self.i_end = self.chunks[rank]
         self.wmax = max(max(int(w) - 2, 0) for w in np.atleast_1d(windows))
@@ -29,6 +33,16 @@ class ShardPlan:
         self.l0, self.l1 = l0, max(l1, l0)
         self.max_chunk = max(b - a for a, b in self.chunks)
         self.n_total = n_total
+
+    def rebalanced(self, measured_ms):
+        """A new plan after one measured run: measured_ms[r] = device time rank r spent on its chunk (all ranks pass
+        the same list).  Returns self when the model had no cost array (equal chunks) or nothing moves."""
+        if self.cost is None or self.world == 1:
+            return self
+        chunks, corrected = pt.rebalanced_chunks(self.cost, self.chunks, measured_ms, self.n_total)
+        if chunks == self.chunks:
+            return self
+        return ShardPlan(*self._args, self.rank, self.world, chunks=chunks, cost=corrected)
 
     def subset(self, lines):
         return {k: np.ascontiguousarray(np.asarray(v)[self.l0:self.l1]) for k, v in lines.items()}

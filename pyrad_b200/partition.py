@@ -107,6 +107,20 @@ def balanced_chunks(cost, n_total, nranks, block=ALIGN):
     return [(min(c0 * block, n_total), min(c1 * block, n_total)) for c0, c1 in zip(cuts[:-1], cuts[1:])]
 
 
+def rebalanced_chunks(cost, chunks, measured, n_total, block=ALIGN):
+    """One feedback step: `measured[r]` is what rank r actually took on `chunks[r]`.  The model's cost of every block
+    is rescaled by its rank's measured/predicted ratio (the model cannot know, e.g., that high-wavenumber lines carry
+    wider Doppler cores and so more Gaussian work per pair) and the cuts are recomputed on the corrected cost."""
+    cost = np.asarray(cost, dtype=np.float64)
+    corrected = cost.copy()
+    for (a, b), t in zip(chunks, measured):
+        b0, b1 = a // block, (b + block - 1) // block
+        pred = cost[b0:b1].sum()
+        if pred > 0 and t > 0:
+            corrected[b0:b1] *= t / pred
+    return balanced_chunks(corrected, n_total, len(chunks), block), corrected
+
+
 def equal_chunks(n_total, nranks, block=ALIGN):
     nb = (n_total + block - 1) // block
     return balanced_chunks(np.ones(nb), n_total, nranks, block)

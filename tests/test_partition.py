@@ -65,6 +65,26 @@ def test_time_cost_weights_classes_and_points():
                        pt.block_time_cost(idx, n_total, [1]))
 
 
+def test_feedback_rebalancing_moves_work_off_the_slow_rank():
+    rng = np.random.default_rng(4)
+    n_total = 2_000_000
+    idx = np.sort(rng.integers(0, n_total, 400_000))
+    cost = pt.block_time_cost(idx, n_total, [5000, 800, 60])
+    chunks = pt.balanced_chunks(cost, n_total, 4)
+    # the model is blind to a cost that grows with wavenumber: rank r really takes (1 + 0.1 r) x its prediction
+    true = cost * (1 + 0.3 * np.arange(len(cost)) / len(cost))
+    per = lambda ch, c: [c[a // pt.ALIGN:(b + pt.ALIGN - 1) // pt.ALIGN].sum() for a, b in ch]
+    measured = per(chunks, true)
+    new, corrected = pt.rebalanced_chunks(cost, chunks, measured, n_total)
+    assert new[0][0] == 0 and new[-1][1] == n_total and all(a[1] == b[0] for a, b in zip(new[:-1], new[1:]))
+    assert max(per(new, true)) < max(measured)                       # the slowest rank got lighter
+    assert max(per(new, true)) <= 1.03 * np.sum(true) / 4 + true.max()
+    plan = pd.ShardPlan(np.sort(rng.uniform(0, 2000, 50_000)), 0.0, 0.001, n_total, [5000, 60], 1, 4)
+    again = plan.rebalanced([1.0, 1.3, 1.0, 1.0])
+    assert again is not plan and again.chunks != plan.chunks and again.chunks[1][1] - again.chunks[1][0] < plan.chunks[1][1] - plan.chunks[1][0]
+    assert pd.ShardPlan(np.zeros(0), 0.0, 0.001, 8192, [5], 0, 1).rebalanced([1.0]).chunks == [(0, 8192)]
+
+
 def test_line_subset_reaches_every_window():
     ln = synth.make_lines(5000, 0.0, 100.0, 5)
     idx = pt.line_index(ln["nu"], 0.0, 0.01)
