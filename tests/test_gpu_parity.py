@@ -399,3 +399,46 @@ def test_tma_staged_fold_equals_register_fold(engine, n_layers, rmax):
     assert np.array_equal(tr0, tr1)
     np.testing.assert_allclose(rad1, rad0, rtol=2e-6, atol=0)
     assert np.isfinite(rad1).all() and 0 <= tr1.min() <= tr1.max() <= 1
+
+
+def test_error_behaviour_is_loud_and_specific(engine):
+    """Nothing is silently clamped or degraded: call-order violations, bad arguments, grids too large for exact FP32
+    offsets and non-finite line data each come back as their own error code with a message."""
+    from pyrad_b200 import _lib
+    w = small_cell(n_lines=500)
+    L = w["lines"]
+
+    def code_of(fn):
+        with pytest.raises(_lib.EngineError) as ei:
+            fn()
+        assert str(ei.value)
+        return ei.value.code
+
+    engine.upload_lines(L, 1)
+    assert code_of(lambda: engine.layer_prepass(296, 1013.0, [4e-4], [44.0], [286.0], [286.0], 500)) == -3   # grid not set
+    engine.set_grid(600.0, 0.01, 10000)
+    assert code_of(engine.line_sum) == -3                                                  # no prepass yet
+    assert code_of(lambda: engine.set_grid(600.0, -0.01, 10000)) == -2
+    assert code_of(lambda: engine.set_grid(600.0, 0.01, 10000, 5000, 4000)) == -2
+    assert code_of(lambda: engine.layer_prepass(296, 1013.0, [4e-4], [44.0], [286.0], [286.0], 0)) == -2   # window < 1 sample
+    assert code_of(lambda: engine.layer_prepass(-5.0, 1013.0, [4e-4], [44.0], [286.0], [286.0], 500)) == -2
+    unsorted = {k: v[::-1].copy() for k, v in L.items()}
+    assert code_of(lambda: engine.upload_lines(unsorted, 1)) == -2
+    grp = dict(L); grp["group"] = np.full(len(L["nu"]), 3, dtype=np.int32)
+    assert code_of(lambda: engine.upload_lines(grp, 2)) == -2                              # group id out of range
+    # a chunk of 2^24 points cannot keep integer offsets exact in FP32: the caller is told to shard
+    engine.upload_lines(L, 1)
+    engine.set_grid(600.0, 0.00001, 1 << 24)
+    assert code_of(lambda: engine.layer_prepass(296, 1013.0, [4e-4], [44.0], [286.0], [286.0], 500)) == -4
+    # non-finite line data surfaces when the sum is read, not as NaNs in the spectrum
+    bad = {k: v.copy() for k, v in L.items()}
+    bad["gamma_air"][7] = np.nan
+    engine.upload_lines(bad, 1)
+    engine.set_grid(600.0, 0.01, 10000)
+    engine.layer_prepass(296, 1013.0, [4e-4], [44.0], [286.0], [286.0], 500)
+    assert code_of(engine.line_sum) == -4
+    # and the engine is still usable afterwards
+    engine.upload_lines(L, 1)
+    engine.set_grid(600.0, 0.01, 10000)
+    engine.layer_prepass(296, 1013.0, [4e-4], [44.0], [286.0], [286.0], 500)
+    assert np.isfinite(engine.line_sum()).all()
