@@ -98,6 +98,11 @@ int     prb_ingest_hitran_csv(prb_engine *e, const char *text, int64_t n_bytes, 
 int     prb_download_lines(prb_engine *e, double *nu0, double *s296, double *einstein_a, double *elower,
                            double *gamma_air, double *gamma_self, double *delta_air, double *n_air);
 int64_t prb_line_count(prb_engine *e);                  /* lines on the device; < 0 when none */
+/* xsc cross-section table text (two space-separated columns; returnXscFileContents pyradUtilities.py:680-696) parsed
+ * on the device: rows that are not exactly two numbers are skipped, as the reference skips them.  capacity = entries
+ * the two output arrays can hold (the row count of the text is always enough); n_rows_out = rows kept. */
+int     prb_parse_xsc_text(prb_engine *e, const char *text, int64_t n_bytes, int64_t capacity, double *wavenumber,
+                           double *cross_section, int64_t *n_rows_out);
 int     prb_debug_parse_double(const char *text, int64_t n_bytes, double *value);   /* host-side run of the device parser */
 
 /* ---- grid (a10/a11): point i of the FULL grid sits at range_min + i*res, i in [0, n_total).

@@ -45,6 +45,7 @@ PROTOTYPES = {
     "prb_ingest_hitran_csv": (C.c_int, [_vp, C.c_char_p, _i64, _d, _d, _lp]),
     "prb_download_lines": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "prb_line_count": (_i64, [_vp]),
+    "prb_parse_xsc_text": (C.c_int, [_vp, C.c_char_p, _i64, _i64, _dp, _dp, _lp]),
     "prb_debug_parse_double": (C.c_int, [C.c_char_p, _i64, _dp]),
     "prb_set_grid": (C.c_int, [_vp, _d, _d, _i64, _i64, _i64]),
     "prb_layer_prepass": (C.c_int, [_vp, _d, _d, _i32, _dp, _dp, _dp, _dp, _dp, _i64]),

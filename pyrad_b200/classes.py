@@ -430,7 +430,7 @@ class Molecule(list, _Spectral):
     def _init_xsc(self, spec):
         """xsc branch (pyradClasses.py:466-505): table -> 0.01 grid (np.interp when coarser) -> aligned placement."""
         name, filename = list(spec.items())[0]
-        wn, xs = _io.read_xsc_table(name, filename, DATA_ROOT)
+        wn, xs = _io.read_xsc_table(name, filename, DATA_ROOT, engine())
         info = _io.parse_xsc_filename(filename)
         rmin, rmax = (float(v) for v in info["RANGE"].split("-"))
         temp = int(float(info["TEMP"]))

@@ -1577,6 +1577,66 @@ extern "C" int prb_ingest_hitran_csv(prb_engine *e, const char *text, int64_t n_
     return PRB_OK;
 }
 
+// Two-column xsc table text -> (wavenumber, cross section) arrays, parsed on the device like the line lists.
+extern "C" int prb_parse_xsc_text(prb_engine *e, const char *text, int64_t n_bytes, int64_t capacity, double *wavenumber,
+                                  double *cross_section, int64_t *n_rows_out) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (n_bytes < 0 || (n_bytes > 0 && !text) || capacity < 0 || !n_rows_out || (capacity > 0 && (!wavenumber || !cross_section)))
+        return fail(PRB_ERR_ARG, "prb_parse_xsc_text: bad arguments");
+    if (n_bytes > (int64_t(1) << 31)) return fail(PRB_ERR_ARG, "prb_parse_xsc_text: more than 2 GiB of text");
+    CK(cudaSetDevice(e->device));
+    *n_rows_out = 0;
+    if (n_bytes == 0) return PRB_OK;
+    IngestScratch &g = e->ingest;
+    const int64_t n_pad = std::max<int64_t>((n_bytes + 15) & ~int64_t(15), 16);
+    CK(g.text.ensure(n_pad));
+    CK(g.nl.ensure(n_pad));
+    CK(g.scal.ensure(8));
+    CK(cudaMemsetAsync(g.text.p + (n_pad - 16), 0, 16, e->stream));
+    CK(cudaMemcpyAsync(g.text.p, text, n_bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(g.scal.p, 0, 64, e->stream));
+    k5_mark_newlines<<<(unsigned)((n_pad / 16 + 255) / 256), 256, 0, e->stream>>>(g.text.p, n_bytes, g.nl.p, g.scal.p);
+    CK(cudaGetLastError());
+    unsigned long long n_nl_u = 0;
+    CK(cudaMemcpyAsync(&n_nl_u, g.scal.p, sizeof n_nl_u, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    const int64_t n_nl = (int64_t)n_nl_u;
+    const int64_t n_rows = n_nl + (text[n_bytes - 1] != '\n' ? 1 : 0);
+    if (n_rows == 0) return PRB_OK;
+    CK(g.nlpos.ensure(n_nl + 1));
+    size_t tmp_bytes = 0;
+    thrust::counting_iterator<int64_t> counting(0);
+    long long *d_selected = reinterpret_cast<long long *>(g.scal.p + 4);
+    CK(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, counting, g.nl.p, g.nlpos.p, d_selected, n_bytes, e->stream));
+    CK(g.tmp.ensure(tmp_bytes));
+    CK(cub::DeviceSelect::Flagged(g.tmp.p, tmp_bytes, counting, g.nl.p, g.nlpos.p, d_selected, n_bytes, e->stream));
+    for (int c = 0; c < 4; ++c) CK(g.cols[c].ensure(n_rows));
+    CK(g.keep.ensure(n_rows));
+    CK(g.pos.ensure(n_rows + 1));
+    k5_parse_xsc_rows<<<(unsigned)((n_rows + K5_ROWS - 1) / K5_ROWS), K5_ROWS, 0, e->stream>>>(g.text.p, n_bytes, g.nlpos.p, n_nl,
+                                                                                             n_rows, g.cols[0].p, g.cols[1].p, g.keep.p);
+    CK(cudaGetLastError());
+    size_t tmp2 = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, g.keep.p, g.pos.p, n_rows, e->stream));
+    CK(g.tmp.ensure(tmp2));
+    CK(cub::DeviceScan::ExclusiveSum(g.tmp.p, tmp2, g.keep.p, g.pos.p, n_rows, e->stream));
+    int32_t last_pos = 0, last_keep = 0;
+    CK(cudaMemcpyAsync(&last_pos, g.pos.p + (n_rows - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(&last_keep, g.keep.p + (n_rows - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    const int64_t kept = (int64_t)last_pos + last_keep;
+    *n_rows_out = kept;
+    if (kept > capacity) return fail(PRB_ERR_ARG, "prb_parse_xsc_text: output capacity too small (n_rows_out holds the count)");
+    if (kept == 0) return PRB_OK;
+    k5_scatter2<<<(unsigned)((n_rows + 255) / 256), 256, 0, e->stream>>>(g.cols[0].p, g.cols[1].p, g.keep.p, g.pos.p, n_rows,
+                                                                       g.cols[2].p, g.cols[3].p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(wavenumber, g.cols[2].p, sizeof(double) * kept, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(cross_section, g.cols[3].p, sizeof(double) * kept, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PRB_OK;
+}
+
 extern "C" int prb_download_lines(prb_engine *e, double *nu0, double *s296, double *einstein_a, double *elower,
                                   double *gamma_air, double *gamma_self, double *delta_air, double *n_air) {
     if (!e || !e->lines_set) return fail(PRB_ERR_STATE, "prb_download_lines: no line list on the device");

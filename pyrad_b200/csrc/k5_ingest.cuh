@@ -121,6 +121,46 @@ k5_parse_rows(const char *__restrict__ text, int64_t n, const int64_t *__restric
     if (st == ROW_BAD) atomicMin(first_bad, (unsigned long long)r);
 }
 
+// xsc cross-section tables (returnXscFileContents pyradUtilities.py:680-696): a row is kept when, stripped and split at
+// runs of SPACES, it has exactly two tokens that both parse as numbers; anything else is skipped (the reference logs
+// "line skipped").  Leading '#' rows are comments (openReturnLines :100-101).
+__global__ void __launch_bounds__(K5_ROWS)
+k5_parse_xsc_rows(const char *__restrict__ text, int64_t n, const int64_t *__restrict__ nl_pos, int64_t n_nl, int64_t n_rows,
+                  double *__restrict__ wn, double *__restrict__ xs, int32_t *__restrict__ keep) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int64_t b = r == 0 ? 0 : nl_pos[r - 1] + 1;
+    const int64_t e = r < n_nl ? nl_pos[r] : n;
+    const char *p = text + b, *end = text + e;
+    while (p < end && is_ws(*p)) ++p;                             // line.strip()
+    while (end > p && is_ws(end[-1])) --end;
+    int32_t k = 0;
+    if (p < end && *p != '#') {
+        const char *t1 = p;
+        while (t1 < end && *t1 != ' ') ++t1;                      // first token: up to the first space
+        const char *t2 = t1;
+        while (t2 < end && *t2 == ' ') ++t2;                      // the run of spaces
+        const char *t3 = t2;
+        while (t3 < end && *t3 != ' ') ++t3;                      // second token must reach the end of the row
+        double a, c;
+        if (t1 > p && t2 > t1 && t3 == end && t3 > t2 && parse_double(p, t1, &a) && parse_double(t2, t3, &c)) {
+            wn[r] = a;
+            xs[r] = c;
+            k = 1;
+        }
+    }
+    keep[r] = k;
+}
+
+__global__ void __launch_bounds__(256)
+k5_scatter2(const double *__restrict__ a, const double *__restrict__ b, const int32_t *__restrict__ keep,
+            const int32_t *__restrict__ pos, int64_t n_rows, double *__restrict__ oa, double *__restrict__ ob) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows || !keep[r]) return;
+    oa[pos[r]] = a[r];
+    ob[pos[r]] = b[r];
+}
+
 // The reference's dict keyed by nu: a later row with the same wavenumber replaces the earlier one.  Files are
 // ascending in nu, so duplicates are adjacent (only comment rows can sit between them).
 __global__ void __launch_bounds__(256)

@@ -128,6 +128,15 @@ class Engine:
         _lib.check(self._lib.prb_download_lines(self._h, *[_dp(cols[k]) for k in names]))
         return cols
 
+    def parse_xsc_text(self, text):
+        """Two-column xsc table bytes -> (wavenumber, cross section) float64 arrays, parsed on the device (K5)."""
+        blob = bytes(text)
+        cap = blob.count(b"\n") + 1
+        wn, xs = np.empty(cap), np.empty(cap)
+        n = C.c_int64()
+        _lib.check(self._lib.prb_parse_xsc_text(self._h, blob, len(blob), cap, _dp(wn), _dp(xs), C.byref(n)))
+        return wn[:n.value].copy(), xs[:n.value].copy()
+
     def set_grid(self, range_min, res, n_total, i_begin=0, i_end=None):
         i_end = n_total if i_end is None else i_end
         _lib.check(self._lib.prb_set_grid(self._h, float(range_min), float(res), int(n_total), int(i_begin),

@@ -115,19 +115,16 @@ def parse_xsc_filename(filename):
     return out
 
 
-def read_xsc_table(name, filename, root=None):
+def read_xsc_table(name, filename, root=None, engine=None):
+    """(wavenumber, cross section) of an xsc table file (returnXscFileContents :680-696), parsed on the device."""
     path = os.path.join(data_dir(root), "xsc", name, filename)
-    rows = _rows(path)
-    if rows is None:
+    if not os.path.isfile(path):
         raise FileNotFoundError(path)
-    wn, xs = [], []
-    for row in rows:
-        parts = re.split("[ ]+", row.strip())
-        if len(parts) == 2:
-            try:
-                a, b = float(parts[0]), float(parts[1])
-            except ValueError:
-                continue
-            wn.append(a)
-            xs.append(b)
-    return np.array(wn), np.array(xs)
+    if engine is None:
+        raise ValueError("read_xsc_table needs the CUDA engine (there is no host parser in this package)")
+    with open(path, "rb") as f:
+        blob = f.read()
+    head = blob.split(b"\n", 1)[0]
+    if not blob or NULL_TAG.encode() in head:
+        raise FileNotFoundError(path)
+    return engine.parse_xsc_text(blob)

@@ -114,3 +114,25 @@ def test_device_ingest_edge_cases(engine):
         engine.ingest_csv(b"2,1,5.5,1e-20\n", 0.0, 10.0)               # too few cells
     with pytest.raises(_lib.EngineError):
         engine.ingest_csv(one + b"\n" + one.replace(b"5.5", b"4.5") + b"\n", 0.0, 10.0)   # descending wavenumbers
+
+
+@pytest.mark.gpu
+def test_device_xsc_table_parse_matches_oracle_reader(engine):
+    fx, fy = synth.make_xsc_table(800.0, 860.0, 0.02, 9)
+    rows = ["%r     %r" % (float(a), float(b)) for a, b in zip(fx, fy)]
+    rows[5] = "  " + rows[5] + "   "                     # stripped
+    rows[9] = rows[9].replace("     ", " ")              # any run of spaces separates
+    rows[11] = "%.6f\t%.6e" % (fx[11], fy[11])           # a tab is not a separator: float() fails, row skipped
+    rows[20] = rows[20] + " 7"                           # three tokens: skipped
+    rows[30] = "garbage here"                            # not numbers: skipped
+    rows.insert(40, "")                                  # blank row: skipped
+    rows.insert(50, "# comment")                         # skipped
+    rows[60] = "%.4E %.3E\r" % (fx[58], fy[58])          # exponent formats, CRLF
+    text = ("# header line\n" + "\n".join(rows)).encode()
+    ref_rows = text.decode().split("\n")[1:]
+    wn_ref, xs_ref = ph.read_xsc_rows(ref_rows)
+    wn, xs = engine.parse_xsc_text(text)
+    assert 0 < len(wn_ref) < len(rows)
+    np.testing.assert_array_equal(wn, wn_ref)
+    np.testing.assert_array_equal(xs, xs_ref)
+    assert engine.parse_xsc_text(b"")[0].size == 0 and engine.parse_xsc_text(b"# nothing\n\n")[0].size == 0
