@@ -375,6 +375,11 @@ def main():
     if not args.no_atmosphere:
         atm = run_atmosphere(e, args, rank, world, ext, peaks, use_peer)
 
+    # ---- secondary object: the cfg5 stress sweep (5M lines, 5M points, 25 cm-1 cutoff), strong-sharded like the atmosphere
+    stress = None
+    if not args.no_atmosphere:
+        stress = run_stress(e, rank, world, ext, use_peer)
+
     # ---- secondary object: line-list ingestion (section 8(f) row 1), rank 0 at N = 1
     ingest = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -426,6 +431,8 @@ def main():
         }
         if atm:
             line["atmosphere"] = atm
+        if stress:
+            line["stress_sweep"] = stress
         if ingest:
             line["ingest"] = ingest
         if cpu:
@@ -467,6 +474,61 @@ def run_ingest(e, w):
             "api": "prb_ingest_hitran_csv (pageable host text in, device SoA out; H2D copy inside the timed region)",
             "cpu_reference_lines_per_s": len(sample) / cpu_s, "cpu_sample_rows": len(sample), "bit_exact_vs_cpu": ok,
             "host_text_formatting_s": fmt_s}
+
+
+def run_stress(e, rank, world, ext, use_peer):
+    """cfg5: one gas cell, 5M synthetic lines, 0-5000 cm-1 @ 0.001 cm-1, fixed 25 cm-1 cutoff (W = 25 000, ~2.5e11
+    accumulations), split over the N ranks by wavenumber chunk; the finished spectra gathered as in the headline."""
+    import torch
+    import torch.distributed as dist
+    from pyrad_b200 import distributed as pd
+    from pyrad_b200 import engine as eng
+    from pyrad_b200 import partition as pt
+    from pyrad_b200 import workloads
+
+    w = workloads.cfg5()
+    sp = w["species"]
+    n_total = eng.grid_len(w["range_min"], w["range_max"], w["res"])
+    win = eng.window_len(w["cutoff"], w["res"])
+    plan = pd.ShardPlan(w["lines"]["nu"], w["range_min"], w["res"], n_total, [win], rank, world)
+    e.upload_lines(plan.subset(w["lines"]), n_groups=len(sp))
+    e.set_grid(w["range_min"], w["res"], n_total, plan.i_begin, plan.i_end)
+    if use_peer:
+        e.peer_disconnect()
+        pd.connect_peers(e, rank, world, plan.max_chunk, dist)
+    T, P = w["T"], w["P"]
+    args_ = ([w["depth_cm"]], [T], [P], [w["conc"]], [s.molmass for s in sp], [[s.q(T) for s in sp]], [s.q296 for s in sp],
+             [win], 288.0, w["range_max"])
+    nc = plan.i_end - plan.i_begin
+
+    def run():
+        e.atmosphere(*args_)
+        if world > 1 and not use_peer:
+            rad_p, tr_p = e.atmosphere_result_dev()
+            pd.all_gather_spectra(pd.device_tensor(rad_p, nc), plan, dist)
+            pd.all_gather_spectra(pd.device_tensor(tr_p, nc), plan, dist)
+
+    run()
+    times = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a.record(ext)
+        run()
+        b.record(ext)
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    tm = torch.tensor([float(np.median(times))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm.item())
+    idx = np.trunc((w["lines"]["nu"] - w["range_min"]) / w["res"]).astype(np.int64)
+    pairs = float(pt.block_pair_cost(idx, n_total, [win]).sum())
+    return {"workload": "cfg5: 5M synthetic lines, 0-5000 cm-1 @ 0.001 cm-1 (%d points), fixed 25 cm-1 cutoff (W = %d)" % (n_total, win),
+            "pairs": pairs, "ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "scaling": "strong", "n_gpus": world,
+            "ms_runs_this_rank": [float(t) for t in times]}
 
 
 def run_atmosphere(e, args, rank, world, ext, peaks, use_peer):
