@@ -210,6 +210,22 @@ extern "C" int prb_create(int device, prb_engine **out) {
         delete e;
         return fail(PRB_ERR_CUDA, "prb_create: cudaStreamCreate failed");
     }
+    // opt-in shared memory of the kernels that stage through it (per device, so here and not in process-wide statics)
+    cudaError_t ae = cudaSuccess;
+    auto want = [&](const void *fn, size_t bytes) {
+        if (ae == cudaSuccess) ae = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    };
+    want((const void *)k2_line_sum<2>, K2_SMEM_BYTES<2>(true));
+    want((const void *)k2_line_sum<4>, K2_SMEM_BYTES<4>(true));
+    want((const void *)k2_line_sum<8>, K2_SMEM_BYTES<8>(true));
+    want((const void *)k2_line_sum<16>, K2_SMEM_BYTES<16>(true));
+    want((const void *)k2_point, sizeof(KPSmem));
+    want((const void *)k3_fold_tma, sizeof(K3TSmem));
+    if (ae != cudaSuccess) {
+        cudaStreamDestroy(e->stream);
+        delete e;
+        return fail(PRB_ERR_CUDA, std::string("prb_create: cudaFuncSetAttribute failed: ") + cudaGetErrorString(ae));
+    }
     *out = e;
     return PRB_OK;
 }
@@ -617,12 +633,6 @@ static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
     if (a.n_tiles == 0) return cudaSuccess;
     const bool staging = a.fuse.enabled && a.fuse.n_dst > 1;
     const size_t smem = K2_SMEM_BYTES<P>(staging);
-    static size_t attr_bytes = 0;                               // per template instance
-    if (smem > attr_bytes) {
-        cudaError_t ce = cudaFuncSetAttribute(k2_line_sum<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (ce != cudaSuccess) return ce;
-        attr_bytes = smem;
-    }
     const int64_t items = (int64_t)a.n_tiles * a.n_layers;
     const int grid = (int)std::min<int64_t>(items, (int64_t)K2_MIN_CTAS * e->prop.multiProcessorCount);
     k2_line_sum<P><<<grid, K2_THREADS, smem, e->stream>>>(a);
@@ -648,9 +658,6 @@ static cudaError_t launch_k2_sub(prb_engine *e, K2Args a, cudaStream_t st) {
     if (a.n_tiles <= 0) return cudaSuccess;
     const bool staging = a.fuse.enabled && a.fuse.n_dst > 1;
     const size_t smem = K2_SMEM_BYTES<P>(staging);
-    cudaError_t ce = cudaFuncSetAttribute(k2_line_sum<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)K2_SMEM_BYTES<P>(true));
-    if (ce != cudaSuccess) return ce;
     const int grid = std::min(a.n_tiles, K2_MIN_CTAS * e->prop.multiProcessorCount);
     k2_line_sum<P><<<grid, K2_THREADS, smem, st>>>(a);
     return cudaGetLastError();
@@ -690,11 +697,6 @@ static int run_line_sum(prb_engine *e, const LayerJob *jobs, int n, const K2Laye
     if (fuse) a.fuse = *fuse;
     cudaError_t ce;
     if (jobs[0].narrow == 2) {
-        static bool kp_attr = false;
-        if (!kp_attr) {
-            CK(cudaFuncSetAttribute(k2_point, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KPSmem)));
-            kp_attr = true;
-        }
         a.n_tiles = (a.n_chunk + KP_TILE - 1) / KP_TILE;
         for (int k0 = 0; k0 < n && a.n_tiles > 0; k0 += 65535) {        // grid.y limit
             K2Args b = a;
@@ -1131,11 +1133,6 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
     if (e->timing) CK(cudaEventRecord(e->ev[3 * n_batches], e->stream));
     if (nc > 0 && !fused) {
         if (e->k3_tma && n_layers >= K3T_LAYERS) {
-            static bool k3_attr = false;
-            if (!k3_attr) {
-                CK(cudaFuncSetAttribute(k3_fold_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3TSmem)));
-                k3_attr = true;
-            }
             const int64_t n_strips = (nc + K3T_STRIP - 1) / K3T_STRIP;
             const int grid = (int)std::min<int64_t>(n_strips, K3T_MINB * (int64_t)e->prop.multiProcessorCount);
             // linear interpolation of B over 3 grid steps: relative error <= (3 dx)^2 / 8 * max(6 / nu^2, (c2/T)^2);
