@@ -1687,7 +1687,7 @@ extern "C" int prb_set_result_host(prb_engine *e, float *radiance_host, float *t
 // One call from HOST line columns to HOST spectra with the copies overlapped with the compute in both directions:
 //   * the S296 column goes first (the FP32 scale of the records needs max|S|), then the other columns in S pieces,
 //     wavenumber ascending, on a copy stream;
-//   * the grid chunk is cut into S pieces of ONE WAVE of K2 tiles each (2 CTAs x SM count); piece s of the lines is
+//   * the grid chunk is cut into S pieces of TWO WAVES of K2 tiles each (2 x 2 CTAs x SM count); piece s of the lines is
 //     what sub-launch s needs beyond the earlier pieces (its tiles' windows plus margin), so K0/K1/K2 of piece s start
 //     as soon as its lines have landed while the later pieces are still crossing PCIe;
 //   * finished tiles leave through K2's fused epilogue: into the device result arrays, every peer's gather buffer
@@ -1714,7 +1714,9 @@ extern "C" int prb_gas_cell_host(prb_engine *e, int64_t n, const double *nu0, co
     const int ppt = pick_ppt(e, wm);
     const int tile_pts = K2_CONSUMERS * 32 * ppt;
     const int n_tiles = (int)((nc + tile_pts - 1) / tile_pts);
-    const int wave = K2_MIN_CTAS * e->prop.multiProcessorCount;
+    // K2 tiles per piece in waves of resident CTAs: measured on cfg2 (ms per call) 1 wave 1.72, 2 waves 1.65, 3 waves 1.65
+    static const int waves_per_piece = getenv("PRB_PIPE_WAVES") ? std::max(1, atoi(getenv("PRB_PIPE_WAVES"))) : 2;
+    const int wave = waves_per_piece * K2_MIN_CTAS * e->prop.multiProcessorCount;
     const int S = (n_tiles + wave - 1) / wave;
     const bool pipelined = e->k2_variant == PRB_K2_CLASSED && e->fuse_single && wm >= e->narrow_wm && S >= 2 && n >= 4096;
     if (!pipelined) {
