@@ -50,6 +50,24 @@ def test_number_parser_matches_python_float():
         assert _parse(lib, s)[0] == -7, s                      # PRB_ERR_PARSE: fail loudly, as float() raises
 
 
+def test_number_parser_property_any_decimal_literal():
+    """Property test (hypothesis): every decimal literal with at most 19 significant digits converts to exactly the
+    double Python's float() returns -- sign of zero, subnormals, overflow to inf included."""
+    from hypothesis import given, settings, strategies as st
+    lib = _lib.load()
+    literal = st.from_regex(r"[ ]{0,2}[+-]?(([0-9]{1,12}(\.[0-9]{0,7})?)|(\.[0-9]{1,12}))([eE][+-]?[0-9]{1,3})?[ ]{0,2}", fullmatch=True)
+
+    @settings(max_examples=3000, deadline=None)
+    @given(literal)
+    def check(s):
+        rc, v = _parse(lib, s)
+        ref = float(s)
+        assert rc == 0, s
+        assert (v == ref and np.signbit(v) == np.signbit(ref)) or (np.isinf(ref) and np.isinf(v) and (v > 0) == (ref > 0)), (s, v, ref)
+
+    check()
+
+
 @pytest.mark.parametrize("name", G.CELL_CASES)
 def test_oracle_reader_keeps_what_the_reference_kept(name, tmp_path):
     g = G.load(name)
