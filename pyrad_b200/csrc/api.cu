@@ -979,9 +979,11 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
     // tails per atmosphere instead of one per layer, which is what strong scaling over small chunks needs.
     std::stable_sort(jobs.begin(), jobs.end(), [](const LayerJob &x, const LayerJob &y) { return x.wm > y.wm; });
     int64_t slots = 1;
-    if (e->batch_layers && n_layers > 1) {
+    if (e->batch_layers && n_layers > 1 && e->rec_slots >= n_layers && e->rec_budget_mb == 0) {
+        slots = n_layers;                                       // the records of every layer are already resident
+    } else if (e->batch_layers && n_layers > 1) {
         size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
+        CK(cudaMemGetInfo(&free_b, &total_b));                  // (a driver query: only when the batch has to be sized)
         const size_t per_layer = (size_t)36 * (size_t)std::max<int64_t>(e->n_alloc, 1);
         const size_t have = (size_t)e->rec_slots * per_layer;               // already allocated records count as free
         const size_t budget = e->rec_budget_mb > 0 ? (size_t)e->rec_budget_mb << 20 : (free_b + have) / 4;
