@@ -52,6 +52,16 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": SM_MAX_MHZ_DEFAULT}, "fallback"
 
 
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1
+    when NCCL_DEBUG is set), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved
+    descriptor."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (recipe in B200_PROFILING.md)."""
@@ -159,7 +169,7 @@ def cpu_baseline_sample(budget_s=12.0):
                       "on the same core" % (k, pairs, secs, lit)}
 
 
-def reference_arm(args):
+def reference_arm(args, out):
     """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python that cannot
     travel to the GPU box) on all host cores; each step = one 10 cm-1 cfg2 window per core."""
     rank = int(os.environ.get("RANK", "0"))
@@ -193,7 +203,7 @@ def reference_arm(args):
                                    "windows of 10 cm-1" % (cores, args.steps, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
     return 0
 
 
@@ -213,8 +223,9 @@ def main():
     ap.add_argument("--atm-lines", type=int, default=5_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    out = claim_stdout()
     if args.impl == "reference":
-        return reference_arm(args)
+        return reference_arm(args, out)
 
     import torch
     import torch.distributed as dist
@@ -437,7 +448,7 @@ def main():
             line["ingest"] = ingest
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

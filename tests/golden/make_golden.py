@@ -128,6 +128,60 @@ def case_xsc(name, file_res, rmin_f, rmax_f, layer_rmin, layer_rmax, seed):
                                                         out["T_after"], out["P_after"]))
 
 
+def _folder_bytes(d):
+    return {f: open(os.path.join(d, f), "rb").read() for f in sorted(os.listdir(d))}
+
+
+def _pack_files(prefix, files):
+    """{name: bytes} -> npz-friendly arrays: names (unicode), one uint8 blob, offsets."""
+    names = sorted(files)
+    blob = b"".join(files[n] for n in names)
+    offs = np.cumsum([0] + [len(files[n]) for n in names])
+    return {prefix + "_names": np.array(names), prefix + "_blob": np.frombuffer(blob, dtype=np.uint8),
+            prefix + "_offsets": offs.astype(np.int64)}
+
+
+def case_xsc_files(name):
+    """the xsc FILE utilities run for real -- changeResXscFile (pyradUtilities.py:515-534: table ->
+    np.interp onto arange(min, max, BASE_RESOLUTION) -> rewritten text file) and mergeXsc (:549-597: files of equal
+    T and P summed onto the union range and rewritten).  Input and output folders are stored byte for byte."""
+    wd = tempfile.mkdtemp(prefix="pyrad_golden_")
+    rh.seed_workdir(wd)
+    out = {}
+    # (1) one coarse table per folder member: 0.05 and 0.03 cm-1 spacing, and one already at 0.01
+    specs = [("CFC11", 296.0, 760.0, 830.0, 860.0, 0.05, 11), ("CFC11", 273.0, 7.5, 1050.0, 1062.0, 0.03, 12),
+             ("CFC11", 253.0, 100.2, 810.0, 815.0, 0.01, 13)]
+    for sp in specs:
+        mol, T, torr, lo, hi, res, seed = sp
+        fx, fy = synth.make_xsc_table(lo, hi, res, seed)
+        rh.write_xsc_file(wd, mol, T, torr, lo, hi, res, fx, fy)
+    d = os.path.join(wd, "data", "xsc", "CFC11")
+    out.update(_pack_files("res_in", _folder_bytes(d)))
+    ref = rh.load_reference(wd)
+    with rh.quiet():
+        for f in sorted(os.listdir(d)):
+            ref.utils.changeResXscFile(os.path.join(d, f))
+    out.update(_pack_files("res_out", _folder_bytes(d)))
+    # (2) merge: folder of pyrad-adjusted files (the header glued to the first row, as writeXscFile leaves it) --
+    # two (T, P) groups: three disjoint/abutting ranges at 296 K / 760 Torr, two at 250 K / 100 Torr
+    d2 = os.path.join(wd, "data", "xsc", "HCFC22")
+    os.makedirs(d2)
+    groups = [(296.0, 760.0, [(800.0, 810.0, 21), (820.0, 835.0, 22), (835.0, 840.0, 23)]),
+              (250.0, 100.0, [(1100.0, 1104.0, 24), (1090.0, 1095.0, 25)])]
+    with rh.quiet():
+        for T, torr, parts in groups:
+            for lo, hi, seed in parts:
+                x = np.arange(lo, hi, ref.utils.BASE_RESOLUTION)
+                _, y = synth.make_xsc_table(lo, hi, 0.01, seed)
+                ref.utils.writeXscFile(x, y[: len(x)], lo, hi, T, torr, "HCFC22", d2, "N2", "07-19")
+    out.update(_pack_files("merge_in", _folder_bytes(d2)))
+    with rh.quiet():
+        ref.utils.mergeXsc("HCFC22")
+    out.update(_pack_files("merge_out", _folder_bytes(d2)))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: (list(v) if k.endswith("_names") else v.shape) for k, v in out.items()})
+
+
 def case_kat(name):
     """Known-answer values straight from the real physics modules."""
     wd = tempfile.mkdtemp(prefix="pyrad_golden_")
@@ -155,6 +209,9 @@ def case_kat(name):
 if __name__ == "__main__":
     if not rh.available():
         raise SystemExit("the reference is not mounted at %s" % rh.REFERENCE_DIR)
+    if len(sys.argv) > 1 and sys.argv[1] == "xsc_files":          # regenerate only this case
+        case_xsc_files("xsc_files")
+        raise SystemExit(0)
     case_kat("kat")
     case_gas_cell("cell_co2_1atm", ["co2"], [400e-6], 1500, 600.0, 700.0, 296, 1013.0, 10.0, 101)
     case_gas_cell("cell_lowp", ["co2", "h2o"], [400e-6, 0.005], 900, 640.0, 690.0, 220, 5.0, 1000.0, 202)
@@ -164,3 +221,4 @@ if __name__ == "__main__":
     case_gas_cell("cell_highp_dynres", ["co2"], [0.02], 400, 600.0, 700.0, 300, 20000.0, 5.0, 505)
     case_xsc("xsc_native_res", 0.01, 830.0, 860.0, 800.0, 900.0, 606)
     case_xsc("xsc_coarse_res", 0.05, 830.0, 860.0, 800.0, 900.0, 707)
+    case_xsc_files("xsc_files")

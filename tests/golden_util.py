@@ -22,3 +22,11 @@ def lines_of(g, group, cutoff=None, rmin=None, rmax=None):
         m = (ln["nu"] > lo) & (ln["nu"] < hi)
         ln = {k: v[m] for k, v in ln.items()}
     return ln
+
+
+def files_of(g, prefix):
+    """{file name: bytes} of a folder stored by make_golden._pack_files."""
+    names = [str(n) for n in g[prefix + "_names"]]
+    blob = g[prefix + "_blob"].tobytes()
+    offs = g[prefix + "_offsets"]
+    return {n: blob[int(offs[i]):int(offs[i + 1])] for i, n in enumerate(names)}

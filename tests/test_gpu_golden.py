@@ -141,3 +141,47 @@ def test_mirror_column_spectrum_equals_layer_by_layer_transmission(data_root):
         t_ref = t_ref * C.getTransmittance(layer)
     assert np.abs(trans - t_ref).max() <= H.T_ABS_TOL
     np.testing.assert_allclose(rad, ref, rtol=3e-5)
+
+
+# ---------------------------------------------------------------- xsc file utilities
+def _seed_folder(root, folder, files):
+    import os
+    d = os.path.join(root, "data", "xsc", folder)
+    os.makedirs(d)
+    for name, blob in files.items():
+        with open(os.path.join(d, name), "wb") as f:
+            f.write(blob)
+    return d
+
+
+def _folder(d):
+    import os
+    return {n: open(os.path.join(d, n), "rb").read() for n in sorted(os.listdir(d))}
+
+
+def test_change_res_xsc_file_is_byte_identical_to_the_reference(data_root):
+    from pyrad_b200 import xsc_files as xf
+    g = G.load("xsc_files")
+    d = _seed_folder(data_root, "CFC11", G.files_of(g, "res_in"))
+    written = xf.changeResFolder("CFC11")
+    want = G.files_of(g, "res_out")
+    got = _folder(d)
+    assert sorted(written) == sorted(want) == sorted(got)
+    for name in want:
+        assert got[name] == want[name], name
+    # the rewritten table is a usable xsc molecule of the mirror (same path as test_mirror_matches_reference_xsc)
+    layer = C.Layer(100.0, 250, 500.0, 800.0, 900.0)
+    xm = layer.addMolecule({"CFC11": "CFC11_296.0K-760.0Torr_830.0-860.0_0.01_air_00_00.txt"}, concentration=250e-12)
+    assert layer.T == 296 and np.count_nonzero(C.getCrossSection(xm)) > 2900
+
+
+def test_merge_xsc_is_byte_identical_to_the_reference(data_root):
+    from pyrad_b200 import xsc_files as xf
+    g = G.load("xsc_files")
+    d = _seed_folder(data_root, "HCFC22", G.files_of(g, "merge_in"))
+    written = xf.mergeXsc("HCFC22")
+    want = G.files_of(g, "merge_out")
+    got = _folder(d)
+    assert sorted(written) == sorted(want) == sorted(got)
+    for name in want:
+        assert got[name] == want[name], name

@@ -103,3 +103,19 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "line-gridpoint evals/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_xsc_file_name_parser_matches_the_oracle():
+    """Host logic of the xsc file utilities (no GPU): the product's parseXscFileName against the oracle's restatement
+    of pyradUtilities.py:611-641 and against names the real reference wrote (tests/golden/xsc_files.npz)."""
+    from oracle import physics as ph
+    from pyrad_b200 import xsc_files as xf
+    from tests import golden_util as G
+    g = G.load("xsc_files")
+    names = [str(n) for p in ("res_in", "res_out", "merge_in", "merge_out") for n in g[p + "_names"]]
+    names.append("CFC-11_278.1K-760.3Torr_810.0-880.0_0.03_00_00.txt")     # no broadener field
+    for n in names:
+        got, want = xf.parseXscFileName(n), ph.parse_xsc_file_name(n)
+        for k, v in want.items():
+            assert got[k] == v, (n, k)
+        assert got["LONG_FILENAME"] == n and got["SHORT_FILENAME"] + ".txt" == n

@@ -140,3 +140,33 @@ def test_scatter_scalar_and_gather_forms_agree():
     # T = 296 with Q(T) = Q(296) leaves S unchanged
     p = ph.LineParams(ln, 296, 300.0, 4e-4, 43.98983, 286.09, 286.09)
     np.testing.assert_allclose(p.S, ln["sw"], rtol=1e-15)
+
+
+# ---------------------------------------------------------------- xsc file utilities
+def test_oracle_reproduces_reference_change_res_xsc_file():
+    g = G.load("xsc_files")
+    src, want = G.files_of(g, "res_in"), G.files_of(g, "res_out")
+    got = dict(ph.change_res_xsc_file(name, blob) for name, blob in src.items())
+    assert sorted(got) == sorted(want)
+    for name in want:
+        assert got[name] == want[name], name                     # byte for byte
+
+
+def test_oracle_reproduces_reference_merge_xsc():
+    g = G.load("xsc_files")
+    src, want = G.files_of(g, "merge_in"), G.files_of(g, "merge_out")
+    got = ph.merge_xsc(src)
+    assert sorted(got) == sorted(want)
+    for name in want:
+        assert got[name] == want[name], name
+    # a group that mixes resolutions is refused (pyradUtilities.py:583-586)
+    mixed = dict(src)
+    k = sorted(mixed)[0]
+    mixed[k.replace("_0.01_", "_0.05_")] = mixed.pop(k)
+    assert ph.merge_xsc(mixed) is False
+
+
+def test_xsc_file_name_fields():
+    p = ph.parse_xsc_file_name("HCFC22_296.0K-760.0Torr_800.0-840.0_0.01_N2_07_19.txt")
+    assert p == {"RANGE": "800.0-840.0", "MOLECULE_SHORT_NAME": "HCFC22", "TEMP": "296.0", "PRESSURE": "760.0",
+                 "RES": "0.01", "ID": "07-19", "BROADENER": "N2"}
