@@ -133,6 +133,8 @@ struct prb_engine {
     DevBuf<K2Layer> k2tab;
     LayerJob last;
     int k2_variant = PRB_K2_CLASSED, k2_ppt = 0;
+    DevBuf<double> far_lag;      // PRB_K2_FARFIELD: Lagrange weights [256][K2_FAR_NODES] (built at prb_create)
+    float far_delta[K2_FAR_NODES] = {};
     int64_t narrow_wm = 100;     // windows with W-2 below this use k2_narrow
     bool batch_layers = true;    // prb_atmosphere: one K1 launch + one K2 launch per kernel class
     bool k3_tma = true;          // layer fold: k matrix staged by TMA (k3_fold_tma) instead of register-held loads
@@ -183,6 +185,8 @@ static int64_t chunk_len(const prb_engine *e) { return e->i_end - e->i_begin; }
 extern "C" int prb_abi_version(void) { return PRB_ABI_VERSION; }
 extern "C" const char *prb_last_error(void) { return g_err.c_str(); }
 
+static int build_far_table(prb_engine *e);
+
 extern "C" int prb_create(int device, prb_engine **out) {
     if (!out) return fail(PRB_ERR_ARG, "prb_create: out is NULL");
     *out = nullptr;
@@ -219,12 +223,18 @@ extern "C" int prb_create(int device, prb_engine **out) {
     want((const void *)k2_line_sum<4>, K2_SMEM_BYTES<4>(true));
     want((const void *)k2_line_sum<8>, K2_SMEM_BYTES<8>(true));
     want((const void *)k2_line_sum<16>, K2_SMEM_BYTES<16>(true));
+    want((const void *)k2_line_sum<8, true>, K2_SMEM_BYTES<8>(true));
     want((const void *)k2_point, sizeof(KPSmem));
     want((const void *)k3_fold_tma, sizeof(K3TSmem));
     if (ae != cudaSuccess) {
         cudaStreamDestroy(e->stream);
         delete e;
         return fail(PRB_ERR_CUDA, std::string("prb_create: cudaFuncSetAttribute failed: ") + cudaGetErrorString(ae));
+    }
+    if (cudaSetDevice(device) != cudaSuccess || build_far_table(e) != PRB_OK) {
+        cudaStreamDestroy(e->stream);
+        delete e;
+        return fail(PRB_ERR_CUDA, "prb_create: far-field table upload failed");
     }
     *out = e;
     return PRB_OK;
@@ -314,9 +324,35 @@ extern "C" int prb_device_info(prb_engine *e, int *sm_count, int *cc_major, int 
     return PRB_OK;
 }
 
+// classed kernels (per-warp window classes, thread-per-point kernels for narrow windows): every variant but GENERAL
+static inline bool k2_classed(const prb_engine *e) { return e->k2_variant != PRB_K2_GENERAL; }
+
+// Chebyshev nodes of a 256-point span on [-0.5, 255.5] as FP32 offsets from its first point, and the Lagrange weight of
+// every node at every point (FP64, built from the ROUNDED offsets so that kernel and table agree exactly).
+static int build_far_table(prb_engine *e) {
+    const double pi = 3.14159265358979323846;
+    double node[K2_FAR_NODES];
+    for (int k = 0; k < K2_FAR_NODES; ++k) {
+        e->far_delta[k] = (float)(0.5 * (K2_FAR_SPAN - 1) + 0.5 * K2_FAR_SPAN * std::cos((2 * k + 1) * pi / (2 * K2_FAR_NODES)));
+        node[k] = (double)e->far_delta[k];
+    }
+    std::vector<double> lag((size_t)K2_FAR_SPAN * K2_FAR_NODES);
+    for (int i = 0; i < K2_FAR_SPAN; ++i)
+        for (int k = 0; k < K2_FAR_NODES; ++k) {
+            double w = 1.0;
+            for (int j = 0; j < K2_FAR_NODES; ++j)
+                if (j != k) w *= ((double)i - node[j]) / (node[k] - node[j]);
+            lag[(size_t)i * K2_FAR_NODES + k] = w;
+        }
+    CK(e->far_lag.ensure(lag.size()));
+    CK(cudaMemcpy(e->far_lag.p, lag.data(), sizeof(double) * lag.size(), cudaMemcpyHostToDevice));
+    return PRB_OK;
+}
+
 extern "C" int prb_set_k2_variant(prb_engine *e, int variant, int ppt) {
     if (!e) return fail(PRB_ERR_ARG, "null engine");
-    if (variant != PRB_K2_GENERAL && variant != PRB_K2_CLASSED) return fail(PRB_ERR_ARG, "unknown K2 variant");
+    if (variant != PRB_K2_GENERAL && variant != PRB_K2_CLASSED && variant != PRB_K2_FARFIELD)
+        return fail(PRB_ERR_ARG, "unknown K2 variant");
     if (ppt != 0 && ppt != 2 && ppt != 4 && ppt != 8 && ppt != 16)
         return fail(PRB_ERR_ARG, "points_per_thread must be 0 (auto), 2, 4, 8 or 16");
     e->k2_variant = variant;
@@ -483,7 +519,7 @@ static LayerJob plan_job(const prb_engine *e, double T, double P, int64_t W, dou
     // 1 = k2_narrow (binary-search thread-per-point: windows of a few points, where building the table costs more
     //     than it saves -- measured on B200 -- and forced thresholds above 511)
     j.narrow = 0;
-    if (e->k2_variant == PRB_K2_CLASSED && j.wm < e->narrow_wm)
+    if (k2_classed(e) && j.wm < e->narrow_wm)
         j.narrow = (e->point_kernel && j.wm >= KP_MIN_WM && j.wm <= KP_MAX_WM) ? 2 : 1;
     j.ppt = pick_ppt(e, j.wm);
     j.valid = true;
@@ -635,7 +671,13 @@ static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
     const size_t smem = K2_SMEM_BYTES<P>(staging);
     const int64_t items = (int64_t)a.n_tiles * a.n_layers;
     const int grid = (int)std::min<int64_t>(items, (int64_t)K2_MIN_CTAS * e->prop.multiProcessorCount);
-    k2_line_sum<P><<<grid, K2_THREADS, smem, e->stream>>>(a);
+    if (P == 8 && a.variant == PRB_K2_FARFIELD) {
+        a.far_lag = e->far_lag.p;
+        for (int k = 0; k < K2_FAR_NODES; ++k) a.far_delta[k] = e->far_delta[k];
+        k2_line_sum<8, true><<<grid, K2_THREADS, smem, e->stream>>>(a);
+    } else {
+        k2_line_sum<P><<<grid, K2_THREADS, smem, e->stream>>>(a);
+    }
     return cudaGetLastError();
 }
 
@@ -659,7 +701,13 @@ static cudaError_t launch_k2_sub(prb_engine *e, K2Args a, cudaStream_t st) {
     const bool staging = a.fuse.enabled && a.fuse.n_dst > 1;
     const size_t smem = K2_SMEM_BYTES<P>(staging);
     const int grid = std::min(a.n_tiles, K2_MIN_CTAS * e->prop.multiProcessorCount);
-    k2_line_sum<P><<<grid, K2_THREADS, smem, st>>>(a);
+    if (P == 8 && a.variant == PRB_K2_FARFIELD) {
+        a.far_lag = e->far_lag.p;
+        for (int k = 0; k < K2_FAR_NODES; ++k) a.far_delta[k] = e->far_delta[k];
+        k2_line_sum<8, true><<<grid, K2_THREADS, smem, st>>>(a);
+    } else {
+        k2_line_sum<P><<<grid, K2_THREADS, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 
@@ -1016,7 +1064,7 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
         ++dst.n;
     }
     const double dx = e->n_total > 1 ? (range_max - e->range_min) / (double)(e->n_total - 1) : 0.0;
-    const bool fused = n_layers == 1 && e->fuse_single && !jobs[0].narrow && e->k2_variant == PRB_K2_CLASSED;
+    const bool fused = n_layers == 1 && e->fuse_single && !jobs[0].narrow && k2_classed(e);
     K2Fuse fuse{};
     if (fused) {
         fuse.enabled = 1;
@@ -1720,7 +1768,7 @@ extern "C" int prb_gas_cell_host(prb_engine *e, int64_t n, const double *nu0, co
     static const int waves_per_piece = getenv("PRB_PIPE_WAVES") ? std::max(1, atoi(getenv("PRB_PIPE_WAVES"))) : 2;
     const int wave = waves_per_piece * K2_MIN_CTAS * e->prop.multiProcessorCount;
     const int S = (n_tiles + wave - 1) / wave;
-    const bool pipelined = e->k2_variant == PRB_K2_CLASSED && e->fuse_single && wm >= e->narrow_wm && S >= 2 && n >= 4096;
+    const bool pipelined = k2_classed(e) && e->fuse_single && wm >= e->narrow_wm && S >= 2 && n >= 4096;
     if (!pipelined) {
         int rc = prb_upload_lines(e, n, nu0, s296, gamma_air, gamma_self, elower, n_air, delta_air, group, n_groups);
         if (rc) return rc;

@@ -122,7 +122,24 @@ struct K2Args {
     int out_mode;              // PRB_OUT_F64 / PRB_OUT_F32
     DevState *st;              // tile_counter of this launch
     K2Fuse fuse;
+    // far-field variant (k2_line_sum<8, true>): Lagrange weights of the span's points, [256][K2_FAR_NODES], and the node
+    // offsets from the span's first point (FP32; the table is built from these rounded values)
+    const double *far_lag;
+    float far_delta[8];
 };
+
+// Far-field evaluation of the Lorentz wings (variant PRB_K2_FARFIELD, 256-point spans only).  A line whose centre lies
+// more than K2_FAR_RADIUS grid points from the centre of a warp's span, and whose window covers the whole span,
+// contributes a function of the grid coordinate that is analytic on the span with poles at least that far away:
+// its Chebyshev interpolant through K2_FAR_NODES nodes is accurate to ~(h / (D + sqrt(D^2 - h^2)))^nodes, h = 128,
+// D >= 512 -> 7e-8 of that line's own contribution (scripts/proto/farfield_numerics.py measures 3e-8..7e-8 of the
+// total on the BASELINE shapes).  Such lines are therefore summed at the 8 nodes of the span -- 8 evaluations instead
+// of 256 -- and the node sums are interpolated to the points once per tile.  Lines near the span, lines whose window
+// edge crosses it, and every Gaussian core go through the exact per-point paths as before.
+constexpr int K2_FAR_NODES = 8;
+constexpr float K2_FAR_RADIUS = 512.f;
+constexpr int K2_FAR_SPAN = 256;
+constexpr int K2_FAR_FLUSH = 16;          // triples (48 lines of one lane's chain) between FP64 flushes
 
 // One ring slot: a chunk of staged line records plus its descriptor.
 struct K2Desc {
@@ -278,9 +295,19 @@ __device__ __forceinline__ void gauss_pass(const float4 *sA, const float4 *sB, c
             const int j = jb + __ffs(m) - 1;
             m &= m - 1;
             const float4 b = sB[j];
-            const float2 nf = splat(sA[j].x), C2 = splat(b.w);
+            const float nfx = sA[j].x;
+            const float2 nf = splat(nfx), C2 = splat(b.w);
+#if PRB_K2_GAUSS_BLOCKSKIP
+            // the span is H blocks of 64 consecutive points (one packed point pair per lane each): a block the near
+            // zone [f - Dg, f + Dg] does not reach is skipped (warp-uniform; the same criterion that admitted the line)
+            const float dgj = sD[j];
+            const float zlo = -nfx - dgj - wbf, zhi = -nfx + dgj - wbf;      // near zone relative to the span start
+#endif
 #pragma unroll
             for (int h = 0; h < H; ++h) {
+#if PRB_K2_GAUSS_BLOCKSKIP
+                if (zhi < (float)(64 * h) || zlo > (float)(64 * h + 63)) continue;
+#endif
                 const float2 e = __fadd2_rn(s.fi[h], nf);
                 const float2 arg = __fmul2_rn(C2, __fmul2_rn(e, e));
                 float2 g = splat(b.z);
@@ -294,6 +321,50 @@ __device__ __forceinline__ void gauss_pass(const float4 *sA, const float4 *sB, c
         }
     }
     if (since) s.flush();
+}
+
+// Far-field pass over lines [js, je): lane = (node pair kp = lane & 3, line sub-group lane >> 2).  A lane evaluates the
+// Lorentz terms of every 8th line at its two nodes, three lines per reciprocal, in ascending line order; the FP32
+// partial sums are flushed into the lane's FP64 node accumulators.  d = (wb - idx) + delta: the first sum is an exact
+// small integer, so the node's fractional offset survives FP32 at any grid size.
+struct FarAcc {
+    double v0, v1;
+};
+__device__ __forceinline__ void far_pass(const float4 *sA, const float4 *sB, int js, int je, float wbf, float2 del,
+                                         FarAcc &fa) {
+    if (je <= js) return;                                   // warp-uniform
+    const int sub = (int)(threadIdx.x & 31) >> 2;
+    const float2 wb2 = splat(wbf);
+    const float2 zero = make_float2(0.f, 0.f);
+    float2 part = zero;
+    int since = 0;
+    for (int j0 = js; j0 < je; j0 += 24) {                  // warp-uniform trip count; short chains pad with A = 0
+        const int j1 = j0 + sub, j2 = j1 + 8, j3 = j1 + 16;
+        const int k1 = min(j1, je - 1), k2 = min(j2, je - 1), k3 = min(j3, je - 1);
+        const float4 a1 = sA[k1], a2 = sA[k2], a3 = sA[k3];
+        const float2 B1 = ldB(sB, k1), B2 = ldB(sB, k2), B3 = ldB(sB, k3);
+        const float2 A1 = j1 < je ? hi2(a1) : zero, A2 = j2 < je ? hi2(a2) : zero, A3 = j3 < je ? hi2(a3) : zero;
+        const float2 e1 = __fadd2_rn(__fadd2_rn(wb2, lo2(a1)), del);
+        const float2 e2 = __fadd2_rn(__fadd2_rn(wb2, lo2(a2)), del);
+        const float2 e3 = __fadd2_rn(__fadd2_rn(wb2, lo2(a3)), del);
+        const float2 q1 = __ffma2_rn(e1, e1, B1);
+        const float2 q2 = __ffma2_rn(e2, e2, B2);
+        const float2 q3 = __ffma2_rn(e3, e3, B3);
+        const float2 p23 = __fmul2_rn(q2, q3);
+        const float2 t = __ffma2_rn(A3, q2, __fmul2_rn(A2, q3));
+        const float2 num = __ffma2_rn(q1, t, __fmul2_rn(A1, p23));
+        const float2 den = __fmul2_rn(q1, p23);
+        const float2 r = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+        part = __ffma2_rn(num, r, part);
+        if (++since == K2_FAR_FLUSH) {
+            fa.v0 += (double)part.x;
+            fa.v1 += (double)part.y;
+            part = zero;
+            since = 0;
+        }
+    }
+    fa.v0 += (double)part.x;
+    fa.v1 += (double)part.y;
 }
 
 // Plain one-line-at-a-time evaluation of every staged line (variant PRB_K2_GENERAL): the A/B check
@@ -319,9 +390,10 @@ __device__ __forceinline__ void general_all(const float4 *sA, const float4 *sB, 
     }
 }
 
-template <int P>
+template <int P, bool FAR = false>
 __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2Args a) {
     static_assert(P >= 2 && P % 2 == 0, "points per thread must be even (packed FP32x2)");
+    static_assert(!FAR || 32 * P == K2_FAR_SPAN, "the far-field table is built for 256-point spans");
     constexpr int H = P / 2;
     constexpr int TILE = K2_CONSUMERS * 32 * P;
     constexpr int SPAN = 32 * P;                      // points per consumer warp
@@ -407,6 +479,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
     for (int p = 0; p < P; ++p) s.acc(p) = 0.0;
     int wb = 0;
     float wbf = 0.f, we1f = 0.f;
+    FarAcc far{0.0, 0.0};                                  // FAR: this lane's two node sums of the current tile
 
     for (uint32_t it = 0;; ++it) {
         const uint32_t stage = it % K2_STAGES;
@@ -429,6 +502,8 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             }
 #pragma unroll
             for (int p = 0; p < P; ++p) s.acc(p) = 0.0;
+            far.v0 = 0.0;
+            far.v1 = 0.0;
         }
         const int cnt = d.cnt;
         const float4 *sA = sm.rA[stage];
@@ -450,10 +525,15 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             if (t1 >= t4) { t1 = t5; t4 = t5; }                // window narrower than the span: all masked
             const float g0 = fmaxf(wbf - dgmax, t0);           // Gaussian cores can only come from [g0, g1)
             const float g1 = fminf(we1f + 1.f + dgmax, t5);
-            int c0 = 0, c1 = 0, c4 = 0, c5 = 0, cg0 = 0, cg1 = 0;
+            int c0 = 0, c1 = 0, c4 = 0, c5 = 0, cg0 = 0, cg1 = 0, cfl = 0, cfr = 0;
+            // FAR: idx < tfl or idx > tfr, i.e. more than K2_FAR_RADIUS from the span centre wb + (SPAN-1)/2; integer
+            // thresholds, exact in FP32, so the split does not depend on the shard origin
+            const float tfl = wbf + (float)((SPAN - 1) / 2) - K2_FAR_RADIUS;
+            const float tfr = wbf + (float)(SPAN / 2) + K2_FAR_RADIUS;
             for (int j = lane; j < cnt; j += 32) {
                 const float f = -sA[j].x;
                 c0 += f < t0; c1 += f < t1; c4 += f < t4; c5 += f < t5; cg0 += f < g0; cg1 += f < g1;
+                if (FAR) { cfl += f < tfl; cfr += f <= tfr; }
             }
             const int b0 = __reduce_add_sync(0xffffffffu, c0);
             const int b1 = __reduce_add_sync(0xffffffffu, c1);
@@ -462,7 +542,18 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             const int bg0 = __reduce_add_sync(0xffffffffu, cg0);
             const int bg1 = __reduce_add_sync(0xffffffffu, cg1);
             lorentz_paired<H, true>(sA, sB, b0, b1, wmf, s);
-            lorentz_paired<H, false>(sA, sB, b1, b4, wmf, s);
+            if (FAR) {
+                // full-cover lines [b1, b4) split by distance from the span: far left | near | far right
+                const int bfl = min(max(__reduce_add_sync(0xffffffffu, cfl), b1), b4);
+                const int bfr = min(max(__reduce_add_sync(0xffffffffu, cfr), bfl), b4);
+                const int kp = lane & 3;
+                const float2 del = make_float2(a.far_delta[2 * kp], a.far_delta[2 * kp + 1]);
+                far_pass(sA, sB, b1, bfl, wbf, del, far);
+                lorentz_paired<H, false>(sA, sB, bfl, bfr, wmf, s);
+                far_pass(sA, sB, bfr, b4, wbf, del, far);
+            } else {
+                lorentz_paired<H, false>(sA, sB, b1, b4, wmf, s);
+            }
             lorentz_paired<H, true>(sA, sB, b4, b5, wmf, s);
             if (dgmax > 0.f) {                                  // [bg0, bg1) lies inside [b0, b5)
                 gauss_pass<H, true>(sA, sB, sD, bg0, min(bg1, b1), wbf, we1f, wmf, s);
@@ -488,11 +579,29 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
                 if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free again
                 consumer_barrier();
             }
+            double fv[K2_FAR_NODES];
+            if (FAR) {
+                // node sums: add the eight line sub-groups (fixed tree), then every lane fetches all eight nodes
+                double v0 = far.v0, v1 = far.v1;
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                    v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                }
+#pragma unroll
+                for (int k = 0; k < K2_FAR_NODES; ++k) fv[k] = __shfl_sync(0xffffffffu, (k & 1) ? v1 : v0, k >> 1);
+            }
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const int i = wb + 32 * p + lane;
+                double farp = 0.0;
+                if (FAR) {
+                    const double *lw = a.far_lag + (32 * p + lane) * K2_FAR_NODES;
+#pragma unroll
+                    for (int k = 0; k < K2_FAR_NODES; ++k) farp = fma(fv[k], __ldg(lw + k), farp);
+                }
                 if (i < a.n_chunk) {
-                    const double v = s.acc(p) * inv_scale;
+                    const double v = (FAR ? s.acc(p) + farp : s.acc(p)) * inv_scale;
                     if (a.out_mode == 0) reinterpret_cast<double *>(out)[i] = v;
                     else reinterpret_cast<float *>(out)[i] = (float)v;
                     if (a.fuse.enabled) {

@@ -9,7 +9,7 @@ K_BOLTZ = 1.38064852E-23          # pyradClasses.py:16
 P0 = 1013.25
 
 OUT_F64, OUT_F32 = 0, 1
-K2_GENERAL, K2_CLASSED = 0, 1
+K2_GENERAL, K2_CLASSED, K2_FARFIELD = 0, 1, 2
 OPT_BATCH_LAYERS, OPT_FUSE_SINGLE_LAYER, OPT_RECORD_BUDGET_MB, OPT_POINT_KERNEL, OPT_FOLD_TMA = 1, 2, 3, 4, 5
 PEER_HANDLE_BYTES = 64
 

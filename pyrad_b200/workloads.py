@@ -42,6 +42,21 @@ def cfg2(n_lines=500_000, rmax=3000.0):
                     [0.01, 400e-6, 1.8e-6, 5e-8], 10.0, synth.SEED0 + 2)
 
 
+def cfg3(n_lines=50_000):
+    """gas cell combining line-by-line CO2 / H2O with xsc cross-section tables CFC-11 (native 0.01 cm-1 spacing) and
+    HCFC-22 (0.05 cm-1, re-gridded by np.interp) on the same 500-800 cm-1 grid at 0.01 cm-1.  Both tables are
+    296 K / 760 Torr files, and an xsc molecule forces the layer to its file's T and P (pyradClasses.py:488-491), so
+    the cell sits at 760 Torr / 0.75006."""
+    P = 760.0 / 0.75006
+    w = gas_cell(["co2", "h2o"], n_lines, 500.0, 800.0, 0.01, 296, P, [400e-6, 0.01], 10.0, synth.SEED0 + 3)
+    w["xsc"] = []
+    for name, res, a, b, conc, k in (("CFC11", 0.01, 560.0, 620.0, 250e-12, 31), ("HCFC22", 0.05, 700.0, 780.0, 230e-12, 32)):
+        x, y = synth.make_xsc_table(a, b, res, synth.SEED0 + k)
+        w["xsc"].append({"name": name, "res": res, "range_min": a, "range_max": b, "conc": conc, "T": 296.0,
+                         "torr": 760.0, "wavenumber": x, "intensity": y})
+    return w
+
+
 def cfg5(n_lines=5_000_000, rmax=5000.0, res=0.001, cutoff=25.0):
     """stress sweep: 5M synthetic lines, 0-5000 cm-1 at 0.001 cm-1, 25 cm-1 cutoff."""
     return gas_cell(["h2o", "co2", "ch4", "o3"], n_lines, 0.0, rmax, res, 296, 1013.25,

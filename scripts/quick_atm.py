@@ -22,6 +22,8 @@ def main():
         e.set_option(eng.OPT_POINT_KERNEL, 0)
     if os.environ.get("QA_NARROW"):
         e.set_narrow_threshold(int(os.environ["QA_NARROW"]))
+    if os.environ.get("QA_VARIANT"):
+        e.set_k2_variant(int(os.environ["QA_VARIANT"]), 0)
     if os.environ.get("QA_NOBATCH"):
         e.set_option(eng.OPT_BATCH_LAYERS, 0)      # per-layer launches: exact per-layer timings
     args = (w["depth_cm"], w["T"], w["P"], w["conc"], [s.molmass for s in sp], qt, [s.q296 for s in sp], win, w["t_surface"], w["range_max"])

@@ -182,6 +182,59 @@ def case_xsc_files(name):
     print(name, {k: (list(v) if k.endswith("_names") else v.shape) for k, v in out.items()})
 
 
+def case_cfg3_mini(name):
+    """BASELINE cfg3 in miniature, run by the real reference: line-by-line CO2 + H2O next to TWO xsc tables (CFC-11 at
+    its native 0.01 cm-1, HCFC-22 at 0.05 cm-1 -> np.interp) on one 0.01 cm-1 grid.  Both tables are 296 K / 760 Torr
+    files, so the layer ends up at their T and P (pyradClasses.py:488-491)."""
+    wd = tempfile.mkdtemp(prefix="pyrad_golden_")
+    rh.seed_workdir(wd)
+    rmin, rmax, depth = 600.0, 700.0, 10.0
+    T_file, torr = 296, 760.0
+    cutoff = torr / 0.75006 / 1013.25 * 5
+    lo, hi = max(rmin - cutoff, 0.0), rmax + cutoff
+    names, conc = ["co2", "h2o"], [400e-6, 0.01]
+    sps = [synth.species(s) for s in names]
+    all_lines = []
+    for g, sp in enumerate(sps):
+        ln = synth.make_lines(1200, lo - 1.0, hi + 1.0, 808 + 17 * g)
+        seed_species(wd, sp, ln, int((lo - 1.0) / 100) * 100, hi + 101.0)
+        all_lines.append(ln)
+    tables = [("CFC11", 0.01, 620.0, 650.0, 250e-12, 811), ("HCFC22", 0.05, 660.0, 690.0, 230e-12, 812)]
+    out = {"species": np.array(names), "conc": np.array(conc), "molmass": np.array([s.molmass for s in sps]),
+           "q296": np.array([s.q296 for s in sps]), "range_min": rmin, "range_max": rmax, "depth": depth,
+           "xsc_names": np.array([t[0] for t in tables]), "xsc_res": np.array([t[1] for t in tables]),
+           "xsc_rmin": np.array([t[2] for t in tables]), "xsc_rmax": np.array([t[3] for t in tables]),
+           "xsc_conc": np.array([t[4] for t in tables]), "surface_T": 288}
+    fnames = []
+    for i, (mol, res, a, b, _, seed) in enumerate(tables):
+        fx, fy = synth.make_xsc_table(a, b, res, seed)
+        fnames.append(rh.write_xsc_file(wd, mol, float(T_file), torr, a, b, res, fx, fy))
+        out["xsc_x_%d" % i], out["xsc_y_%d" % i] = fx, fy
+    ref = rh.load_reference(wd)
+    C = ref.classes
+    with rh.quiet():
+        layer = C.Layer(depth, 280, 900.0, rmin, rmax)
+        xms = [layer.addMolecule({t[0]: f}, concentration=t[4]) for t, f in zip(tables, fnames)]
+        mols = [layer.addMolecule(n, concentration=c) for n, c in zip(names, conc)]
+        out["T_after"], out["P_after"] = layer.T, layer.P
+        out["qT"] = np.array([s.q(layer.T) for s in sps])
+        out["res"], out["cutoff"] = layer.resolution, layer.distanceFromCenter
+        out["xaxis"] = np.asarray(layer.xAxis)
+        for i, xm in enumerate(xms):
+            out["xsc_sigma_%d" % i] = np.asarray(C.getCrossSection(xm), dtype=np.float64)
+        for g, m in enumerate(mols):
+            out["sigma_%d" % g] = np.asarray(C.getCrossSection(m[0]))
+        out["layer_abscoef"] = np.asarray(C.getAbsCoef(layer))
+        out["layer_transmittance"] = np.asarray(C.getTransmittance(layer))
+        surf = ref.planck.planckWavenumber(layer.xAxis, 288)
+        out["layer_transmission"] = np.asarray(layer.transmission(surf))
+    for g, ln in enumerate(all_lines):
+        out.update(pack_lines("lines%d" % g, ln))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "N=%d T,P after=%s,%s xsc nonzero=%s" % (len(out["layer_abscoef"]), out["T_after"], out["P_after"],
+                                                         [int(np.count_nonzero(out["xsc_sigma_%d" % i])) for i in range(2)]))
+
+
 def case_kat(name):
     """Known-answer values straight from the real physics modules."""
     wd = tempfile.mkdtemp(prefix="pyrad_golden_")
@@ -209,8 +262,8 @@ def case_kat(name):
 if __name__ == "__main__":
     if not rh.available():
         raise SystemExit("the reference is not mounted at %s" % rh.REFERENCE_DIR)
-    if len(sys.argv) > 1 and sys.argv[1] == "xsc_files":          # regenerate only this case
-        case_xsc_files("xsc_files")
+    if len(sys.argv) > 1:                                          # regenerate only the named late additions
+        {"xsc_files": case_xsc_files, "cfg3_mini": case_cfg3_mini}[sys.argv[1]](sys.argv[1])
         raise SystemExit(0)
     case_kat("kat")
     case_gas_cell("cell_co2_1atm", ["co2"], [400e-6], 1500, 600.0, 700.0, 296, 1013.0, 10.0, 101)
@@ -222,3 +275,4 @@ if __name__ == "__main__":
     case_xsc("xsc_native_res", 0.01, 830.0, 860.0, 800.0, 900.0, 606)
     case_xsc("xsc_coarse_res", 0.05, 830.0, 860.0, 800.0, 900.0, 707)
     case_xsc_files("xsc_files")
+    case_cfg3_mini("cfg3_mini")

@@ -87,3 +87,52 @@ def test_cfg1_size_properties(engine):
         H.engine_prepass(engine, ws)
         parts.append(engine.line_sum())
     assert H.k_rel_err(parts[0] + parts[1], base).max() <= 2e-6
+
+
+def test_cfg3_full_size_line_by_line_plus_xsc_tables(engine, tmp_path):
+    """cfg3 (30 000 points, 50k CO2 + H2O lines, CFC-11 and HCFC-22 xsc tables on the same grid) through the host mirror on
+    an on-disk data tree, every spectrum against the oracle on the same inputs."""
+    from oracle import ref_harness as rh          # only its data-tree writers (test infrastructure)
+    from pyrad_b200 import classes as C
+    w = workloads.cfg3()
+    root = str(tmp_path)
+    C.set_engine(engine)
+    C.DATA_ROOT = root
+    C.Layer.hasAtmosphere = False
+    try:
+        for g, sp in enumerate(w["species"]):
+            ln = dict(w["per_group_lines"][g])
+            rh.write_params(root, sp.global_iso, sp.name, sp.mol_id, 1, 0.99, sp.q296, 1, sp.molmass)
+            rh.write_q_table(root, sp.global_iso, range(100, 501), [sp.q(t) for t in range(100, 501)])
+            rh.write_line_segments(root, sp.global_iso, sp.mol_id, 1, ln, int(ln["nu"].min() / 100) * 100, ln["nu"].max() + 101)
+        layer = C.Layer(w["depth_cm"], w["T"], w["P"], w["range_min"], w["range_max"])
+        xms = []
+        for x in w["xsc"]:
+            f = rh.write_xsc_file(root, x["name"], x["T"], x["torr"], x["range_min"], x["range_max"], x["res"],
+                                  x["wavenumber"], x["intensity"])
+            xms.append(layer.addMolecule({x["name"]: f}, concentration=x["conc"]))
+        mols = [layer.addMolecule(sp.name, concentration=c) for sp, c in zip(w["species"], w["conc"])]
+        assert layer.T == w["T"] and layer.P == w["P"]          # the tables' T and P are the cell's: nothing was overwritten
+        xa = ph.x_axis(w["range_min"], w["range_max"], w["res"])
+        np.testing.assert_array_equal(layer.xAxis, xa)
+        k_ref = np.zeros(len(xa))
+        for x, xm in zip(w["xsc"], xms):
+            sig = ph.xsc_cross_section(xa, x["wavenumber"], x["intensity"], x["range_min"], x["range_max"], x["res"])
+            np.testing.assert_allclose(C.getCrossSection(xm), sig, rtol=1e-14, atol=0)
+            assert np.count_nonzero(sig) > 5000
+            k_ref += ph.abs_coef(sig, x["conc"], w["P"], w["T"])
+        for g, (sp, m) in enumerate(zip(w["species"], mols)):
+            ln = H.kept(w["per_group_lines"][g], w["range_min"], w["range_max"], w["cutoff"])
+            assert len(m[0]) == len(ln["nu"]) > 20_000
+            sig = ph.cross_section(ln, w["T"], w["P"], w["conc"][g], sp.molmass, sp.q(w["T"]), sp.q296,
+                                   w["range_min"], w["range_max"], w["res"], w["cutoff"])
+            assert H.k_rel_err(C.getCrossSection(m[0]), sig).max() <= H.K_REL_TOL
+            k_ref += ph.abs_coef(sig, w["conc"][g], w["P"], w["T"])
+        assert H.k_rel_err(C.getAbsCoef(layer), k_ref).max() <= H.K_REL_TOL
+        t_ref = ph.transmittance(k_ref, w["depth_cm"])
+        assert np.abs(C.getTransmittance(layer) - t_ref).max() <= H.T_ABS_TOL
+        surf = ph.planck_wavenumber(xa, 288)
+        rad_ref = ph.transmission(t_ref, surf, ph.planck_wavenumber(xa, w["T"]))
+        np.testing.assert_allclose(layer.transmission(surf), rad_ref, rtol=2e-5)
+    finally:
+        C.DATA_ROOT = None

@@ -106,6 +106,31 @@ def test_mirror_matches_reference_xsc(name, data_root):
     assert np.abs(C.getTransmittance(layer) - g["layer_transmittance"]).max() <= H.T_ABS_TOL
 
 
+def test_mirror_matches_reference_cfg3_miniature(data_root):
+    """cfg3 in miniature: CO2 + H2O line by line next to two xsc tables (one native 0.01 cm-1, one 0.05 cm-1 re-gridded
+    on the device), every spectrum against what the real reference produced on the same files."""
+    g = G.load("cfg3_mini")
+    names = [str(s) for s in g["species"]]
+    for i, s in enumerate(names):
+        seed(data_root, g, i, s)
+    fnames = [rh.write_xsc_file(data_root, str(g["xsc_names"][i]), 296.0, 760.0, float(g["xsc_rmin"][i]),
+                                float(g["xsc_rmax"][i]), float(g["xsc_res"][i]), g["xsc_x_%d" % i], g["xsc_y_%d" % i])
+              for i in range(2)]
+    layer = C.Layer(float(g["depth"]), 280, 900.0, float(g["range_min"]), float(g["range_max"]))
+    xms = [layer.addMolecule({str(g["xsc_names"][i]): fnames[i]}, concentration=float(g["xsc_conc"][i])) for i in range(2)]
+    mols = [layer.addMolecule(s, concentration=float(c)) for s, c in zip(names, g["conc"])]
+    assert layer.T == int(g["T_after"]) and layer.P == float(g["P_after"])
+    np.testing.assert_array_equal(layer.xAxis, g["xaxis"])
+    for i, xm in enumerate(xms):
+        np.testing.assert_allclose(C.getCrossSection(xm), g["xsc_sigma_%d" % i], rtol=1e-14, atol=0)
+    for i, m in enumerate(mols):
+        assert H.k_rel_err(C.getCrossSection(m[0]), g["sigma_%d" % i]).max() <= H.K_REL_TOL
+    assert H.k_rel_err(C.getAbsCoef(layer), g["layer_abscoef"]).max() <= H.K_REL_TOL
+    assert np.abs(C.getTransmittance(layer) - g["layer_transmittance"]).max() <= H.T_ABS_TOL
+    surf = layer.planck(int(g["surface_T"]))
+    np.testing.assert_allclose(layer.transmission(surf), g["layer_transmission"], rtol=2e-5)
+
+
 def test_mirror_error_behaviour(data_root):
     g = G.load("cell_co2_1atm")
     seed(data_root, g, 0, "co2")

@@ -442,3 +442,63 @@ def test_error_behaviour_is_loud_and_specific(engine):
     engine.set_grid(600.0, 0.01, 10000)
     engine.layer_prepass(296, 1013.0, [4e-4], [44.0], [286.0], [286.0], 500)
     assert np.isfinite(engine.line_sum()).all()
+
+
+# ---------------------------------------------------------------- opt-in far-field variant (PRB_K2_FARFIELD)
+def _farfield_cell(P, T):
+    return workloads.gas_cell(["h2o", "co2", "ch4", "o3"], 6000, 1000.0, 1040.0, 0.001, T, P,
+                              [0.01, 400e-6, 1.8e-6, 5e-8], 10.0, 29)
+
+
+@pytest.mark.parametrize("P,T", [(1013.25, 296), (353.4, 250), (220.0, 225)])
+def test_k2_farfield_variant_matches_exact_paths_and_oracle(engine, P, T):
+    """Lorentz wings of far lines summed at 8 Chebyshev nodes per 256-point span and interpolated: within 1e-6 of the
+    exact per-point kernel (predicted ~5e-8) and within the north_star tolerance of the oracle."""
+    w = _farfield_cell(P, T)
+    H.engine_setup(engine, w)
+    wts = [eng.number_density_weight(c, P, T) for c in w["conc"]]
+    H.engine_prepass(engine, w, weights=wts)
+    exact = engine.line_sum()
+    engine.set_k2_variant(eng.K2_FARFIELD, 0)
+    try:
+        H.engine_prepass(engine, w, weights=wts)
+        far = engine.line_sum()
+        again = engine.line_sum()
+    finally:
+        engine.set_k2_variant(eng.K2_CLASSED, 0)
+    assert np.array_equal(far, again)                               # deterministic
+    d = H.k_rel_err(far, exact)
+    assert 0 < d.max() <= 1e-6, d.max()                             # a different evaluation, the same spectrum
+    sig = H.oracle_sigma_groups(w)
+    ref = sum(ph.abs_coef(sig[g], w["conc"][g], P, T) for g in range(4))
+    err = H.k_rel_err(far, ref)
+    assert err.max() <= H.K_REL_TOL, err.max()
+
+
+def test_k2_farfield_variant_is_shard_invariant_and_feeds_the_fused_paths(engine):
+    """Node positions are tile-relative, so tile-aligned shards reproduce the unsharded far-field result bit for bit;
+    the single-layer fused epilogue (atmosphere call) and the FP32 k row see the same sums."""
+    w = _farfield_cell(1013.25, 296)
+    sp = w["species"]
+    n = H.engine_setup(engine, w)
+    win = eng.window_len(w["cutoff"], w["res"])
+    mol, q296, qt = [s.molmass for s in sp], [s.q296 for s in sp], [s.q(w["T"]) for s in sp]
+    args = ([w["depth_cm"]], [w["T"]], [w["P"]], [w["conc"]], mol, [qt], q296, [win], 288.0, w["range_max"])
+    engine.atmosphere(*args)
+    _, tr_exact = engine.atmosphere_read()
+    engine.set_k2_variant(eng.K2_FARFIELD, 0)
+    try:
+        H.engine_prepass(engine, w)
+        full = engine.line_sum()
+        parts = []
+        for a, b in ((0, 8192), (8192, 28672), (28672, n)):
+            H.engine_setup(engine, w, a, b)
+            H.engine_prepass(engine, w)
+            parts.append(engine.line_sum())
+        assert np.array_equal(np.concatenate(parts), full)
+        H.engine_setup(engine, w)
+        engine.atmosphere(*args)
+        _, tr_far = engine.atmosphere_read()
+    finally:
+        engine.set_k2_variant(eng.K2_CLASSED, 0)
+    assert np.abs(tr_far - tr_exact).max() <= 1e-6

@@ -122,6 +122,32 @@ def test_oracle_reproduces_reference_xsc(name):
     assert np.abs(ph.transmittance(k, float(g["depth"])) - g["layer_transmittance"]).max() <= 1e-13
 
 
+def test_oracle_reproduces_reference_cfg3_miniature():
+    """cfg3 in miniature (two line-by-line molecules + two xsc tables on one grid), outputs of the real reference."""
+    g = G.load("cfg3_mini")
+    rmin, rmax = float(g["range_min"]), float(g["range_max"])
+    T, P = float(g["T_after"]), float(g["P_after"])
+    assert (T, P) == (296, 760.0 / 0.75006)
+    k = np.zeros(len(g["xaxis"]))
+    for i in range(2):
+        sig = ph.xsc_cross_section(g["xaxis"], g["xsc_x_%d" % i], g["xsc_y_%d" % i], float(g["xsc_rmin"][i]),
+                                   float(g["xsc_rmax"][i]), float(g["xsc_res"][i]))
+        np.testing.assert_array_equal(sig, g["xsc_sigma_%d" % i])
+        k = k + ph.abs_coef(sig, float(g["xsc_conc"][i]), P, T)
+    for i in range(2):
+        # kept lines follow the layer's ORIGINAL pressure (900 hPa), see test_oracle_reproduces_reference_xsc
+        ln = G.lines_of(g, i, ph.layer_cutoff(900.0), rmin, rmax)
+        sig = ph.cross_section(ln, T, P, float(g["conc"][i]), float(g["molmass"][i]), float(g["qT"][i]),
+                               float(g["q296"][i]), rmin, rmax, float(g["res"]), ph.layer_cutoff(P))
+        np.testing.assert_allclose(sig, g["sigma_%d" % i], rtol=1e-12)
+        k = k + ph.abs_coef(sig, float(g["conc"][i]), P, T)
+    np.testing.assert_allclose(k, g["layer_abscoef"], rtol=1e-12)
+    t = ph.transmittance(k, float(g["depth"]))
+    assert np.abs(t - g["layer_transmittance"]).max() <= 1e-13
+    rad = ph.transmission(t, ph.planck_wavenumber(g["xaxis"], 288), ph.planck_wavenumber(g["xaxis"], T))
+    np.testing.assert_allclose(rad, g["layer_transmission"], rtol=1e-12)
+
+
 def test_scatter_scalar_and_gather_forms_agree():
     from pyrad_b200 import synth
     ln = synth.make_lines(150, 598.0, 612.0, 3)
