@@ -219,6 +219,7 @@ def main():
                          "over NVLink from inside the compute kernel (default), 'nccl' = a separate NCCL all-gather")
     ap.add_argument("--no-atmosphere", action="store_true", help="skip the secondary 100-layer atmosphere object")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-farfield", action="store_true", help="skip the secondary far-field (PRB_K2_FARFIELD) measurements")
     ap.add_argument("--atm-layers", type=int, default=100)
     ap.add_argument("--atm-lines", type=int, default=5_000_000)
     args = ap.parse_args()
@@ -381,6 +382,69 @@ def main():
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / e2e_steps * 1e3,
            "api": "prb_gas_cell_host with prb_set_result_host: pinned host buffers in and out, line columns uploaded in wavenumber pieces under the compute, results stored into host memory tile by tile from inside K2"}
 
+    # ---- secondary object: the same cell with the opt-in far-field variant of K2 (Lorentz wings of far lines summed at
+    # 8 Chebyshev nodes per warp span and interpolated).  The headline above is the exact per-point kernel.
+    far = None
+    if not args.no_farfield:
+        k_exact = torch.empty(n_chunk, dtype=torch.float64, device="cuda")
+        k_far = torch.empty(n_chunk, dtype=torch.float64, device="cuda")
+        e.layer_prepass(T, P, conc[0], molmass, qt[0], q296, win, wts)
+        e.line_sum_dev(k_exact.data_ptr(), eng.OUT_F64)
+        e.set_k2_variant(eng.K2_FARFIELD, 0)
+        try:
+            e.layer_prepass(T, P, conc[0], molmass, qt[0], q296, win, wts)
+            e.line_sum_dev(k_far.data_ptr(), eng.OUT_F64)
+            torch.cuda.synchronize()
+            floor = 1e-40 * float(k_exact.abs().max().item())
+            rel = float(((k_far - k_exact).abs() / torch.clamp(k_exact.abs(), min=floor)).max().item())
+            fk2 = []
+            for i in range(3 + 10):
+                flush_buf.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(ext)
+                e.line_sum_dev(kbuf.data_ptr(), eng.OUT_F32)
+                b.record(ext)
+                torch.cuda.synchronize()
+                if i >= 3:
+                    fk2.append(a.elapsed_time(b))
+            fsteps = max(3, min(args.steps, 50))
+            for _ in range(3):
+                flush_buf.zero_()
+                step_device()
+            sync_all()
+            fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(fsteps)]
+            for a, b in fev:
+                flush_buf.zero_()
+                a.record(ext)
+                step_device()
+                b.record(ext)
+            sync_all()
+            tf = torch.tensor([sum(a.elapsed_time(b) for a, b in fev) / fsteps], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            far_ms = float(tf.item())
+            e.set_result_host(h_rad.numpy(), h_tr.numpy())
+            for _ in range(2):
+                step_e2e()
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                step_e2e()
+            sync_all()
+            te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
+            e.set_result_host()
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            far = {"variant": "PRB_K2_FARFIELD (opt-in): lines farther than two span lengths from a warp's 128/256-point span and "
+                              "covering it fully are summed at 8 Chebyshev nodes of the span and interpolated once per tile; "
+                              "every pair's contribution is in the result, far pairs are not evaluated one by one",
+                   "k2_ms": float(np.mean(fk2)), "k2_equivalent_pairs_per_s": pairs_rank / (float(np.mean(fk2)) * 1e-3),
+                   "ms_per_step": far_ms, "equivalent_pairs_per_s": pairs_all / (far_ms * 1e-3),
+                   "e2e_ms_per_step": float(te.item()) * 1e3, "e2e_equivalent_pairs_per_s": pairs_all / float(te.item()),
+                   "max_rel_diff_of_k_vs_exact_kernel": rel, "steps": fsteps}
+        finally:
+            e.set_k2_variant(eng.K2_CLASSED, 0)
+
     # ---- secondary object: the 100-layer atmosphere (cfg4), strong-sharded by wavenumber chunk
     atm = None
     if not args.no_atmosphere:
@@ -389,7 +453,7 @@ def main():
     # ---- secondary object: the cfg5 stress sweep (5M lines, 5M points, 25 cm-1 cutoff), strong-sharded like the atmosphere
     stress = None
     if not args.no_atmosphere:
-        stress = run_stress(e, rank, world, ext, use_peer)
+        stress = run_stress(e, rank, world, ext, use_peer, not args.no_farfield)
 
     # ---- secondary object: line-list ingestion (section 8(f) row 1), rank 0 at N = 1
     ingest = None
@@ -440,6 +504,8 @@ def main():
                                      "1/3 MUFU per Lorentz pair (triple reciprocal), hence > 1"},
             "wall_s_timed_region": wall,
         }
+        if far:
+            line["farfield"] = far
         if atm:
             line["atmosphere"] = atm
         if stress:
@@ -487,7 +553,7 @@ def run_ingest(e, w):
             "host_text_formatting_s": fmt_s}
 
 
-def run_stress(e, rank, world, ext, use_peer):
+def run_stress(e, rank, world, ext, use_peer, farfield=True):
     """cfg5: one gas cell, 5M synthetic lines, 0-5000 cm-1 @ 0.001 cm-1, fixed 25 cm-1 cutoff (W = 25 000, ~2.5e11
     accumulations), split over the N ranks by wavenumber chunk; the finished spectra gathered as in the headline."""
     import torch
@@ -535,9 +601,33 @@ def run_stress(e, rank, world, ext, use_peer):
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms = float(tm.item())
+    far = None
+    if farfield:
+        e.set_k2_variant(eng.K2_FARFIELD, 0)
+        try:
+            run()
+            ftimes = []
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                a.record(ext)
+                run()
+                b.record(ext)
+                torch.cuda.synchronize()
+                ftimes.append(a.elapsed_time(b))
+            tf = torch.tensor([float(np.median(ftimes))], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            far = {"ms": float(tf.item()), "ms_runs_this_rank": [float(t) for t in ftimes]}
+        finally:
+            e.set_k2_variant(eng.K2_CLASSED, 0)
     idx = np.trunc((w["lines"]["nu"] - w["range_min"]) / w["res"]).astype(np.int64)
     pairs = float(pt.block_pair_cost(idx, n_total, [win]).sum())
-    return {"workload": "cfg5: 5M synthetic lines, 0-5000 cm-1 @ 0.001 cm-1 (%d points), fixed 25 cm-1 cutoff (W = %d)" % (n_total, win),
+    if far:
+        far["equivalent_pairs_per_s"] = pairs / (far["ms"] * 1e-3)
+    return {"farfield": far, "workload": "cfg5: 5M synthetic lines, 0-5000 cm-1 @ 0.001 cm-1 (%d points), fixed 25 cm-1 cutoff (W = %d)" % (n_total, win),
             "pairs": pairs, "ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "scaling": "strong", "n_gpus": world,
             "ms_runs_this_rank": [float(t) for t in times]}
 
@@ -629,6 +719,31 @@ def run_atmosphere(e, args, rank, world, ext, peaks, use_peer):
     from pyrad_b200 import partition as pt
     pairs = float(pt.block_pair_cost(idx, n_total, win).sum())
     tim = e.atmosphere_timing()
+    far = None
+    if not args.no_farfield:
+        e.set_k2_variant(eng.K2_FARFIELD, 0)
+        try:
+            run()
+            torch.cuda.synchronize()
+            ftimes = []
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                a.record(ext)
+                run()
+                b.record(ext)
+                torch.cuda.synchronize()
+                ftimes.append(a.elapsed_time(b))
+            ftim = e.atmosphere_timing()
+            tf = torch.tensor([float(np.median(ftimes)), ftim["k2_ms"]], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            far = {"ms_per_spectrum": float(tf[0].item()), "max_rank_k2_ms": float(tf[1].item()),
+                   "ms_runs_this_rank": [float(t) for t in ftimes]}
+        finally:
+            e.set_k2_variant(eng.K2_CLASSED, 0)
     e.set_timing(False)
     tim_max = dict(tim)
     if world > 1:                                   # slowest rank per stage (the step ends when the slowest rank does)
@@ -643,7 +758,7 @@ def run_atmosphere(e, args, rank, world, ext, peaks, use_peer):
             "scaling": "strong", "n_gpus": world, "chunk_points_rank0": nc, "launches": e.atmosphere_launches(),
             "partition": "pair-count x measured-class-cost model" + (", one feedback step on the warm-up run's per-rank times" if rebalanced else ""),
             "gather": "none" if world == 1 else ("peer stores fused into K3" if use_peer else "nccl"),
-            "rank0_stage_ms": tim, "max_rank_stage_ms": tim_max,
+            "rank0_stage_ms": tim, "max_rank_stage_ms": tim_max, "farfield": far,
             "roofline_k3": {"bound": "hbm", "achieved": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                             "frac": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9 / hbm,
                             "traffic": load_traffic("k3_fold_f32@cfg4") if world == 1 and len(win) == 100 else None,

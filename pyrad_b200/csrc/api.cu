@@ -133,8 +133,10 @@ struct prb_engine {
     DevBuf<K2Layer> k2tab;
     LayerJob last;
     int k2_variant = PRB_K2_CLASSED, k2_ppt = 0;
-    DevBuf<double> far_lag;      // PRB_K2_FARFIELD: Lagrange weights [256][K2_FAR_NODES] (built at prb_create)
-    float far_delta[K2_FAR_NODES] = {};
+    // PRB_K2_FARFIELD: per span length (index 0: 128 points, P = 4; index 1: 256 points, P = 8) the Lagrange weights
+    // [span][K2_FAR_NODES] and the FP32 node offsets (built at prb_create)
+    DevBuf<double> far_lag[2];
+    float far_delta[2][K2_FAR_NODES] = {};
     int64_t narrow_wm = 100;     // windows with W-2 below this use k2_narrow
     bool batch_layers = true;    // prb_atmosphere: one K1 launch + one K2 launch per kernel class
     bool k3_tma = true;          // layer fold: k matrix staged by TMA (k3_fold_tma) instead of register-held loads
@@ -223,6 +225,7 @@ extern "C" int prb_create(int device, prb_engine **out) {
     want((const void *)k2_line_sum<4>, K2_SMEM_BYTES<4>(true));
     want((const void *)k2_line_sum<8>, K2_SMEM_BYTES<8>(true));
     want((const void *)k2_line_sum<16>, K2_SMEM_BYTES<16>(true));
+    want((const void *)k2_line_sum<4, true>, K2_SMEM_BYTES<4>(true));
     want((const void *)k2_line_sum<8, true>, K2_SMEM_BYTES<8>(true));
     want((const void *)k2_point, sizeof(KPSmem));
     want((const void *)k3_fold_tma, sizeof(K3TSmem));
@@ -327,26 +330,39 @@ extern "C" int prb_device_info(prb_engine *e, int *sm_count, int *cc_major, int 
 // classed kernels (per-warp window classes, thread-per-point kernels for narrow windows): every variant but GENERAL
 static inline bool k2_classed(const prb_engine *e) { return e->k2_variant != PRB_K2_GENERAL; }
 
-// Chebyshev nodes of a 256-point span on [-0.5, 255.5] as FP32 offsets from its first point, and the Lagrange weight of
+// Chebyshev nodes of a span on [-0.5, span - 0.5] as FP32 offsets from its first point, and the Lagrange weight of
 // every node at every point (FP64, built from the ROUNDED offsets so that kernel and table agree exactly).
 static int build_far_table(prb_engine *e) {
     const double pi = 3.14159265358979323846;
-    double node[K2_FAR_NODES];
-    for (int k = 0; k < K2_FAR_NODES; ++k) {
-        e->far_delta[k] = (float)(0.5 * (K2_FAR_SPAN - 1) + 0.5 * K2_FAR_SPAN * std::cos((2 * k + 1) * pi / (2 * K2_FAR_NODES)));
-        node[k] = (double)e->far_delta[k];
-    }
-    std::vector<double> lag((size_t)K2_FAR_SPAN * K2_FAR_NODES);
-    for (int i = 0; i < K2_FAR_SPAN; ++i)
+    for (int t = 0; t < 2; ++t) {
+        const int span = t == 0 ? 128 : 256;
+        double node[K2_FAR_NODES];
         for (int k = 0; k < K2_FAR_NODES; ++k) {
-            double w = 1.0;
-            for (int j = 0; j < K2_FAR_NODES; ++j)
-                if (j != k) w *= ((double)i - node[j]) / (node[k] - node[j]);
-            lag[(size_t)i * K2_FAR_NODES + k] = w;
+            e->far_delta[t][k] = (float)(0.5 * (span - 1) + 0.5 * span * std::cos((2 * k + 1) * pi / (2 * K2_FAR_NODES)));
+            node[k] = (double)e->far_delta[t][k];
         }
-    CK(e->far_lag.ensure(lag.size()));
-    CK(cudaMemcpy(e->far_lag.p, lag.data(), sizeof(double) * lag.size(), cudaMemcpyHostToDevice));
+        std::vector<double> lag((size_t)span * K2_FAR_NODES);
+        for (int i = 0; i < span; ++i)
+            for (int k = 0; k < K2_FAR_NODES; ++k) {
+                double w = 1.0;
+                for (int j = 0; j < K2_FAR_NODES; ++j)
+                    if (j != k) w *= ((double)i - node[j]) / (node[k] - node[j]);
+                lag[(size_t)i * K2_FAR_NODES + k] = w;
+            }
+        CK(e->far_lag[t].ensure(lag.size()));
+        CK(cudaMemcpy(e->far_lag[t].p, lag.data(), sizeof(double) * lag.size(), cudaMemcpyHostToDevice));
+    }
     return PRB_OK;
+}
+
+// PRB_K2_FARFIELD launches k2_line_sum<P, true> where a table exists (P = 4, 8); other P run the exact kernel.
+template <int P>
+static bool far_args(const prb_engine *e, K2Args &a) {
+    if (a.variant != PRB_K2_FARFIELD || (P != 4 && P != 8)) return false;
+    const int t = P == 4 ? 0 : 1;
+    a.far_lag = e->far_lag[t].p;
+    for (int k = 0; k < K2_FAR_NODES; ++k) a.far_delta[k] = e->far_delta[t][k];
+    return true;
 }
 
 extern "C" int prb_set_k2_variant(prb_engine *e, int variant, int ppt) {
@@ -671,13 +687,8 @@ static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
     const size_t smem = K2_SMEM_BYTES<P>(staging);
     const int64_t items = (int64_t)a.n_tiles * a.n_layers;
     const int grid = (int)std::min<int64_t>(items, (int64_t)K2_MIN_CTAS * e->prop.multiProcessorCount);
-    if (P == 8 && a.variant == PRB_K2_FARFIELD) {
-        a.far_lag = e->far_lag.p;
-        for (int k = 0; k < K2_FAR_NODES; ++k) a.far_delta[k] = e->far_delta[k];
-        k2_line_sum<8, true><<<grid, K2_THREADS, smem, e->stream>>>(a);
-    } else {
-        k2_line_sum<P><<<grid, K2_THREADS, smem, e->stream>>>(a);
-    }
+    if (far_args<P>(e, a)) k2_line_sum<(P == 4 ? 4 : 8), true><<<grid, K2_THREADS, smem, e->stream>>>(a);
+    else k2_line_sum<P><<<grid, K2_THREADS, smem, e->stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -701,13 +712,8 @@ static cudaError_t launch_k2_sub(prb_engine *e, K2Args a, cudaStream_t st) {
     const bool staging = a.fuse.enabled && a.fuse.n_dst > 1;
     const size_t smem = K2_SMEM_BYTES<P>(staging);
     const int grid = std::min(a.n_tiles, K2_MIN_CTAS * e->prop.multiProcessorCount);
-    if (P == 8 && a.variant == PRB_K2_FARFIELD) {
-        a.far_lag = e->far_lag.p;
-        for (int k = 0; k < K2_FAR_NODES; ++k) a.far_delta[k] = e->far_delta[k];
-        k2_line_sum<8, true><<<grid, K2_THREADS, smem, st>>>(a);
-    } else {
-        k2_line_sum<P><<<grid, K2_THREADS, smem, st>>>(a);
-    }
+    if (far_args<P>(e, a)) k2_line_sum<(P == 4 ? 4 : 8), true><<<grid, K2_THREADS, smem, st>>>(a);
+    else k2_line_sum<P><<<grid, K2_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 

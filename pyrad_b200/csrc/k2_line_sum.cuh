@@ -122,23 +122,22 @@ struct K2Args {
     int out_mode;              // PRB_OUT_F64 / PRB_OUT_F32
     DevState *st;              // tile_counter of this launch
     K2Fuse fuse;
-    // far-field variant (k2_line_sum<8, true>): Lagrange weights of the span's points, [256][K2_FAR_NODES], and the node
-    // offsets from the span's first point (FP32; the table is built from these rounded values)
+    // far-field variant (k2_line_sum<P, true>, P = 4 or 8): Lagrange weights of the span's points, [32 P][K2_FAR_NODES], and
+    // the node offsets from the span's first point (FP32; the table is built from these rounded values)
     const double *far_lag;
     float far_delta[8];
 };
 
-// Far-field evaluation of the Lorentz wings (variant PRB_K2_FARFIELD, 256-point spans only).  A line whose centre lies
-// more than K2_FAR_RADIUS grid points from the centre of a warp's span, and whose window covers the whole span,
+// Far-field evaluation of the Lorentz wings (variant PRB_K2_FARFIELD; spans of 128 and 256 points).  A line whose
+// centre lies more than two span lengths from the centre of a warp's span, and whose window covers the whole span,
 // contributes a function of the grid coordinate that is analytic on the span with poles at least that far away:
-// its Chebyshev interpolant through K2_FAR_NODES nodes is accurate to ~(h / (D + sqrt(D^2 - h^2)))^nodes, h = 128,
-// D >= 512 -> 7e-8 of that line's own contribution (scripts/proto/farfield_numerics.py measures 3e-8..7e-8 of the
+// its Chebyshev interpolant through K2_FAR_NODES nodes is accurate to ~(h / (D + sqrt(D^2 - h^2)))^nodes, h = span/2,
+// D >= 2 span -> 7e-8 of that line's own contribution (scripts/proto/farfield_numerics.py measures 3e-8..7e-8 of the
 // total on the BASELINE shapes).  Such lines are therefore summed at the 8 nodes of the span -- 8 evaluations instead
-// of 256 -- and the node sums are interpolated to the points once per tile.  Lines near the span, lines whose window
+// of 128 or 256 -- and the node sums are interpolated to the points once per tile.  Lines near the span, lines whose window
 // edge crosses it, and every Gaussian core go through the exact per-point paths as before.
 constexpr int K2_FAR_NODES = 8;
-constexpr float K2_FAR_RADIUS = 512.f;
-constexpr int K2_FAR_SPAN = 256;
+constexpr int K2_FAR_RADIUS_SPANS = 2;    // far = more than this many span lengths from the span centre (512 of 256 points)
 constexpr int K2_FAR_FLUSH = 16;          // triples (48 lines of one lane's chain) between FP64 flushes
 
 // One ring slot: a chunk of staged line records plus its descriptor.
@@ -295,19 +294,9 @@ __device__ __forceinline__ void gauss_pass(const float4 *sA, const float4 *sB, c
             const int j = jb + __ffs(m) - 1;
             m &= m - 1;
             const float4 b = sB[j];
-            const float nfx = sA[j].x;
-            const float2 nf = splat(nfx), C2 = splat(b.w);
-#if PRB_K2_GAUSS_BLOCKSKIP
-            // the span is H blocks of 64 consecutive points (one packed point pair per lane each): a block the near
-            // zone [f - Dg, f + Dg] does not reach is skipped (warp-uniform; the same criterion that admitted the line)
-            const float dgj = sD[j];
-            const float zlo = -nfx - dgj - wbf, zhi = -nfx + dgj - wbf;      // near zone relative to the span start
-#endif
+            const float2 nf = splat(sA[j].x), C2 = splat(b.w);
 #pragma unroll
             for (int h = 0; h < H; ++h) {
-#if PRB_K2_GAUSS_BLOCKSKIP
-                if (zhi < (float)(64 * h) || zlo > (float)(64 * h + 63)) continue;
-#endif
                 const float2 e = __fadd2_rn(s.fi[h], nf);
                 const float2 arg = __fmul2_rn(C2, __fmul2_rn(e, e));
                 float2 g = splat(b.z);
@@ -393,7 +382,7 @@ __device__ __forceinline__ void general_all(const float4 *sA, const float4 *sB, 
 template <int P, bool FAR = false>
 __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2Args a) {
     static_assert(P >= 2 && P % 2 == 0, "points per thread must be even (packed FP32x2)");
-    static_assert(!FAR || 32 * P == K2_FAR_SPAN, "the far-field table is built for 256-point spans");
+    static_assert(!FAR || P == 4 || P == 8, "far-field tables exist for 128- and 256-point spans");
     constexpr int H = P / 2;
     constexpr int TILE = K2_CONSUMERS * 32 * P;
     constexpr int SPAN = 32 * P;                      // points per consumer warp
@@ -526,10 +515,10 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             const float g0 = fmaxf(wbf - dgmax, t0);           // Gaussian cores can only come from [g0, g1)
             const float g1 = fminf(we1f + 1.f + dgmax, t5);
             int c0 = 0, c1 = 0, c4 = 0, c5 = 0, cg0 = 0, cg1 = 0, cfl = 0, cfr = 0;
-            // FAR: idx < tfl or idx > tfr, i.e. more than K2_FAR_RADIUS from the span centre wb + (SPAN-1)/2; integer
+            // FAR: idx < tfl or idx > tfr, i.e. more than two span lengths from the span centre wb + (SPAN-1)/2; integer
             // thresholds, exact in FP32, so the split does not depend on the shard origin
-            const float tfl = wbf + (float)((SPAN - 1) / 2) - K2_FAR_RADIUS;
-            const float tfr = wbf + (float)(SPAN / 2) + K2_FAR_RADIUS;
+            const float tfl = wbf + (float)((SPAN - 1) / 2 - K2_FAR_RADIUS_SPANS * SPAN);
+            const float tfr = wbf + (float)(SPAN / 2 + K2_FAR_RADIUS_SPANS * SPAN);
             for (int j = lane; j < cnt; j += 32) {
                 const float f = -sA[j].x;
                 c0 += f < t0; c1 += f < t1; c4 += f < t4; c5 += f < t5; cg0 += f < g0; cg1 += f < g1;

@@ -18,14 +18,18 @@ def sample_points(n, k, seed):
     return np.unique(np.concatenate([edge, rng.integers(0, n, k)]))
 
 
-def check_sampled(engine, w, weights_mode, P=None, T=None, n_pts=48, seed=0):
+def check_sampled(engine, w, weights_mode, P=None, T=None, n_pts=48, seed=0, variant=eng.K2_CLASSED):
     P = w["P"] if P is None else P
     T = w["T"] if T is None else T
     cutoff = P / 1013.25 * 5 if P != w["P"] else w["cutoff"]
     n = H.engine_setup(engine, w)
     wts = [eng.number_density_weight(c, P, T) for c in w["conc"]] if weights_mode else None
-    H.engine_prepass(engine, w, weights=wts, T=T, P=P, cutoff=cutoff)
-    out = engine.line_sum()
+    engine.set_k2_variant(variant, 0)
+    try:
+        H.engine_prepass(engine, w, weights=wts, T=T, P=P, cutoff=cutoff)
+        out = engine.line_sum()
+    finally:
+        engine.set_k2_variant(eng.K2_CLASSED, 0)
     pts = sample_points(n, n_pts, seed)
     sig = H.oracle_sigma_groups(w, T=T, P=P, cutoff=cutoff, points=pts)
     if weights_mode:
@@ -87,6 +91,20 @@ def test_cfg1_size_properties(engine):
         H.engine_prepass(engine, ws)
         parts.append(engine.line_sum())
     assert H.k_rel_err(parts[0] + parts[1], base).max() <= 2e-6
+
+
+def test_cfg2_full_size_farfield_variant_sampled_against_oracle(engine):
+    """cfg2 with the opt-in far-field variant of K2: same tolerance against the oracle as the exact kernel."""
+    w = workloads.cfg2()
+    out = check_sampled(engine, w, weights_mode=True, variant=eng.K2_FARFIELD)
+    assert np.all(np.isfinite(out)) and np.all(out >= 0)
+
+
+@pytest.mark.parametrize("P,T", [(353.4, 250), (150.0, 225)])
+def test_atmosphere_layer_shapes_full_size_farfield_variant_sampled(engine, P, T):
+    """cfg4-sized line list under the far-field variant: a 256-point-span layer (P = 8) and a 128-point-span layer (P = 4)."""
+    w = workloads.cfg5(cutoff=5.0)
+    check_sampled(engine, w, weights_mode=True, P=P, T=T, n_pts=24, seed=int(P), variant=eng.K2_FARFIELD)
 
 
 def test_cfg3_full_size_line_by_line_plus_xsc_tables(engine, tmp_path):

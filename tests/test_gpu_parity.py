@@ -450,7 +450,7 @@ def _farfield_cell(P, T):
                               [0.01, 400e-6, 1.8e-6, 5e-8], 10.0, 29)
 
 
-@pytest.mark.parametrize("P,T", [(1013.25, 296), (353.4, 250), (220.0, 225)])
+@pytest.mark.parametrize("P,T", [(1013.25, 296), (353.4, 250), (220.0, 225), (150.0, 220), (100.0, 215)])
 def test_k2_farfield_variant_matches_exact_paths_and_oracle(engine, P, T):
     """Lorentz wings of far lines summed at 8 Chebyshev nodes per 256-point span and interpolated: within 1e-6 of the
     exact per-point kernel (predicted ~5e-8) and within the north_star tolerance of the oracle."""
