@@ -217,25 +217,35 @@ class Engine:
                                            float(ax0), float(adelta), fy.size, _dp(fx), _dp(fy), _dp(out)))
         return out
 
-    def atmosphere(self, depth_cm, t_layer, p_layer, conc, molmass, q_t, q_296, window, t_surface, range_max):
-        """conc, q_t: (L, G); molmass, q_296: (G,).  Runs K1+K2 per layer and the K3 fold on the device."""
+    def atmosphere_call(self, depth_cm, t_layer, p_layer, conc, molmass, q_t, q_296, window, t_surface, range_max):
+        """The prb_atmosphere call with its arguments marshalled ONCE: returns a zero-argument callable for callers that
+        repeat the same column (a step loop) -- per call only the ctypes transition is left on the host."""
         L = len(t_layer)
         g = self.n_groups
-        conc = _f64(np.broadcast_to(np.asarray(conc, dtype=np.float64), (L, g)))
-        q_t = _f64(np.broadcast_to(np.asarray(q_t, dtype=np.float64), (L, g)))
-        molmass = _f64(np.broadcast_to(np.asarray(molmass, dtype=np.float64), (g,)))
-        q_296 = _f64(np.broadcast_to(np.asarray(q_296, dtype=np.float64), (g,)))
-        depth = _f64(np.broadcast_to(np.asarray(depth_cm, dtype=np.float64), (L,)))
+        keep = [_f64(np.broadcast_to(np.asarray(depth_cm, dtype=np.float64), (L,))), _f64(t_layer), _f64(p_layer),
+                _f64(np.broadcast_to(np.asarray(conc, dtype=np.float64), (L, g))),
+                _f64(np.broadcast_to(np.asarray(molmass, dtype=np.float64), (g,))),
+                _f64(np.broadcast_to(np.asarray(q_t, dtype=np.float64), (L, g))),
+                _f64(np.broadcast_to(np.asarray(q_296, dtype=np.float64), (g,)))]
         win = np.ascontiguousarray(window, dtype=np.int64)
-        _lib.check(self._lib.prb_atmosphere(self._h, L, g, _dp(depth), _dp(_f64(t_layer)), _dp(_f64(p_layer)),
-                                            _dp(conc), _dp(molmass), _dp(q_t), _dp(q_296),
-                                            win.ctypes.data_as(C.POINTER(C.c_int64)), float(t_surface),
-                                            float(range_max)))
+        ptrs = [_dp(a) for a in keep] + [win.ctypes.data_as(C.POINTER(C.c_int64))]
+        fn, h, ts, rm = self._lib.prb_atmosphere, self._h, float(t_surface), float(range_max)
 
-    def gas_cell_host(self, lines, n_groups, range_min, res, n_total, i_begin, i_end, depth_cm, T, P, conc, molmass,
-                      q_t, q_296, window, t_surface, range_max):
-        """upload_lines + set_grid + atmosphere(one layer) in ONE call with the host->device copies overlapped with
-        the compute (prb_gas_cell_host).  Results: atmosphere_read*(), or the buffers given to set_result_host()."""
+        def call():
+            rc = fn(h, L, g, *ptrs, ts, rm)
+            if rc:
+                _lib.check(rc)
+        call.keepalive = (keep, win)
+        return call
+
+    def atmosphere(self, depth_cm, t_layer, p_layer, conc, molmass, q_t, q_296, window, t_surface, range_max):
+        """conc, q_t: (L, G); molmass, q_296: (G,).  Runs K1+K2 per layer and the K3 fold on the device."""
+        self.atmosphere_call(depth_cm, t_layer, p_layer, conc, molmass, q_t, q_296, window, t_surface, range_max)()
+
+    def gas_cell_host_call(self, lines, n_groups, range_min, res, n_total, i_begin, i_end, depth_cm, T, P, conc, molmass,
+                           q_t, q_296, window, t_surface, range_max):
+        """prb_gas_cell_host with its arguments marshalled once (see atmosphere_call); the line columns are read from
+        the given host arrays on every call."""
         cols = [_f64(lines[k]) for k in ("nu", "sw", "gamma_air", "gamma_self", "elower", "n_air", "delta_air")]
         n = cols[0].size
         grp = lines.get("group") if hasattr(lines, "get") else None
@@ -245,15 +255,30 @@ class Engine:
             gp = grp.ctypes.data_as(C.POINTER(C.c_int32))
         g = int(n_groups)
         arrs = [_f64(np.broadcast_to(np.asarray(a, dtype=np.float64), (g,))) for a in (conc, molmass, q_t, q_296)]
-        _lib.check(self._lib.prb_gas_cell_host(self._h, n, *[_dp(c) for c in cols], gp, g, float(range_min), float(res),
-                                               int(n_total), int(i_begin), int(i_end), float(depth_cm), float(T), float(P),
-                                               *[_dp(a) for a in arrs], int(window), float(t_surface), float(range_max)))
-        self.n_lines, self.n_groups = n, g
-        self.n_chunk = int(i_end) - int(i_begin)
-        self.n_total = int(n_total)
-        self.i_begin, self.i_end = int(i_begin), int(i_end)
-        self._res = float(res)
-        self.range_min = float(range_min)
+        args = ([self._h, n] + [_dp(c) for c in cols] + [gp, g, float(range_min), float(res), int(n_total), int(i_begin),
+                int(i_end), float(depth_cm), float(T), float(P)] + [_dp(a) for a in arrs] +
+                [int(window), float(t_surface), float(range_max)])
+        fn = self._lib.prb_gas_cell_host
+
+        def call():
+            rc = fn(*args)
+            if rc:
+                _lib.check(rc)
+            self.n_lines, self.n_groups = n, g
+            self.n_chunk = int(i_end) - int(i_begin)
+            self.n_total = int(n_total)
+            self.i_begin, self.i_end = int(i_begin), int(i_end)
+            self._res = float(res)
+            self.range_min = float(range_min)
+        call.keepalive = (cols, grp, arrs)
+        return call
+
+    def gas_cell_host(self, lines, n_groups, range_min, res, n_total, i_begin, i_end, depth_cm, T, P, conc, molmass,
+                      q_t, q_296, window, t_surface, range_max):
+        """upload_lines + set_grid + atmosphere(one layer) in ONE call with the host->device copies overlapped with
+        the compute (prb_gas_cell_host).  Results: atmosphere_read*(), or the buffers given to set_result_host()."""
+        self.gas_cell_host_call(lines, n_groups, range_min, res, n_total, i_begin, i_end, depth_cm, T, P, conc, molmass,
+                                q_t, q_296, window, t_surface, range_max)()
 
     def atmosphere_read(self):
         rad = np.empty(self.n_chunk)
