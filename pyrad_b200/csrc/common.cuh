@@ -43,9 +43,6 @@ constexpr unsigned int FLAG_OVERFLOW = 1u, FLAG_NONFINITE = 2u;
 #ifndef PRB_K2_ACC_SMEM
 #define PRB_K2_ACC_SMEM 0
 #endif
-#ifndef PRB_K2_CLASSIFY_SEARCH
-#define PRB_K2_CLASSIFY_SEARCH 1     // class boundaries of a staged slot by two-level ballot search (1) or by counting (0)
-#endif
 constexpr int K2_CONSUMERS = PRB_K2_CONSUMERS;        // math warps per CTA
 constexpr int K2_THREADS = 32 * (K2_CONSUMERS + 1);   // + one TMA producer warp
 #ifndef PRB_K2_CHUNK

@@ -514,47 +514,43 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             if (t1 >= t4) { t1 = t5; t4 = t5; }                // window narrower than the span: all masked
             const float g0 = fmaxf(wbf - dgmax, t0);           // Gaussian cores can only come from [g0, g1)
             const float g1 = fminf(we1f + 1.f + dgmax, t5);
-#if PRB_K2_CLASSIFY_SEARCH
-            // The staged lines are sorted, so "how many lie below t" is a search, not a count: one sample per block of
-            // 32 lines (loaded once, shared by all thresholds), a ballot picks the block the boundary falls in, a second
-            // ballot over that block's 32 lines places it -- two shared-memory reads and two ballots per threshold
-            // instead of a pass over the whole slot.  Same integers as counting.
-            static_assert(K2_CHUNK <= 1024, "one level-1 sample per lane");
-            const float f1 = -sA[min(32 * lane + 31, cnt - 1)].x;
-            const bool v1 = 32 * lane < cnt;
-            auto below = [&](float t) -> int {
-                const int nb = __popc(__ballot_sync(0xffffffffu, v1 && f1 < t));   // whole blocks below t (a prefix)
-                const int j2 = 32 * nb + lane;
-                const bool l2 = j2 < cnt && -sA[min(j2, cnt - 1)].x < t;
-                return min(32 * nb, cnt) + __popc(__ballot_sync(0xffffffffu, l2));
-            };
-            const int b0 = below(t0), b1 = below(t1), b4 = below(t4), b5 = below(t5), bg0 = below(g0), bg1 = below(g1);
             // FAR: idx < tfl or idx > tfr, i.e. more than two span lengths from the span centre wb + (SPAN-1)/2; integer
             // thresholds, exact in FP32, so the split does not depend on the shard origin
             const float tfl = wbf + (float)((SPAN - 1) / 2 - K2_FAR_RADIUS_SPANS * SPAN);
             const float tfr = wbf + (float)(SPAN / 2 + K2_FAR_RADIUS_SPANS * SPAN);
-            int nfl = 0, nfr = 0;
-            if (FAR) { nfl = below(tfl); nfr = below(tfr + 1.f); }       // idx <= tfr  <=>  idx < tfr + 1 (integers)
-#else
-            int c0 = 0, c1 = 0, c4 = 0, c5 = 0, cg0 = 0, cg1 = 0, cfl = 0, cfr = 0;
-            // FAR: idx < tfl or idx > tfr, i.e. more than two span lengths from the span centre wb + (SPAN-1)/2; integer
-            // thresholds, exact in FP32, so the split does not depend on the shard origin
-            const float tfl = wbf + (float)((SPAN - 1) / 2 - K2_FAR_RADIUS_SPANS * SPAN);
-            const float tfr = wbf + (float)(SPAN / 2 + K2_FAR_RADIUS_SPANS * SPAN);
-            for (int j = lane; j < cnt; j += 32) {
-                const float f = -sA[j].x;
-                c0 += f < t0; c1 += f < t1; c4 += f < t4; c5 += f < t5; cg0 += f < g0; cg1 += f < g1;
-                if (FAR) { cfl += f < tfl; cfr += f <= tfr; }
+            int b0, b1, b4, b5, bg0, bg1, nfl = 0, nfr = 0;
+            if (FAR) {
+                // The staged lines are sorted, so "how many lie below t" is a search, not a count: one sample per block
+                // of 32 lines (loaded once, shared by all thresholds), a ballot picks the block the boundary falls in, a
+                // second ballot over that block's 32 lines places it -- two shared-memory reads and two ballots per
+                // threshold instead of a pass over the whole slot.  Same integers as counting.  (Measured: worth 4 % of the
+                // far-field kernel; in the exact kernel it changed the register allocation for the worse, so that one
+                // keeps counting -- profiles/r01_k2_experiments.txt.)
+                static_assert(K2_CHUNK <= 1024, "one level-1 sample per lane");
+                const float f1 = -sA[min(32 * lane + 31, cnt - 1)].x;
+                const bool v1 = 32 * lane < cnt;
+                auto below = [&](float t) -> int {
+                    const int nb = __popc(__ballot_sync(0xffffffffu, v1 && f1 < t));   // whole blocks below t (a prefix)
+                    const int j2 = 32 * nb + lane;
+                    const bool l2 = j2 < cnt && -sA[min(j2, cnt - 1)].x < t;
+                    return min(32 * nb, cnt) + __popc(__ballot_sync(0xffffffffu, l2));
+                };
+                b0 = below(t0); b1 = below(t1); b4 = below(t4); b5 = below(t5); bg0 = below(g0); bg1 = below(g1);
+                nfl = below(tfl);
+                nfr = below(tfr + 1.f);                                   // idx <= tfr  <=>  idx < tfr + 1 (integers)
+            } else {
+                int c0 = 0, c1 = 0, c4 = 0, c5 = 0, cg0 = 0, cg1 = 0;
+                for (int j = lane; j < cnt; j += 32) {
+                    const float f = -sA[j].x;
+                    c0 += f < t0; c1 += f < t1; c4 += f < t4; c5 += f < t5; cg0 += f < g0; cg1 += f < g1;
+                }
+                b0 = __reduce_add_sync(0xffffffffu, c0);
+                b1 = __reduce_add_sync(0xffffffffu, c1);
+                b4 = __reduce_add_sync(0xffffffffu, c4);
+                b5 = __reduce_add_sync(0xffffffffu, c5);
+                bg0 = __reduce_add_sync(0xffffffffu, cg0);
+                bg1 = __reduce_add_sync(0xffffffffu, cg1);
             }
-            const int b0 = __reduce_add_sync(0xffffffffu, c0);
-            const int b1 = __reduce_add_sync(0xffffffffu, c1);
-            const int b4 = __reduce_add_sync(0xffffffffu, c4);
-            const int b5 = __reduce_add_sync(0xffffffffu, c5);
-            const int bg0 = __reduce_add_sync(0xffffffffu, cg0);
-            const int bg1 = __reduce_add_sync(0xffffffffu, cg1);
-            int nfl = 0, nfr = 0;
-            if (FAR) { nfl = __reduce_add_sync(0xffffffffu, cfl); nfr = __reduce_add_sync(0xffffffffu, cfr); }
-#endif
             lorentz_paired<H, true>(sA, sB, b0, b1, wmf, s);
             if (FAR) {
                 // full-cover lines [b1, b4) split by distance from the span: far left | near | far right
