@@ -448,6 +448,20 @@ def main():
                    "ms_per_step": far_ms, "equivalent_pairs_per_s": pairs_all / (far_ms * 1e-3),
                    "e2e_ms_per_step": float(te.item()) * 1e3, "e2e_equivalent_pairs_per_s": pairs_all / float(te.item()),
                    "max_rel_diff_of_k_vs_exact_kernel": rel, "steps": fsteps}
+            try:
+                # what the far-field kernel really evaluates on this rank's chunk (host-side restatement of its integer
+                # class tests, tests/test_partition.py): pairs evaluated point by point + node evaluations, and the
+                # FP32 lane-slots they cost (13 packed instructions per 6 pairs, 16 per 6 node evaluations)
+                from pyrad_b200 import partition as pt
+                ex_pairs, node_evals = pt.farfield_work(pt.line_index(w["lines"]["nu"], w["range_min"], w["res"]),
+                                                        w["i_begin"], w["i_end"], win, 256)
+                slots = ex_pairs * 13.0 / 3.0 + node_evals * 16.0 / 3.0
+                peak_slots = SM_COUNT * 128 * float(peaks.get("sm_max_mhz", SM_MAX_MHZ_DEFAULT)) * 1e6
+                far["evaluated_pairs_this_rank"] = int(ex_pairs)
+                far["node_evaluations_this_rank"] = int(node_evals)
+                far["k2_fp32_lane_slot_frac"] = slots / (far["k2_ms"] * 1e-3) / peak_slots
+            except Exception as exc:                      # accounting only: never let it cost the bench line
+                far["work_accounting_error"] = repr(exc)
         finally:
             e.set_k2_variant(eng.K2_CLASSED, 0)
 

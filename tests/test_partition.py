@@ -135,3 +135,26 @@ def test_world_size_2_gloo_all_gather_assembles_the_unsharded_spectrum():
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert res[0][2] == res[1][2]                       # both ranks derived the same plan
+
+
+def test_farfield_work_accounting_matches_brute_force():
+    """partition.farfield_work restates the far-field kernel's integer class tests; checked against a direct count."""
+    rng = np.random.default_rng(5)
+    idx = np.sort(rng.integers(-300, 6000, 900))
+    for (a, b, window, span) in ((0, 4096, 1400, 256), (4096, 5500, 1400, 256), (0, 4096, 700, 128), (0, 1000, 200, 128)):
+        wm = window - 2
+        exact, nodes = pt.farfield_work(idx, a, b, window, span)
+        want_exact = want_nodes = 0
+        for first in range(a, b, span):
+            last = first + span - 1
+            pts = min(last, b - 1) - first + 1
+            for f in idx:
+                covered = sum(1 for i in range(first, first + pts) if abs(i - f) <= wm)
+                full = last - wm <= f <= first + wm
+                far = full and (f < first + (span - 1) // 2 - 2 * span or f > first + span // 2 + 2 * span)
+                if far:
+                    want_nodes += 8
+                else:
+                    want_exact += covered
+        assert (exact, nodes) == (want_exact, want_nodes), (a, b, window, span)
+    assert pt.farfield_work(idx, 0, 4096, 1400, 256)[1] > 0
