@@ -235,6 +235,7 @@ extern "C" int prb_create(int device, prb_engine **out) {
         return fail(PRB_ERR_CUDA, std::string("prb_create: cudaFuncSetAttribute failed: ") + cudaGetErrorString(ae));
     }
     if (cudaSetDevice(device) != cudaSuccess || build_far_table(e) != PRB_OK) {
+        e->far_lag[0].release(); e->far_lag[1].release();
         cudaStreamDestroy(e->stream);
         delete e;
         return fail(PRB_ERR_CUDA, "prb_create: far-field table upload failed");
@@ -266,6 +267,7 @@ extern "C" int prb_destroy(prb_engine *e) {
     e->blk_d.release();
     e->ingest.release();
     e->tile_bounds_buf[0].release(); e->tile_bounds_buf[1].release();
+    e->far_lag[0].release(); e->far_lag[1].release();
     e->dev_scal.release();
     if (e->pin_scal) cudaFreeHost(e->pin_scal);
     for (auto x : e->pipe_ev) cudaEventDestroy(x);
