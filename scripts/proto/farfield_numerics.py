@@ -69,6 +69,19 @@ def run(P, T, span, m, R, n_lines=60000, rmax=360.0, seed_spans=8, f32=False):
     print("P=%7.2f W-2=%5d span=%d m=%d R=%d: far fraction %.2f  max rel err of total %.2e" % (P, wm, span, m, R, np.mean(fracs), worst))
 
 if __name__ == "__main__":
+    # shipped geometry (radius = 2 spans from the centre, 8 nodes) on the window classes it runs on, then alternatives
+    print("# shipped: span 256 (k2_line_sum<8>), span 128 (k2_line_sum<4>), radius 2 spans, 8 nodes")
     for (P, T) in ((1013.25, 296), (353.4, 250), (250.0, 230)):
-        for m, R in ((8, 512), (8, 384), (6, 512), (10, 384), (8, 768)):
+        run(P, T, 256, 8, 512)
+    for (P, T) in ((150.0, 225), (100.0, 215), (60.0, 215)):
+        run(P, T, 128, 8, 256)
+    print("# alternatives for the next round: nodes x radius, and 64-point spans for the narrow wide-kernel class")
+    for (P, T) in ((1013.25, 296), (250.0, 230)):
+        for m, R in ((8, 384), (6, 512), (10, 384), (12, 320), (8, 768)):
             run(P, T, 256, m, R)
+    for (P, T) in ((150.0, 225), (60.0, 215)):
+        for m, R in ((10, 192), (12, 160), (6, 256)):
+            run(P, T, 128, m, R)
+    for (P, T) in ((40.0, 215), (25.0, 220)):
+        for m, R in ((8, 128), (10, 96)):
+            run(P, T, 64, m, R)
