@@ -16,6 +16,9 @@
  *   pyradPlanck.py:38-44     planckWavenumber                               > prb_layer_stream (K3)
  *   pyradClasses.py:784-787  Layer.transmission                            /
  *   pyradClasses.py:159-162,493-500 xsc np.interp + aligned placement      -> prb_xsc_place
+ *   pyradUtilities.py:515-597 changeResXscFile / mergeXsc (file re-gridding) -> prb_parse_xsc_text + prb_xsc_place
+ *   pyradUtilities.py:173-189,421-448 HITRAN-online CSV rows -> line arrays -> prb_ingest_hitran_csv
+ *   pyradClasses.py:409-428,26-29 line survey, integrateSpectrum            -> prb_line_survey, prb_integrate_spectrum
  *   (absent upstream) multi-layer fold of Layer.transmission   -> prb_atmosphere
  *
  * Conventions: every entry point is extern "C", returns int (0 = PRB_OK, < 0 = error) unless
