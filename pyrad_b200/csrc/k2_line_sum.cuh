@@ -131,9 +131,10 @@ struct K2Args {
 // Far-field evaluation of the Lorentz wings (variant PRB_K2_FARFIELD; spans of 128 and 256 points).  A line whose
 // centre lies more than two span lengths from the centre of a warp's span, and whose window covers the whole span,
 // contributes a function of the grid coordinate that is analytic on the span with poles at least that far away:
-// its Chebyshev interpolant through K2_FAR_NODES nodes is accurate to ~(h / (D + sqrt(D^2 - h^2)))^nodes, h = span/2,
-// D >= 2 span -> 7e-8 of that line's own contribution (scripts/proto/farfield_numerics.py measures 3e-8..7e-8 of the
-// total on the BASELINE shapes).  Such lines are therefore summed at the 8 nodes of the span -- 8 evaluations instead
+// its Chebyshev interpolant through K2_FAR_NODES nodes converges like (h / (D + sqrt(D^2 - h^2)))^nodes, h = span/2,
+// D >= 2 span -> 7e-8, times a constant of order ten for the line nearest the threshold.  The FP64 model of this
+// algorithm (oracle/farfield_model.py, tests/test_farfield_model.py) measures a median error of 3e-9 of k and a worst
+// case of 1.4e-7 .. 6.5e-7 on the BASELINE window classes; the kernel shows 6.6e-7 against the exact kernel on cfg2.  Such lines are therefore summed at the 8 nodes of the span -- 8 evaluations instead
 // of 128 or 256 -- and the node sums are interpolated to the points once per tile.  Lines near the span, lines whose window
 // edge crosses it, and every Gaussian core go through the exact per-point paths as before.
 constexpr int K2_FAR_NODES = 8;

@@ -1,6 +1,8 @@
 """Numerical prototype (CPU, numpy FP64/FP32) of a far-field scheme for K2: lines whose centre lies far from a warp's
 span are evaluated at m Chebyshev nodes of the span and interpolated, instead of at every point.  Prints the error of the
-interpolated far-field sum relative to the exact total k at the span's points, for cfg2-like and atmosphere-like cells."""
+interpolated far-field sum relative to the exact total k at the span's points, for cfg2-like and atmosphere-like cells,
+on a handful of RANDOM spans (the worst case over all spans is several times larger: oracle/farfield_model.py and
+tests/test_farfield_model.py pin it)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np

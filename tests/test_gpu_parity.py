@@ -453,7 +453,8 @@ def _farfield_cell(P, T):
 @pytest.mark.parametrize("P,T", [(1013.25, 296), (353.4, 250), (220.0, 225), (150.0, 220), (100.0, 215)])
 def test_k2_farfield_variant_matches_exact_paths_and_oracle(engine, P, T):
     """Lorentz wings of far lines summed at 8 Chebyshev nodes per 256-point span and interpolated: within 1e-6 of the
-    exact per-point kernel (predicted ~5e-8) and within the north_star tolerance of the oracle."""
+    exact per-point kernel (the FP64 model of the algorithm, tests/test_farfield_model.py, bounds the worst case at 6.5e-7)
+    and within the north_star tolerance of the oracle."""
     w = _farfield_cell(P, T)
     H.engine_setup(engine, w)
     wts = [eng.number_density_weight(c, P, T) for c in w["conc"]]
