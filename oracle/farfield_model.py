@@ -46,11 +46,12 @@ def line_records(lines, T, P, conc, molmass, qT, q296, range_min, res, weight=1.
     return ph.line_index(lines["nu"], range_min, res), cL / res ** 2, (hL / res) ** 2, cG, C
 
 
-def line_sum(idx, A, B, G, C, n, window, span, farfield=True, nodes=NODES, radius_spans=RADIUS_SPANS):
+def line_sum(idx, A, B, G, C, n, window, span, farfield=True, nodes=NODES, radius_spans=RADIUS_SPANS, radius_points=None):
     """k[0..n) with the kernel's class logic per span of `span` points: lines whose window |d| <= W-2 covers the whole span
     and whose index lies beyond the integer far thresholds are summed at the nodes (Lorentz term only; their Gaussian
     cores still point by point) and interpolated; every other (line, point) pair exactly.  Returns (k, far pair fraction)."""
     wm = max(int(window) - 2, 0)
+    radius = int(radius_spans * span) if radius_points is None else int(radius_points)   # design studies: any radius
     out = np.zeros(n)
     lag = lagrange_table(span, nodes)
     xn = node_offsets(span, nodes)
@@ -62,7 +63,7 @@ def line_sum(idx, A, B, G, C, n, window, span, farfield=True, nodes=NODES, radiu
         full = (idx >= last - wm) & (idx <= first + wm)
         far = np.zeros_like(full)
         if farfield:
-            far = full & ((idx < first + (span - 1) // 2 - radius_spans * span) | (idx > first + span // 2 + radius_spans * span))
+            far = full & ((idx < first + (span - 1) // 2 - radius) | (idx > first + span // 2 + radius))
         near = reach & ~far
         d = pts[:, None] - idx[None, near]
         inside = np.abs(d) <= wm
