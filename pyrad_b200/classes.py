@@ -741,12 +741,5 @@ def returnPlot(obj, propertyToPlot):
     return False
 
 
-# First isotopologue ids used by the workloads / tests; the full HITRAN table is data, not path logic.
-HITRAN_GLOBAL_ISO = {1: {1: 1, 2: 2, 3: 3, 4: 4, 5: 5, 6: 6, 7: 129},
-                     2: {1: 7, 2: 8, 3: 9, 4: 10, 5: 11, 6: 12, 7: 13, 8: 14, 9: 121, 10: 15, 11: 120, 12: 122},
-                     3: {1: 16, 2: 17, 3: 18, 4: 19, 5: 20},
-                     4: {1: 21, 2: 22, 3: 23, 4: 24, 5: 25},
-                     5: {1: 26, 2: 27, 3: 28, 4: 29, 5: 30, 6: 31},
-                     6: {1: 32, 2: 33, 3: 34, 4: 35},
-                     7: {1: 36, 2: 37, 3: 38}}
-MOLECULE_ID = {"h2o": 1, "co2": 2, "o3": 3, "n2o": 4, "co": 5, "ch4": 6, "o2": 7}
+# the reference's id tables (pyradClasses.py:951-1022), all 49 molecules
+from .hitran_tables import HITRAN_GLOBAL_ISO, MOLECULE_ID  # noqa: E402

@@ -121,7 +121,6 @@ struct prb_engine {
     int64_t n_total = 0, i_begin = 0, i_end = 0;
     bool grid_set = false;
     DevBuf<int32_t> idx;
-    std::vector<int32_t> h_idx;
 
     // per-layer
     DevBuf<float4> recA, recB;
@@ -169,6 +168,8 @@ struct prb_engine {
     // atmosphere
     DevBuf<float> kmat, rad, trans;
     float *res_rad = nullptr, *res_trans = nullptr;   // where the last prb_atmosphere left its spectra
+    float *read_stage = nullptr;                      // pinned staging of prb_atmosphere_read
+    size_t read_stage_cap = 0;
     float *host_rad_dev = nullptr, *host_trans_dev = nullptr;   // device views of the caller's pinned result buffers
     int64_t host_result_len = 0;
     int last_launches = 0;                            // kernels launched by the last prb_atmosphere
@@ -264,6 +265,7 @@ extern "C" int prb_destroy(prb_engine *e) {
     e->kmat.release(); e->rad.release(); e->trans.release(); e->fold.release();
     e->k2tab.release(); e->ring_d.release(); e->peer_err.release();
     if (e->blk_h) cudaFreeHost(e->blk_h);
+    if (e->read_stage) cudaFreeHost(e->read_stage);
     e->blk_d.release();
     e->ingest.release();
     e->tile_bounds_buf[0].release(); e->tile_bounds_buf[1].release();
@@ -452,10 +454,7 @@ extern "C" int prb_set_grid(prb_engine *e, double range_min, double res, int64_t
     const int64_t na = e->n_alloc;
     k0_line_index<<<(unsigned)((na + 255) / 256), 256, 0, e->stream>>>(e->nu0.p, e->n_lines, 0, na, range_min, res,
                                                                       e->idx.p);
-    CK(cudaGetLastError());
-    e->h_idx.resize(na);
-    CK(cudaMemcpyAsync(e->h_idx.data(), e->idx.p, sizeof(int32_t) * na, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());                                     // enqueue only: the indices never visit the host
     e->range_min = range_min;
     e->res = res;
     e->n_total = n_total;
@@ -514,10 +513,9 @@ static int check_segment(prb_engine *e, int64_t wm) {
 static int pick_ppt(const prb_engine *e, int64_t wm) {
     if (e->k2_ppt) return e->k2_ppt;
     // a warp spans 32*P points: keep the span well inside the window so most lines cover it fully
-    static const int64_t t8 = getenv("PRB_PPT8_MIN") ? atoll(getenv("PRB_PPT8_MIN")) : 1024;   // development overrides
-    static const int64_t t4 = getenv("PRB_PPT4_MIN") ? atoll(getenv("PRB_PPT4_MIN")) : 256;
-    if (wm >= t8) return 8;
-    if (wm >= t4) return 4;
+    // (thresholds measured per layer on B200, profiles/r01_k2_experiments.txt)
+    if (wm >= 1024) return 8;
+    if (wm >= 256) return 4;
     return 2;
 }
 
@@ -526,13 +524,11 @@ static LayerJob plan_job(const prb_engine *e, double T, double P, int64_t W, dou
     LayerJob j;
     j.T = T; j.P = P; j.W = W; j.scale = scale;
     j.wm = std::max<int64_t>(W - 2, 0);
-    const int64_t n = e->n_lines;
-    // lines that can reach the owned chunk: idx in [i_begin - wm, i_end - 1 + wm]
-    const int32_t *hb = e->h_idx.data();
-    const int64_t klo = e->i_begin - j.wm, khi = e->i_end - 1 + j.wm;
-    j.l0 = std::lower_bound(hb, hb + n, klo, [](int32_t a, int64_t k) { return (int64_t)a < k; }) - hb;
-    j.l1 = std::upper_bound(hb, hb + n, khi, [](int64_t k, int32_t a) { return k < (int64_t)a; }) - hb;
-    if (j.l1 < j.l0) j.l1 = j.l0;
+    // The prepass covers the whole uploaded list and K2's producer searches all of it for every tile: callers upload
+    // the lines that can reach the owned chunk (ShardPlan.subset), so narrowing the range here bought nothing and cost
+    // a device-to-host copy of the index array plus a synchronisation in every prb_set_grid.
+    j.l0 = 0;
+    j.l1 = e->n_lines;
     // kernel kind: 0 = k2_line_sum (wide), 2 = k2_point (table-driven thread-per-point, 16 <= W-2 <= 511),
     // 1 = k2_narrow (binary-search thread-per-point: windows of a few points, where building the table costs more
     //     than it saves -- measured on B200 -- and forced thresholds above 511)
@@ -625,7 +621,8 @@ extern "C" int prb_layer_prepass(prb_engine *e, double T, double P, int32_t n_gr
     j.st_dev = e->st.p;
     rc = run_prepass(e, &j, 1, DebugOut{});
     if (rc) return rc;
-    CK(cudaStreamSynchronize(e->stream));                       // h, row (pageable) must outlive the copies
+    // (no synchronisation: a copy from pageable memory has left its source when cudaMemcpyAsync returns, and the
+    // K1 layer table travels as a kernel parameter)
     e->last = j;
     return PRB_OK;
 }
@@ -673,8 +670,10 @@ extern "C" int prb_debug_line_params(prb_engine *e, double *nu_shift, double *ga
     if (gamma_d) CK(cudaMemcpyAsync(gamma_d, e->scratch_c.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
     if (s_t) CK(cudaMemcpyAsync(s_t, e->scratch_d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
     if (regime) CK(cudaMemcpyAsync(regime, reg.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    std::vector<int32_t> h_idx(index ? n : 0);
+    if (index && n) CK(cudaMemcpyAsync(h_idx.data(), e->idx.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    if (index) for (int64_t i = 0; i < n; ++i) index[i] = e->h_idx[i];
+    if (index) for (int64_t i = 0; i < n; ++i) index[i] = h_idx[i];
     r4.release(); r5.release(); r2.release(); reg.release(); st.release();
     return PRB_OK;
 }
@@ -835,14 +834,21 @@ extern "C" int64_t prb_pair_count(prb_engine *e) {
         fail(PRB_ERR_STATE, "prb_pair_count: run prb_layer_prepass first");
         return -1;
     }
-    const int64_t wm = e->last.wm, b = e->i_begin, en = e->i_end - 1;
-    int64_t total = 0;
-    for (int64_t l = e->last.l0; l < e->last.l1; ++l) {
-        const int64_t c = e->h_idx[l];
-        const int64_t lo = std::max(c - wm, b), hi = std::min(c + wm, en);
-        if (hi >= lo) total += hi - lo + 1;
+    if (cudaSetDevice(e->device) != cudaSuccess || e->dev_scal.ensure(8) != cudaSuccess) {
+        fail(PRB_ERR_CUDA, "prb_pair_count: device setup failed");
+        return -1;
     }
-    return total;
+    unsigned long long total = 0;
+    cudaMemsetAsync(e->dev_scal.p + 4, 0, sizeof(unsigned long long), e->stream);
+    if (e->n_lines > 0)
+        k0_pair_count<<<(unsigned)std::min<int64_t>((e->n_lines + 255) / 256, 4096), 256, 0, e->stream>>>(
+            e->idx.p, e->n_lines, e->last.wm, e->i_begin, e->i_end - 1, e->dev_scal.p + 4);
+    cudaMemcpyAsync(&total, e->dev_scal.p + 4, sizeof total, cudaMemcpyDeviceToHost, e->stream);
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        fail(PRB_ERR_CUDA, "prb_pair_count: device reduction failed");
+        return -1;
+    }
+    return (int64_t)total;
 }
 
 // ------------------------------------------------------------------------------------ K3 (host buffers)
@@ -1286,14 +1292,23 @@ extern "C" int prb_atmosphere_read(prb_engine *e, double *radiance_host, double 
     if (!e || !e->atm_layers) return fail(PRB_ERR_STATE, "prb_atmosphere_read: run prb_atmosphere first");
     CK(cudaSetDevice(e->device));
     const int64_t nc = chunk_len(e);
-    std::vector<float> tmp(nc);
+    // both spectra cross PCIe into one pinned staging block (grown on demand, kept), then widen to the caller's doubles
+    if ((size_t)nc * 2 > e->read_stage_cap) {
+        if (e->read_stage) cudaFreeHost(e->read_stage);
+        e->read_stage = nullptr;
+        e->read_stage_cap = 0;
+        CK(cudaMallocHost((void **)&e->read_stage, sizeof(float) * std::max<size_t>((size_t)nc * 2, 1)));
+        e->read_stage_cap = (size_t)nc * 2;
+    }
     const float *src[2] = {e->res_rad, e->res_trans};
     double *dst[2] = {radiance_host, transmittance_host};
+    for (int k = 0; k < 2; ++k)
+        if (dst[k] && nc) CK(cudaMemcpyAsync(e->read_stage + (size_t)k * nc, src[k], sizeof(float) * nc, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     for (int k = 0; k < 2; ++k) {
         if (!dst[k]) continue;
-        CK(cudaMemcpyAsync(tmp.data(), src[k], sizeof(float) * nc, cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
-        for (int64_t i = 0; i < nc; ++i) dst[k][i] = (double)tmp[i];
+        const float *t = e->read_stage + (size_t)k * nc;
+        for (int64_t i = 0; i < nc; ++i) dst[k][i] = (double)t[i];
     }
     return PRB_OK;
 }
@@ -1519,16 +1534,7 @@ extern "C" int prb_ingest_hitran_csv(prb_engine *e, const char *text, int64_t n_
     if (n_bytes < 0 || (n_bytes > 0 && !text)) return fail(PRB_ERR_ARG, "prb_ingest_hitran_csv: bad arguments");
     if (n_bytes > (int64_t(1) << 36)) return fail(PRB_ERR_ARG, "prb_ingest_hitran_csv: more than 64 GiB of text; ingest in pieces");
     CK(cudaSetDevice(e->device));
-    const bool trace = getenv("PRB_INGEST_TIMING") != nullptr;           // development aid: phase times on stderr
-    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t_prev = now();
-    auto lap = [&](const char *what) {
-        if (!trace) return;
-        cudaStreamSynchronize(e->stream);
-        const double t = now();
-        fprintf(stderr, "[ingest] %-28s %8.3f ms\n", what, t - t_prev);
-        t_prev = t;
-    };
+    auto lap = [&](const char *) {};                             // (phase timing hook of the development builds)
     const int64_t n_pad = std::max<int64_t>((n_bytes + 15) & ~int64_t(15), 16);
     // scratch lives in the engine and only grows (device allocation is far slower than the parse itself)
     IngestScratch &g = e->ingest;
@@ -1773,7 +1779,7 @@ extern "C" int prb_gas_cell_host(prb_engine *e, int64_t n, const double *nu0, co
     const int tile_pts = K2_CONSUMERS * 32 * ppt;
     const int n_tiles = (int)((nc + tile_pts - 1) / tile_pts);
     // K2 tiles per piece in waves of resident CTAs: measured on cfg2 (ms per call) 1 wave 1.72, 2 waves 1.65, 3 waves 1.65
-    static const int waves_per_piece = getenv("PRB_PIPE_WAVES") ? std::max(1, atoi(getenv("PRB_PIPE_WAVES"))) : 2;
+    const int waves_per_piece = 2;
     const int wave = waves_per_piece * K2_MIN_CTAS * e->prop.multiProcessorCount;
     const int S = (n_tiles + wave - 1) / wave;
     const bool pipelined = k2_classed(e) && e->fuse_single && wm >= e->narrow_wm && S >= 2 && n >= 4096;
@@ -1859,22 +1865,20 @@ extern "C" int prb_gas_cell_host(prb_engine *e, int64_t n, const double *nu0, co
 
     rc = atmosphere_impl(e, 1, n_groups, &depth_cm, &t_layer, &p_layer, conc, molmass, q_t, q_296, &window_len, t_surface,
                          range_max, &pipe);
-    // what prb_upload_lines checks on the host, checked on the device after the fact; and the index array for the
-    // host-side planning of later calls
+    // what prb_upload_lines checks on the host, checked on the device after the fact (the header says so: on
+    // PRB_ERR_ARG from this check the output buffers hold garbage)
     k0_validate_lines<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->nu0.p, group ? e->group.p : nullptr, n, n_groups,
                                                                         reinterpret_cast<unsigned int *>(e->dev_scal.p + 1));
-    e->h_idx.resize(e->n_alloc);
-    cudaMemcpyAsync(e->h_idx.data(), e->idx.p, sizeof(int32_t) * e->n_alloc, cudaMemcpyDeviceToHost, e->stream);
     cudaMemcpyAsync(e->pin_scal, e->dev_scal.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream);
     CK(cudaStreamSynchronize(e->copy_stream));
     CK(cudaStreamSynchronize(e->stream2));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaGetLastError());
+    if (rc) return rc;                                          // a failed launch sequence: its own message stands
     memcpy(&e->s_max, e->pin_scal, sizeof(double));             // max|S296|, for the planning of later calls
     const unsigned int vf = (unsigned int)e->pin_scal[1];
     if (vf & 1u) return fail(PRB_ERR_ARG, "prb_gas_cell_host: nu0 must be ascending");
     if (vf & 2u) return fail(PRB_ERR_ARG, "prb_gas_cell_host: group id out of range");
-    if (rc) return rc;
     e->lines_set = true;
     e->grid_set = true;
     return PRB_OK;

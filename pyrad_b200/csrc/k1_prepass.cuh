@@ -80,6 +80,22 @@ __global__ void k0_pick_scale(const unsigned long long *__restrict__ smax_bits, 
     for (int r = 0; r < n_rows; ++r) inv_scale_rows[(size_t)r * row_stride_doubles] = 1.0 / sc;
 }
 
+// Number of (line, grid point) accumulations of the reference on the owned chunk [i_lo, i_hi] for the window |d| <= wm
+// (the metric's numerator).  Integer sum: the atomics only combine per-warp partial counts.
+__global__ void __launch_bounds__(256)
+k0_pair_count(const int32_t *__restrict__ idx, int64_t n, int64_t wm, int64_t i_lo, int64_t i_hi,
+              unsigned long long *__restrict__ out) {
+    unsigned long long c = 0;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t x = idx[l];
+        const int64_t lo = max(x - wm, i_lo), hi = min(x + wm, i_hi);
+        if (hi >= lo) c += (unsigned long long)(hi - lo + 1);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 __global__ void __launch_bounds__(256)
 k0_validate_lines(const double *__restrict__ nu0, const int32_t *__restrict__ group, int64_t n, int n_groups,
                   unsigned int *__restrict__ flags) {

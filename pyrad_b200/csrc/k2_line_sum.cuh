@@ -24,7 +24,7 @@
 //     (one MUFU.RCP per TWO (line, point) pairs), written with Blackwell's packed FP32x2 instructions
 //     (FADD2/FMUL2/FFMA2: two grid points per instruction), so a (line, point) pair costs 2 issue slots
 //     of FP32-pipe work + 0.5 MUFU.  The Gaussian core G*exp2(C d^2) is a separate pass over the few
-//     lines whose near zone (|d| <= Dg: beyond it the term is < 1e-9 of the Lorentz term) meets the span.
+//     lines whose near zone (|d| <= Dg: beyond it the term is < 2e-7 of the same line's Lorentz term) meets the span.
 //   * tensor cores are deliberately unused: this is not a dense contraction.
 #pragma once
 #include "common.cuh"

@@ -82,6 +82,25 @@ k3_xsc_place(int64_t n_out, int64_t dst0, int64_t src0, int64_t count, int inter
 
 constexpr int K3_UNROLL = 8;
 
+// Optical depth of the whole column: the per-layer terms -tau_l log2(e) are summed in FP32 over groups of
+// K3_TAU_GROUP consecutive layers (aligned to the layer index, so every fold kernel forms the same groups) and the
+// group sums are added into a double-float (hi, lo) pair with an error-free TwoSum.  A plain FP32 running sum over
+// 100 layers loses up to ~100 * 2^-24 of tau, i.e. up to 2e-6 of the total transmittance at tau ~ 1 -- more than the
+// 1e-6 the path promises; this way the error stays below 4 * 2^-24 * tau (|dT| <= 9e-8) for six FP32 instructions per
+// point per four layers (FP64 accumulators would cost the fold kernel eight registers it does not have).
+constexpr int K3_TAU_GROUP = 4;
+__device__ __forceinline__ void tau_flush(float (&tau)[4], float (&hi)[4], float (&lo)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float s = __fadd_rn(hi[q], tau[q]);
+        const float bp = __fsub_rn(s, hi[q]);
+        const float err = __fadd_rn(__fsub_rn(hi[q], __fsub_rn(s, bp)), __fsub_rn(tau[q], bp));
+        lo[q] = __fadd_rn(lo[q], err);
+        hi[q] = s;
+        tau[q] = 0.f;
+    }
+}
+
 // ---- atmosphere fold, FP32 storage, float4 per thread --------------------------------------------
 struct FoldLayer {
     float neg_depth_log2e;   // -depth * log2(e): T = exp2(k * this)
@@ -122,6 +141,7 @@ k3_fold_f32(const float *__restrict__ kmat, int64_t ld, int n_layers, const Fold
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i0 = v << 2;
         float nu[4], a3[4], rad[4], tau[4];
+        float tau_hi[4], tau_lo[4];                              // optical depth of the column, see K3_TAU_GROUP
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const double x = axis_value(i_begin + i0 + q, n_total, x0, dx, x_last);
@@ -129,6 +149,8 @@ k3_fold_f32(const float *__restrict__ kmat, int64_t ld, int n_layers, const Fold
             a3[q] = (float)(2E8 * hPlanck * (cLight * cLight) * (x * x * x));
             rad[q] = planck_f32(a3[q], c2_over_tsurf * nu[q]);   // I_0 = B(nu, T_surface)
             tau[q] = 0.f;
+            tau_hi[q] = 0.f;
+            tau_lo[q] = 0.f;
         }
         // layers in groups of K3_UNROLL: all of a group's loads are issued before its math, so every thread keeps
         // K3_UNROLL x 16 B in flight (the kernel is latency bound otherwise); the k matrix is read exactly once,
@@ -153,11 +175,14 @@ k3_fold_f32(const float *__restrict__ kmat, int64_t ld, int n_layers, const Fold
                         rad[q] = fmaf(t, rad[q] - b, b);                  // T*I + (1-T)*B
                         tau[q] += e;
                     }
+                    if (((l0 + j) & (K3_TAU_GROUP - 1)) == K3_TAU_GROUP - 1) tau_flush(tau, tau_hi, tau_lo);
                 }
             }
         }
+        tau_flush(tau, tau_hi, tau_lo);
         const float4 r4 = make_float4(rad[0], rad[1], rad[2], rad[3]);
-        const float4 t4 = make_float4(exp2f(tau[0]), exp2f(tau[1]), exp2f(tau[2]), exp2f(tau[3]));
+        const float4 t4 = make_float4(exp2f(tau_hi[0] + tau_lo[0]), exp2f(tau_hi[1] + tau_lo[1]), exp2f(tau_hi[2] + tau_lo[2]),
+                                      exp2f(tau_hi[3] + tau_lo[3]));
         const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll 1
         for (int d = 0; d < dst.n; ++d) {
@@ -200,6 +225,7 @@ constexpr int K3T_MINB = PRB_K3T_MINB;                 // resident CTAs per SM t
 
 struct K3TSmem {
     float k[K3T_SLOTS][K3T_LAYERS][K3T_STRIP];
+    float2 tau[4][K3T_THREADS];            // (hi, lo) optical-depth accumulators of every thread's four points
     uint64_t full[K3T_SLOTS];
 };
 
@@ -236,6 +262,16 @@ k3_fold_tma(const float *__restrict__ kmat, int64_t ld, int n_layers, const Fold
         for (int64_t s = 0; s < min(n_steps, (int64_t)(K3T_SLOTS - 1)); ++s) issue(s);
 
     float nu[4], a3[4], rad[4], tau[4];
+    // the column's (hi, lo) optical depth lives in shared memory, touched once per K3_TAU_GROUP layers: the register
+    // budget of 5 CTAs per SM (48) has no room for it
+    auto tau_flush_smem = [&]() {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 v = sm.tau[q][tid]; hi[q] = v.x; lo[q] = v.y; }
+        tau_flush(tau, hi, lo);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sm.tau[q][tid] = make_float2(hi[q], lo[q]);
+    };
     bool interp = false;
     int64_t i0 = 0;
     for (int64_t step = 0; step < n_steps; ++step) {
@@ -251,6 +287,7 @@ k3_fold_tma(const float *__restrict__ kmat, int64_t ld, int n_layers, const Fold
                 a3[q] = (float)(2E8 * hPlanck * (cLight * cLight) * (x * x * x));
                 rad[q] = planck_f32(a3[q], c2_over_tsurf * nu[q]);
                 tau[q] = 0.f;
+                sm.tau[q][tid] = make_float2(0.f, 0.f);
             }
             interp = nu[0] >= nu_interp_min;
         }
@@ -293,13 +330,18 @@ k3_fold_tma(const float *__restrict__ kmat, int64_t ld, int n_layers, const Fold
                         rad[q] = fmaf(t, rad[q] - b[q], b[q]);
                         tau[q] += e;
                     }
+                    if (((g * K3T_LAYERS + r) & (K3_TAU_GROUP - 1)) == K3_TAU_GROUP - 1) tau_flush_smem();
                 }
             }
         }
         __syncthreads();                               // every thread is done with this slot: it may be refilled
         if (g == groups - 1 && i0 < n_chunk) {
+            tau_flush_smem();
+            float tt4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float2 v = sm.tau[q][tid]; tt4[q] = exp2f(v.x + v.y); }
             const float4 r4 = make_float4(rad[0], rad[1], rad[2], rad[3]);
-            const float4 t4 = make_float4(exp2f(tau[0]), exp2f(tau[1]), exp2f(tau[2]), exp2f(tau[3]));
+            const float4 t4 = make_float4(tt4[0], tt4[1], tt4[2], tt4[3]);
             const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll 1
             for (int d = 0; d < dst.n; ++d) {

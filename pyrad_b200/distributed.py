@@ -30,6 +30,10 @@ class ShardPlan:
         # lines whose window reaches the chunk (+1 line of slack each side, harmless)
         l0 = int(np.searchsorted(idx, self.i_begin - self.wmax, side="left"))
         l1 = int(np.searchsorted(idx, self.i_end - 1 + self.wmax, side="right"))
+        # the subset starts on a multiple of four lines: K2 aligns its staging chunks to four records in the coordinates
+        # of the UPLOADED list, so this keeps every tile's chunk boundaries -- hence the triple grouping and the FP32
+        # flush points -- those of the unsharded run (bitwise shard invariance, tests/test_partition.py)
+        l0 &= ~3
         self.l0, self.l1 = l0, max(l1, l0)
         self.max_chunk = max(b - a for a, b in self.chunks)
         self.n_total = n_total

@@ -129,7 +129,7 @@ def equal_chunks(n_total, nranks, block=ALIGN):
 def lines_for_chunk(nu0, range_min, res, i_begin, i_end, wmax):
     """Slice [l0, l1) of the (sorted) line list whose windows can reach [i_begin, i_end) with |d| <= wmax."""
     idx = line_index(nu0, range_min, res)
-    l0 = int(np.searchsorted(idx, i_begin - wmax, side="left"))
+    l0 = int(np.searchsorted(idx, i_begin - wmax, side="left")) & ~3      # four-line alignment: see ShardPlan
     l1 = int(np.searchsorted(idx, i_end - 1 + wmax, side="right"))
     return l0, max(l1, l0)
 

@@ -62,3 +62,65 @@ def engine_prepass(e, w, weights=None, T=None, P=None, conc=None, cutoff=None):
     sp = w["species"]
     e.layer_prepass(T, P, conc, [s.molmass for s in sp], [s.q(T) for s in sp], [s.q296 for s in sp],
                     eng.window_len(cutoff, w["res"]), weights)
+
+
+def boundary_points(n, k_random, seed, tile=2048, span=256, n_tiles=24):
+    """Deterministic sample of grid indices that stresses the kernels' class boundaries: the first and last points,
+    both sides of `n_tiles` tile edges (k*tile-1, k*tile) and warp-span edges (k*span-1, k*span, k*span+1) spread over
+    the grid, plus `k_random` seeded random points."""
+    rng = np.random.default_rng(seed)
+    edge = [0, 1, 2, 3, n // 2, n - 3, n - 2, n - 1]
+    tiles = np.unique(rng.integers(1, max(n // tile, 2), n_tiles))
+    for t in tiles:
+        edge += [t * tile - 1, t * tile]
+        s = t * tile + span * int(rng.integers(1, tile // span))
+        edge += [s - 1, s, s + 1]
+    pts = np.concatenate([np.array(edge, dtype=np.int64), rng.integers(0, n, k_random)])
+    return np.unique(pts[(pts >= 0) & (pts < n)])
+
+
+def _lines_near(idx, lines, points, wm):
+    """The sub-list of `lines` (ascending) whose index lies within wm of at least one of `points`."""
+    lo = np.searchsorted(idx, points - wm, side="left")
+    hi = np.searchsorted(idx, points + wm, side="right")
+    mark = np.zeros(len(idx) + 1, dtype=np.int64)
+    np.add.at(mark, lo, 1)
+    np.add.at(mark, hi, -1)
+    sel = np.nonzero(np.cumsum(mark[:-1]) > 0)[0]
+    return {k: np.asarray(v)[sel] for k, v in lines.items()}
+
+
+def oracle_layer_k_at(w, points, T, P, conc, cutoff):
+    """k(nu) of one layer at the grid indices `points` (oracle gather form, only the lines that can reach them)."""
+    points = np.asarray(points, dtype=np.int64)
+    wm = max(ph.window_len(cutoff, w["res"]) - 2, 0)
+    k = np.zeros(len(points))
+    for g, sp in enumerate(w["species"]):
+        ln = w["per_group_lines"][g]
+        idx = w.setdefault("_idx_cache", {}).get(g)
+        if idx is None:
+            idx = w["_idx_cache"][g] = ph.line_index(ln["nu"], w["range_min"], w["res"])
+        sub = _lines_near(idx, ln, points, wm)
+        if len(sub["nu"]) == 0:
+            continue
+        sig = ph.cross_section_at(points, sub, T, P, conc[g], sp.molmass, sp.q(T), sp.q296, w["range_min"],
+                                  w["range_max"], w["res"], cutoff)
+        k += ph.abs_coef(sig, conc[g], P, T)
+    return k
+
+
+def oracle_column_at(w, points, t_surface):
+    """Radiance and total transmittance of a column workload at the grid indices `points`: per layer the oracle's
+    k -> exp(-k u) -> T I + (1 - T) B fold (pyradClasses.py:707-716, 784-787), bottom to top from B(nu, t_surface)."""
+    points = np.asarray(points, dtype=np.int64)
+    xa = ph.x_axis(w["range_min"], w["range_max"], w["res"])[points]
+    rad = ph.planck_wavenumber(xa, t_surface)
+    total = np.ones(len(points))
+    layers = np.atleast_1d(w["T"])
+    for l in range(len(layers)):
+        T, P = w["T"][l], w["P"][l]
+        k = oracle_layer_k_at(w, points, T, P, w["conc"][l], w["cutoff"][l])
+        t = ph.transmittance(k, w["depth_cm"][l])
+        rad = ph.transmission(t, rad, ph.planck_wavenumber(xa, T))
+        total = total * t
+    return rad, total

@@ -12,13 +12,13 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-def sample_points(n, k, seed):
-    rng = np.random.default_rng(seed)
-    edge = np.array([0, 1, 2, n // 2, n - 3, n - 2, n - 1])
-    return np.unique(np.concatenate([edge, rng.integers(0, n, k)]))
+def sample_points(n, k, seed, tile=2048):
+    """>= k sampled grid indices: random ones plus both sides of tile and warp-span edges (where the kernels'
+    masked / unmasked / far classes flip) and the ends of the grid."""
+    return H.boundary_points(n, k, seed, tile=tile)
 
 
-def check_sampled(engine, w, weights_mode, P=None, T=None, n_pts=48, seed=0, variant=eng.K2_CLASSED):
+def check_sampled(engine, w, weights_mode, P=None, T=None, n_pts=1000, seed=0, variant=eng.K2_CLASSED):
     P = w["P"] if P is None else P
     T = w["T"] if T is None else T
     cutoff = P / 1013.25 * 5 if P != w["P"] else w["cutoff"]
@@ -31,11 +31,11 @@ def check_sampled(engine, w, weights_mode, P=None, T=None, n_pts=48, seed=0, var
     finally:
         engine.set_k2_variant(eng.K2_CLASSED, 0)
     pts = sample_points(n, n_pts, seed)
-    sig = H.oracle_sigma_groups(w, T=T, P=P, cutoff=cutoff, points=pts)
+    assert len(pts) >= n_pts
     if weights_mode:
-        ref = sum(ph.abs_coef(sig[g], w["conc"][g], P, T) for g in range(len(w["species"])))
+        ref = H.oracle_layer_k_at(w, pts, T, P, w["conc"], cutoff)
     else:
-        ref = sig.sum(axis=0)
+        ref = H.oracle_sigma_groups(w, T=T, P=P, cutoff=cutoff, points=pts).sum(axis=0)
     floor = H.K_FLOOR_REL * np.abs(out).max()
     err = np.abs(out[pts] - ref) / np.maximum(np.abs(ref), floor)
     assert err.max() <= H.K_REL_TOL, (err.max(), pts[err.argmax()])
@@ -54,14 +54,14 @@ def test_cfg2_full_size_sampled_against_oracle(engine):
 def test_atmosphere_layer_shapes_full_size_sampled(engine, P, T):
     """cfg4-sized line list (5M lines, 5M points) at three layer pressures: wide, mid and narrow windows."""
     w = workloads.cfg5(cutoff=5.0)
-    check_sampled(engine, w, weights_mode=True, P=P, T=T, n_pts=24, seed=int(P))
+    check_sampled(engine, w, weights_mode=True, P=P, T=T, seed=int(P))
 
 
 def test_cfg5_stress_sweep_full_size_sampled(engine):
     """cfg5: 5M lines, 5M points, 25 cm-1 cutoff (W = 25 000, ~2.5e11 accumulations) against the oracle's gather form
     at sampled points, plus the exact accumulate count."""
     w = workloads.cfg5()
-    out = check_sampled(engine, w, weights_mode=True, n_pts=16, seed=5)
+    out = check_sampled(engine, w, weights_mode=True, seed=5)
     n = eng.grid_len(w["range_min"], w["range_max"], w["res"])
     idx = ph.line_index(w["lines"]["nu"], w["range_min"], w["res"])
     assert engine.pair_count() == ph.pair_count(idx, n, eng.window_len(w["cutoff"], w["res"])) > 2.4e11
@@ -74,7 +74,7 @@ def test_cfg1_size_properties(engine):
     n = H.engine_setup(engine, w)
     H.engine_prepass(engine, w)
     base = engine.line_sum()
-    ref_pts = sample_points(n, 40, 3)
+    ref_pts = sample_points(n, 1000, 3)
     sig = H.oracle_sigma_groups(w, points=ref_pts)[0]
     assert H.k_rel_err(base[ref_pts], sig).max() <= H.K_REL_TOL
     # linearity: S -> 4 S (a power of two: bitwise equal thanks to the power-of-two scaling)
@@ -104,7 +104,7 @@ def test_cfg2_full_size_farfield_variant_sampled_against_oracle(engine):
 def test_atmosphere_layer_shapes_full_size_farfield_variant_sampled(engine, P, T):
     """cfg4-sized line list under the far-field variant: a 256-point-span layer (P = 8) and a 128-point-span layer (P = 4)."""
     w = workloads.cfg5(cutoff=5.0)
-    check_sampled(engine, w, weights_mode=True, P=P, T=T, n_pts=24, seed=int(P), variant=eng.K2_FARFIELD)
+    check_sampled(engine, w, weights_mode=True, P=P, T=T, seed=int(P), variant=eng.K2_FARFIELD)
 
 
 def test_cfg3_full_size_line_by_line_plus_xsc_tables(engine, tmp_path):
@@ -154,3 +154,71 @@ def test_cfg3_full_size_line_by_line_plus_xsc_tables(engine, tmp_path):
         np.testing.assert_allclose(layer.transmission(surf), rad_ref, rtol=2e-5)
     finally:
         C.DATA_ROOT = None
+
+
+def _column(engine, w):
+    sp = w["species"]
+    win = [eng.window_len(c, w["res"]) for c in np.atleast_1d(w["cutoff"])]
+    T, P = np.atleast_1d(w["T"]), np.atleast_1d(w["P"])
+    qt = np.array([[s.q(t) for s in sp] for t in T])
+    conc = np.atleast_2d(w["conc"])
+    depth = np.broadcast_to(np.asarray(w["depth_cm"], dtype=np.float64), (len(T),))
+    engine.atmosphere(depth, T, P, conc, [s.molmass for s in sp], qt, [s.q296 for s in sp], win,
+                      w.get("t_surface", 288.0), w["range_max"])
+    return engine.atmosphere_read()
+
+
+def _as_column(w):
+    """A single-layer gas-cell workload in the column layout of H.oracle_column_at."""
+    c = dict(w)
+    c["T"], c["P"] = [w["T"]], [w["P"]]
+    c["conc"], c["cutoff"], c["depth_cm"] = [w["conc"]], [w["cutoff"]], [w["depth_cm"]]
+    return c
+
+
+@pytest.mark.parametrize("depth_scale", [1.0, 2e-5])
+def test_cfg4_full_size_column_sampled(engine, depth_scale):
+    """The north-star configuration itself: the 100-layer, 5 M-line, 5 M-point atmosphere through prb_atmosphere
+    (K1 for the whole column, the batched line sums of every kernel class, the K3 fold), radiance and TOTAL
+    transmittance against the oracle's layer-by-layer fold at > 256 grid points: both sides of tile and warp-span
+    edges, the first points next to 0 cm-1, the last points, random points.  Reference: pyradClasses.py:707-716, 784-787.
+    The bench column (depth_scale 1) is opaque everywhere (median optical depth 2.4e4: its total transmittance is 0 and its
+    radiance is the emission of the upper layers), so the same column -- same lines, same k matrix -- is also run with
+    1.4 cm layers (median optical depth ~0.5), where the 100-term optical-depth sum decides the total transmittance."""
+    w = workloads.atmosphere()
+    w["depth_cm"] = w["depth_cm"] * depth_scale
+    n = H.engine_setup(engine, w)
+    assert n == 5_000_000 and len(w["T"]) == 100 and len(w["lines"]["nu"]) >= 4_900_000
+    rad, tr = _column(engine, w)
+    pts = H.boundary_points(n, 200, 44, n_tiles=16)
+    assert len(pts) >= 256
+    rad_ref, tr_ref = H.oracle_column_at(w, pts, w["t_surface"])
+    phys = np.isfinite(tr_ref) & (tr_ref <= 1.0)                  # next to 0 cm-1 the reference's negative Doppler widths
+    assert (~phys).sum() <= 2                                     # give k < 0 and "transmittances" above 1 (or inf)
+    err_t = np.abs(tr[pts][phys] - tr_ref[phys])
+    assert err_t.max() <= H.T_ABS_TOL, (err_t.max(), pts[phys][err_t.argmax()])
+    ok = np.isfinite(rad_ref) & phys                              # nu = 0: NaN in the reference (0/0)
+    assert np.isnan(rad[0]) and np.isfinite(rad[1:]).all()
+    np.testing.assert_allclose(rad[pts][ok], rad_ref[ok], rtol=2e-5)
+    if depth_scale < 1:                                           # the thin column has structure at these points
+        assert (tr_ref[phys] < 0.45).sum() > 20 and (tr_ref[phys] > 0.6).sum() > 20
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg5"])
+def test_fused_epilogue_full_size_transmittance_and_radiance(engine, cfg):
+    """cfg2 / cfg5 as ONE engine call (prb_atmosphere with one layer: K2's fused epilogue turns the finished k tile into
+    transmittance and radiance): |dT| <= 1e-6 and radiance rtol 2e-5 against the oracle at >= 1000 boundary-inclusive
+    points -- k within 1e-5 does not by itself bound T."""
+    w = workloads.cfg2() if cfg == "cfg2" else workloads.cfg5()
+    n = H.engine_setup(engine, w)
+    rad, tr = _column(engine, w)
+    assert engine.atmosphere_launches() == 2                       # K1 + K2 (fused), no separate K3
+    pts = sample_points(n, 1000, 21)
+    rad_ref, tr_ref = H.oracle_column_at(_as_column(w), pts, 288.0)
+    phys = np.isfinite(tr_ref) & (tr_ref <= 1.0)                  # k < 0 next to 0 cm-1 (negative Doppler widths)
+    assert (~phys).sum() <= 4
+    err_t = np.abs(tr[pts][phys] - tr_ref[phys])
+    assert err_t.max() <= H.T_ABS_TOL, (err_t.max(), pts[phys][err_t.argmax()])
+    ok = np.isfinite(rad_ref) & phys
+    np.testing.assert_allclose(rad[pts][ok], rad_ref[ok], rtol=2e-5)
+    assert 0.05 < np.median(tr_ref[phys]) < 0.95

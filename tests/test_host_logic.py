@@ -119,3 +119,33 @@ def test_xsc_file_name_parser_matches_the_oracle():
         for k, v in want.items():
             assert got[k] == v, (n, k)
         assert got["LONG_FILENAME"] == n and got["SHORT_FILENAME"] + ".txt" == n
+
+
+def test_hitran_id_tables_equal_the_reference_tables():
+    """MOLECULE_ID and HITRAN_GLOBAL_ISO (pyradClasses.py:951-1022) carried in full: all 49 molecules and every
+    isotopologue row, compared with the reference source when it is mounted (the build container), and pinned by
+    count and spot values everywhere else."""
+    from pyrad_b200 import classes as C
+    assert len(C.MOLECULE_ID) == 49 and sorted(C.MOLECULE_ID.values()) == list(range(1, 50))
+    assert set(C.HITRAN_GLOBAL_ISO) == set(range(1, 50))
+    assert sum(len(v) for v in C.HITRAN_GLOBAL_ISO.values()) == 126
+    assert C.MOLECULE_ID["so2"] == 9 and C.MOLECULE_ID["nh3"] == 11 and C.MOLECULE_ID["cocl2"] == 49
+    assert C.getGlobalIsotope(C.MOLECULE_ID["so2"], 2) == [42, 43]
+    assert C.getGlobalIsotope(2, 12)[-1] == 122 and C.getGlobalIsotope(16, 2) == [19, 11]      # the reference's rows, sic
+    ref = "/root/reference/pyradClasses.py"
+    if os.path.isfile(ref):
+        src = open(ref).read()
+        ns = {}
+        for name in ("HITRAN_GLOBAL_ISO", "MOLECULE_ID"):
+            i = src.index(name + " = {")
+            depth, j = 0, i
+            while True:                                    # the dict literal: up to its matching brace
+                ch = src[j]
+                depth += ch == "{"
+                depth -= ch == "}"
+                j += 1
+                if ch == "}" and depth == 0:
+                    break
+            exec(src[i:j], ns)
+        assert ns["HITRAN_GLOBAL_ISO"] == C.HITRAN_GLOBAL_ISO
+        assert ns["MOLECULE_ID"] == C.MOLECULE_ID

@@ -89,8 +89,10 @@ def test_line_subset_reaches_every_window():
     ln = synth.make_lines(5000, 0.0, 100.0, 5)
     idx = pt.line_index(ln["nu"], 0.0, 0.01)
     l0, l1 = pt.lines_for_chunk(ln["nu"], 0.0, 0.01, 4096, 8192, 498)
-    inside = (idx >= 4096 - 498) & (idx <= 8191 + 498)
-    assert np.array_equal(np.nonzero(inside)[0], np.arange(l0, l1))
+    inside = np.nonzero((idx >= 4096 - 498) & (idx <= 8191 + 498))[0]
+    # every line that reaches the chunk, from a start rounded down to a multiple of four lines (K2's staging chunks
+    # then fall where they do in the unsharded run: bitwise shard invariance)
+    assert l0 % 4 == 0 and inside[0] - 3 <= l0 <= inside[0] and l1 == inside[-1] + 1
 
 
 def _worker(rank, world, port, q):
