@@ -9,8 +9,8 @@ import numpy as np
 
 from . import physics as ph
 
-NODES = 8
-RADIUS_SPANS = 2
+NODES = 16
+RADIUS_SPANS = 1
 
 
 def node_offsets(span, nodes=NODES):

@@ -345,13 +345,13 @@ static int build_far_table(prb_engine *e) {
             e->far_delta[t][k] = (float)(0.5 * (span - 1) + 0.5 * span * std::cos((2 * k + 1) * pi / (2 * K2_FAR_NODES)));
             node[k] = (double)e->far_delta[t][k];
         }
-        std::vector<double> lag((size_t)span * K2_FAR_NODES);
+        std::vector<double> lag((size_t)span * K2_FAR_NODES);      // node-major: [node][point]
         for (int i = 0; i < span; ++i)
             for (int k = 0; k < K2_FAR_NODES; ++k) {
                 double w = 1.0;
                 for (int j = 0; j < K2_FAR_NODES; ++j)
                     if (j != k) w *= ((double)i - node[j]) / (node[k] - node[j]);
-                lag[(size_t)i * K2_FAR_NODES + k] = w;
+                lag[(size_t)k * span + i] = w;
             }
         CK(e->far_lag[t].ensure(lag.size()));
         CK(cudaMemcpy(e->far_lag[t].p, lag.data(), sizeof(double) * lag.size(), cudaMemcpyHostToDevice));

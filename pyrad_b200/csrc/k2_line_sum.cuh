@@ -122,23 +122,27 @@ struct K2Args {
     int out_mode;              // PRB_OUT_F64 / PRB_OUT_F32
     DevState *st;              // tile_counter of this launch
     K2Fuse fuse;
-    // far-field variant (k2_line_sum<P, true>, P = 4 or 8): Lagrange weights of the span's points, [32 P][K2_FAR_NODES], and
-    // the node offsets from the span's first point (FP32; the table is built from these rounded values)
+    // far-field variant (k2_line_sum<P, true>, P = 4 or 8): Lagrange weights of the span's points, [K2_FAR_NODES][32 P]
+    // (node-major: a warp reads 32 consecutive doubles), and the node offsets from the span's first point (FP32; the
+    // table is built from these rounded values)
     const double *far_lag;
-    float far_delta[8];
+    float far_delta[16];
 };
 
 // Far-field evaluation of the Lorentz wings (variant PRB_K2_FARFIELD; spans of 128 and 256 points).  A line whose
-// centre lies more than two span lengths from the centre of a warp's span, and whose window covers the whole span,
+// centre lies more than ONE span length from the centre of a warp's span, and whose window covers the whole span,
 // contributes a function of the grid coordinate that is analytic on the span with poles at least that far away:
-// its Chebyshev interpolant through K2_FAR_NODES nodes converges like (h / (D + sqrt(D^2 - h^2)))^nodes, h = span/2,
-// D >= 2 span -> 7e-8, times a constant of order ten for the line nearest the threshold.  The FP64 model of this
-// algorithm (oracle/farfield_model.py, tests/test_farfield_model.py) measures a median error of 3e-9 of k and a worst
-// case of 1.4e-7 .. 6.5e-7 on the BASELINE window classes; the kernel shows 6.6e-7 against the exact kernel on cfg2.  Such lines are therefore summed at the 8 nodes of the span -- 8 evaluations instead
-// of 128 or 256 -- and the node sums are interpolated to the points once per tile.  Lines near the span, lines whose window
-// edge crosses it, and every Gaussian core go through the exact per-point paths as before.
-constexpr int K2_FAR_NODES = 8;
-constexpr int K2_FAR_RADIUS_SPANS = 2;    // far = more than this many span lengths from the span centre (512 of 256 points)
+// its Chebyshev interpolant through K2_FAR_NODES = 16 nodes converges like (h / (D + sqrt(D^2 - h^2)))^nodes, h = span/2,
+// D >= span -> (2 + sqrt 3)^-16 = 7e-10, times a constant of order ten for the line nearest the threshold.  The FP64
+// model of this algorithm (oracle/farfield_model.py, tests/test_farfield_model.py) measures a worst case of 1e-8 of k on
+// the BASELINE window classes.  Such lines are summed at the 16 nodes of the span -- 16 evaluations instead of 128 or
+// 256 -- and the node sums are interpolated to the points once per tile.  Lines within 1.5 spans of the span's centre,
+// lines whose window edge crosses the span, and every Gaussian core go through the exact per-point paths as before.
+// (Round 1 shipped 8 nodes at a radius of two spans: worst case 6.5e-7, and a far class of 87 / 48 / 57 / 0 % of the
+// pairs at 1013 / 250 / 150 / 60 hPa instead of 92 / 69 / 74 / 35 %.)
+constexpr int K2_FAR_NODES = 16;
+constexpr int K2_FAR_RADIUS_SPANS = 1;    // far = more than this many span lengths from the span centre
+constexpr int K2_FAR_SUBGROUPS = 64 / K2_FAR_NODES;   // line sub-groups: a lane = (node pair, sub-group)
 constexpr int K2_FAR_FLUSH = 16;          // triples (48 lines of one lane's chain) between FP64 flushes
 
 // One ring slot: a chunk of staged line records plus its descriptor.
@@ -313,8 +317,8 @@ __device__ __forceinline__ void gauss_pass(const float4 *sA, const float4 *sB, c
     if (since) s.flush();
 }
 
-// Far-field pass over lines [js, je): lane = (node pair kp = lane & 3, line sub-group lane >> 2).  A lane evaluates the
-// Lorentz terms of every 8th line at its two nodes, three lines per reciprocal, in ascending line order; the FP32
+// Far-field pass over lines [js, je): lane = (node pair kp = lane & 7, line sub-group lane >> 3).  A lane evaluates the
+// Lorentz terms of every 4th line at its two nodes, three lines per reciprocal, in ascending line order; the FP32
 // partial sums are flushed into the lane's FP64 node accumulators.  d = (wb - idx) + delta: the first sum is an exact
 // small integer, so the node's fractional offset survives FP32 at any grid size.
 struct FarAcc {
@@ -323,13 +327,14 @@ struct FarAcc {
 __device__ __forceinline__ void far_pass(const float4 *sA, const float4 *sB, int js, int je, float wbf, float2 del,
                                          FarAcc &fa) {
     if (je <= js) return;                                   // warp-uniform
-    const int sub = (int)(threadIdx.x & 31) >> 2;
+    constexpr int G = K2_FAR_SUBGROUPS;
+    const int sub = (int)(threadIdx.x & 31) / (K2_FAR_NODES / 2);
     const float2 wb2 = splat(wbf);
     const float2 zero = make_float2(0.f, 0.f);
     float2 part = zero;
     int since = 0;
-    for (int j0 = js; j0 < je; j0 += 24) {                  // warp-uniform trip count; short chains pad with A = 0
-        const int j1 = j0 + sub, j2 = j1 + 8, j3 = j1 + 16;
+    for (int j0 = js; j0 < je; j0 += 3 * G) {               // warp-uniform trip count; short chains pad with A = 0
+        const int j1 = j0 + sub, j2 = j1 + G, j3 = j1 + 2 * G;
         const int k1 = min(j1, je - 1), k2 = min(j2, je - 1), k3 = min(j3, je - 1);
         const float4 a1 = sA[k1], a2 = sA[k2], a3 = sA[k3];
         const float2 B1 = ldB(sB, k1), B2 = ldB(sB, k2), B3 = ldB(sB, k3);
@@ -515,7 +520,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             if (t1 >= t4) { t1 = t5; t4 = t5; }                // window narrower than the span: all masked
             const float g0 = fmaxf(wbf - dgmax, t0);           // Gaussian cores can only come from [g0, g1)
             const float g1 = fminf(we1f + 1.f + dgmax, t5);
-            // FAR: idx < tfl or idx > tfr, i.e. more than two span lengths from the span centre wb + (SPAN-1)/2; integer
+            // FAR: idx < tfl or idx > tfr, i.e. more than K2_FAR_RADIUS_SPANS span lengths from the span centre wb + (SPAN-1)/2; integer
             // thresholds, exact in FP32, so the split does not depend on the shard origin
             const float tfl = wbf + (float)((SPAN - 1) / 2 - K2_FAR_RADIUS_SPANS * SPAN);
             const float tfr = wbf + (float)(SPAN / 2 + K2_FAR_RADIUS_SPANS * SPAN);
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
                 // full-cover lines [b1, b4) split by distance from the span: far left | near | far right
                 const int bfl = min(max(nfl, b1), b4);
                 const int bfr = min(max(nfr, bfl), b4);
-                const int kp = lane & 3;
+                const int kp = lane & (K2_FAR_NODES / 2 - 1);
                 const float2 del = make_float2(a.far_delta[2 * kp], a.far_delta[2 * kp + 1]);
                 far_pass(sA, sB, b1, bfl, wbf, del, far);
                 lorentz_paired<H, false>(sA, sB, bfl, bfr, wmf, s);
@@ -590,29 +595,29 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
                 if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free again
                 consumer_barrier();
             }
-            double fv[K2_FAR_NODES];
             if (FAR) {
-                // node sums: add the eight line sub-groups (fixed tree), then every lane fetches all eight nodes
+                // node sums: add the line sub-groups (fixed tree), then interpolate to the thread's points -- node by
+                // node, each node's sum broadcast from the lane that holds it, the Lagrange weights read as 32
+                // consecutive doubles per (node, row of the span) -- straight into the FP64 accumulators
                 double v0 = far.v0, v1 = far.v1;
 #pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
+                for (int o = K2_FAR_NODES / 2; o < 32; o <<= 1) {
                     v0 += __shfl_xor_sync(0xffffffffu, v0, o);
                     v1 += __shfl_xor_sync(0xffffffffu, v1, o);
                 }
+#pragma unroll 2
+                for (int k = 0; k < K2_FAR_NODES; ++k) {
+                    const double fk = __shfl_sync(0xffffffffu, (k & 1) ? v1 : v0, k >> 1);
+                    const double *lw = a.far_lag + k * SPAN + lane;
 #pragma unroll
-                for (int k = 0; k < K2_FAR_NODES; ++k) fv[k] = __shfl_sync(0xffffffffu, (k & 1) ? v1 : v0, k >> 1);
+                    for (int p = 0; p < P; ++p) s.acc(p) = fma(fk, __ldg(lw + 32 * p), s.acc(p));
+                }
             }
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const int i = wb + 32 * p + lane;
-                double farp = 0.0;
-                if (FAR) {
-                    const double *lw = a.far_lag + (32 * p + lane) * K2_FAR_NODES;
-#pragma unroll
-                    for (int k = 0; k < K2_FAR_NODES; ++k) farp = fma(fv[k], __ldg(lw + k), farp);
-                }
                 if (i < a.n_chunk) {
-                    const double v = (FAR ? s.acc(p) + farp : s.acc(p)) * inv_scale;
+                    const double v = s.acc(p) * inv_scale;
                     if (a.out_mode == 0) reinterpret_cast<double *>(out)[i] = v;
                     else reinterpret_cast<float *>(out)[i] = (float)v;
                     if (a.fuse.enabled) {
@@ -621,9 +626,8 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
                         const float nu = (float)x;
                         const float a3 = (float)(2E8 * hPlanck * (cLight * cLight) * (x * x * x));
                         const float e = (float)v * a.fuse.neg_depth_log2e;
-                        const float t = k3_ex2(e);
                         const float b = planck_f32(a3, a.fuse.c2_over_t * nu);
-                        const float rad = fmaf(t, planck_f32(a3, a.fuse.c2_over_tsurf * nu) - b, b);
+                        const float rad = k3_fold_step(planck_f32(a3, a.fuse.c2_over_tsurf * nu), e, b);
                         const float tr = exp2f(0.f + e);
                         if (bulk) {
                             stage_rad[i - d.tile0] = rad;

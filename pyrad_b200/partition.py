@@ -140,7 +140,7 @@ def assemble(gathered, chunks):
     return np.concatenate(parts) if parts else np.zeros(0)
 
 
-def farfield_work(idx, i_begin, i_end, window, span, radius_spans=2, nodes=8):
+def farfield_work(idx, i_begin, i_end, window, span, radius_spans=1, nodes=16):
     """What the far-field variant of K2 (PRB_K2_FARFIELD) actually evaluates on the chunk [i_begin, i_end)
     for one layer of window W: (pairs evaluated point by point, node evaluations).  A warp span starts at
     i_begin + k * span; a line is summed at the span's `nodes` Chebyshev nodes instead of at its points when its window

@@ -75,6 +75,35 @@ def main():
                                   "max_abs_T_vs_exact": float(np.abs(tr[fin] - ref[1][fin]).max()),
                                   "max_rel_rad_vs_exact": float((np.abs(rad - ref[0])[ok] / np.abs(ref[0][ok])).max())}
             print(tag, "atm variant", v, res["atm_v%d" % v], flush=True)
+    # ---- cfg5 stress sweep (W = 25 000), whole call
+    if os.environ.get("QF_STRESS", "1") == "1":
+        w = workloads.cfg5()
+        sp = w["species"]
+        n = eng.grid_len(w["range_min"], w["range_max"], w["res"])
+        e.upload_lines(w["lines"], len(sp)); e.set_grid(w["range_min"], w["res"], n)
+        T, P = w["T"], w["P"]
+        args = ([w["depth_cm"]], [T], [P], [w["conc"]], [s.molmass for s in sp], [[s.q(T) for s in sp]], [s.q296 for s in sp],
+                [eng.window_len(w["cutoff"], w["res"])], 288.0, w["range_max"])
+        ref = None
+        for v in variants:
+            e.set_k2_variant(v, 0)
+            e.atmosphere(*args); e.synchronize()
+            ms = []
+            for _ in range(3):
+                with torch.cuda.stream(stream):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    e.atmosphere(*args)
+                    b.record(stream)
+                e.synchronize(); torch.cuda.synchronize()
+                ms.append(a.elapsed_time(b))
+            rad = np.empty(n, dtype=np.float32); tr = np.empty(n, dtype=np.float32)
+            e.atmosphere_read_f32(rad, tr)
+            if ref is None:
+                ref = tr.copy()
+            fin = np.isfinite(ref) & np.isfinite(tr)
+            res["cfg5_v%d" % v] = {"ms": float(np.median(ms)), "max_abs_T_vs_exact": float(np.abs(tr[fin] - ref[fin]).max())}
+            print(tag, "cfg5 variant", v, res["cfg5_v%d" % v], flush=True)
     e.set_k2_variant(1, 0)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/quick_far_%s.json" % tag, "w"), indent=1)

@@ -1,7 +1,7 @@
 """CPU pin of the far-field variant's ALGORITHM (oracle/farfield_model.py: the kernel's class thresholds, FP32-rounded
 Chebyshev nodes and Lagrange table in FP64 numpy) against the exact oracle: the approximation error the design states
-(below 1e-6 of k in the worst case -- a valley of the spectrum dominated by one strong line just
-beyond the far threshold --, ~5e-8 typically) holds on the window classes the variant runs on.  The CUDA kernel itself is compared with
+(16 nodes at a radius of one span -- below 2e-8 of k in the worst case, a valley of the spectrum
+dominated by one strong line just beyond the far threshold, 1e-11 typically) holds on the window classes the variant runs on.  The CUDA kernel itself is compared with
 the exact kernel and the oracle in tests/test_gpu_parity.py / test_gpu_fullsize.py."""
 import numpy as np
 import pytest
@@ -44,8 +44,8 @@ def test_unified_form_reproduces_the_oracle_exactly():
 
 
 @pytest.mark.parametrize("P,T,span", [(1013.25, 296, 256), (353.4, 250, 256), (250.0, 230, 256), (150.0, 225, 128),
-                                      (100.0, 215, 128)])
-def test_farfield_interpolation_error_is_below_1e6_of_k(P, T, span):
+                                      (100.0, 215, 128), (60.0, 215, 128)])
+def test_farfield_interpolation_error_is_below_2e8_of_k(P, T, span):
     w = _cell(P, T)
     n = ph.grid_len(w["range_min"], w["range_max"], w["res"])
     win = ph.window_len(w["cutoff"], w["res"])
@@ -53,9 +53,9 @@ def test_farfield_interpolation_error_is_below_1e6_of_k(P, T, span):
     exact, _ = fm.line_sum(*rec, n, win, span, farfield=False)
     far, frac = fm.line_sum(*rec, n, win, span, farfield=True)
     err = np.abs(far - exact) / np.maximum(np.abs(exact), 1e-40 * np.abs(exact).max())
-    assert err.max() <= 1e-6, (P, span, err.max())
-    assert np.median(err) <= 1e-7, (P, span, np.median(err))
-    assert frac > 0.15, frac                                 # the far class is not empty on these windows
+    assert err.max() <= 2e-8, (P, span, err.max())          # 16 nodes, far = beyond one span length (measured <= 9.2e-9)
+    assert np.median(err) <= 1e-10, (P, span, np.median(err))
+    assert frac > 0.3, frac                                  # the far class is not empty on these windows
     # the host-side accounting (partition.farfield_work) counts the same far pairs as the model
     ex_pairs, node_evals = pt.farfield_work(rec[0], 0, n, win, span)
     idx = rec[0]

@@ -153,9 +153,9 @@ def test_farfield_work_accounting_matches_brute_force():
             for f in idx:
                 covered = sum(1 for i in range(first, first + pts) if abs(i - f) <= wm)
                 full = last - wm <= f <= first + wm
-                far = full and (f < first + (span - 1) // 2 - 2 * span or f > first + span // 2 + 2 * span)
+                far = full and (f < first + (span - 1) // 2 - span or f > first + span // 2 + span)
                 if far:
-                    want_nodes += 8
+                    want_nodes += 16
                 else:
                     want_exact += covered
         assert (exact, nodes) == (want_exact, want_nodes), (a, b, window, span)
