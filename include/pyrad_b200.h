@@ -82,6 +82,10 @@ void       *prb_stream(prb_engine *e);                  /* the engine's cudaStre
 int         prb_synchronize(prb_engine *e);             /* stream sync + deferred device status */
 int         prb_device_info(prb_engine *e, int *sm_count, int *cc_major, int *cc_minor,
                             int *sm_clock_khz, size_t *free_bytes, size_t *total_bytes);
+/* Roofline denominators measured on this device (bench.py): FP32 lane-FMAs per second of a packed-FFMA2 and of a scalar
+ * FFMA instruction stream, and the float4 copy bandwidth (read + write bytes per second); any pointer may be NULL. */
+int         prb_measure_peaks(prb_engine *e, double *ffma2_lane_fma_per_s, double *ffma_lane_fma_per_s,
+                              double *copy_bytes_per_s);
 int         prb_set_k2_variant(prb_engine *e, int variant, int points_per_thread /* 0 = auto */);
 /* windows with W-2 < wm_below use the thread-per-point kernel k2_narrow (0 = never, <0 = default 100) */
 int         prb_set_narrow_threshold(prb_engine *e, int64_t wm_below);

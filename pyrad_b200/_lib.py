@@ -39,6 +39,7 @@ PROTOTYPES = {
     "prb_synchronize": (C.c_int, [_vp]),
     "prb_device_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "prb_measure_peaks": (C.c_int, [_vp, _dp, _dp, _dp]),
     "prb_set_k2_variant": (C.c_int, [_vp, C.c_int, C.c_int]),
     "prb_set_narrow_threshold": (C.c_int, [_vp, _i64]),
     "prb_upload_lines": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _i32]),

@@ -19,6 +19,7 @@
 #include "k3_stream.cuh"
 #include "k4_derived.cuh"
 #include "k5_ingest.cuh"
+#include "k9_peaks.cuh"
 #include <thrust/iterator/counting_iterator.h>
 
 using namespace prb;
@@ -136,6 +137,8 @@ struct prb_engine {
     // [span][K2_FAR_NODES] and the FP32 node offsets (built at prb_create)
     DevBuf<double> far_lag[2];
     float far_delta[2][K2_FAR_NODES] = {};
+    DevBuf<double> far_lag2[2];                       // level 2: domains of K2_FAR2_SPANS spans
+    float far_delta2[2][K2_FAR_NODES] = {};
     int64_t narrow_wm = 100;     // windows with W-2 below this use k2_narrow
     bool batch_layers = true;    // prb_atmosphere: one K1 launch + one K2 launch per kernel class
     bool k3_tma = true;          // layer fold: k matrix staged by TMA (k3_fold_tma) instead of register-held loads
@@ -226,8 +229,8 @@ extern "C" int prb_create(int device, prb_engine **out) {
     want((const void *)k2_line_sum<4>, K2_SMEM_BYTES<4>(true));
     want((const void *)k2_line_sum<8>, K2_SMEM_BYTES<8>(true));
     want((const void *)k2_line_sum<16>, K2_SMEM_BYTES<16>(true));
-    want((const void *)k2_line_sum<4, true>, K2_SMEM_BYTES<4>(true));
-    want((const void *)k2_line_sum<8, true>, K2_SMEM_BYTES<8>(true));
+    want((const void *)k2_line_sum_far<4>, K2_SMEM_BYTES<4>(true));
+    want((const void *)k2_line_sum_far<8>, K2_SMEM_BYTES<8>(true));
     want((const void *)k2_point, sizeof(KPSmem));
     want((const void *)k3_fold_tma, sizeof(K3TSmem));
     if (ae != cudaSuccess) {
@@ -236,7 +239,7 @@ extern "C" int prb_create(int device, prb_engine **out) {
         return fail(PRB_ERR_CUDA, std::string("prb_create: cudaFuncSetAttribute failed: ") + cudaGetErrorString(ae));
     }
     if (cudaSetDevice(device) != cudaSuccess || build_far_table(e) != PRB_OK) {
-        e->far_lag[0].release(); e->far_lag[1].release();
+        e->far_lag[0].release(); e->far_lag[1].release(); e->far_lag2[0].release(); e->far_lag2[1].release();
         cudaStreamDestroy(e->stream);
         delete e;
         return fail(PRB_ERR_CUDA, "prb_create: far-field table upload failed");
@@ -269,7 +272,7 @@ extern "C" int prb_destroy(prb_engine *e) {
     e->blk_d.release();
     e->ingest.release();
     e->tile_bounds_buf[0].release(); e->tile_bounds_buf[1].release();
-    e->far_lag[0].release(); e->far_lag[1].release();
+    e->far_lag[0].release(); e->far_lag[1].release(); e->far_lag2[0].release(); e->far_lag2[1].release();
     e->dev_scal.release();
     if (e->pin_scal) cudaFreeHost(e->pin_scal);
     for (auto x : e->pipe_ev) cudaEventDestroy(x);
@@ -310,6 +313,63 @@ extern "C" int prb_synchronize(prb_engine *e) {
     return PRB_OK;
 }
 
+// Roofline denominators measured here and now (k9_peaks.cuh): FP32 lane-FMAs per second of the packed FFMA2 and the
+// scalar FFMA instruction streams (best of `reps` launches each, CUDA events on the engine stream) and the float4 copy
+// bandwidth (read + write bytes) over a buffer well beyond the L2.
+extern "C" int prb_measure_peaks(prb_engine *e, double *ffma2_lane_fma_per_s, double *ffma_lane_fma_per_s,
+                                 double *copy_bytes_per_s) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    CK(cudaSetDevice(e->device));
+    const int sms = e->prop.multiProcessorCount;
+    const int grid = sms * 8, iters = 4096, reps = 5;
+    DevBuf<float> sink;
+    CK(sink.ensure((size_t)grid * 256));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    auto best_ms = [&](const std::function<void()> &launch, float *out) -> int {
+        float best = 1e30f;
+        for (int r = 0; r < reps + 1; ++r) {                       // the first launch warms clocks and instruction cache
+            CK(cudaEventRecord(a, e->stream));
+            launch();
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(b, e->stream));
+            CK(cudaEventSynchronize(b));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, a, b));
+            if (r) best = std::min(best, ms);
+        }
+        *out = best;
+        return PRB_OK;
+    };
+    int rc;
+    float ms = 0;
+    const double lane_fma = (double)grid * 256 * (double)iters * K9_UNROLL * K9_CHAINS * 2;
+    if (ffma2_lane_fma_per_s) {
+        if ((rc = best_ms([&] { k9_ffma2_peak<<<grid, 256, 0, e->stream>>>(sink.p, iters, 1.5f); }, &ms))) return rc;
+        *ffma2_lane_fma_per_s = lane_fma / (ms * 1e-3);
+    }
+    if (ffma_lane_fma_per_s) {
+        if ((rc = best_ms([&] { k9_ffma_peak<<<grid, 256, 0, e->stream>>>(sink.p, iters, 1.5f); }, &ms))) return rc;
+        *ffma_lane_fma_per_s = lane_fma / (ms * 1e-3);
+    }
+    if (copy_bytes_per_s) {
+        const int64_t n4 = (int64_t)64 << 20;                      // 1 GiB each way
+        DevBuf<float4> src, dst;
+        CK(src.ensure((size_t)n4));
+        CK(dst.ensure((size_t)n4));
+        CK(cudaMemsetAsync(src.p, 0, sizeof(float4) * n4, e->stream));
+        if ((rc = best_ms([&] { k9_copy<<<sms * 16, 256, 0, e->stream>>>(src.p, dst.p, n4); }, &ms))) return rc;
+        *copy_bytes_per_s = 2.0 * sizeof(float4) * (double)n4 / (ms * 1e-3);
+        src.release();
+        dst.release();
+    }
+    sink.release();
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return PRB_OK;
+}
+
 extern "C" int prb_device_info(prb_engine *e, int *sm_count, int *cc_major, int *cc_minor, int *sm_clock_khz,
                                size_t *free_bytes, size_t *total_bytes) {
     if (!e) return fail(PRB_ERR_ARG, "null engine");
@@ -338,12 +398,11 @@ static inline bool k2_classed(const prb_engine *e) { return e->k2_variant != PRB
 // every node at every point (FP64, built from the ROUNDED offsets so that kernel and table agree exactly).
 static int build_far_table(prb_engine *e) {
     const double pi = 3.14159265358979323846;
-    for (int t = 0; t < 2; ++t) {
-        const int span = t == 0 ? 128 : 256;
+    auto build = [&](int span, float *delta, DevBuf<double> &dev) -> int {
         double node[K2_FAR_NODES];
         for (int k = 0; k < K2_FAR_NODES; ++k) {
-            e->far_delta[t][k] = (float)(0.5 * (span - 1) + 0.5 * span * std::cos((2 * k + 1) * pi / (2 * K2_FAR_NODES)));
-            node[k] = (double)e->far_delta[t][k];
+            delta[k] = (float)(0.5 * (span - 1) + 0.5 * span * std::cos((2 * k + 1) * pi / (2 * K2_FAR_NODES)));
+            node[k] = (double)delta[k];
         }
         std::vector<double> lag((size_t)span * K2_FAR_NODES);      // node-major: [node][point]
         for (int i = 0; i < span; ++i)
@@ -353,8 +412,15 @@ static int build_far_table(prb_engine *e) {
                     if (j != k) w *= ((double)i - node[j]) / (node[k] - node[j]);
                 lag[(size_t)k * span + i] = w;
             }
-        CK(e->far_lag[t].ensure(lag.size()));
-        CK(cudaMemcpy(e->far_lag[t].p, lag.data(), sizeof(double) * lag.size(), cudaMemcpyHostToDevice));
+        CK(dev.ensure(lag.size()));
+        CK(cudaMemcpy(dev.p, lag.data(), sizeof(double) * lag.size(), cudaMemcpyHostToDevice));
+        return PRB_OK;
+    };
+    for (int t = 0; t < 2; ++t) {
+        const int span = t == 0 ? 128 : 256;
+        int rc = build(span, e->far_delta[t], e->far_lag[t]);
+        if (rc == PRB_OK) rc = build(span * K2_FAR2_SPANS, e->far_delta2[t], e->far_lag2[t]);
+        if (rc) return rc;
     }
     return PRB_OK;
 }
@@ -365,7 +431,8 @@ static bool far_args(const prb_engine *e, K2Args &a) {
     if (a.variant != PRB_K2_FARFIELD || (P != 4 && P != 8)) return false;
     const int t = P == 4 ? 0 : 1;
     a.far_lag = e->far_lag[t].p;
-    for (int k = 0; k < K2_FAR_NODES; ++k) a.far_delta[k] = e->far_delta[t][k];
+    a.far_lag2 = e->far_lag2[t].p;
+    for (int k = 0; k < K2_FAR_NODES; ++k) { a.far_delta[k] = e->far_delta[t][k]; a.far_delta2[k] = e->far_delta2[t][k]; }
     return true;
 }
 
@@ -688,7 +755,7 @@ static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
     const size_t smem = K2_SMEM_BYTES<P>(staging);
     const int64_t items = (int64_t)a.n_tiles * a.n_layers;
     const int grid = (int)std::min<int64_t>(items, (int64_t)K2_MIN_CTAS * e->prop.multiProcessorCount);
-    if (far_args<P>(e, a)) k2_line_sum<(P == 4 ? 4 : 8), true><<<grid, K2_THREADS, smem, e->stream>>>(a);
+    if (far_args<P>(e, a)) k2_line_sum_far<(P == 4 ? 4 : 8)><<<grid, K2_THREADS, smem, e->stream>>>(a);
     else k2_line_sum<P><<<grid, K2_THREADS, smem, e->stream>>>(a);
     return cudaGetLastError();
 }
@@ -713,7 +780,7 @@ static cudaError_t launch_k2_sub(prb_engine *e, K2Args a, cudaStream_t st) {
     const bool staging = a.fuse.enabled && a.fuse.n_dst > 1;
     const size_t smem = K2_SMEM_BYTES<P>(staging);
     const int grid = std::min(a.n_tiles, K2_MIN_CTAS * e->prop.multiProcessorCount);
-    if (far_args<P>(e, a)) k2_line_sum<(P == 4 ? 4 : 8), true><<<grid, K2_THREADS, smem, st>>>(a);
+    if (far_args<P>(e, a)) k2_line_sum_far<(P == 4 ? 4 : 8)><<<grid, K2_THREADS, smem, st>>>(a);
     else k2_line_sum<P><<<grid, K2_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }

@@ -127,6 +127,9 @@ struct K2Args {
     // table is built from these rounded values)
     const double *far_lag;
     float far_delta[16];
+    // level 2 of the far field: the same for a DOMAIN of K2_FAR2_SPANS consecutive spans, table [K2_FAR_NODES][domain]
+    const double *far_lag2;
+    float far_delta2[16];
 };
 
 // Far-field evaluation of the Lorentz wings (variant PRB_K2_FARFIELD; spans of 128 and 256 points).  A line whose
@@ -144,6 +147,25 @@ constexpr int K2_FAR_NODES = 16;
 constexpr int K2_FAR_RADIUS_SPANS = 1;    // far = more than this many span lengths from the span centre
 constexpr int K2_FAR_SUBGROUPS = 64 / K2_FAR_NODES;   // line sub-groups: a lane = (node pair, sub-group)
 constexpr int K2_FAR_FLUSH = 16;          // triples (48 lines of one lane's chain) between FP64 flushes
+// Level 2: K2_FAR2_SPANS consecutive spans (the warps w with equal w / K2_FAR2_SPANS) form a DOMAIN.  A line whose
+// window covers the whole domain and whose centre lies more than one domain length from the domain's centre is summed
+// at the 16 Chebyshev nodes of the DOMAIN -- same geometry ratio, same error bound as level 1 -- by the domain's warps
+// together (each takes every K2_FAR2_SPANS-th group of lines), 16 evaluations per domain instead of 16 per span.  The
+// warps' node sums meet in shared memory once per tile (fixed order) and are interpolated to the points with a second
+// Lagrange table.  Every level-2 line is a level-1 far line of each span of the domain, so level 1 simply skips them.
+#ifndef PRB_K2_FAR2_SPANS
+#define PRB_K2_FAR2_SPANS 8
+#endif
+constexpr int K2_FAR2_SPANS = PRB_K2_FAR2_SPANS;
+#ifndef PRB_K2_FAR2_ENABLE
+#define PRB_K2_FAR2_ENABLE 1
+#endif
+constexpr bool K2_FAR2 = PRB_K2_FAR2_ENABLE != 0;      // development switch: level 1 only
+// Level 2 pays for its once-per-tile meeting of the warps (a barrier and a second interpolation) only when most of the
+// window lies beyond a domain: it runs for windows of at least this many domain lengths (cfg5's 25 cm-1 cutoff; the
+// 5 cm-1 windows of cfg2 / cfg4 measured 15 % slower with it, profiles/r02_k2_farfield.txt).
+constexpr int K2_FAR2_MIN_DOMAINS = 4;
+static_assert(K2_CONSUMERS % K2_FAR2_SPANS == 0, "a tile is a whole number of level-2 domains");
 
 // One ring slot: a chunk of staged line records plus its descriptor.
 struct K2Desc {
@@ -161,6 +183,9 @@ struct K2Smem {
     K2Desc desc[K2_STAGES];
     uint64_t full[K2_STAGES];      // producer -> consumers: TMA bytes landed (+ descriptor written)
     uint64_t empty[K2_STAGES];     // consumers -> producer: all consumer warps are done with the slot
+    double far2[2][K2_CONSUMERS][K2_FAR_NODES];   // far-field level 2: every warp's node sums, double buffered by tile parity
+    double2 faracc[2][K2_CONSUMERS * 32];         // far-field: every lane's two FP64 node sums, level 1 and level 2 (touched
+                                                  // once per far_pass call: eight registers the hot loops get back)
 };
 
 // Dynamic shared memory of k2_line_sum<P>: K2Smem | FP64 accumulators (PRB_K2_ACC_SMEM) | peer staging (2 x TILE floats).
@@ -324,42 +349,63 @@ __device__ __forceinline__ void gauss_pass(const float4 *sA, const float4 *sB, c
 struct FarAcc {
     double v0, v1;
 };
+__device__ __forceinline__ float2 far_triple(const float4 &a1, const float4 &a2, const float4 &a3, const float2 &B1,
+                                             const float2 &B2, const float2 &B3, const float2 &A1, const float2 &A2,
+                                             const float2 &A3, const float2 &wb2, const float2 &del, const float2 &part) {
+    const float2 e1 = __fadd2_rn(__fadd2_rn(wb2, lo2(a1)), del);
+    const float2 e2 = __fadd2_rn(__fadd2_rn(wb2, lo2(a2)), del);
+    const float2 e3 = __fadd2_rn(__fadd2_rn(wb2, lo2(a3)), del);
+    const float2 q1 = __ffma2_rn(e1, e1, B1);
+    const float2 q2 = __ffma2_rn(e2, e2, B2);
+    const float2 q3 = __ffma2_rn(e3, e3, B3);
+    const float2 p23 = __fmul2_rn(q2, q3);
+    const float2 t = __ffma2_rn(A3, q2, __fmul2_rn(A2, q3));
+    const float2 num = __ffma2_rn(q1, t, __fmul2_rn(A1, p23));
+    const float2 den = __fmul2_rn(q1, p23);
+    const float2 r = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+    return __ffma2_rn(num, r, part);
+}
+template <int G>
 __device__ __forceinline__ void far_pass(const float4 *sA, const float4 *sB, int js, int je, float wbf, float2 del,
-                                         FarAcc &fa) {
-    if (je <= js) return;                                   // warp-uniform
-    constexpr int G = K2_FAR_SUBGROUPS;
-    const int sub = (int)(threadIdx.x & 31) / (K2_FAR_NODES / 2);
+                                         double2 *acc, int sub) {
+    const int n = je - js;
+    if (n <= 0) return;                                     // warp-uniform
+    const double2 acc0 = *acc;
+    FarAcc fa{acc0.x, acc0.y};
     const float2 wb2 = splat(wbf);
     const float2 zero = make_float2(0.f, 0.f);
-    float2 part = zero;
-    int since = 0;
-    for (int j0 = js; j0 < je; j0 += 3 * G) {               // warp-uniform trip count; short chains pad with A = 0
+    // whole groups of 3 G lines: every lane's triple exists, nothing to clamp or select; FP32 partial sums of at most
+    // K2_FAR_FLUSH triples go into the FP64 node accumulators
+    int full = n / (3 * G);
+    const float4 *pa = sA + js + sub;
+    const float4 *pb = sB + js + sub;
+    while (full > 0) {
+        const int m = min(full, K2_FAR_FLUSH);
+        float2 part = zero;
+#pragma unroll 2
+        for (int i = 0; i < m; ++i) {
+            const float4 a1 = pa[0], a2 = pa[G], a3 = pa[2 * G];
+            const float2 B1 = ldB(pb, 0), B2 = ldB(pb, G), B3 = ldB(pb, 2 * G);
+            part = far_triple(a1, a2, a3, B1, B2, B3, hi2(a1), hi2(a2), hi2(a3), wb2, del, part);
+            pa += 3 * G;
+            pb += 3 * G;
+        }
+        fa.v0 += (double)part.x;
+        fa.v1 += (double)part.y;
+        full -= m;
+    }
+    // the ragged last group: missing lines are padded with A = 0 copies of the last line
+    const int j0 = js + (n / (3 * G)) * (3 * G);
+    if (j0 < je) {
         const int j1 = j0 + sub, j2 = j1 + G, j3 = j1 + 2 * G;
         const int k1 = min(j1, je - 1), k2 = min(j2, je - 1), k3 = min(j3, je - 1);
         const float4 a1 = sA[k1], a2 = sA[k2], a3 = sA[k3];
-        const float2 B1 = ldB(sB, k1), B2 = ldB(sB, k2), B3 = ldB(sB, k3);
         const float2 A1 = j1 < je ? hi2(a1) : zero, A2 = j2 < je ? hi2(a2) : zero, A3 = j3 < je ? hi2(a3) : zero;
-        const float2 e1 = __fadd2_rn(__fadd2_rn(wb2, lo2(a1)), del);
-        const float2 e2 = __fadd2_rn(__fadd2_rn(wb2, lo2(a2)), del);
-        const float2 e3 = __fadd2_rn(__fadd2_rn(wb2, lo2(a3)), del);
-        const float2 q1 = __ffma2_rn(e1, e1, B1);
-        const float2 q2 = __ffma2_rn(e2, e2, B2);
-        const float2 q3 = __ffma2_rn(e3, e3, B3);
-        const float2 p23 = __fmul2_rn(q2, q3);
-        const float2 t = __ffma2_rn(A3, q2, __fmul2_rn(A2, q3));
-        const float2 num = __ffma2_rn(q1, t, __fmul2_rn(A1, p23));
-        const float2 den = __fmul2_rn(q1, p23);
-        const float2 r = make_float2(rcp_approx(den.x), rcp_approx(den.y));
-        part = __ffma2_rn(num, r, part);
-        if (++since == K2_FAR_FLUSH) {
-            fa.v0 += (double)part.x;
-            fa.v1 += (double)part.y;
-            part = zero;
-            since = 0;
-        }
+        const float2 part = far_triple(a1, a2, a3, ldB(sB, k1), ldB(sB, k2), ldB(sB, k3), A1, A2, A3, wb2, del, zero);
+        fa.v0 += (double)part.x;
+        fa.v1 += (double)part.y;
     }
-    fa.v0 += (double)part.x;
-    fa.v1 += (double)part.y;
+    *acc = make_double2(fa.v0, fa.v1);
 }
 
 // Plain one-line-at-a-time evaluation of every staged line (variant PRB_K2_GENERAL): the A/B check
@@ -385,8 +431,8 @@ __device__ __forceinline__ void general_all(const float4 *sA, const float4 *sB, 
     }
 }
 
-template <int P, bool FAR = false>
-__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2Args a) {
+template <int P, bool FAR>
+__device__ __forceinline__ void k2_line_sum_body(const K2Args &a) {
     static_assert(P >= 2 && P % 2 == 0, "points per thread must be even (packed FP32x2)");
     static_assert(!FAR || P == 4 || P == 8, "far-field tables exist for 128- and 256-point spans");
     constexpr int H = P / 2;
@@ -474,7 +520,11 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
     for (int p = 0; p < P; ++p) s.acc(p) = 0.0;
     int wb = 0;
     float wbf = 0.f, we1f = 0.f;
-    FarAcc far{0.0, 0.0};                                  // FAR: this lane's two node sums of the current tile
+    double2 *far = &sm.faracc[0][tid];                     // FAR: this lane's two node sums of the current tile
+    double2 *far2 = &sm.faracc[1][tid];                    // ... and of its level-2 domain (its share of the lines)
+    float dbf = 0.f;                                       // first point of the warp's level-2 domain
+    uint32_t tile_par = 0;                                 // parity of the tiles this CTA has finished (sm.far2 buffer)
+    bool use2 = false;                                     // level 2 on for this tile's layer (uniform over the CTA)
 
     for (uint32_t it = 0;; ++it) {
         const uint32_t stage = it % K2_STAGES;
@@ -497,8 +547,12 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             }
 #pragma unroll
             for (int p = 0; p < P; ++p) s.acc(p) = 0.0;
-            far.v0 = 0.0;
-            far.v1 = 0.0;
+            if (FAR) {
+                *far = make_double2(0.0, 0.0);
+                *far2 = make_double2(0.0, 0.0);
+            }
+            dbf = (float)(d.tile0 + (warp / K2_FAR2_SPANS) * (K2_FAR2_SPANS * SPAN));
+            use2 = FAR && K2_FAR2 && wmf >= (float)(K2_FAR2_MIN_DOMAINS * K2_FAR2_SPANS * SPAN);
         }
         const int cnt = d.cnt;
         const float4 *sA = sm.rA[stage];
@@ -524,14 +578,15 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             // thresholds, exact in FP32, so the split does not depend on the shard origin
             const float tfl = wbf + (float)((SPAN - 1) / 2 - K2_FAR_RADIUS_SPANS * SPAN);
             const float tfr = wbf + (float)(SPAN / 2 + K2_FAR_RADIUS_SPANS * SPAN);
-            int b0, b1, b4, b5, bg0, bg1, nfl = 0, nfr = 0;
+            int b1, b4, bg0, bg1;
             if (FAR) {
                 // The staged lines are sorted, so "how many lie below t" is a search, not a count: one sample per block
                 // of 32 lines (loaded once, shared by all thresholds), a ballot picks the block the boundary falls in, a
                 // second ballot over that block's 32 lines places it -- two shared-memory reads and two ballots per
                 // threshold instead of a pass over the whole slot.  Same integers as counting.  (Measured: worth 4 % of the
                 // far-field kernel; in the exact kernel it changed the register allocation for the worse, so that one
-                // keeps counting -- profiles/r01_k2_experiments.txt.)
+                // keeps counting -- profiles/r01_k2_experiments.txt.)  Every boundary is looked up right before the pass
+                // that needs it, so few of them are alive at a time.
                 static_assert(K2_CHUNK <= 1024, "one level-1 sample per lane");
                 const float f1 = -sA[min(32 * lane + 31, cnt - 1)].x;
                 const bool v1 = 32 * lane < cnt;
@@ -541,36 +596,66 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
                     const bool l2 = j2 < cnt && -sA[min(j2, cnt - 1)].x < t;
                     return min(32 * nb, cnt) + __popc(__ballot_sync(0xffffffffu, l2));
                 };
-                b0 = below(t0); b1 = below(t1); b4 = below(t4); b5 = below(t5); bg0 = below(g0); bg1 = below(g1);
-                nfl = below(tfl);
-                nfr = below(tfr + 1.f);                                   // idx <= tfr  <=>  idx < tfr + 1 (integers)
+                constexpr int S2 = K2_FAR2_SPANS * SPAN;
+                const int kp = lane & (K2_FAR_NODES / 2 - 1);
+                const int sub = lane / (K2_FAR_NODES / 2);
+                const float2 del = make_float2(a.far_delta[2 * kp], a.far_delta[2 * kp + 1]);
+                const float2 del2 = make_float2(a.far_delta2[2 * kp], a.far_delta2[2 * kp + 1]);
+                const int sub2 = (warp % K2_FAR2_SPANS) * K2_FAR_SUBGROUPS + sub;
+                // level 2 (use2): the same tests for the warp's domain [db, db + S2), identical in the domain's warps;
+                // full cover of the domain: u1 <= idx < u4.  Its lines [c1, cfl) and [cfr, c4) lie inside the level-1 far
+                // ranges [b1, bfl) and [bfr, b4): level 1 takes what is left of those on either side.
+                const float u1 = dbf + (float)(S2 - 1) - wmf, u4 = dbf + wmf + 1.f;
+                const bool l2on = use2 && u1 < u4;
+                b1 = below(t1);
+                lorentz_paired<H, true>(sA, sB, below(t0), b1, wmf, s);           // window edge crosses the span (left)
+                b4 = below(t4);
+                // full-cover lines [b1, b4) split by distance from the span: far left | near | far right
+                const int bfl = min(max(below(tfl), b1), b4);
+                if (l2on) {
+                    const int c4 = below(u4);
+                    const int c1 = min(below(u1), c4);
+                    const int cfl = min(max(below(dbf + (float)((S2 - 1) / 2 - K2_FAR_RADIUS_SPANS * S2)), c1), c4);
+                    const int l1a = min(max(c1, b1), bfl), l1b = min(max(cfl, l1a), bfl);
+                    far_pass<K2_FAR_SUBGROUPS>(sA, sB, b1, l1a, wbf, del, far, sub);
+                    far_pass<K2_FAR2_SPANS * K2_FAR_SUBGROUPS>(sA, sB, c1, cfl, dbf, del2, far2, sub2);
+                    far_pass<K2_FAR_SUBGROUPS>(sA, sB, l1b, bfl, wbf, del, far, sub);
+                } else {
+                    far_pass<K2_FAR_SUBGROUPS>(sA, sB, b1, bfl, wbf, del, far, sub);
+                }
+                const int bfr = min(max(below(tfr + 1.f), bfl), b4);               // idx <= tfr  <=>  idx < tfr + 1 (integers)
+                lorentz_paired<H, false>(sA, sB, bfl, bfr, wmf, s);
+                if (l2on) {
+                    const int c4 = below(u4);
+                    const int c1 = min(below(u1), c4);
+                    const int cfl = min(max(below(dbf + (float)((S2 - 1) / 2 - K2_FAR_RADIUS_SPANS * S2)), c1), c4);
+                    const int cfr = min(max(below(dbf + (float)(S2 / 2 + K2_FAR_RADIUS_SPANS * S2) + 1.f), cfl), c4);
+                    const int r1a = min(max(cfr, bfr), b4), r1b = min(max(c4, r1a), b4);
+                    far_pass<K2_FAR_SUBGROUPS>(sA, sB, bfr, r1a, wbf, del, far, sub);
+                    far_pass<K2_FAR2_SPANS * K2_FAR_SUBGROUPS>(sA, sB, cfr, c4, dbf, del2, far2, sub2);
+                    far_pass<K2_FAR_SUBGROUPS>(sA, sB, r1b, b4, wbf, del, far, sub);
+                } else {
+                    far_pass<K2_FAR_SUBGROUPS>(sA, sB, bfr, b4, wbf, del, far, sub);
+                }
+                lorentz_paired<H, true>(sA, sB, b4, below(t5), wmf, s);           // window edge crosses the span (right)
+                bg0 = below(g0);
+                bg1 = below(g1);
             } else {
                 int c0 = 0, c1 = 0, c4 = 0, c5 = 0, cg0 = 0, cg1 = 0;
                 for (int j = lane; j < cnt; j += 32) {
                     const float f = -sA[j].x;
                     c0 += f < t0; c1 += f < t1; c4 += f < t4; c5 += f < t5; cg0 += f < g0; cg1 += f < g1;
                 }
-                b0 = __reduce_add_sync(0xffffffffu, c0);
+                const int b0 = __reduce_add_sync(0xffffffffu, c0);
                 b1 = __reduce_add_sync(0xffffffffu, c1);
                 b4 = __reduce_add_sync(0xffffffffu, c4);
-                b5 = __reduce_add_sync(0xffffffffu, c5);
+                const int b5 = __reduce_add_sync(0xffffffffu, c5);
                 bg0 = __reduce_add_sync(0xffffffffu, cg0);
                 bg1 = __reduce_add_sync(0xffffffffu, cg1);
-            }
-            lorentz_paired<H, true>(sA, sB, b0, b1, wmf, s);
-            if (FAR) {
-                // full-cover lines [b1, b4) split by distance from the span: far left | near | far right
-                const int bfl = min(max(nfl, b1), b4);
-                const int bfr = min(max(nfr, bfl), b4);
-                const int kp = lane & (K2_FAR_NODES / 2 - 1);
-                const float2 del = make_float2(a.far_delta[2 * kp], a.far_delta[2 * kp + 1]);
-                far_pass(sA, sB, b1, bfl, wbf, del, far);
-                lorentz_paired<H, false>(sA, sB, bfl, bfr, wmf, s);
-                far_pass(sA, sB, bfr, b4, wbf, del, far);
-            } else {
+                lorentz_paired<H, true>(sA, sB, b0, b1, wmf, s);
                 lorentz_paired<H, false>(sA, sB, b1, b4, wmf, s);
+                lorentz_paired<H, true>(sA, sB, b4, b5, wmf, s);
             }
-            lorentz_paired<H, true>(sA, sB, b4, b5, wmf, s);
             if (dgmax > 0.f) {                                  // [bg0, bg1) lies inside [b0, b5)
                 gauss_pass<H, true>(sA, sB, sD, bg0, min(bg1, b1), wbf, we1f, wmf, s);
                 gauss_pass<H, false>(sA, sB, sD, max(bg0, b1), min(bg1, b4), wbf, we1f, wmf, s);
@@ -599,18 +684,41 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
                 // node sums: add the line sub-groups (fixed tree), then interpolate to the thread's points -- node by
                 // node, each node's sum broadcast from the lane that holds it, the Lagrange weights read as 32
                 // consecutive doubles per (node, row of the span) -- straight into the FP64 accumulators
-                double v0 = far.v0, v1 = far.v1;
+                double v0 = far->x, v1 = far->y, w0 = far2->x, w1 = far2->y;
 #pragma unroll
                 for (int o = K2_FAR_NODES / 2; o < 32; o <<= 1) {
                     v0 += __shfl_xor_sync(0xffffffffu, v0, o);
                     v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                    w0 += __shfl_xor_sync(0xffffffffu, w0, o);
+                    w1 += __shfl_xor_sync(0xffffffffu, w1, o);
                 }
+                // level 2: the domain's warps pool their node sums (fixed order), lane k holds node k of the domain
+                if (use2 && lane < K2_FAR_NODES / 2) {
+                    sm.far2[tile_par][warp][2 * lane] = w0;
+                    sm.far2[tile_par][warp][2 * lane + 1] = w1;
+                }
+                if (use2) consumer_barrier();
+                double dn = 0.0;
+                if (use2 && lane < K2_FAR_NODES) {
+                    const int wd = (warp / K2_FAR2_SPANS) * K2_FAR2_SPANS;
+#pragma unroll
+                    for (int q = 0; q < K2_FAR2_SPANS; ++q) dn += sm.far2[tile_par][wd + q][lane];
+                }
+                if (use2) tile_par ^= 1u;
+                constexpr int S2 = K2_FAR2_SPANS * SPAN;
+                const double *lw2base = a.far_lag2 + (warp % K2_FAR2_SPANS) * SPAN + lane;
 #pragma unroll 2
                 for (int k = 0; k < K2_FAR_NODES; ++k) {
                     const double fk = __shfl_sync(0xffffffffu, (k & 1) ? v1 : v0, k >> 1);
                     const double *lw = a.far_lag + k * SPAN + lane;
 #pragma unroll
                     for (int p = 0; p < P; ++p) s.acc(p) = fma(fk, __ldg(lw + 32 * p), s.acc(p));
+                    if (use2) {
+                        const double gk = __shfl_sync(0xffffffffu, dn, k);
+                        const double *lw2 = lw2base + k * S2;
+#pragma unroll
+                        for (int p = 0; p < P; ++p) s.acc(p) = fma(gk, __ldg(lw2 + 32 * p), s.acc(p));
+                    }
                 }
             }
 #pragma unroll
@@ -656,6 +764,19 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2A
             }
         }
     }
+}
+
+// The exact kernel: 96 registers (2 CTAs x 288 threads, ptxas' own bound for that launch shape).
+template <int P>
+__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2Args a) {
+    k2_line_sum_body<P, false>(a);
+}
+// The far-field variant (same launch shape: 96 registers is the most that lets two CTAs share an SM -- the register
+// file is per SM sub-partition, 16 384 each, and two CTAs put five warps on one of them; 112 was tried and halves the
+// occupancy).
+template <int P>
+__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum_far(const K2Args a) {
+    k2_line_sum_body<P, true>(a);
 }
 
 }  // namespace prb

@@ -84,6 +84,13 @@ class Engine:
         return {"sm_count": sm.value, "cc": (ma.value, mi.value), "sm_clock_khz": khz.value,
                 "free_bytes": fr.value, "total_bytes": to.value}
 
+    def measure_peaks(self):
+        """Roofline denominators measured on this device: FP32 lane-FMA/s (packed FFMA2 and scalar FFMA streams) and the
+        float4 copy bandwidth in bytes/s (read + write)."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _lib.check(self._lib.prb_measure_peaks(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"ffma2_lane_fma_per_s": a.value, "ffma_lane_fma_per_s": b.value, "copy_bytes_per_s": c.value}
+
     def set_k2_variant(self, variant=K2_CLASSED, points_per_thread=0):
         _lib.check(self._lib.prb_set_k2_variant(self._h, int(variant), int(points_per_thread)))
 

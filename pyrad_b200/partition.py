@@ -140,29 +140,43 @@ def assemble(gathered, chunks):
     return np.concatenate(parts) if parts else np.zeros(0)
 
 
-def farfield_work(idx, i_begin, i_end, window, span, radius_spans=1, nodes=16):
+def farfield_work(idx, i_begin, i_end, window, span, radius_spans=1, nodes=16, level2_spans=8, level2_min_domains=4):
     """What the far-field variant of K2 (PRB_K2_FARFIELD) actually evaluates on the chunk [i_begin, i_end)
     for one layer of window W: (pairs evaluated point by point, node evaluations).  A warp span starts at
     i_begin + k * span; a line is summed at the span's `nodes` Chebyshev nodes instead of at its points when its window
     covers the whole span (idx in [last - wm, first + wm]) and its centre lies beyond the far thresholds
     idx < first + (span-1)//2 - radius_spans*span  or  idx > first + span//2 + radius_spans*span  -- the kernel's own
-    integer tests (k2_line_sum.cuh).  Host-side accounting only (roofline of the far-field kernel, cost models)."""
+    integer tests (k2_line_sum.cuh).  Level 2 applies the same test to domains of `level2_spans` spans: a line far from
+    a whole domain costs `nodes` evaluations per DOMAIN and none in the domain's spans; the kernel switches level 2 on for
+    windows of at least `level2_min_domains` domain lengths.  Host-side accounting only
+    (roofline of the far-field kernel, cost models)."""
     idx = np.sort(np.asarray(idx, dtype=np.int64))
     wm = max(int(window) - 2, 0)
     n_chunk = int(i_end) - int(i_begin)
     if n_chunk <= 0 or idx.size == 0:
         return 0, 0
-    first = int(i_begin) + np.arange((n_chunk + span - 1) // span, dtype=np.int64) * span
-    last = first + span - 1
-    pts = np.minimum(last, int(i_end) - 1) - first + 1               # real points of the (possibly ragged) last span
     count = lambda lo, hi: np.maximum(np.searchsorted(idx, hi, side="left") - np.searchsorted(idx, lo, side="left"), 0)
+
+    def far_counts(length):
+        """per block of `length` points from i_begin: (far lines, real points of the block)"""
+        first = int(i_begin) + np.arange((n_chunk + length - 1) // length, dtype=np.int64) * length
+        last = first + length - 1
+        pts = np.minimum(last, int(i_end) - 1) - first + 1           # real points of the (possibly ragged) last block
+        full_lo, full_hi = last - wm, first + wm + 1                 # full cover: full_lo <= idx < full_hi
+        tfl = first + (length - 1) // 2 - radius_spans * length      # far left:  idx < tfl
+        tfr = first + length // 2 + radius_spans * length            # far right: idx > tfr
+        far = count(full_lo, np.minimum(tfl, full_hi)) + count(np.maximum(tfr + 1, full_lo), full_hi)
+        return np.where(full_lo >= full_hi, 0, far), pts
+
     # every accumulation of the reference on these points: lines with |i - idx| <= wm
     i = np.arange(int(i_begin), int(i_end), dtype=np.int64)
     pairs_all = int((np.searchsorted(idx, i + wm, side="right") - np.searchsorted(idx, i - wm, side="left")).sum())
-    full_lo, full_hi = last - wm, first + wm + 1                     # full cover: full_lo <= idx < full_hi
-    none = full_lo >= full_hi
-    tfl = first + (span - 1) // 2 - radius_spans * span              # far left:  idx < tfl
-    tfr = first + span // 2 + radius_spans * span                    # far right: idx > tfr
-    far = count(full_lo, np.minimum(tfl, full_hi)) + count(np.maximum(tfr + 1, full_lo), full_hi)
-    far = np.where(none, 0, far)
-    return pairs_all - int((far * pts).sum()), int(far.sum()) * nodes
+    far1, pts1 = far_counts(span)
+    far_pairs = int((far1 * pts1).sum())                             # level-2 lines are level-1 far lines of every span
+    node_evals = int(far1.sum()) * nodes
+    if level2_spans and wm >= level2_min_domains * level2_spans * span:
+        far2, _ = far_counts(span * level2_spans)
+        # a level-2 line is skipped by each of its domain's spans (level2_spans of them, fewer in a ragged last domain)
+        spans_in_dom = np.minimum(level2_spans, (n_chunk + span - 1) // span - np.arange(len(far2)) * level2_spans)
+        node_evals += int(far2.sum()) * nodes - int((far2 * spans_in_dom).sum()) * nodes
+    return pairs_all - far_pairs, node_evals

@@ -64,8 +64,28 @@ def test_farfield_interpolation_error_is_below_2e8_of_k(P, T, span):
     assert node_evals % fm.NODES == 0 and node_evals > 0
 
 
+def test_farfield_level2_interpolation_error_on_a_stress_sweep_window():
+    """Level 2 (lines far from a whole 2048-point tile summed at the tile's 16 nodes) switches on for windows of at least
+    four tile lengths: cfg5's 25 cm-1 cutoff (W = 25 000) on a 6 cm-1 cell.  Same error bound as level 1; most of the far
+    lines are level-2 lines, so the node evaluations drop well below level 1 alone."""
+    w = workloads.gas_cell(["h2o", "co2", "ch4", "o3"], 6000, 1000.0, 1006.0, 0.001, 296, 1013.25,
+                           [0.01, 400e-6, 1.8e-6, 5e-8], 10.0, 32, cutoff=25.0)
+    n = ph.grid_len(w["range_min"], w["range_max"], w["res"])
+    win = ph.window_len(w["cutoff"], w["res"])
+    assert win - 2 >= fm.LEVEL2_MIN_DOMAINS * fm.LEVEL2_SPANS * 256
+    rec = _records(w)
+    exact, _ = fm.line_sum(*rec, n, win, 256, farfield=False)
+    far, frac = fm.line_sum(*rec, n, win, 256, farfield=True)
+    err = np.abs(far - exact) / np.maximum(np.abs(exact), 1e-40 * np.abs(exact).max())
+    assert err.max() <= 2e-8, err.max()
+    assert frac > 0.9, frac
+    _, evals2 = pt.farfield_work(rec[0], 0, n, win, 256)
+    _, evals1 = pt.farfield_work(rec[0], 0, n, win, 256, level2_spans=0)
+    assert 0 < evals2 < 0.4 * evals1, (evals2, evals1)
+
+
 def test_lagrange_table_is_a_partition_of_unity_and_exact_on_polynomials():
-    for span in (128, 256):
+    for span in (128, 256, 2048):
         w = fm.lagrange_table(span)
         np.testing.assert_allclose(w.sum(axis=1), 1.0, rtol=0, atol=1e-12)
         x = fm.node_offsets(span)

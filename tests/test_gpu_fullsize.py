@@ -107,6 +107,13 @@ def test_atmosphere_layer_shapes_full_size_farfield_variant_sampled(engine, P, T
     check_sampled(engine, w, weights_mode=True, P=P, T=T, seed=int(P), variant=eng.K2_FARFIELD)
 
 
+def test_cfg5_full_size_farfield_variant_sampled_against_oracle(engine):
+    """cfg5 under the far-field variant, where both of its levels carry most of the lines (W = 25 000)."""
+    w = workloads.cfg5()
+    out = check_sampled(engine, w, weights_mode=True, seed=5, variant=eng.K2_FARFIELD)
+    assert np.all(np.isfinite(out))
+
+
 def test_cfg3_full_size_line_by_line_plus_xsc_tables(engine, tmp_path):
     """cfg3 (30 000 points, 50k CO2 + H2O lines, CFC-11 and HCFC-22 xsc tables on the same grid) through the host mirror on
     an on-disk data tree, every spectrum against the oracle on the same inputs."""

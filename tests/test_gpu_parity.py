@@ -476,6 +476,36 @@ def test_k2_farfield_variant_matches_exact_paths_and_oracle(engine, P, T):
     assert err.max() <= H.K_REL_TOL, err.max()
 
 
+def test_k2_farfield_level2_on_a_stress_sweep_window(engine):
+    """cfg5's 25 cm-1 cutoff (W = 25 000 >= four tile lengths) switches level 2 on: lines far from a whole 2048-point tile
+    are summed once per tile by the eight warps together.  Same bounds as level 1, deterministic, and tile-aligned shards
+    reproduce the unsharded result bit for bit."""
+    w = workloads.gas_cell(["h2o", "co2", "ch4", "o3"], 30000, 1000.0, 1020.0, 0.001, 296, 1013.25,
+                           [0.01, 400e-6, 1.8e-6, 5e-8], 10.0, 33, cutoff=25.0)
+    n = H.engine_setup(engine, w)
+    wts = [eng.number_density_weight(c, w["P"], w["T"]) for c in w["conc"]]
+    H.engine_prepass(engine, w, weights=wts)
+    exact = engine.line_sum()
+    engine.set_k2_variant(eng.K2_FARFIELD, 0)
+    try:
+        H.engine_prepass(engine, w, weights=wts)
+        far = engine.line_sum()
+        assert np.array_equal(far, engine.line_sum())
+        parts = []
+        for a, b in ((0, 4096), (4096, 14336), (14336, n)):
+            H.engine_setup(engine, w, a, b)
+            H.engine_prepass(engine, w, weights=wts)
+            parts.append(engine.line_sum())
+        assert np.array_equal(np.concatenate(parts), far)
+    finally:
+        engine.set_k2_variant(eng.K2_CLASSED, 0)
+    d = H.k_rel_err(far, exact)
+    assert 0 < d.max() <= 1e-6, d.max()
+    pts = H.boundary_points(n, 300, 7, n_tiles=6)
+    ref = H.oracle_layer_k_at(w, pts, w["T"], w["P"], w["conc"], w["cutoff"])
+    assert H.k_rel_err(far[pts], ref).max() <= H.K_REL_TOL
+
+
 def test_k2_farfield_variant_is_shard_invariant_and_feeds_the_fused_paths(engine):
     """Node positions are tile-relative, so tile-aligned shards reproduce the unsharded far-field result bit for bit;
     the single-layer fused epilogue (atmosphere call) and the FP32 k row see the same sums."""

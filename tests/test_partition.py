@@ -140,23 +140,36 @@ def test_world_size_2_gloo_all_gather_assembles_the_unsharded_spectrum():
 
 
 def test_farfield_work_accounting_matches_brute_force():
-    """partition.farfield_work restates the far-field kernel's integer class tests; checked against a direct count."""
+    """partition.farfield_work restates the far-field kernel's integer class tests (level 1: spans, level 2: domains of
+    four spans); checked against a direct count."""
     rng = np.random.default_rng(5)
     idx = np.sort(rng.integers(-300, 6000, 900))
-    for (a, b, window, span) in ((0, 4096, 1400, 256), (4096, 5500, 1400, 256), (0, 4096, 700, 128), (0, 1000, 200, 128)):
+
+    def far(f, first, length, wm):
+        last = first + length - 1
+        full = last - wm <= f <= first + wm
+        return full and (f < first + (length - 1) // 2 - length or f > first + length // 2 + length)
+
+    for (a, b, window, span, l2) in ((0, 4096, 1400, 256, 0), (4096, 5500, 1400, 256, 0), (0, 4096, 700, 128, 0),
+                                     (0, 1000, 200, 128, 0), (0, 4096, 2600, 256, 4), (2048, 5500, 2600, 128, 4),
+                                     (0, 4096, 2600, 128, 8)):
         wm = window - 2
-        exact, nodes = pt.farfield_work(idx, a, b, window, span)
+        exact, nodes = pt.farfield_work(idx, a, b, window, span, level2_spans=l2, level2_min_domains=0)
         want_exact = want_nodes = 0
         for first in range(a, b, span):
-            last = first + span - 1
-            pts = min(last, b - 1) - first + 1
+            pts = min(first + span - 1, b - 1) - first + 1
+            dfirst = a + ((first - a) // (span * l2)) * span * l2 if l2 else 0
             for f in idx:
                 covered = sum(1 for i in range(first, first + pts) if abs(i - f) <= wm)
-                full = last - wm <= f <= first + wm
-                far = full and (f < first + (span - 1) // 2 - span or f > first + span // 2 + span)
-                if far:
+                if l2 and far(f, dfirst, span * l2, wm):
+                    assert far(f, first, span, wm)                       # level 2 is a subset of level 1
+                    want_nodes += 16 if first == dfirst else 0           # once per domain
+                elif far(f, first, span, wm):
                     want_nodes += 16
                 else:
                     want_exact += covered
-        assert (exact, nodes) == (want_exact, want_nodes), (a, b, window, span)
+        assert (exact, nodes) == (want_exact, want_nodes), (a, b, window, span, l2)
     assert pt.farfield_work(idx, 0, 4096, 1400, 256)[1] > 0
+    assert pt.farfield_work(idx, 0, 4096, 2600, 256, level2_spans=4, level2_min_domains=0)[1] < pt.farfield_work(idx, 0, 4096, 2600, 256, level2_spans=0)[1]
+    # the kernel's own rule: no level 2 below four domain lengths of window
+    assert pt.farfield_work(idx, 0, 4096, 2600, 256) == pt.farfield_work(idx, 0, 4096, 2600, 256, level2_spans=0)
