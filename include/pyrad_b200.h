@@ -49,7 +49,7 @@ extern "C" {
 #define PRB_ERR_PEER        -6   /* peer-memory gather: IPC mapping failed or a rank did not arrive */
 #define PRB_ERR_PARSE       -7   /* text ingestion: a row or number is not in the expected format */
 
-#define PRB_ABI_VERSION      2
+#define PRB_ABI_VERSION      3
 
 /* prb_line_sum output modes */
 #define PRB_OUT_F64          0   /* double per grid point */
@@ -159,6 +159,19 @@ int prb_planck(prb_engine *e, int64_t n, double x0, double dx, double x_last, do
 int prb_xsc_place(prb_engine *e, int64_t n_out, int64_t dst0, int64_t src0, int64_t count,
                   int interp, double ax0, double adelta,
                   int64_t n_file, const double *file_x, const double *file_y, double *out);
+
+/* ---- resident xsc tables (a17 on the device-resident path; pyradClasses.py:466-505, 707-712).  An xsc molecule's cross
+ * section is its table, whatever the layer: prb_xsc_resident keeps table `slot` (0 .. 7; an existing slot or the next free
+ * one) on the device together with its placement plan -- the arguments of prb_xsc_place, n_out = the grid's n_total --
+ * and the engine resamples it onto the owned grid chunk once per grid.  prb_set_xsc_conc gives the tables' mole fractions
+ * per layer (L x n_xsc, row-major) for the following prb_atmosphere / prb_gas_cell_host calls with that many layers:
+ * every layer's k(nu) then includes  sigma_t(nu) * conc[l][t] * P_l / 1e4 / kB / T_l  (added to the finished line sum
+ * inside the line-sum kernel's epilogue).  prb_xsc_clear drops all tables. */
+int prb_xsc_resident(prb_engine *e, int32_t slot, int64_t n_out, int64_t dst0, int64_t src0, int64_t count,
+                     int interp, double ax0, double adelta,
+                     int64_t n_file, const double *file_x, const double *file_y);
+int prb_set_xsc_conc(prb_engine *e, int32_t n_layers, int32_t n_xsc, const double *conc);
+int prb_xsc_clear(prb_engine *e);
 
 /* ---- atmosphere (cfg 4): L layers bottom -> top on the owned chunk, everything on the device:
  * per layer K1 + K2 (absorption-coefficient mode, FP32 row of the k matrix), then ONE K3 pass

@@ -453,8 +453,11 @@ class Molecule(list, _Spectral):
             a0 = float(x_axis[0])
             ad = float(x_axis[1] - x_axis[0]) if len(x_axis) > 1 else .01
             sigma = engine().xsc_place(n, dst0, src0, count, wn, xs, interp=True, ax0=a0, adelta=ad)
+            self._xsc_plan = dict(n_out=n, dst0=dst0, src0=src0, count=count, file_x=wn, file_y=xs, interp=True, ax0=a0, adelta=ad)
         else:
             sigma = engine().xsc_place(n, dst0, src0, count, None, xs, interp=False)
+            self._xsc_plan = dict(n_out=n, dst0=dst0, src0=src0, count=count, file_x=None, file_y=xs, interp=False)
+        self._xsc_key = (name, filename)
         dummy.crossSection = sigma
         dummy.progressCrossSection = True
         self.crossSection = sigma
@@ -685,8 +688,9 @@ class Atmosphere(list):
         """The whole column on the device in ONE engine call (prb_atmosphere): K1 for every layer, the batched line
         sums, and the fold  I <- T_l I + (1 - T_l) B(nu, T_l)  starting from I_0 = B(nu, surfaceTemperature).
         Returns (radiance, total transmittance) on the layers' common grid.  Same physics as ``transmission`` above,
-        without one host round trip per layer and isotope; needs layers that share range and base resolution, carry
-        the same line-by-line molecules in the same order, and no xsc molecules."""
+        without one host round trip per layer and isotope; needs layers that share range and base resolution and carry
+        the same line-by-line molecules in the same order.  xsc molecules (up to eight distinct tables over the column)
+        stay resident on the device and enter every layer's k(nu) inside the line-sum kernel (prb_xsc_resident)."""
         layers = list(self)
         if not layers:
             raise ValueError("atmosphere has no layers")
@@ -695,12 +699,20 @@ class Atmosphere(list):
             if (l.rangeMin, l.rangeMax) != (ref.rangeMin, ref.rangeMax) or l.resolution != BASE_RESOLUTION:
                 raise ValueError("columnSpectrum needs layers on one grid at the base resolution "
                                  "(build them with dynamicResolution=False)")
-            if [iso.globalIsoNumber for m in l for iso in m if not m.exotic] != \
-                    [iso.globalIsoNumber for m in ref for iso in m if not m.exotic] or any(m.exotic for m in l):
-                raise ValueError("columnSpectrum needs the same line-by-line isotopologues in every layer and no xsc molecules")
+            if [iso.globalIsoNumber for m in l if not m.exotic for iso in m] != \
+                    [iso.globalIsoNumber for m in ref if not m.exotic for iso in m]:
+                raise ValueError("columnSpectrum needs the same line-by-line isotopologues in every layer")
+        # xsc tables of the column, in order of first appearance; a layer without a table carries it at mole fraction 0
+        tables = {}
+        for l in layers:
+            for m in l:
+                if m.exotic:
+                    tables.setdefault(m._xsc_key, m)
+        if len(tables) > 8:
+            raise ValueError("columnSpectrum carries at most eight distinct xsc tables")
         # line source: the layer with the widest cutoff read the widest wavenumber range from the data tree
         widest = max(layers, key=lambda l: l.distanceFromCenter)
-        isos = [iso for m in widest for iso in m]
+        isos = [iso for m in widest if not m.exotic for iso in m]
         cols = {k: np.concatenate([iso._cols[k] for iso in isos]) if isos else np.zeros(0)
                 for k in ("nu", "sw", "gamma_air", "gamma_self", "elower", "n_air", "delta_air")}
         group = np.concatenate([np.full(len(iso._cols["nu"]), g, dtype=np.int32) for g, iso in enumerate(isos)]) \
@@ -712,13 +724,25 @@ class Atmosphere(list):
         e = engine()
         e.upload_lines(lines, n_groups=max(len(isos), 1))
         e.set_grid(ref.rangeMin, BASE_RESOLUTION, n)
-        conc = [[m.concentration for m in l for _ in m] for l in layers]
-        q_t = [[iso.q[l.T] for m in l for iso in m] for l in layers]          # KeyError on a non-tabulated T
+        conc = [[m.concentration for m in l if not m.exotic for _ in m] for l in layers]
+        q_t = [[iso.q[l.T] for m in l if not m.exotic for iso in m] for l in layers]   # KeyError on a non-tabulated T
         window = [_eng.window_len(l.distanceFromCenter, BASE_RESOLUTION) for l in layers]
-        e.atmosphere([l.depth for l in layers], [l.T for l in layers], [l.P for l in layers], conc,
-                     [iso.molmass for iso in isos], q_t, [iso.q296 for iso in isos], window, surfaceTemperature,
-                     ref.rangeMax)
-        return e.atmosphere_read()
+        e.xsc_clear()
+        try:
+            for slot, m in enumerate(tables.values()):
+                e.xsc_resident(slot, **m._xsc_plan)
+            if tables:
+                # several molecules of one table in a layer add up, like their absCoef terms do
+                e.set_xsc_conc([[sum(m.concentration for m in l if m.exotic and m._xsc_key == key) for key in tables]
+                                for l in layers])
+            if not isos:                                           # xsc molecules only: an empty line list
+                conc, q_t = [[0.0]] * len(layers), [[1.0]] * len(layers)
+            e.atmosphere([l.depth for l in layers], [l.T for l in layers], [l.P for l in layers], conc,
+                         [iso.molmass for iso in isos] or [1.0], q_t, [iso.q296 for iso in isos] or [1.0], window,
+                         surfaceTemperature, ref.rangeMax)
+            return e.atmosphere_read()
+        finally:
+            e.xsc_clear()
 
 
 def getGlobalIsotope(ID, isotopeDepth):

@@ -74,6 +74,15 @@ struct LayerJob {
     DevState *st_dev = nullptr;
     void *out_dev = nullptr;
     bool valid = false;
+    double xsc_w[K2_MAX_XSC] = {};   // absCoef weights of the resident xsc tables in this layer (0: none)
+};
+
+// A resident xsc cross-section table (prb_xsc_resident): the file's samples and its placement plan.
+struct XscTable {
+    int64_t n_out = 0, dst0 = 0, src0 = 0, count = 0, n_file = 0;
+    int interp = 0;
+    double ax0 = 0, adelta = 0;
+    DevBuf<double> fx, fy;
 };
 
 // Peer-memory gather buffers (multi-GPU, one process per GPU on one NVLink/NVSwitch node).
@@ -164,6 +173,17 @@ struct prb_engine {
     DevBuf<K2Layer> ring_d;
     cudaEvent_t ring_ev[RING] = {};
     int ring_next = 0;
+
+    // resident xsc tables and their per-layer mole fractions for the next prb_atmosphere / prb_gas_cell_host
+    XscTable xsc[K2_MAX_XSC];
+    int n_xsc = 0;
+    DevBuf<double> xsc_rows;                          // [n_xsc][xsc_ld] on the owned chunk
+    int64_t xsc_ld = 0;
+    bool xsc_rows_valid = false;
+    int64_t xsc_sig[3] = {-1, -1, -1};                // (i_begin, i_end, n_total) the rows were built for
+    int xsc_build_launches = 0;                       // resampling kernels enqueued since the last prb_atmosphere counted them
+    std::vector<double> xsc_conc;                     // [xsc_conc_layers][n_xsc]
+    int xsc_conc_layers = 0;
 
     // outputs / scratch
     DevBuf<double> out64;
@@ -274,6 +294,8 @@ extern "C" int prb_destroy(prb_engine *e) {
     e->tile_bounds_buf[0].release(); e->tile_bounds_buf[1].release();
     e->far_lag[0].release(); e->far_lag[1].release(); e->far_lag2[0].release(); e->far_lag2[1].release();
     e->dev_scal.release();
+    e->xsc_rows.release();
+    for (auto &x : e->xsc) { x.fx.release(); x.fy.release(); }
     if (e->pin_scal) cudaFreeHost(e->pin_scal);
     for (auto x : e->pipe_ev) cudaEventDestroy(x);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -529,6 +551,7 @@ extern "C" int prb_set_grid(prb_engine *e, double range_min, double res, int64_t
     e->i_end = i_end;
     e->grid_set = true;
     e->last.valid = false;
+    e->xsc_rows_valid = false;
     return PRB_OK;
 }
 
@@ -771,6 +794,7 @@ static void fill_k2_row(const prb_engine *e, const LayerJob &j, K2Layer &t) {
     t.l_end = (int)j.l1;
     t.wm = (int)j.wm;
     t.pad = 0;
+    for (int x = 0; x < K2_MAX_XSC; ++x) t.xsc_w[x] = j.xsc_w[x];
 }
 
 // A sub-launch of k2_line_sum<P> over tiles [a.tile_base, a.tile_base + a.n_tiles) of one layer (pipelined upload).
@@ -804,10 +828,12 @@ static int tile_bounds(prb_engine *e, K2Args &b) {
 // ONE K2 launch for jobs[0..n), which must share a kernel class (all narrow, or all the same ppt) and be sorted
 // widest window first.  tab_dev holds the n table rows (fill_k2_row); the launch's tile counter lives in jobs[0]'s
 // state block and must be zero (stream-ordered) when the kernel starts.
+static void xsc_args(const prb_engine *e, K2Args &a);
 static int run_line_sum(prb_engine *e, const LayerJob *jobs, int n, const K2Layer *tab_dev, int out_mode,
-                        const K2Fuse *fuse) {
+                        const K2Fuse *fuse, bool with_xsc = false) {
     if (n <= 0) return PRB_OK;
     K2Args a{};
+    if (with_xsc) xsc_args(e, a);
     a.layers = tab_dev;
     a.n_layers = n;
     a.idx = e->idx.p;
@@ -984,11 +1010,86 @@ extern "C" int prb_xsc_place(prb_engine *e, int64_t n_out, int64_t dst0, int64_t
     if (interp) CK(cudaMemcpyAsync(e->scratch_a.p, file_x, sizeof(double) * n_file, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->scratch_c.p, file_y, sizeof(double) * n_file, cudaMemcpyHostToDevice, e->stream));
     k3_xsc_place<<<stream_grid(e, n_out), 256, 0, e->stream>>>(n_out, dst0, src0, count, interp, ax0, adelta, n_file,
-                                                              e->scratch_a.p, e->scratch_c.p, e->scratch_b.p);
+                                                              e->scratch_a.p, e->scratch_c.p, e->scratch_b.p, 0);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, e->scratch_b.p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return PRB_OK;
+}
+
+// ------------------------------------------------------------------------------------ resident xsc tables
+// An xsc molecule's cross section does not depend on the layer (the table IS the spectrum at its own T and P,
+// pyradClasses.py:466-505), so the table is kept on the device with its placement plan and resampled onto the owned grid
+// chunk once per grid (k3_xsc_place: np.interp arithmetic + aligned placement); every layer's line sum then picks up
+// sigma_t * conc_t P / 1e4 / kB / T in K2's epilogue (k2_add_xsc) -- no separate pass over k, no host round trip.
+extern "C" int prb_xsc_resident(prb_engine *e, int32_t slot, int64_t n_out, int64_t dst0, int64_t src0, int64_t count,
+                                int interp, double ax0, double adelta, int64_t n_file, const double *file_x,
+                                const double *file_y) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (slot < 0 || slot >= K2_MAX_XSC || slot > e->n_xsc)
+        return fail(PRB_ERR_ARG, "prb_xsc_resident: slot must be an existing table or the next free one (at most 8 tables)");
+    if (n_out < 0 || count < 0 || n_file < 1 || !file_y || (interp && !file_x))
+        return fail(PRB_ERR_ARG, "prb_xsc_resident: bad arguments");
+    CK(cudaSetDevice(e->device));
+    XscTable &t = e->xsc[slot];
+    t.n_out = n_out; t.dst0 = dst0; t.src0 = src0; t.count = count; t.interp = interp; t.ax0 = ax0; t.adelta = adelta;
+    t.n_file = n_file;
+    CK(t.fx.ensure(n_file));
+    CK(t.fy.ensure(n_file));
+    if (interp) CK(cudaMemcpyAsync(t.fx.p, file_x, sizeof(double) * n_file, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(t.fy.p, file_y, sizeof(double) * n_file, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));                       // the caller's arrays are free again
+    if (slot == e->n_xsc) ++e->n_xsc;
+    e->xsc_rows_valid = false;
+    return PRB_OK;
+}
+
+extern "C" int prb_xsc_clear(prb_engine *e) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    e->n_xsc = 0;
+    e->xsc_rows_valid = false;
+    e->xsc_conc.clear();
+    e->xsc_conc_layers = 0;
+    return PRB_OK;
+}
+
+extern "C" int prb_set_xsc_conc(prb_engine *e, int32_t n_layers, int32_t n_xsc, const double *conc) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (n_layers < 0 || n_xsc != e->n_xsc || (n_layers > 0 && n_xsc > 0 && !conc))
+        return fail(PRB_ERR_ARG, "prb_set_xsc_conc: n_xsc must equal the number of resident tables");
+    e->xsc_conc.assign(conc, conc + (size_t)n_layers * n_xsc);
+    e->xsc_conc_layers = n_layers;
+    return PRB_OK;
+}
+
+// The resident tables resampled onto the owned chunk (rebuilt when the grid or a table changed); enqueue only.
+static int ensure_xsc_rows(prb_engine *e) {
+    if (e->n_xsc == 0) return PRB_OK;
+    if (e->xsc_rows_valid && e->xsc_sig[0] == e->i_begin && e->xsc_sig[1] == e->i_end && e->xsc_sig[2] == e->n_total)
+        return PRB_OK;
+    const int64_t nc = chunk_len(e);
+    e->xsc_ld = (nc + 3) & ~int64_t(3);
+    CK(e->xsc_rows.ensure((size_t)std::max<int64_t>(e->xsc_ld, 1) * e->n_xsc));
+    for (int t = 0; t < e->n_xsc; ++t) {
+        const XscTable &x = e->xsc[t];
+        if (x.n_out != e->n_total)
+            return fail(PRB_ERR_ARG, "resident xsc table was planned for a different grid length (prb_xsc_resident n_out)");
+        if (nc > 0)
+            k3_xsc_place<<<stream_grid(e, nc), 256, 0, e->stream>>>(nc, x.dst0, x.src0, x.count, x.interp, x.ax0, x.adelta,
+                                                                    x.n_file, x.fx.p, x.fy.p,
+                                                                    e->xsc_rows.p + (size_t)t * e->xsc_ld, e->i_begin);
+        CK(cudaGetLastError());
+        ++e->xsc_build_launches;
+    }
+    e->xsc_rows_valid = true;
+    e->xsc_sig[0] = e->i_begin; e->xsc_sig[1] = e->i_end; e->xsc_sig[2] = e->n_total;
+    return PRB_OK;
+}
+
+static void xsc_args(const prb_engine *e, K2Args &a) {
+    a.n_xsc = e->n_xsc;
+    a.xsc_sigma = e->xsc_rows.p;
+    a.xsc_ld = e->xsc_ld;
 }
 
 // ------------------------------------------------------------------------------------ atmosphere
@@ -1035,6 +1136,10 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
     if (ps.connected && nc > ps.ld) return fail(PRB_ERR_ARG, "prb_atmosphere: owned chunk exceeds the peer gather slot");
     if (e->host_rad_dev && nc > e->host_result_len)
         return fail(PRB_ERR_ARG, "prb_atmosphere: owned chunk exceeds the host result buffers (prb_set_result_host)");
+    if (e->n_xsc > 0 && e->xsc_conc_layers != n_layers)
+        return fail(PRB_ERR_ARG, "prb_atmosphere: resident xsc tables need their mole fractions for these layers "
+                                 "(prb_set_xsc_conc with the same n_layers), or prb_xsc_clear");
+    if ((rc = ensure_xsc_rows(e))) return rc;
 
     // Everything small the kernels of this call read -- status blocks (zeroed: flags + tile counters), per-(layer,
     // group) params, fold constants, the K2 launch table (K1's is a kernel parameter) -- is built in ONE pinned block and uploaded with
@@ -1093,6 +1198,8 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
         } else {
             jobs[l] = plan_job(e, t_layer[l], p_layer[l], window_len[l], pick_scale(e->s_max, w_max));
         }
+        for (int x = 0; x < e->n_xsc; ++x)                      // absCoef of an xsc molecule, same factor (:581-583)
+            jobs[l].xsc_w[x] = e->xsc_conc[(size_t)l * e->n_xsc + x] * p_layer[l] / 1E4 / kBoltz / t_layer[l];
         jobs[l].gp_dev = gp_dev + (size_t)l * n_groups;
         jobs[l].st_dev = st_dev + l;
         jobs[l].out_dev = e->kmat.p + (size_t)l * e->kmat_ld;
@@ -1179,7 +1286,8 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
         }
     }
     CK(cudaMemcpyAsync(e->blk_d.p, e->blk_h, blk_bytes, cudaMemcpyHostToDevice, e->stream));
-    int launches = 0;
+    int launches = e->xsc_build_launches;
+    e->xsc_build_launches = 0;
     e->extra_launches = 0;
     if (pipe) {
         if (!fused) return fail(PRB_ERR_STATE, "pipelined upload needs the fused single-layer path");
@@ -1230,6 +1338,7 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
             ka.out_mode = PRB_OUT_F32;
             ka.st = st_dev + sidx;
             ka.fuse = fuse;
+            xsc_args(e, ka);
             ka.tile_base = pipe->tile_lo[sidx];
             ka.n_tiles = pipe->tile_hi[sidx] - pipe->tile_lo[sidx];
             cudaError_t ce;
@@ -1254,7 +1363,7 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
         for (int c0 = b0; c0 < b1;) {                            // runs of one kernel class (sorted by window)
             int c1 = c0 + 1;
             while (c1 < b1 && jobs[c1].narrow == jobs[c0].narrow && (jobs[c0].narrow || jobs[c1].ppt == jobs[c0].ppt)) ++c1;
-            rc = run_line_sum(e, jobs.data() + c0, c1 - c0, k2_dev + c0, PRB_OUT_F32, fused ? &fuse : nullptr);
+            rc = run_line_sum(e, jobs.data() + c0, c1 - c0, k2_dev + c0, PRB_OUT_F32, fused ? &fuse : nullptr, true);
             if (rc) return rc;
             ++launches;
             c0 = c1;

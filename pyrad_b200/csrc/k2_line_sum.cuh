@@ -82,6 +82,7 @@ __device__ __forceinline__ int warp_lower_bound(const int32_t *__restrict__ idx,
 // One layer of a (possibly multi-layer) launch.  A launch walks work items (layer, tile) handed out by one
 // dynamic counter, layers in table order (the host sorts them widest window first, so the expensive items
 // start first and the tail of the launch is made of cheap ones).
+constexpr int K2_MAX_XSC = 8;   // resident xsc cross-section tables a layer can carry (prb_xsc_resident)
 struct K2Layer {
     const float4 *recA;
     const float4 *recB;
@@ -91,6 +92,7 @@ struct K2Layer {
     int l_begin, l_end;        // line range prepared by K1 for this shard and window
     int wm;                    // W-2 clamped at 0: max |d| that still accumulates
     int pad;
+    double xsc_w[K2_MAX_XSC];  // absCoef weight conc P / 1e4 / kB / T of every resident xsc table in this layer
 };
 
 // Optional fused single-layer epilogue (gas cell): the pointwise layer physics of K3 applied to the finished
@@ -130,7 +132,19 @@ struct K2Args {
     // level 2 of the far field: the same for a DOMAIN of K2_FAR2_SPANS consecutive spans, table [K2_FAR_NODES][domain]
     const double *far_lag2;
     float far_delta2[16];
+    // resident xsc tables (pyradClasses.py:466-505, 707-712): sigma[t * xsc_ld + i] on the owned chunk; the finished line
+    // sum of a layer gets  + sum_t sigma_t[i] * xsc_w[t]  in the epilogue, before it is rounded to the output type
+    const double *xsc_sigma;
+    long long xsc_ld;
+    int n_xsc;
 };
+
+// k of one grid point: the line sum plus the layer's xsc molecules (Layer.absCoef adds molecule by molecule, :707-712).
+__device__ __forceinline__ double k2_add_xsc(const K2Args &a, const K2Layer *L, int i, double v) {
+    for (int t = 0; t < a.n_xsc; ++t)
+        v = __dadd_rn(v, __dmul_rn(__ldg(a.xsc_sigma + (long long)t * a.xsc_ld + i), __ldg(&L->xsc_w[t])));
+    return v;
+}
 
 // Far-field evaluation of the Lorentz wings (variant PRB_K2_FARFIELD; spans of 128 and 256 points).  A line whose
 // centre lies more than ONE span length from the centre of a warp's span, and whose window covers the whole span,
@@ -725,7 +739,7 @@ __device__ __forceinline__ void k2_line_sum_body(const K2Args &a) {
             for (int p = 0; p < P; ++p) {
                 const int i = wb + 32 * p + lane;
                 if (i < a.n_chunk) {
-                    const double v = s.acc(p) * inv_scale;
+                    const double v = k2_add_xsc(a, L, i, s.acc(p) * inv_scale);
                     if (a.out_mode == 0) reinterpret_cast<double *>(out)[i] = v;
                     else reinterpret_cast<float *>(out)[i] = (float)v;
                     if (a.fuse.enabled) {

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(KN_THREADS, 4) k2_narrow(const K2Args a) {
     for (int r = 0; r < KN_ROUNDS; ++r) {
         const int i = tile0 + r * KN_THREADS + tid;
         if (i < a.n_chunk) {
-            const double v = acc[r] * inv_scale;
+            const double v = k2_add_xsc(a, L, i, acc[r] * inv_scale);
             if (a.out_mode == 0) reinterpret_cast<double *>(out)[i] = v;
             else reinterpret_cast<float *>(out)[i] = (float)v;
         }

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(KP_THREADS, 4) k2_point(const K2Args a) {
     for (int r = 0; r < KP_ROUNDS; ++r) {
         const int i = tile0 + r * KP_THREADS + tid;
         if (i < a.n_chunk) {
-            const double v = acc[r] * inv_scale;
+            const double v = k2_add_xsc(a, L, i, acc[r] * inv_scale);
             if (a.out_mode == 0) reinterpret_cast<double *>(out)[i] = v;
             else reinterpret_cast<float *>(out)[i] = (float)v;
         }

@@ -65,11 +65,14 @@ __device__ __forceinline__ double np_interp(double x, const double *__restrict__
     return __dadd_rn(__dmul_rn(slope, __dsub_rn(x, xp[lo])), fp[lo]);
 }
 
+// out[0 .. n_out) holds the grid points [i_first, i_first + n_out) of the placement (i_first = 0: the whole grid; the
+// resident tables of the atmosphere path are built for the owned chunk only).
 __global__ void __launch_bounds__(256)
 k3_xsc_place(int64_t n_out, int64_t dst0, int64_t src0, int64_t count, int interp, double ax0, double adelta,
-             int64_t n_file, const double *__restrict__ fx, const double *__restrict__ fy, double *__restrict__ out) {
+             int64_t n_file, const double *__restrict__ fx, const double *__restrict__ fy, double *__restrict__ out,
+             int64_t i_first) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = i - dst0;
+        const int64_t j = i_first + i - dst0;
         double v = 0.0;
         if (j >= 0 && j < count) {
             const int64_t m = src0 + j;

@@ -224,6 +224,22 @@ class Engine:
                                            float(ax0), float(adelta), fy.size, _dp(fx), _dp(fy), _dp(out)))
         return out
 
+    def xsc_resident(self, slot, n_out, dst0, src0, count, file_x, file_y, interp, ax0=0.0, adelta=0.0):
+        """Keep xsc table `slot` on the device with its placement plan (the arguments of xsc_place); the following
+        atmosphere() / gas_cell_host() calls add it to every layer's k(nu) with the mole fractions of set_xsc_conc()."""
+        fy = _f64(file_y)
+        fx = _f64(file_x) if file_x is not None else None
+        _lib.check(self._lib.prb_xsc_resident(self._h, int(slot), int(n_out), int(dst0), int(src0), int(count),
+                                              int(bool(interp)), float(ax0), float(adelta), fy.size, _dp(fx), _dp(fy)))
+
+    def set_xsc_conc(self, conc):
+        """conc: (L, n_xsc) mole fractions of the resident xsc tables in every layer of the next atmosphere() call."""
+        c = _f64(np.atleast_2d(conc))
+        _lib.check(self._lib.prb_set_xsc_conc(self._h, c.shape[0], c.shape[1], _dp(c)))
+
+    def xsc_clear(self):
+        _lib.check(self._lib.prb_xsc_clear(self._h))
+
     def atmosphere_call(self, depth_cm, t_layer, p_layer, conc, molmass, q_t, q_296, window, t_surface, range_max):
         """The prb_atmosphere call with its arguments marshalled ONCE: returns a zero-argument callable for callers that
         repeat the same column (a step loop) -- per call only the ctypes transition is left on the host."""

@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     for s in syms:
         assert hasattr(lib, s), "libpyrad_b200.so does not export %s" % s
     assert sorted(_lib.PROTOTYPES) == syms, "ctypes prototypes and header differ"
-    assert lib.prb_abi_version() == 2
+    assert lib.prb_abi_version() == 3
 
 
 def test_header_has_no_torch_or_cxx_types():

@@ -163,6 +163,60 @@ def test_cfg3_full_size_line_by_line_plus_xsc_tables(engine, tmp_path):
         C.DATA_ROOT = None
 
 
+@pytest.mark.parametrize("xsc_scale", [1.0, 1e6])
+def test_cfg3_full_size_through_one_engine_call(engine, xsc_scale):
+    """cfg3 at full size as ONE prb_atmosphere call through the C ABI: CO2 + H2O line lists (two groups) and the CFC-11 /
+    HCFC-22 xsc tables resident on the device (prb_xsc_resident: the native-resolution table placed, the 0.05 cm-1 table
+    re-gridded with np.interp's arithmetic), added to the line sum in K2's epilogue.  k, transmittance and radiance at
+    EVERY grid point against the oracle (pyradClasses.py:466-505, 581-587, 707-716, 784-787).  At cfg3's own mole fractions
+    (250 / 230 ppt) the tables' optical depth is 5e-7 -- below the transmittance tolerance --, so the cell is also run with
+    them a million times more abundant (optical depth 0.5), where a missing or misplaced table fails every assertion."""
+    import torch
+    from pyrad_b200 import classes as C
+    from pyrad_b200 import distributed as pd
+    w = workloads.cfg3()
+    for x in w["xsc"]:
+        x["conc"] = x["conc"] * xsc_scale
+    n = H.engine_setup(engine, w)
+    xa = ph.x_axis(w["range_min"], w["range_max"], w["res"])
+    k_ref = np.zeros(n)
+    engine.xsc_clear()
+    try:
+        for slot, x in enumerate(w["xsc"]):
+            grid01 = np.arange(x["range_min"], x["range_max"], .01)
+            dst0, src0, count, out_len = C._merge_plan(xa, grid01)
+            assert out_len == n
+            coarse = x["res"] > .01
+            engine.xsc_resident(slot, n, dst0, src0, count, x["wavenumber"] if coarse else None, x["intensity"], coarse,
+                                ax0=float(grid01[0]), adelta=float(grid01[1] - grid01[0]))
+            sig = ph.xsc_cross_section(xa, x["wavenumber"], x["intensity"], x["range_min"], x["range_max"], x["res"])
+            assert np.count_nonzero(sig) > 5000
+            k_ref += ph.abs_coef(sig, x["conc"], w["P"], w["T"])
+        engine.set_xsc_conc([[x["conc"] for x in w["xsc"]]])
+        rad, tr = _column(engine, w)
+        assert engine.atmosphere_launches() == 4                  # two table resamplings + K1 + K2 (fused): one engine call
+        kp, ld = engine.atmosphere_kmatrix_dev()
+        k = pd.device_tensor(kp, ld)[:n].cpu().numpy().astype(np.float64)
+        # a second call reuses the resampled tables
+        rad2, tr2 = _column(engine, w)
+        assert engine.atmosphere_launches() == 2 and np.array_equal(tr, tr2) and np.array_equal(rad, rad2, equal_nan=True)
+    finally:
+        engine.xsc_clear()
+    for g, sp in enumerate(w["species"]):
+        ln = H.kept(w["per_group_lines"][g], w["range_min"], w["range_max"], w["cutoff"])
+        sig = ph.cross_section(ln, w["T"], w["P"], w["conc"][g], sp.molmass, sp.q(w["T"]), sp.q296, w["range_min"],
+                               w["range_max"], w["res"], w["cutoff"])
+        k_ref += ph.abs_coef(sig, w["conc"][g], w["P"], w["T"])
+    assert H.k_rel_err(k, k_ref).max() <= H.K_REL_TOL             # (FP32 row of the k matrix: 6e-8 of rounding on top)
+    t_ref = ph.transmittance(k_ref, w["depth_cm"])
+    assert np.abs(tr - t_ref).max() <= H.T_ABS_TOL
+    rad_ref = ph.transmission(t_ref, ph.planck_wavenumber(xa, 288.0), ph.planck_wavenumber(xa, w["T"]))
+    np.testing.assert_allclose(rad, rad_ref, rtol=2e-5)
+    # without the tables the call is a different spectrum
+    _, tr0 = _column(engine, w)
+    assert (np.abs(tr0 - t_ref).max() > 1e-3) == (xsc_scale > 1)
+
+
 def _column(engine, w):
     sp = w["species"]
     win = [eng.window_len(c, w["res"]) for c in np.atleast_1d(w["cutoff"])]

@@ -4,6 +4,7 @@ REAL reference produced (tests/golden/make_golden.py).  Reads like the reference
 import numpy as np
 import pytest
 
+from oracle import physics as ph
 from oracle import ref_harness as rh          # only its data-tree writers (test infrastructure)
 from pyrad_b200 import classes as C
 from pyrad_b200 import synth
@@ -131,6 +132,33 @@ def test_mirror_matches_reference_cfg3_miniature(data_root):
     np.testing.assert_allclose(layer.transmission(surf), g["layer_transmission"], rtol=2e-5)
 
 
+def test_cfg3_miniature_through_one_engine_call(data_root):
+    """The same cell as ONE engine call (Atmosphere.columnSpectrum -> prb_atmosphere): both xsc tables resident on the
+    device (prb_xsc_resident), resampled onto the grid there, and added to the line sum inside K2's epilogue -- against
+    the real reference's transmittance and Layer.transmission on the same files (pyradClasses.py:466-505, 707-716, 784-787).
+    (At the golden's ppt mole fractions the tables are a 1e-7 effect; the column test below and the full-size cfg3 test
+    run them abundant enough to fail on a missing table.)"""
+    g = G.load("cfg3_mini")
+    names = [str(s) for s in g["species"]]
+    for i, s in enumerate(names):
+        seed(data_root, g, i, s)
+    fnames = [rh.write_xsc_file(data_root, str(g["xsc_names"][i]), 296.0, 760.0, float(g["xsc_rmin"][i]),
+                                float(g["xsc_rmax"][i]), float(g["xsc_res"][i]), g["xsc_x_%d" % i], g["xsc_y_%d" % i])
+              for i in range(2)]
+    atm = C.Atmosphere("cfg3")
+    layer = atm.addLayer(float(g["depth"]), 280, 900.0, float(g["range_min"]), float(g["range_max"]), dynamicResolution=False)
+    for i in range(2):
+        layer.addMolecule({str(g["xsc_names"][i]): fnames[i]}, concentration=float(g["xsc_conc"][i]))
+    for s, c in zip(names, g["conc"]):
+        layer.addMolecule(s, concentration=float(c))
+    assert layer.T == int(g["T_after"]) and layer.P == float(g["P_after"])
+    e = C.engine()
+    rad, trans = atm.columnSpectrum(int(g["surface_T"]))
+    assert e.atmosphere_launches() == 4                            # two table resamplings, K1, K2 (fused epilogue): no K3
+    assert np.abs(trans - g["layer_transmittance"]).max() <= H.T_ABS_TOL
+    np.testing.assert_allclose(rad, g["layer_transmission"], rtol=2e-5)
+
+
 def test_mirror_error_behaviour(data_root):
     g = G.load("cell_co2_1atm")
     seed(data_root, g, 0, "co2")
@@ -166,6 +194,40 @@ def test_mirror_column_spectrum_equals_layer_by_layer_transmission(data_root):
         t_ref = t_ref * C.getTransmittance(layer)
     assert np.abs(trans - t_ref).max() <= H.T_ABS_TOL
     np.testing.assert_allclose(rad, ref, rtol=3e-5)
+
+
+def test_mirror_column_spectrum_carries_xsc_molecules(data_root):
+    """A column whose layers carry xsc molecules -- one table in every layer at different mole fractions, a second one
+    in a single layer -- through ONE engine call, against the layer-by-layer fold of Layer.transmission (FP64 host path,
+    which the goldens pin against the real reference)."""
+    g = G.load("cfg3_mini")
+    names = [str(s) for s in g["species"]]
+    for i, s in enumerate(names):
+        seed(data_root, g, i, s)
+    fnames = [rh.write_xsc_file(data_root, str(g["xsc_names"][i]), 296.0, 760.0, float(g["xsc_rmin"][i]),
+                                float(g["xsc_rmax"][i]), float(g["xsc_res"][i]), g["xsc_x_%d" % i], g["xsc_y_%d" % i])
+              for i in range(2)]
+    atm = C.Atmosphere("column with xsc")
+    rmin, rmax = float(g["range_min"]), float(g["range_max"])
+    for k, depth in enumerate((30.0, 50.0, 80.0)):
+        layer = atm.addLayer(depth, 280, 900.0, rmin, rmax, dynamicResolution=False)
+        layer.addMolecule({str(g["xsc_names"][0]): fnames[0]}, concentration=float(g["xsc_conc"][0]) * (k + 1) * 2e5)
+        if k == 1:
+            layer.addMolecule({str(g["xsc_names"][1]): fnames[1]}, concentration=float(g["xsc_conc"][1]) * 1e6)
+        for s, c in zip(names, g["conc"]):
+            layer.addMolecule(s, concentration=float(c))
+    rad, trans = atm.columnSpectrum(288)
+    ref = atm.transmission(atm[0].planck(288))
+    t_ref = np.ones_like(ref)
+    for layer in atm:
+        t_ref = t_ref * C.getTransmittance(layer)
+    assert np.abs(trans - t_ref).max() <= H.T_ABS_TOL
+    np.testing.assert_allclose(rad, ref, rtol=3e-5)
+    # and the engine is clean afterwards: the same column without its xsc molecules differs
+    for layer in atm:
+        layer[:] = [m for m in layer if not m.exotic]
+    _, trans2 = atm.columnSpectrum(288)
+    assert np.abs(trans2 - t_ref).max() > 1e-4
 
 
 # ---------------------------------------------------------------- xsc file utilities (SURVEY 8(f) row 4)
