@@ -97,6 +97,17 @@ int prb_upload_lines(prb_engine *e, int64_t n,
                      const double *elower, const double *n_air, const double *delta_air,
                      const int32_t *group, int32_t n_groups);
 
+/* Grouped line list (section 8(b): per-group output rows in one pass; pyradClasses.py:350-359, 498-503, 566-576): the
+ * host objects hold one line list per isotopologue, each ascending in nu0.  They are uploaded as they are -- group g is
+ * entries [offsets[g], offsets[g+1]) of the columns, offsets[0] = 0, no merge sort -- and prb_line_sum_groups returns one
+ * cross-section row per group from ONE prepass + ONE line-sum launch (every group walks only its own lines).  Replaces
+ * prb_upload_lines; prb_set_grid / prb_layer_prepass / prb_pair_count / prb_line_survey work as before, prb_line_sum and
+ * prb_atmosphere need the single ascending list of prb_upload_lines. */
+int prb_upload_line_groups(prb_engine *e, int32_t n_groups, const int64_t *offsets,
+                           const double *nu0, const double *s296,
+                           const double *gamma_air, const double *gamma_self,
+                           const double *elower, const double *n_air, const double *delta_air);
+
 /* Line list straight from HITRAN-online CSV text (section 8(f) row 1; pyradUtilities.py:173-189, 421-448): `text`
  * is the concatenation of the segment files (host memory; rows molec,iso,nu,sw,a,elower,gamma_air,gamma_self,
  * delta_air,n_air; rows starting with '#' are skipped).  Parsed ON THE DEVICE with exact decimal->double
@@ -133,6 +144,16 @@ int prb_layer_prepass(prb_engine *e, double T, double P, int32_t n_groups,
 /* ---- K2 (a7-a10): sum of line shapes into the owned grid chunk; out has i_end-i_begin entries. */
 int prb_line_sum(prb_engine *e, double *out_host);
 int prb_line_sum_dev(prb_engine *e, void *out_dev, int out_mode);
+/* Per-group rows of the last prepass, one K2 launch: out_host [n_groups][i_end-i_begin] row-major, or NULL to leave
+ * the rows on the device for prb_layer_spectra_resident. */
+int prb_line_sum_groups(prb_engine *e, double *out_host);
+/* absCoef / transmittance / Layer.transmission (pyradClasses.py:581-587, 707-716, 784-787) from rows already on the
+ * device: k = sum_g sigma_g * group_weight[g] (the rows of the last prb_line_sum_groups) + sum_t xsc_t * xsc_weight[t]
+ * (the resident xsc tables; xsc_weight NULL: none).  FP64 host buffers of chunk length; any output may be NULL; the
+ * wavenumber axis is linspace(range_min, range_max, n_total) as in prb_atmosphere. */
+int prb_layer_spectra_resident(prb_engine *e, const double *group_weight, const double *xsc_weight,
+                               double depth_cm, double t_layer, double range_max, const double *radiance_in,
+                               double *abs_coef, double *transmittance, double *radiance_out);
 int64_t prb_pair_count(prb_engine *e);                  /* accumulations of the last prepass' window on the owned chunk; <0 = error */
 
 /* ---- K1 introspection for parity tests: FP64 per-line values of the last prepass (host buffers,

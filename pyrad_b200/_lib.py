@@ -43,6 +43,7 @@ PROTOTYPES = {
     "prb_set_k2_variant": (C.c_int, [_vp, C.c_int, C.c_int]),
     "prb_set_narrow_threshold": (C.c_int, [_vp, _i64]),
     "prb_upload_lines": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _i32]),
+    "prb_upload_line_groups": (C.c_int, [_vp, _i32, _lp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "prb_ingest_hitran_csv": (C.c_int, [_vp, C.c_char_p, _i64, _d, _d, _lp]),
     "prb_download_lines": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "prb_line_count": (_i64, [_vp]),
@@ -52,6 +53,8 @@ PROTOTYPES = {
     "prb_layer_prepass": (C.c_int, [_vp, _d, _d, _i32, _dp, _dp, _dp, _dp, _dp, _i64]),
     "prb_line_sum": (C.c_int, [_vp, _dp]),
     "prb_line_sum_dev": (C.c_int, [_vp, _vp, C.c_int]),
+    "prb_line_sum_groups": (C.c_int, [_vp, _dp]),
+    "prb_layer_spectra_resident": (C.c_int, [_vp, _dp, _dp, _d, _d, _d, _dp, _dp, _dp, _dp]),
     "prb_pair_count": (_i64, [_vp]),
     "prb_debug_line_params": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _ip, _lp]),
     "prb_layer_stream": (C.c_int, [_vp, _i64, _i32, _dp, _dp, _d, _d, _d, _d, _d, _dp, _dp, _dp, _dp]),

@@ -40,6 +40,8 @@ DATA_ROOT = None
 _MAX_SPAN = 1 << 23
 
 _ENGINE = None
+#: state key of the Layer whose per-isotopologue rows the engine currently holds (Layer._device_rows)
+_RESIDENT_KEY = None
 
 
 def engine():
@@ -51,8 +53,9 @@ def engine():
 
 
 def set_engine(e):
-    global _ENGINE
+    global _ENGINE, _RESIDENT_KEY
     _ENGINE = e
+    _RESIDENT_KEY = None
 
 
 def _n_base(obj):
@@ -108,9 +111,11 @@ def resetCrossSection(obj):
             obj.progressCrossSection = False
     else:
         obj.progressCrossSection = False
+        obj._cs = None                                # the layer's own sum is rebuilt from its molecules on demand
+    if isinstance(obj, Isotope):
+        return                                        # its children are lines (views): nothing to reset
     for child in obj:
-        if not isinstance(child, Line):
-            resetCrossSection(child)
+        resetCrossSection(child)
 
 
 def resetData(obj):
@@ -284,6 +289,10 @@ class _Spectral:
 
 
 class Isotope(list, _Spectral):
+    """An isotopologue and its lines.  The reference fills the list with one Line object per transition
+    (pyradClasses.py:350-359); here the transitions live in SoA columns and the list protocol hands out Line VIEWS on
+    demand (len / iteration / indexing / linelist()), so a 5 M-line list costs its columns, not 5 M Python objects."""
+
     def __init__(self, number, molecule):
         list.__init__(self)
         self.molecule = molecule
@@ -322,20 +331,50 @@ class Isotope(list, _Spectral):
     def molMass(self):
         return self.molmass / 1000 / avo
 
+    # -- the list protocol over the SoA columns (views are created when asked for)
+    def __len__(self):
+        return len(self._cols["nu"])
+
+    def __bool__(self):
+        return True
+
+    def __iter__(self):
+        return (Line(self, i) for i in range(len(self)))
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [Line(self, j) for j in range(*i.indices(len(self)))]
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError("line index out of range")
+        return Line(self, i)
+
+    def __eq__(self, other):
+        return self is other
+
+    def __ne__(self, other):
+        return self is not other
+
+    __hash__ = object.__hash__
+
     def clearLines(self):
-        del self[:]
         self._cols = {kname: np.zeros(0) for kname in _io.LINE_COLUMNS}
 
     def setLines(self, cols, q_table=None):
-        """Attach a line list directly (SoA float64 columns, ascending nu) instead of reading the data tree."""
-        self._cols = {kname: np.ascontiguousarray(cols[kname], dtype=np.float64) for kname in _io.LINE_COLUMNS}
-        del self[:]
-        self.extend(Line(self, i) for i in range(len(self._cols["nu"])))
+        """Attach a line list directly (SoA float64 columns, ascending nu) instead of reading the data tree.  A column
+        that is absent (the Einstein A of a synthetic list) reads as zeros."""
+        n = len(cols["nu"])
+        self._cols = {kname: (np.ascontiguousarray(cols[kname], dtype=np.float64) if kname in cols else np.zeros(n))
+                      for kname in _io.LINE_COLUMNS}
         if q_table is not None:
             self.q = q_table
         self.progressCrossSection = False
 
     def getData(self):
+        global _RESIDENT_KEY
+        _RESIDENT_KEY = None                          # the device parser replaces the engine's line list
         cols = _io.gather_lines(self.globalIsoNumber, self.layer.effectiveRangeMin, self.layer.effectiveRangeMax,
                                 DATA_ROOT, engine())
         self.setLines(cols, _io.read_q_table(self.globalIsoNumber, DATA_ROOT))
@@ -346,6 +385,14 @@ class Isotope(list, _Spectral):
         res = layer.resolution
         n_res = int((self.rangeMax - self.rangeMin) / res)
         q_t = self.q[layer.T]                                  # KeyError on a non-tabulated T, as the reference
+        rows = layer._group_rows() if isinstance(layer, Layer) else None
+        if rows is not None and id(self) in rows:
+            # ONE upload + ONE prepass + ONE line-sum launch made every isotopologue's row of this layer
+            self.crossSection = rows[id(self)]
+            self.progressCrossSection = True
+            return
+        global _RESIDENT_KEY
+        _RESIDENT_KEY = None
         e = engine()
         window = _eng.window_len(layer.distanceFromCenter, res)
         wm = max(window - 2, 0)
@@ -371,6 +418,8 @@ class Isotope(list, _Spectral):
         n_out = _n_base(self)
         nu = self._cols["nu"]
         if nu.size:
+            global _RESIDENT_KEY
+            _RESIDENT_KEY = None
             e = engine()
             e.upload_lines(self._cols, 1)
             e.set_grid(self.layer.rangeMin, self.layer.resolution, max(n_out, 1))
@@ -381,7 +430,7 @@ class Isotope(list, _Spectral):
         return survey
 
     def linelist(self):
-        return list(self)
+        return [Line(self, i) for i in range(len(self))]
 
     def planck(self, temperature):
         return self.layer.planck(temperature)
@@ -553,7 +602,8 @@ class Layer(list, _Spectral):
         else:
             self.atmosphere = atmosphere
             self.hasAtmosphere = atmosphere
-        self.crossSection = np.zeros(int((rangeMax - rangeMin) / BASE_RESOLUTION))
+        self._cs = np.zeros(int((rangeMax - rangeMin) / BASE_RESOLUTION))
+        self._rows_cache = (None, None)
         self.progressCrossSection = False
         self.exotic = False
         self.name = name or "layer %s" % self.atmosphere.nextLayerName()
@@ -572,11 +622,30 @@ class Layer(list, _Spectral):
     layer = property(lambda s: s)
 
     def createCrossSection(self):
+        if self._device_rows():
+            # the rows are on the device; the layer's own (unweighted) sum and its children's rows are fetched when
+            # somebody asks for them (crossSection below, Isotope.createCrossSection)
+            self._cs = None
+            self.progressCrossSection = True
+            return
         total = np.zeros(_n_base(self))
         for m in self:
             total += getCrossSection(m)
         self.progressCrossSection = True
         self.crossSection = total
+
+    @property
+    def crossSection(self):
+        if self._cs is None:
+            total = np.zeros(_n_base(self))
+            for m in self:
+                total += getCrossSection(m)
+            self._cs = total
+        return self._cs
+
+    @crossSection.setter
+    def crossSection(self, value):
+        self._cs = value
 
     @property
     def lineSurvey(self):
@@ -603,6 +672,65 @@ class Layer(list, _Spectral):
         if not rows:
             return np.zeros((1, _n_base(self))), [0.0]
         return np.array(rows), [_eng.number_density_weight(m.concentration, self.P, self.T) for m in self]
+
+    # -- the device-resident path of a layer: every isotopologue's line list uploaded as it is (grouped, no merge),
+    #    ONE prepass, ONE line-sum launch with a row per isotopologue, xsc tables resident; k / T / transmission are then
+    #    formed on the device from those rows and only the requested spectrum crosses PCIe
+    def _isos(self):
+        return [iso for m in self if not m.exotic for iso in m]
+
+    def _state_key(self):
+        isos = self._isos()
+        return (id(self), self.T, self.P, self.rangeMin, self.rangeMax, self.resolution, self.distanceFromCenter, BASE_RESOLUTION,
+                tuple((id(iso._cols["nu"]), len(iso), iso.molmass, iso.q296, iso.molecule.concentration) for iso in isos),
+                tuple(m._xsc_key for m in self if m.exotic))
+
+    def _device_rows(self):
+        """Make the engine hold this layer's per-isotopologue rows (and xsc tables); False when the one-pass path does
+        not apply (dynamic resolution coarser than the base grid, a grid too long for one launch, no line-by-line
+        molecule, more than eight xsc tables) -- callers then take the per-isotopologue path."""
+        global _RESIDENT_KEY
+        isos = self._isos()
+        xmols = [m for m in self if m.exotic]
+        n = _n_base(self)
+        window = _eng.window_len(self.distanceFromCenter, self.resolution)
+        if not isos or self.resolution != BASE_RESOLUTION or len(xmols) > 8 or \
+                n + 2 * max(window - 2, 0) + 16384 >= _MAX_SPAN or n < 1:
+            return False
+        key = self._state_key()
+        if _RESIDENT_KEY == key:
+            return True
+        _RESIDENT_KEY = None
+        q_t = [iso.q[self.T] for iso in isos]                  # KeyError on a non-tabulated T, as the reference
+        e = engine()
+        e.upload_line_groups([iso._cols for iso in isos])
+        e.set_grid(self.rangeMin, self.resolution, n)
+        e.layer_prepass(self.T, self.P, [iso.molecule.concentration for iso in isos], [iso.molmass for iso in isos], q_t,
+                        [iso.q296 for iso in isos], window)
+        e.line_sum_groups(to_host=False)
+        e.xsc_clear()
+        for slot, m in enumerate(xmols):
+            e.xsc_resident(slot, **m._xsc_plan)
+        _RESIDENT_KEY = key
+        return True
+
+    def _group_rows(self):
+        """{id(isotopologue): cross-section row} of the layer's one-pass result (one D2H for all rows, cached until the
+        layer's state changes), or None when the one-pass path does not apply."""
+        if not self._device_rows():
+            return None
+        key = self._state_key()
+        if self._rows_cache[0] != key:
+            rows = engine().line_sum_groups(to_host=True)
+            self._rows_cache = (key, {id(iso): rows[g] for g, iso in enumerate(self._isos())})
+        return self._rows_cache[1]
+
+    def _stream(self, want, radiance_in=None):
+        if self._device_rows():
+            w = [_eng.number_density_weight(iso.molecule.concentration, self.P, self.T) for iso in self._isos()]
+            xw = [_eng.number_density_weight(m.concentration, self.P, self.T) for m in self if m.exotic]
+            return engine().layer_spectra_resident(w, self.depth, self.T, self.rangeMax, xw, radiance_in, want=want)
+        return _Spectral._stream(self, want, radiance_in)
 
     def changeRange(self, rangeMin, rangeMax):
         self.rangeMin = rangeMin
@@ -721,6 +849,8 @@ class Atmosphere(list):
         lines = {k: np.ascontiguousarray(v[order]) for k, v in cols.items()}
         lines["group"] = np.ascontiguousarray(group[order])
         n = _n_base(ref)
+        global _RESIDENT_KEY
+        _RESIDENT_KEY = None
         e = engine()
         e.upload_lines(lines, n_groups=max(len(isos), 1))
         e.set_grid(ref.rangeMin, BASE_RESOLUTION, n)

@@ -125,6 +125,10 @@ struct prb_engine {
     bool has_group = false;
     double s_max = 0;
     bool lines_set = false;
+    // grouped line list (prb_upload_line_groups): group g = device entries [seg[g], seg[g] + seg_cnt[g]), ascending within
+    // the group, segments 4-aligned; empty when the list is one globally ascending run (prb_upload_lines)
+    std::vector<int64_t> seg, seg_cnt;
+    bool group_rows_valid = false;   // out64 holds the per-group rows of the last prb_line_sum_groups
 
     // grid
     double range_min = 0, res = 0;
@@ -181,7 +185,7 @@ struct prb_engine {
     int64_t xsc_ld = 0;
     bool xsc_rows_valid = false;
     int64_t xsc_sig[3] = {-1, -1, -1};                // (i_begin, i_end, n_total) the rows were built for
-    int xsc_build_launches = 0;                       // resampling kernels enqueued since the last prb_atmosphere counted them
+    int xsc_build_launches = 0;                       // resampling kernels enqueued so far (a running count)
     std::vector<double> xsc_conc;                     // [xsc_conc_layers][n_xsc]
     int xsc_conc_layers = 0;
 
@@ -528,6 +532,74 @@ extern "C" int prb_upload_lines(prb_engine *e, int64_t n, const double *nu0, con
     e->lines_set = true;
     e->grid_set = false;
     e->last.valid = false;
+    e->seg.clear();
+    e->seg_cnt.clear();
+    e->group_rows_valid = false;
+    return PRB_OK;
+}
+
+// Grouped line list (per-group output rows in one pass).  The host object model holds one line list per
+// isotopologue, each ascending in nu0 (pyradClasses.py:350-359); they are uploaded as they are -- concatenated, no merge
+// sort -- and every group becomes its own work-item row of ONE K2 launch (prb_line_sum_groups), walking only its own
+// lines.  Segments start 16-byte aligned on the device (the TMA staging of K2 aligns its first record down by up to
+// three entries); the gap entries carry group -1 and are inert.
+extern "C" int prb_upload_line_groups(prb_engine *e, int32_t n_groups, const int64_t *offsets, const double *nu0,
+                                      const double *s296, const double *gamma_air, const double *gamma_self,
+                                      const double *elower, const double *n_air, const double *delta_air) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (n_groups < 1 || !offsets || offsets[0] != 0) return fail(PRB_ERR_ARG, "prb_upload_line_groups: bad offsets");
+    for (int g = 0; g < n_groups; ++g)
+        if (offsets[g + 1] < offsets[g]) return fail(PRB_ERR_ARG, "prb_upload_line_groups: offsets must be non-decreasing");
+    const int64_t n = offsets[n_groups];
+    if (n > 2000000000LL) return fail(PRB_ERR_ARG, "prb_upload_line_groups: too many lines");
+    if (n > 0 && (!nu0 || !s296 || !gamma_air || !gamma_self || !elower || !n_air || !delta_air))
+        return fail(PRB_ERR_ARG, "prb_upload_line_groups: NULL column");
+    CK(cudaSetDevice(e->device));
+    std::vector<int64_t> seg(n_groups + 1, 0), cnt(n_groups, 0);
+    for (int g = 0; g < n_groups; ++g) {
+        cnt[g] = offsets[g + 1] - offsets[g];
+        seg[g + 1] = (seg[g] + cnt[g] + 3) & ~int64_t(3);
+    }
+    const int64_t n_dev = seg[n_groups];
+    int rc = alloc_line_storage(e, n_dev);
+    if (rc) return rc;
+    const int64_t na = e->n_alloc;
+    CK(e->group.ensure(na));
+    DevBuf<double> *cols[7] = {&e->nu0, &e->s296, &e->gair, &e->gself, &e->elower, &e->nair, &e->delta};
+    const double *src[7] = {nu0, s296, gamma_air, gamma_self, elower, n_air, delta_air};
+    for (int g = 0; g < n_groups; ++g)
+        for (int c = 0; c < 7 && cnt[g]; ++c)
+            CK(cudaMemcpyAsync(cols[c]->p + seg[g], src[c] + offsets[g], sizeof(double) * cnt[g], cudaMemcpyHostToDevice,
+                               e->stream));
+    std::vector<int32_t> grp((size_t)std::max<int64_t>(n_dev, 1), -1);
+    double smax = 0;
+    bool sorted = true;
+    for (int g = 0; g < n_groups; ++g) {
+        std::fill(grp.begin() + seg[g], grp.begin() + seg[g] + cnt[g], g);
+        for (int64_t i = offsets[g]; i < offsets[g + 1]; ++i) {
+            const double sa = std::fabs(s296[i]);
+            smax = sa > smax ? sa : smax;
+            if (i > offsets[g] && !(nu0[i] >= nu0[i - 1])) sorted = false;
+        }
+    }
+    if (n_dev) {
+        CK(cudaMemcpyAsync(e->group.p, grp.data(), sizeof(int32_t) * n_dev, cudaMemcpyHostToDevice, e->stream));
+        k0_fill_gaps<<<(unsigned)((n_dev + 255) / 256), 256, 0, e->stream>>>(e->nu0.p, e->s296.p, e->group.p, n_dev);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    e->lines_set = false;
+    if (!sorted) return fail(PRB_ERR_ARG, "prb_upload_line_groups: nu0 must be ascending within every group");
+    e->has_group = true;
+    e->n_lines = n_dev;
+    e->n_groups = n_groups;
+    e->s_max = smax;
+    e->lines_set = true;
+    e->grid_set = false;
+    e->last.valid = false;
+    e->seg.assign(seg.begin(), seg.end() - 1);
+    e->seg_cnt = cnt;
+    e->group_rows_valid = false;
     return PRB_OK;
 }
 
@@ -552,6 +624,7 @@ extern "C" int prb_set_grid(prb_engine *e, double range_min, double res, int64_t
     e->grid_set = true;
     e->last.valid = false;
     e->xsc_rows_valid = false;
+    e->group_rows_valid = false;
     return PRB_OK;
 }
 
@@ -714,6 +787,7 @@ extern "C" int prb_layer_prepass(prb_engine *e, double T, double P, int32_t n_gr
     // (no synchronisation: a copy from pageable memory has left its source when cudaMemcpyAsync returns, and the
     // K1 layer table travels as a kernel parameter)
     e->last = j;
+    e->group_rows_valid = false;
     return PRB_OK;
 }
 
@@ -885,6 +959,7 @@ static int run_line_sum(prb_engine *e, const LayerJob *jobs, int n, const K2Laye
 extern "C" int prb_line_sum_dev(prb_engine *e, void *out_dev, int out_mode) {
     if (!e) return fail(PRB_ERR_ARG, "null engine");
     if (!e->last.valid) return fail(PRB_ERR_STATE, "prb_line_sum: run prb_layer_prepass first");
+    if (!e->seg.empty()) return fail(PRB_ERR_STATE, "prb_line_sum: grouped line list -- use prb_line_sum_groups");
     if (!out_dev) return fail(PRB_ERR_ARG, "prb_line_sum_dev: NULL output");
     if (out_mode != PRB_OUT_F64 && out_mode != PRB_OUT_F32) return fail(PRB_ERR_ARG, "prb_line_sum_dev: bad out_mode");
     CK(cudaSetDevice(e->device));
@@ -922,6 +997,79 @@ extern "C" int prb_line_sum(prb_engine *e, double *out_host) {
     return rc;
 }
 
+// Per-group rows in ONE K2 launch: group g is work-item row g (its own line range, its own output row), all rows share
+// the records of the last prepass and the launch's tile counter.  Rows stay on the device (prb_layer_spectra_resident
+// reads them there) and are copied to out_host [n_groups][chunk] when it is not NULL.  For a line list uploaded with
+// prb_upload_lines (one ascending run with group ids) there is a single row: the sum over the groups.
+extern "C" int prb_line_sum_groups(prb_engine *e, double *out_host) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (!e->last.valid) return fail(PRB_ERR_STATE, "prb_line_sum_groups: run prb_layer_prepass first");
+    if (e->seg.empty()) return fail(PRB_ERR_STATE, "prb_line_sum_groups: upload the lines with prb_upload_line_groups");
+    CK(cudaSetDevice(e->device));
+    const int64_t nc = chunk_len(e);
+    const int G = e->n_groups;
+    CK(e->out64.ensure((size_t)std::max<int64_t>(nc, 1) * G));
+    CK(e->k2tab.ensure(G));
+    std::vector<LayerJob> jobs(G, e->last);
+    std::vector<K2Layer> rows(G);
+    for (int g = 0; g < G; ++g) {
+        jobs[g].l0 = e->seg[g];
+        jobs[g].l1 = e->seg[g] + e->seg_cnt[g];
+        jobs[g].out_dev = e->out64.p + (size_t)g * nc;
+        fill_k2_row(e, jobs[g], rows[g]);
+    }
+    CK(cudaMemcpyAsync(e->k2tab.p, rows.data(), sizeof(K2Layer) * G, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(&jobs[0].st_dev->tile_counter, 0, sizeof(unsigned int), e->stream));
+    int rc = run_line_sum(e, jobs.data(), G, e->k2tab.p, PRB_OUT_F64, nullptr);
+    if (rc) return rc;
+    if (out_host && nc) CK(cudaMemcpyAsync(out_host, e->out64.p, sizeof(double) * nc * G, cudaMemcpyDeviceToHost, e->stream));
+    rc = check_flags(e, 1);                                     // synchronises (the pageable table copy has left `rows`)
+    e->group_rows_valid = rc == PRB_OK;
+    return rc;
+}
+
+static unsigned stream_grid(const prb_engine *e, int64_t n, int per_thread);
+static int ensure_xsc_rows(prb_engine *e);
+
+// absCoef / transmittance / Layer.transmission (pyradClasses.py:581-587, 707-716, 784-787) from rows that are already on
+// the device: the per-group cross sections of the last prb_line_sum_groups, weighted by group_weight[g], plus the resident
+// xsc tables weighted by xsc_weight[t] (NULL or n_xsc entries).  Host buffers of chunk length in and out, FP64; the
+// wavenumber axis is linspace(range_min, range_max, n_total) as in prb_atmosphere.
+extern "C" int prb_layer_spectra_resident(prb_engine *e, const double *group_weight, const double *xsc_weight,
+                                          double depth_cm, double t_layer, double range_max, const double *radiance_in,
+                                          double *abs_coef, double *transmittance, double *radiance_out) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (!e->group_rows_valid) return fail(PRB_ERR_STATE, "prb_layer_spectra_resident: run prb_line_sum_groups first");
+    if (!group_weight) return fail(PRB_ERR_ARG, "prb_layer_spectra_resident: NULL weights");
+    if (radiance_out && !radiance_in) return fail(PRB_ERR_ARG, "prb_layer_spectra_resident: radiance_out needs radiance_in");
+    CK(cudaSetDevice(e->device));
+    const int64_t nc = chunk_len(e);
+    if (nc == 0) return PRB_OK;
+    const int G = e->n_groups, X = xsc_weight ? e->n_xsc : 0;
+    int rc = X ? ensure_xsc_rows(e) : PRB_OK;
+    if (rc) return rc;
+    CK(e->scratch_w.ensure(G + K2_MAX_XSC));
+    CK(e->scratch_b.ensure(nc)); CK(e->scratch_c.ensure(nc)); CK(e->scratch_d.ensure(nc));
+    CK(cudaMemcpyAsync(e->scratch_w.p, group_weight, sizeof(double) * G, cudaMemcpyHostToDevice, e->stream));
+    if (X) CK(cudaMemcpyAsync(e->scratch_w.p + G, xsc_weight, sizeof(double) * X, cudaMemcpyHostToDevice, e->stream));
+    if (radiance_out) {
+        CK(e->scratch_a.ensure(nc));
+        CK(cudaMemcpyAsync(e->scratch_a.p, radiance_in, sizeof(double) * nc, cudaMemcpyHostToDevice, e->stream));
+    }
+    const double dx = e->n_total > 1 ? (range_max - e->range_min) / (double)(e->n_total - 1) : 0.0;
+    k3_layer_stream_rows_f64<<<stream_grid(e, nc, 1), 256, 0, e->stream>>>(
+        nc, G, e->out64.p, nc, e->scratch_w.p, X, e->xsc_rows.p, e->xsc_ld, e->scratch_w.p + G, depth_cm, t_layer,
+        e->i_begin, e->n_total, e->range_min, dx, range_max, radiance_out ? e->scratch_a.p : nullptr,
+        abs_coef ? e->scratch_b.p : nullptr, transmittance ? e->scratch_c.p : nullptr,
+        radiance_out ? e->scratch_d.p : nullptr);
+    CK(cudaGetLastError());
+    if (abs_coef) CK(cudaMemcpyAsync(abs_coef, e->scratch_b.p, sizeof(double) * nc, cudaMemcpyDeviceToHost, e->stream));
+    if (transmittance) CK(cudaMemcpyAsync(transmittance, e->scratch_c.p, sizeof(double) * nc, cudaMemcpyDeviceToHost, e->stream));
+    if (radiance_out) CK(cudaMemcpyAsync(radiance_out, e->scratch_d.p, sizeof(double) * nc, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PRB_OK;
+}
+
 extern "C" int64_t prb_pair_count(prb_engine *e) {
     if (!e || !e->last.valid) {
         fail(PRB_ERR_STATE, "prb_pair_count: run prb_layer_prepass first");
@@ -945,7 +1093,8 @@ extern "C" int64_t prb_pair_count(prb_engine *e) {
 }
 
 // ------------------------------------------------------------------------------------ K3 (host buffers)
-static unsigned stream_grid(const prb_engine *e, int64_t n, int per_thread = 1) {
+static unsigned stream_grid(const prb_engine *e, int64_t n, int per_thread = 1);
+static unsigned stream_grid(const prb_engine *e, int64_t n, int per_thread) {
     const int64_t blocks = (n / per_thread + 255) / 256;
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)e->prop.multiProcessorCount * 16));
 }
@@ -1120,6 +1269,9 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
                            double range_max, const UploadPipe *pipe) {
     if (!e) return fail(PRB_ERR_ARG, "null engine");
     if (!e->grid_set && !pipe) return fail(PRB_ERR_STATE, "prb_atmosphere: set the grid first");
+    if (!e->seg.empty() && !pipe)
+        return fail(PRB_ERR_STATE, "prb_atmosphere: the line list was uploaded in groups (prb_upload_line_groups); the column "
+                                   "path needs one ascending list with group ids (prb_upload_lines)");
     if (n_layers < 1 || n_groups != e->n_groups) return fail(PRB_ERR_ARG, "prb_atmosphere: bad n_layers / n_groups");
     if (!depth_cm || !t_layer || !p_layer || !conc || !molmass || !q_t || !q_296 || !window_len)
         return fail(PRB_ERR_ARG, "prb_atmosphere: NULL array");
@@ -1139,7 +1291,9 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
     if (e->n_xsc > 0 && e->xsc_conc_layers != n_layers)
         return fail(PRB_ERR_ARG, "prb_atmosphere: resident xsc tables need their mole fractions for these layers "
                                  "(prb_set_xsc_conc with the same n_layers), or prb_xsc_clear");
+    const int xsc_before = e->xsc_build_launches;
     if ((rc = ensure_xsc_rows(e))) return rc;
+    const int xsc_launches = e->xsc_build_launches - xsc_before;   // table resamplings this call had to enqueue
 
     // Everything small the kernels of this call read -- status blocks (zeroed: flags + tile counters), per-(layer,
     // group) params, fold constants, the K2 launch table (K1's is a kernel parameter) -- is built in ONE pinned block and uploaded with
@@ -1286,8 +1440,7 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
         }
     }
     CK(cudaMemcpyAsync(e->blk_d.p, e->blk_h, blk_bytes, cudaMemcpyHostToDevice, e->stream));
-    int launches = e->xsc_build_launches;
-    e->xsc_build_launches = 0;
+    int launches = xsc_launches;
     e->extra_launches = 0;
     if (pipe) {
         if (!fused) return fail(PRB_ERR_STATE, "pipelined upload needs the fused single-layer path");

@@ -109,6 +109,13 @@ k0_validate_lines(const double *__restrict__ nu0, const int32_t *__restrict__ gr
     if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
 }
 
+// Gap entries of a grouped line list (group < 0): a wavenumber that maps to the sentinel index, zero intensity.
+__global__ void __launch_bounds__(256)
+k0_fill_gaps(double *__restrict__ nu0, double *__restrict__ s296, const int32_t *__restrict__ group, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && group[i] < 0) { nu0[i] = __longlong_as_double(0x7ff0000000000000LL); s296[i] = 0.0; }
+}
+
 __device__ __forceinline__ double pow5(double x) { double x2 = x * x; return x2 * x2 * x; }
 
 // One layer of a (possibly multi-layer) prepass launch.
@@ -193,7 +200,9 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
     const double c2 = cLight * hPlanck * 100 / kBoltz;          // pyradIntensity.py:13
     const int64_t l = l_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = l < l_end;
-    const bool real = in_range && l < n_lines;
+    // (grouped line lists keep every group's segment 16-byte aligned: the few gap entries between segments carry
+    // group -1 and become padding records like the entries past the end)
+    const bool real = in_range && l < n_lines && !(L.group && L.group[l] < 0);
     double nu = 0, delta = 0, gair = 0, gself = 0, nair = 0, elower = 0, s296 = 0;
     float nf = 0.f;
     int g = 0;

@@ -45,6 +45,29 @@ k3_layer_stream_f64(int64_t n, int n_mol, const double *__restrict__ sigma, cons
     }
 }
 
+// The same layer physics on rows that are already on the device: the per-group cross sections of the last
+// prb_line_sum_groups (rows_a) and the resident xsc tables (rows_b), on the owned chunk [i_first, i_first + n) of a grid
+// of n_total points.  k = sum_a sigma_a w_a + sum_b sigma_b w_b, in that order (Layer.absCoef, pyradClasses.py:707-712).
+__global__ void __launch_bounds__(256)
+k3_layer_stream_rows_f64(int64_t n, int n_a, const double *__restrict__ rows_a, int64_t ld_a,
+                         const double *__restrict__ w_a, int n_b, const double *__restrict__ rows_b, int64_t ld_b,
+                         const double *__restrict__ w_b, double depth, double t_layer, int64_t i_first, int64_t n_total,
+                         double x0, double dx, double x_last, const double *__restrict__ rad_in,
+                         double *__restrict__ absc, double *__restrict__ trans, double *__restrict__ rad_out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double k = 0.0;
+        for (int m = 0; m < n_a; ++m) k += rows_a[(int64_t)m * ld_a + i] * w_a[m];
+        for (int m = 0; m < n_b; ++m) k += rows_b[(int64_t)m * ld_b + i] * w_b[m];
+        const double t = exp(-k * depth);
+        if (absc) absc[i] = k;
+        if (trans) trans[i] = t;
+        if (rad_out) {
+            const double b = planck_f64(axis_value(i_first + i, n_total, x0, dx, x_last), t_layer);
+            rad_out[i] = t * rad_in[i] + (1 - t) * b;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k3_planck_f64(int64_t n, double x0, double dx, double x_last, double temp, double *__restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)

@@ -115,6 +115,19 @@ class Engine:
         self.n_lines = n
         self.n_groups = int(n_groups)
 
+    def upload_line_groups(self, groups):
+        """groups: one dict of SoA columns per isotopologue, each ascending in nu -- uploaded as they are (no merge);
+        line_sum_groups() then returns one row per group from one prepass + one line-sum launch."""
+        names = ("nu", "sw", "gamma_air", "gamma_self", "elower", "n_air", "delta_air")
+        off = np.zeros(len(groups) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([np.asarray(g["nu"]).size for g in groups])
+        cols = [_f64(np.concatenate([np.asarray(g[k], dtype=np.float64).ravel() for g in groups])) if len(groups) > 1
+                else _f64(groups[0][k]) for k in names]
+        _lib.check(self._lib.prb_upload_line_groups(self._h, len(groups), off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                    *[_dp(c) for c in cols]))
+        self.n_lines = int(off[-1])
+        self.n_groups = len(groups)
+
     def ingest_csv(self, text, wave_min, wave_max):
         """HITRAN-online CSV bytes -> the engine's line list, parsed on the device (K5).  Returns the line count."""
         blob = bytes(text)
@@ -166,6 +179,26 @@ class Engine:
         out = np.empty(self.n_chunk, dtype=np.float64)
         _lib.check(self._lib.prb_line_sum(self._h, _dp(out)))
         return out
+
+    def line_sum_groups(self, to_host=True):
+        """One row per group (prb_line_sum_groups); to_host=False leaves them on the device for layer_spectra_resident()."""
+        out = np.empty((self.n_groups, self.n_chunk), dtype=np.float64) if to_host else None
+        _lib.check(self._lib.prb_line_sum_groups(self._h, _dp(out)))
+        return out
+
+    def layer_spectra_resident(self, group_weight, depth_cm, t_layer, range_max, xsc_weight=None, radiance_in=None,
+                               want=("abs_coef", "transmittance", "radiance")):
+        """k, T, Layer.transmission from the device-resident per-group rows (+ resident xsc tables): one D2H per output."""
+        w = _f64(group_weight)
+        xw = _f64(xsc_weight) if xsc_weight is not None and len(xsc_weight) else None
+        rin = _f64(radiance_in) if radiance_in is not None else None
+        n = self.n_chunk
+        k = np.empty(n) if "abs_coef" in want else None
+        t = np.empty(n) if "transmittance" in want else None
+        r = np.empty(n) if ("radiance" in want and rin is not None) else None
+        _lib.check(self._lib.prb_layer_spectra_resident(self._h, _dp(w), _dp(xw), float(depth_cm), float(t_layer),
+                                                        float(range_max), _dp(rin), _dp(k), _dp(t), _dp(r)))
+        return k, t, r
 
     def line_sum_dev(self, dev_ptr, out_mode=OUT_F64):
         _lib.check(self._lib.prb_line_sum_dev(self._h, C.c_void_p(int(dev_ptr)), int(out_mode)))

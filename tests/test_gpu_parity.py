@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import physics as ph
+from pyrad_b200 import _lib
 from pyrad_b200 import engine as eng
 from pyrad_b200 import workloads
 from tests import helpers as H
@@ -442,6 +443,46 @@ def test_error_behaviour_is_loud_and_specific(engine):
     engine.set_grid(600.0, 0.01, 10000)
     engine.layer_prepass(296, 1013.0, [4e-4], [44.0], [286.0], [286.0], 500)
     assert np.isfinite(engine.line_sum()).all()
+
+
+# ---------------------------------------------------------------- per-group rows in one pass
+@pytest.mark.parametrize("P,T", [(1013.25, 296), (60.0, 230), (3.0, 250)])
+def test_line_sum_groups_equals_one_run_per_group(engine, P, T):
+    """prb_upload_line_groups + ONE prepass + ONE line-sum launch give every isotopologue's cross-section row
+    (pyradClasses.py:498-503, 566-576: the per-isotope / per-molecule spectra the menus plot); each row is bitwise what a
+    separate upload + prepass + line sum of that group alone gives -- in the wide, table-driven and binary-search kernel
+    classes -- and the device-resident k / T / transmission built from the rows match the FP64 host-buffer path."""
+    w = workloads.gas_cell(["h2o", "co2", "ch4", "o3"], 6000, 1000.0, 1030.0, 0.001, T, P, [0.01, 400e-6, 1.8e-6, 5e-8], 10.0, 41)
+    sp = w["species"]
+    n = eng.grid_len(w["range_min"], w["range_max"], w["res"])
+    win = eng.window_len(w["cutoff"], w["res"])
+    engine.upload_line_groups(w["per_group_lines"])
+    engine.set_grid(w["range_min"], w["res"], n)
+    engine.layer_prepass(T, P, w["conc"], [s.molmass for s in sp], [s.q(T) for s in sp], [s.q296 for s in sp], win)
+    pairs = engine.pair_count()
+    rows = engine.line_sum_groups()
+    assert rows.shape == (4, n)
+    with pytest.raises(_lib.EngineError):
+        engine.line_sum()                                             # the summed row needs the merged list
+    wts = [eng.number_density_weight(c, P, T) for c in w["conc"]]
+    axis = eng.linspace_axis(w["range_min"], w["range_max"], n)
+    surf = ph.planck_wavenumber(ph.x_axis(w["range_min"], w["range_max"], w["res"]), 288)
+    k, t, r = engine.layer_spectra_resident(wts, w["depth_cm"], T, w["range_max"], radiance_in=surf)
+    k2, t2, r2 = engine.layer_stream(rows, wts, w["depth_cm"], T, axis, surf)
+    np.testing.assert_allclose(k, k2, rtol=1e-15, atol=0)
+    np.testing.assert_allclose(t, t2, rtol=1e-14, atol=0)
+    np.testing.assert_allclose(r[1:], r2[1:], rtol=1e-14, atol=0)
+    total = 0
+    for g, s in enumerate(sp):
+        engine.upload_lines(w["per_group_lines"][g], 1)
+        engine.set_grid(w["range_min"], w["res"], n)
+        engine.layer_prepass(T, P, [w["conc"][g]], [s.molmass], [s.q(T)], [s.q296], win)
+        total += engine.pair_count()
+        assert np.array_equal(engine.line_sum(), rows[g]), g
+    assert total == pairs
+    sig = H.oracle_sigma_groups(w)
+    for g in range(4):
+        assert H.k_rel_err(rows[g], sig[g]).max() <= H.K_REL_TOL
 
 
 # ---------------------------------------------------------------- opt-in far-field variant (PRB_K2_FARFIELD)

@@ -149,3 +149,32 @@ def test_hitran_id_tables_equal_the_reference_tables():
             exec(src[i:j], ns)
         assert ns["HITRAN_GLOBAL_ISO"] == C.HITRAN_GLOBAL_ISO
         assert ns["MOLECULE_ID"] == C.MOLECULE_ID
+
+
+def test_isotope_lines_are_views_over_soa_columns(tmp_path, monkeypatch):
+    """Isotope keeps the list protocol of the reference (pyradClasses.py:350-359: a list of Line objects) without
+    holding one Python object per transition: len / iteration / indexing / linelist() hand out views on demand."""
+    from oracle import ref_harness as rh          # only its data-tree writer (test infrastructure)
+    root = str(tmp_path)
+    sp = synth.species("co2")
+    rh.write_params(root, sp.global_iso, sp.name, sp.mol_id, 1, 0.99, sp.q296, 1, sp.molmass)
+    monkeypatch.setattr(C, "DATA_ROOT", root)
+    monkeypatch.setattr(C.Layer, "hasAtmosphere", False)
+    layer = C.Layer(10.0, 296, 1013.25, 600.0, 700.0)
+    mol = C.Molecule("co2", layer, ppm=400)
+    layer.append(mol)
+    iso = mol[0]
+    cols = synth.make_lines(1000, 590.0, 710.0, 5)
+    iso.setLines(cols, {296: sp.q(296)})
+    assert len(iso) == 1000 and bool(iso) and list.__len__(iso) == 0          # no per-line objects are stored
+    first, last = iso[0], iso[-1]
+    assert first.wavenumber == cols["nu"][0] and last.wavenumber == cols["nu"][-1]
+    assert [ln.intensity for ln in iso[10:13]] == list(cols["sw"][10:13])
+    assert sum(1 for _ in iso) == 1000 and len(iso.linelist()) == 1000 and len(C.totalLineList(layer)) == 1000
+    ln = iso[5]
+    assert ln.isotope is iso and ln.molecule is mol and ln.layer is layer
+    assert ln.broadenedLine == cols["nu"][5] + cols["delta_air"][5] * layer.P / C.p0        # pyradClasses.py:252-254
+    C.resetCrossSection(layer)                                                # does not walk the lines
+    iso.clearLines()
+    assert len(iso) == 0 and list(iso) == []
+    np.testing.assert_raises(IndexError, lambda: iso[0])
