@@ -117,6 +117,78 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def pin_rank_to_gpu_numa(gpu_index):
+    """Bind this rank's host threads to the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI device), before
+    any pinned buffer is allocated: eight ranks streaming 56 MB per step through one socket's memory controllers is what
+    the e2e number at N = 8 measured in round 1.  Returns a description for the JSON line; never fatal."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                   # 00000000:1b:00.0 -> 0000:1b:00.0
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "unchanged (GPU-local CPU list empty)"
+        os.sched_setaffinity(0, cpus)
+        return "GPU %d -> CPUs %s (%d)" % (gpu_index, spec, len(cpus))
+    except Exception as exc:
+        return "unchanged (%s)" % type(exc).__name__
+
+
+def timed_runs(ext, run, reps, world, dist):
+    """`reps` runs of `run`, each bracketed by a synchronise (+ barrier) and CUDA events on the launching stream."""
+    import torch
+    out = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a.record(ext)
+        run()
+        b.record(ext)
+        torch.cuda.synchronize()
+        out.append(a.elapsed_time(b))
+    return out
+
+
+def max_over_ranks(values, world, dist):
+    import torch
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def gather_parity(e, plan_chunks, nc, rank, world, dist):
+    """Driver-visible multi-GPU evidence: the spectra the kernels stored into this rank's gather buffer over NVLink
+    (peer stores + flag barrier) against a separate NCCL all-gather of every rank's local result, bit for bit."""
+    import torch
+    from pyrad_b200 import distributed as pd
+    rad_g, tr_g = pd.gathered_spectra(e)
+    rad_p, tr_p = e.atmosphere_result_dev()
+    ld = rad_g.shape[1]
+    ok = True
+    for gathered, ptr in ((rad_g, rad_p), (tr_g, tr_p)):
+        pad = torch.zeros(ld, dtype=torch.float32, device="cuda")
+        pad[:nc] = pd.device_tensor(ptr, nc)
+        ref = torch.empty(world * ld, dtype=torch.float32, device="cuda")
+        dist.all_gather_into_tensor(ref, pad)
+        ref = ref.view(world, ld)
+        for r, (a, b) in enumerate(plan_chunks):
+            # bit patterns, so that NaN (the reference's 0/0 at 0 cm-1) compares equal to itself
+            ok = ok and bool(torch.equal(gathered[r, : b - a].view(torch.int32), ref[r, : b - a].view(torch.int32)))
+    flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag)
+    return "bitwise" if int(flag.item()) == 0 else "MISMATCH on %d rank(s)" % int(flag.item())
+
+
 # ---------------------------------------------------------------------------------------------- CPU side
 def _oracle_window(args):
     """One bounded sample of the cfg2 workload on one core: the oracle's slice-add restatement of
@@ -241,6 +313,7 @@ def main():
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d "
                              "--master-addr 127.0.0.1 --master-port P bench.py --gpus %d ..." % (args.gpus, args.gpus))
+    numa = pin_rank_to_gpu_numa(local)              # before any pinned allocation (first touch decides the NUMA node)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -250,6 +323,8 @@ def main():
     w = workloads.cfg2_shard(rank, world)
     sp = w["species"]
     e = eng.Engine(local)
+    # roofline denominators measured on THIS device, now (FFMA2 / FFMA instruction streams, float4 copy)
+    measured = e.measure_peaks()
     e.upload_lines(w["lines"], n_groups=len(sp))
     e.set_grid(w["range_min"], w["res"], w["n_total"], w["i_begin"], w["i_end"])
     n_chunk = e.n_chunk
@@ -319,6 +394,10 @@ def main():
     wall = time.perf_counter() - wall0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     launches_per_step = e.atmosphere_launches()
+    headline_parity = None
+    if use_peer:
+        chunks = [(r * n_chunk, (r + 1) * n_chunk) for r in range(world)]
+        headline_parity = gather_parity(e, chunks, n_chunk, rank, world, dist)
     tm = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -441,9 +520,7 @@ def main():
             e.set_result_host()
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            far = {"variant": "PRB_K2_FARFIELD (opt-in): lines farther than two span lengths from a warp's 128/256-point span and "
-                              "covering it fully are summed at 8 Chebyshev nodes of the span and interpolated once per tile; "
-                              "every pair's contribution is in the result, far pairs are not evaluated one by one",
+            far = {"variant": FARFIELD_NOTE + " -- NOT the headline: value / e2e / roofline are the exact per-point kernel",
                    "k2_ms": float(np.mean(fk2)), "k2_equivalent_pairs_per_s": pairs_rank / (float(np.mean(fk2)) * 1e-3),
                    "ms_per_step": far_ms, "equivalent_pairs_per_s": pairs_all / (far_ms * 1e-3),
                    "e2e_ms_per_step": float(te.item()) * 1e3, "e2e_equivalent_pairs_per_s": pairs_all / float(te.item()),
@@ -451,12 +528,13 @@ def main():
             try:
                 # what the far-field kernel really evaluates on this rank's chunk (host-side restatement of its integer
                 # class tests, tests/test_partition.py): pairs evaluated point by point + node evaluations, and the
-                # FP32 lane-slots they cost (13 packed instructions per 6 pairs, 16 per 6 node evaluations)
+                # FP32 lane-slots they cost (13 packed instructions per 6 pairs, 19 per 12 node evaluations), against the
+                # measured FFMA2 rate
                 from pyrad_b200 import partition as pt
                 ex_pairs, node_evals = pt.farfield_work(pt.line_index(w["lines"]["nu"], w["range_min"], w["res"]),
                                                         w["i_begin"], w["i_end"], win, 256)
-                slots = ex_pairs * 13.0 / 3.0 + node_evals * 16.0 / 3.0
-                peak_slots = SM_COUNT * 128 * float(peaks.get("sm_max_mhz", SM_MAX_MHZ_DEFAULT)) * 1e6
+                slots = ex_pairs * 13.0 / 3.0 + node_evals * 19.0 / 6.0
+                peak_slots = measured["ffma2_lane_fma_per_s"]
                 far["evaluated_pairs_this_rank"] = int(ex_pairs)
                 far["node_evaluations_this_rank"] = int(node_evals)
                 far["k2_fp32_lane_slot_frac"] = slots / (far["k2_ms"] * 1e-3) / peak_slots
@@ -475,8 +553,14 @@ def main():
     if not args.no_atmosphere:
         stress = run_stress(e, rank, world, ext, use_peer, not args.no_farfield)
 
-    # ---- secondary object: line-list ingestion (section 8(f) row 1), rank 0 at N = 1
-    ingest = None
+    # ---- secondary objects at N = 1: the other BASELINE gas cells (cfg1, cfg3) through the one-call path, the host
+    # mirror on cfg2, line-list ingestion (section 8(f) row 1)
+    ingest = small = mirror = None
+    if rank == 0 and world == 1:
+        from pyrad_b200 import workloads as wl
+        small = {"cfg1": run_small_cell(e, ext, wl.cfg1(), "cfg1: CO2 cell 500-800 cm-1 @ 0.01 cm-1 (30 000 points, 50k lines, W = 500)", flush_buf),
+                 "cfg3": run_small_cell(e, ext, wl.cfg3(), "cfg3: CO2 + H2O line by line + CFC-11 / HCFC-22 xsc tables, 500-800 cm-1 @ 0.01 cm-1", flush_buf)}
+        mirror = run_mirror(e, w, e2e["ms_per_step"])
     if rank == 0 and world == 1 and not args.no_cpu:
         ingest = run_ingest(e, w)
 
@@ -489,14 +573,17 @@ def main():
         sm_max = float(peaks.get("sm_max_mhz", SM_MAX_MHZ_DEFAULT))
         f_hz = sm_max * 1e6
         # FP32-pipe roofline of K2, the pipe that binds the triple-reciprocal formulation (ncu: math_pipe_throttle is
-        # the top stall, pipe_fma_cycles_active ~70 %): 13 packed FP32x2 instructions per six (line, point) pairs =
-        # 4.33 FP32 lane-slots per pair; a lane-slot is what the nominal "2 flop" FMA peak counts, so achieved
-        # TFLOP/s-equivalent = pairs/s x 4.33 x 2 against 148 SM x 128 lanes x 2 x f_max.
-        fp32_peak = SM_COUNT * 128 * 2 * f_hz / 1e12
+        # the top stall, pipe_fma_cycles_active ~70 %).  Denominator: the FFMA2 lane-FMA rate MEASURED on this device a
+        # minute ago (prb_measure_peaks; the nominal 148 SM x 128 lanes x f_max is printed beside it).  Numerator, two
+        # ways: what this kernel executes -- 13 packed FP32x2 instructions per six (line, point) pairs = 4.33 lane-slots
+        # per pair -- and the leanest formulation measured (A-normalised triple, 11 packed = 3.67; scripts/ubench/triple.cu).
+        fp32_nominal = SM_COUNT * 128 * 2 * f_hz / 1e12
+        fp32_peak = measured["ffma2_lane_fma_per_s"] * 2 / 1e12
         k2_pairs_s = pairs_rank / k2_t
-        slots_per_pair = 13.0 / 3.0
+        slots_per_pair, slots_min = 13.0 / 3.0, 11.0 / 3.0
         fp32_ach = k2_pairs_s * slots_per_pair * 2 / 1e12
         mufu_naive_peak = SM_COUNT * 16 * f_hz / 2.0          # 2 MUFU per Voigt pair
+        hbm_measured = measured["copy_bytes_per_s"] / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -506,24 +593,45 @@ def main():
                            ("all-gather fused into K2 (NVLink peer stores + flag barrier)" if use_peer else "NCCL all-gather")),
                        "pairs_per_step": pairs_all, "lines_per_gpu": n_l, "points_per_gpu": n_chunk,
                        "l2": "flushed between timed steps (512 MiB write)",
-                       "numerics": "FP64 prepass, FP32 lineshape evaluation, FP64 accumulation; k stored FP32"},
+                       "numerics": "FP64 prepass, FP32 lineshape evaluation, FP64 accumulation; k stored FP32",
+                       "host_affinity": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "gather_parity": headline_parity,
             "roofline": {"bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": fp32_ach / fp32_peak, "traffic": load_traffic("k2_line_sum<8>@cfg2"),
+                         "frac": fp32_ach / fp32_peak, "frac_minimum_formulation": k2_pairs_s * slots_min * 2 / 1e12 / fp32_peak,
+                         "traffic": load_traffic("k2_line_sum<8>@cfg2"),
                          "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/traffic.json); the kernel is FP32-pipe "
                                          "bound, its algorithmic DRAM traffic is the 18 MB of line records",
                          "kernel": "k2_line_sum<8>",
                          "k2_ms": k2_t * 1e3, "k2_pairs_per_s": k2_pairs_s,
-                         "peak_source": "nominal: 148 SM x 128 FP32 lanes x 2 x %.0f MHz (MEASURED_PEAKS.json has no FP32 "
-                                        "figure; %s file used for the clock)" % (sm_max, peaks_kind),
-                         "algorithmic": "4.33 FP32 lane-slots (x2 flop) per (line, gridpoint) pair: 13 packed FP32x2 instr per 6 pairs in "
-                                        "the triple-reciprocal path (DESIGN.md section 4); real flops are 6.33 per pair"},
+                         "peak_source": "measured",
+                         "peak_how": "prb_measure_peaks in this run: packed FFMA2 stream %.2f TFLOP/s (scalar FFMA stream %.2f; nominal "
+                                     "148 SM x 128 lanes x 2 x %.0f MHz = %.2f); float4 copy %.0f GB/s (MEASURED_PEAKS.json %s: %.0f)" % (
+                                         fp32_peak, measured["ffma_lane_fma_per_s"] * 2 / 1e12, sm_max, fp32_nominal, hbm_measured,
+                                         peaks_kind, float(peaks.get("hbm_gbs", 0.0))),
+                         "algorithmic": "frac: 4.33 FP32 lane-slots (x2 flop) per (line, gridpoint) pair = what k2_line_sum executes "
+                                        "(13 packed FP32x2 instr per 6 pairs, DESIGN.md section 4); frac_minimum_formulation: 3.67 "
+                                        "(11 packed, the leanest variant measured); real flops are 6.33 per pair"},
             "roofline_sfu": {"bound": "sfu", "achieved": k2_pairs_s / 1e9, "peak": mufu_naive_peak / 1e9, "unit": "Gpair/s",
                              "frac": k2_pairs_s / mufu_naive_peak,
                              "note": "SURVEY 8(d) naive bound (2 MUFU per Voigt pair, 16 MUFU/clk/SM); the kernel issues "
                                      "1/3 MUFU per Lorentz pair (triple reciprocal), hence > 1"},
+            "measured_peaks": measured,
             "wall_s_timed_region": wall,
         }
+        # the 1 -> 8 curves of the strong-scaled objects, readable without walking the nested objects
+        if atm:
+            line["atmosphere_ms"] = atm["ms_per_spectrum"]
+            line["atmosphere_exact_ms"] = atm["exact_kernel"]["ms_per_spectrum"]
+            line["atmosphere_spectra_per_s"] = atm["spectra_per_s"]
+        if stress:
+            line["stress_ms"] = stress["ms"]
+            line["stress_exact_ms"] = stress["exact_kernel"]["ms"]
+        if small:
+            line["cfg1"] = small["cfg1"]
+            line["cfg3"] = small["cfg3"]
+        if mirror:
+            line["mirror"] = mirror
         if far:
             line["farfield"] = far
         if atm:
@@ -539,6 +647,147 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def run_small_cell(e, ext, w, name, flush_buf, steps=50):
+    """A BASELINE gas-cell configuration that is not the bench workload (cfg1: the reference's own CPU-runnable case;
+    cfg3: line-by-line + xsc tables) through the same ONE-call path: device-timed steps on resident inputs, and the e2e
+    call from pinned host buffers to pinned host buffers (for cfg3 the xsc tables are re-registered inside every e2e
+    step: they are inputs too)."""
+    import torch
+    from pyrad_b200 import classes as C
+    from pyrad_b200 import engine as eng
+    sp = w["species"]
+    n = eng.grid_len(w["range_min"], w["range_max"], w["res"])
+    win = eng.window_len(w["cutoff"], w["res"])
+    T, P = w["T"], w["P"]
+    molmass, q296, qt = [s.molmass for s in sp], [s.q296 for s in sp], [s.q(T) for s in sp]
+    xa = np.linspace(w["range_min"], w["range_max"], n, endpoint=True)
+    plans = []
+    for x in w.get("xsc", []):
+        grid01 = np.arange(x["range_min"], x["range_max"], .01)
+        dst0, src0, count, _ = C._merge_plan(xa, grid01)
+        coarse = x["res"] > .01
+        plans.append(dict(n_out=n, dst0=dst0, src0=src0, count=count, file_x=x["wavenumber"] if coarse else None,
+                          file_y=x["intensity"], interp=coarse, ax0=float(grid01[0]), adelta=float(grid01[1] - grid01[0])))
+
+    def register_tables():
+        e.xsc_clear()
+        for slot, pl in enumerate(plans):
+            e.xsc_resident(slot, **pl)
+        if plans:
+            e.set_xsc_conc([[x["conc"] for x in w["xsc"]]])
+
+    e.upload_lines(w["lines"], n_groups=len(sp))
+    e.set_grid(w["range_min"], w["res"], n)
+    register_tables()
+    try:
+        e.layer_prepass(T, P, w["conc"], molmass, qt, q296, win)
+        pairs = e.pair_count()
+        call = e.atmosphere_call([w["depth_cm"]], [T], [P], [w["conc"]], molmass, [qt], q296, [win], 288.0, w["range_max"])
+        for _ in range(3):
+            call()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        torch.cuda.synchronize()
+        for a, b in evs:
+            flush_buf.zero_()
+            a.record(ext)
+            call()
+            b.record(ext)
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        launches = e.atmosphere_launches()
+        host = {}
+        keep = []
+        for kname, v in w["lines"].items():
+            tns = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+            keep.append(tns)
+            host[kname] = tns.numpy()
+        h_rad = torch.empty(n, dtype=torch.float32).pin_memory()
+        h_tr = torch.empty(n, dtype=torch.float32).pin_memory()
+        e.set_result_host(h_rad.numpy(), h_tr.numpy())
+        cell = e.gas_cell_host_call(host, len(sp), w["range_min"], w["res"], n, 0, n, w["depth_cm"], T, P, w["conc"], molmass,
+                                    qt, q296, win, 288.0, w["range_max"])
+
+        def e2e_step():
+            if plans:
+                register_tables()
+            cell()
+        for _ in range(2):
+            e2e_step()
+        e.synchronize()
+        reps = 10
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            e2e_step()
+        e.synchronize()
+        e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+        e.set_result_host()
+        n_l = len(w["lines"]["nu"])
+        xsc_bytes = sum(8 * len(x["intensity"]) * (2 if x["res"] > .01 else 1) for x in w.get("xsc", []))
+        return {"workload": name, "pairs": pairs, "points": n, "lines": n_l, "xsc_tables": len(plans),
+                "ms_per_step": ms, "pairs_per_s": pairs / (ms * 1e-3), "launches_per_step": launches,
+                "e2e": {"ms_per_step": e2e_ms, "value": pairs / (e2e_ms * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": int(n_l * (7 * 8 + 4) + xsc_bytes), "d2h_bytes_per_step": int(2 * 4 * n),
+                        "api": "prb_gas_cell_host (+ prb_xsc_resident per table) with prb_set_result_host, pinned buffers"},
+                "mean_transmittance": float(np.nanmean(h_tr.numpy()))}
+    finally:
+        e.xsc_clear()
+
+
+def run_mirror(e, w, e2e_ms):
+    """The reference-facing object model itself (pyrad_b200/classes.py: Layer > Molecule > Isotope) on cfg2 with ordinary
+    PAGEABLE numpy line arrays attached to the isotopologues: getTransmittance(layer) from a cold layer (cross sections
+    reset before every call), i.e. grouped upload + grid index + prepass + one line-sum launch with a row per isotopologue
+    + k -> T on the device + the FP64 transmittance back to the host.  Also: the per-isotopologue rows ("layer and
+    components" plots, pyradClasses.py:566-576) and how long building the objects takes."""
+    import shutil
+    import tempfile
+    from pyrad_b200 import classes as C
+    root = tempfile.mkdtemp(prefix="prb_mirror_")
+    old = (C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere, C._ENGINE)
+    try:
+        for s in w["species"]:                                   # the two small per-isotopologue files the constructors read
+            d = os.path.join(root, "data", str(s.global_iso))
+            os.makedirs(d)
+            with open(os.path.join(d, "params.pyr"), "w") as f:
+                f.write("# params\n%d,%s,%d,1,0.99,%r,1,%r\n" % (s.global_iso, s.name, s.mol_id, float(s.q296), float(s.molmass)))
+        C.set_engine(e)
+        C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere = root, w["res"], False
+        t0 = time.perf_counter()
+        layer = C.Layer(w["depth_cm"], w["T"], w["P"], w["range_min"], w["range_max"], dynamicResolution=False)
+        for g, (s, c) in enumerate(zip(w["species"], w["conc"])):
+            m = C.Molecule(s.name, layer, concentration=c)
+            layer.append(m)
+            m[0].setLines({k: np.array(v) for k, v in w["per_group_lines"][g].items()}, {int(w["T"]): s.q(w["T"])})
+        build_ms = (time.perf_counter() - t0) * 1e3
+        n_lines = sum(len(m[0]) for m in layer)
+
+        def cold_transmittance():
+            C.resetCrossSection(layer)
+            C._RESIDENT_KEY = None
+            return C.getTransmittance(layer)
+        tr = cold_transmittance()
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            tr = cold_transmittance()
+        cold_ms = (time.perf_counter() - t0) / reps * 1e3
+        t0 = time.perf_counter()
+        rows = [C.getCrossSection(m[0]) for m in layer]          # the rows are still on the device: one D2H for all four
+        comp_ms = (time.perf_counter() - t0) * 1e3
+        return {"workload": "cfg2 through pyrad_b200.classes (Layer > Molecule > Isotope), pageable numpy line arrays, float64 results",
+                "lines": n_lines, "points": len(tr), "build_objects_ms": build_ms,
+                "get_transmittance_cold_ms": cold_ms, "vs_c_abi_e2e": cold_ms / e2e_ms if e2e_ms else None,
+                "per_isotopologue_rows_ms": comp_ms, "rows": len(rows),
+                "bytes": {"h2d": int(n_lines * 7 * 8), "d2h_transmittance": int(8 * len(tr)), "d2h_rows": int(8 * len(tr) * len(rows))},
+                "mean_transmittance": float(np.nanmean(tr)),
+                "api": "classes.getTransmittance(layer): prb_upload_line_groups + prb_set_grid + prb_layer_prepass + "
+                       "prb_line_sum_groups + prb_layer_spectra_resident"}
+    finally:
+        C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere = old[0], old[1], old[2]
+        C.set_engine(old[3])
+        shutil.rmtree(root, ignore_errors=True)
 
 
 def run_ingest(e, w):
@@ -573,106 +822,21 @@ def run_ingest(e, w):
             "host_text_formatting_s": fmt_s}
 
 
-def run_stress(e, rank, world, ext, use_peer, farfield=True):
-    """cfg5: one gas cell, 5M synthetic lines, 0-5000 cm-1 @ 0.001 cm-1, fixed 25 cm-1 cutoff (W = 25 000, ~2.5e11
-    accumulations), split over the N ranks by wavenumber chunk; the finished spectra gathered as in the headline."""
+def run_sharded_column(e, w, windows, column_args, rank, world, ext, use_peer, variant, reps, want_timing=False):
+    """One spectrum of a column workload strong-sharded over the ranks by wavenumber chunk, with K2 variant `variant`:
+    plan on the variant's own cost model, place, one warm-up run, ONE feedback step of the cuts from the per-rank device
+    times (N > 1), then `reps` timed runs (CUDA events on the engine stream, barrier + synchronise around each, max over
+    ranks of the median).  Returns the measurements, and -- N > 1 with the peer gather -- the bitwise comparison of the
+    gather buffer with a separate NCCL all-gather."""
     import torch
     import torch.distributed as dist
     from pyrad_b200 import distributed as pd
     from pyrad_b200 import engine as eng
-    from pyrad_b200 import partition as pt
-    from pyrad_b200 import workloads
 
-    w = workloads.cfg5()
     sp = w["species"]
     n_total = eng.grid_len(w["range_min"], w["range_max"], w["res"])
-    win = eng.window_len(w["cutoff"], w["res"])
-    plan = pd.ShardPlan(w["lines"]["nu"], w["range_min"], w["res"], n_total, [win], rank, world)
-    e.upload_lines(plan.subset(w["lines"]), n_groups=len(sp))
-    e.set_grid(w["range_min"], w["res"], n_total, plan.i_begin, plan.i_end)
-    if use_peer:
-        e.peer_disconnect()
-        pd.connect_peers(e, rank, world, plan.max_chunk, dist)
-    T, P = w["T"], w["P"]
-    args_ = ([w["depth_cm"]], [T], [P], [w["conc"]], [s.molmass for s in sp], [[s.q(T) for s in sp]], [s.q296 for s in sp],
-             [win], 288.0, w["range_max"])
-    nc = plan.i_end - plan.i_begin
-
-    def run():
-        e.atmosphere(*args_)
-        if world > 1 and not use_peer:
-            rad_p, tr_p = e.atmosphere_result_dev()
-            pd.all_gather_spectra(pd.device_tensor(rad_p, nc), plan, dist)
-            pd.all_gather_spectra(pd.device_tensor(tr_p, nc), plan, dist)
-
-    run()
-    times = []
-    for _ in range(3):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        a.record(ext)
-        run()
-        b.record(ext)
-        torch.cuda.synchronize()
-        times.append(a.elapsed_time(b))
-    tm = torch.tensor([float(np.median(times))], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms = float(tm.item())
-    far = None
-    if farfield:
-        e.set_k2_variant(eng.K2_FARFIELD, 0)
-        try:
-            run()
-            ftimes = []
-            for _ in range(3):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                a.record(ext)
-                run()
-                b.record(ext)
-                torch.cuda.synchronize()
-                ftimes.append(a.elapsed_time(b))
-            tf = torch.tensor([float(np.median(ftimes))], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-            far = {"ms": float(tf.item()), "ms_runs_this_rank": [float(t) for t in ftimes]}
-        finally:
-            e.set_k2_variant(eng.K2_CLASSED, 0)
-    idx = np.trunc((w["lines"]["nu"] - w["range_min"]) / w["res"]).astype(np.int64)
-    pairs = float(pt.block_pair_cost(idx, n_total, [win]).sum())
-    if far:
-        far["equivalent_pairs_per_s"] = pairs / (far["ms"] * 1e-3)
-    return {"farfield": far, "workload": "cfg5: 5M synthetic lines, 0-5000 cm-1 @ 0.001 cm-1 (%d points), fixed 25 cm-1 cutoff (W = %d)" % (n_total, win),
-            "pairs": pairs, "ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "scaling": "strong", "n_gpus": world,
-            "ms_runs_this_rank": [float(t) for t in times]}
-
-
-def run_atmosphere(e, args, rank, world, ext, peaks, use_peer):
-    """100-layer standard atmosphere, 0-5000 cm-1 @ 0.001 cm-1, ~5M lines: K1+K2 per layer, one K3 fold, one
-    all-gather.  Strong scaling: the N ranks split ONE spectrum by pair-count-balanced wavenumber chunks."""
-    import torch
-    import torch.distributed as dist
-    from pyrad_b200 import distributed as pd
-    from pyrad_b200 import engine as eng
-    from pyrad_b200 import workloads
-
-    w = workloads.atmosphere(n_layers=args.atm_layers, n_lines=args.atm_lines)
-    sp = w["species"]
-    n_total = eng.grid_len(w["range_min"], w["range_max"], w["res"])
-    win = [eng.window_len(c, w["res"]) for c in w["cutoff"]]
-    plan = pd.ShardPlan(w["lines"]["nu"], w["range_min"], w["res"], n_total, win, rank, world)
-    e.upload_lines(plan.subset(w["lines"]), n_groups=len(sp))
-    e.set_grid(w["range_min"], w["res"], n_total, plan.i_begin, plan.i_end)
-    e.set_timing(True)
-    qt = np.array([[s.q(T) for s in sp] for T in w["T"]])
-    molmass = [s.molmass for s in sp]
-    q296 = [s.q296 for s in sp]
-    state = {"plan": plan, "nc": plan.i_end - plan.i_begin}
+    far = variant == eng.K2_FARFIELD
+    state = {}
 
     def place(p):
         """(Re)load this rank's share of plan p: its lines, its chunk, its slot of the peer gather buffers."""
@@ -683,106 +847,130 @@ def run_atmosphere(e, args, rank, world, ext, peaks, use_peer):
             pd.connect_peers(e, rank, world, p.max_chunk, dist)
         state["plan"], state["nc"] = p, p.i_end - p.i_begin
 
-    if use_peer:
-        e.peer_disconnect()
-        pd.connect_peers(e, rank, world, plan.max_chunk, dist)
-
     def run():
         p, nc = state["plan"], state["nc"]
-        e.atmosphere(w["depth_cm"], w["T"], w["P"], w["conc"], molmass, qt, q296, win, w["t_surface"], w["range_max"])
-        if use_peer:
-            return pd.gathered_spectra(e)           # [world, ld] views of the gather buffer the kernels filled
-        rad_p, tr_p = e.atmosphere_result_dev()
-        if world == 1:
-            return rad_p, tr_p                      # one rank: the finished spectra are already where they belong
-        rad = pd.device_tensor(rad_p, nc)
-        tr = pd.device_tensor(tr_p, nc)
-        return pd.all_gather_spectra(rad, p, dist), pd.all_gather_spectra(tr, p, dist)
+        e.atmosphere(*column_args)
+        if world > 1 and not use_peer:
+            rad_p, tr_p = e.atmosphere_result_dev()
+            pd.all_gather_spectra(pd.device_tensor(rad_p, nc), p, dist)
+            pd.all_gather_spectra(pd.device_tensor(tr_p, nc), p, dist)
 
-    run()
-    torch.cuda.synchronize()
-    rebalanced = False
-    if world > 1:
-        # one feedback step on the warm-up run: every rank's measured device time corrects the cost model, the cuts
-        # move (the model cannot know that high-wavenumber lines carry wider Doppler cores), ranks reload their share
-        t0 = e.atmosphere_timing()
-        mine = torch.tensor([t0["k1_ms"] + t0["k2_ms"] + t0["k3_ms"]], dtype=torch.float64, device="cuda")
-        allt = torch.empty(world, dtype=torch.float64, device="cuda")
-        dist.all_gather_into_tensor(allt, mine)
-        plan2 = plan.rebalanced([float(x) for x in allt.tolist()])
-        if plan2 is not plan:
-            place(plan2)
-            rebalanced = True
-            run()
-            torch.cuda.synchronize()
-        dist.barrier()
-    plan, nc = state["plan"], state["nc"]
-    times = []
-    for _ in range(5):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        a.record(ext)
+    e.set_k2_variant(variant, 0)
+    e.set_timing(True)
+    try:
+        place(pd.ShardPlan(w["lines"]["nu"], w["range_min"], w["res"], n_total, windows, rank, world, farfield=far))
         run()
-        b.record(ext)
         torch.cuda.synchronize()
-        times.append(a.elapsed_time(b))
-    # five whole-column runs, the median (a shared box occasionally stalls the host for 10+ ms between the event and
-    # the first launch); every run is listed in the JSON
-    ms = float(np.median(times))
-    tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms = float(tm.item())
-    idx = np.trunc((w["lines"]["nu"] - w["range_min"]) / w["res"]).astype(np.int64)
-    from pyrad_b200 import partition as pt
-    pairs = float(pt.block_pair_cost(idx, n_total, win).sum())
-    tim = e.atmosphere_timing()
-    far = None
-    if not args.no_farfield:
-        e.set_k2_variant(eng.K2_FARFIELD, 0)
-        try:
-            run()
-            torch.cuda.synchronize()
-            ftimes = []
-            for _ in range(3):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                a.record(ext)
+        rebalanced = False
+        if world > 1:
+            t0 = e.atmosphere_timing()
+            mine = torch.tensor([t0["k1_ms"] + t0["k2_ms"] + t0["k3_ms"]], dtype=torch.float64, device="cuda")
+            allt = torch.empty(world, dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(allt, mine)
+            plan2 = state["plan"].rebalanced([float(x) for x in allt.tolist()])
+            if plan2 is not state["plan"]:
+                place(plan2)
+                rebalanced = True
                 run()
-                b.record(ext)
                 torch.cuda.synchronize()
-                ftimes.append(a.elapsed_time(b))
-            ftim = e.atmosphere_timing()
-            tf = torch.tensor([float(np.median(ftimes)), ftim["k2_ms"]], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-            far = {"ms_per_spectrum": float(tf[0].item()), "max_rank_k2_ms": float(tf[1].item()),
-                   "ms_runs_this_rank": [float(t) for t in ftimes]}
-        finally:
-            e.set_k2_variant(eng.K2_CLASSED, 0)
-    e.set_timing(False)
-    tim_max = dict(tim)
-    if world > 1:                                   # slowest rank per stage (the step ends when the slowest rank does)
-        tt = torch.tensor([tim["k1_ms"], tim["k2_ms"], tim["k3_ms"]], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tim_max = dict(zip(("k1_ms", "k2_ms", "k3_ms"), [float(x) for x in tt.tolist()]))
+            dist.barrier()
+        times = timed_runs(ext, run, reps, world, dist)
+        tim = e.atmosphere_timing()
+        ms, k1, k2, k3 = max_over_ranks([float(np.median(times)), tim["k1_ms"], tim["k2_ms"], tim["k3_ms"]], world, dist)
+        parity = gather_parity(e, state["plan"].chunks, state["nc"], rank, world, dist) if (world > 1 and use_peer) else None
+        return {"ms": ms, "ms_runs_this_rank": [float(t) for t in times], "rank0_stage_ms": tim,
+                "max_rank_stage_ms": {"k1_ms": k1, "k2_ms": k2, "k3_ms": k3}, "launches": e.atmosphere_launches(),
+                "chunk_points_rank0": state["nc"], "rebalanced": rebalanced, "gather_parity": parity}
+    finally:
+        e.set_timing(False)
+        e.set_k2_variant(eng.K2_CLASSED, 0)
+
+
+FARFIELD_NOTE = ("K2 variant PRB_K2_FARFIELD: Lorentz wings of lines farther than one span length from a warp's 128/256-point "
+                 "span (and covering it fully) are summed at 16 Chebyshev nodes of the span and interpolated once per tile "
+                 "-- for windows of four tile lengths and more, lines far from the whole 2048-point tile once per tile; "
+                 "interpolation error <= 2e-8 of k (FP64 model, tests/test_farfield_model.py); every pair's contribution is "
+                 "in the result, far pairs are not evaluated one by one")
+
+
+def run_stress(e, rank, world, ext, use_peer, farfield=True):
+    """cfg5: one gas cell, 5M synthetic lines, 0-5000 cm-1 @ 0.001 cm-1, fixed 25 cm-1 cutoff (W = 25 000, ~2.5e11
+    accumulations), split over the N ranks by wavenumber chunk; the finished spectra gathered as in the headline.
+    The object's default is the far-field variant of K2 (spectra/s is not a pair count); the exact per-point kernel --
+    the one the line-gridpoint headline is measured on -- is timed beside it."""
+    from pyrad_b200 import engine as eng
+    from pyrad_b200 import partition as pt
+    from pyrad_b200 import workloads
+
+    w = workloads.cfg5()
+    sp = w["species"]
+    n_total = eng.grid_len(w["range_min"], w["range_max"], w["res"])
+    win = eng.window_len(w["cutoff"], w["res"])
+    T, P = w["T"], w["P"]
+    args_ = ([w["depth_cm"]], [T], [P], [w["conc"]], [s.molmass for s in sp], [[s.q(T) for s in sp]], [s.q296 for s in sp],
+             [win], 288.0, w["range_max"])
+    exact = run_sharded_column(e, w, [win], args_, rank, world, ext, use_peer, eng.K2_CLASSED, 3)
+    far = run_sharded_column(e, w, [win], args_, rank, world, ext, use_peer, eng.K2_FARFIELD, 3) if farfield else None
+    idx = np.trunc((w["lines"]["nu"] - w["range_min"]) / w["res"]).astype(np.int64)
+    pairs = float(pt.block_pair_cost(idx, n_total, [win]).sum())
+    out = {"workload": "cfg5: 5M synthetic lines, 0-5000 cm-1 @ 0.001 cm-1 (%d points), fixed 25 cm-1 cutoff (W = %d)" % (n_total, win),
+           "pairs": pairs, "scaling": "strong", "n_gpus": world,
+           "exact_kernel": {"ms": exact["ms"], "pairs_per_s": pairs / (exact["ms"] * 1e-3),
+                            "ms_runs_this_rank": exact["ms_runs_this_rank"], "gather_parity": exact["gather_parity"]}}
+    head = far or exact
+    out.update({"ms": head["ms"], "spectra_per_s": 1e3 / head["ms"], "ms_runs_this_rank": head["ms_runs_this_rank"],
+                "equivalent_pairs_per_s": pairs / (head["ms"] * 1e-3), "gather_parity": head["gather_parity"],
+                "k2_variant": FARFIELD_NOTE if far else "PRB_K2_CLASSED (exact per-point kernel)"})
+    return out
+
+
+def run_atmosphere(e, args, rank, world, ext, peaks, use_peer):
+    """100-layer standard atmosphere, 0-5000 cm-1 @ 0.001 cm-1, ~5M lines: K1+K2 per layer, one K3 fold, one
+    all-gather.  Strong scaling: the N ranks split ONE spectrum by wavenumber chunks balanced on the kernel's cost model.
+    Default variant of this object: far-field K2; the exact per-point kernel is timed beside it."""
+    from pyrad_b200 import engine as eng
+    from pyrad_b200 import partition as pt
+    from pyrad_b200 import workloads
+
+    w = workloads.atmosphere(n_layers=args.atm_layers, n_lines=args.atm_lines)
+    sp = w["species"]
+    n_total = eng.grid_len(w["range_min"], w["range_max"], w["res"])
+    win = [eng.window_len(c, w["res"]) for c in w["cutoff"]]
+    qt = np.array([[s.q(T) for s in sp] for T in w["T"]])
+    col = (w["depth_cm"], w["T"], w["P"], w["conc"], [s.molmass for s in sp], qt, [s.q296 for s in sp], win,
+           w["t_surface"], w["range_max"])
+    exact = run_sharded_column(e, w, win, col, rank, world, ext, use_peer, eng.K2_CLASSED, 5)
+    far = run_sharded_column(e, w, win, col, rank, world, ext, use_peer, eng.K2_FARFIELD, 5) if not args.no_farfield else None
+    idx = np.trunc((w["lines"]["nu"] - w["range_min"]) / w["res"]).astype(np.int64)
+    pairs = float(pt.block_pair_cost(idx, n_total, win).sum())
+    head = far or exact
+    nc = head["chunk_points_rank0"]
     k3_bytes = len(win) * nc * 4 + nc * 8
+    k1_bytes = len(w["lines"]["nu"]) / max(world, 1) * (56.0 + 36.0 * len(win))      # approx. per rank: columns once + records
     hbm = float(peaks.get("hbm_gbs", 6650.0))
-    return {"workload": "cfg4: %d-layer US-std atmosphere 0-70 km, 0-5000 cm-1 @ 0.001 cm-1 (%d points, %d lines), "
-                        "reference cutoff 5*P/p0 per layer" % (len(win), n_total, len(w["lines"]["nu"])),
-            "spectra_per_s": 1e3 / ms, "ms_per_spectrum": ms, "ms_runs_this_rank": [float(t) for t in times], "pairs": pairs, "pairs_per_s": pairs / (ms * 1e-3),
-            "scaling": "strong", "n_gpus": world, "chunk_points_rank0": nc, "launches": e.atmosphere_launches(),
-            "partition": "pair-count x measured-class-cost model" + (", one feedback step on the warm-up run's per-rank times" if rebalanced else ""),
-            "gather": "none" if world == 1 else ("peer stores fused into K3" if use_peer else "nccl"),
-            "rank0_stage_ms": tim, "max_rank_stage_ms": tim_max, "farfield": far,
-            "roofline_k3": {"bound": "hbm", "achieved": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                            "frac": k3_bytes / (tim["k3_ms"] * 1e-3) / 1e9 / hbm,
-                            "traffic": load_traffic("k3_fold_f32@cfg4") if world == 1 and len(win) == 100 else None,
-                            "algorithmic_bytes": k3_bytes}}
+    k3_ms, k1_ms = head["rank0_stage_ms"]["k3_ms"], head["rank0_stage_ms"]["k1_ms"]
+    out = {"workload": "cfg4: %d-layer US-std atmosphere 0-70 km, 0-5000 cm-1 @ 0.001 cm-1 (%d points, %d lines), "
+                       "reference cutoff 5*P/p0 per layer" % (len(win), n_total, len(w["lines"]["nu"])),
+           "k2_variant": FARFIELD_NOTE if far else "PRB_K2_CLASSED (exact per-point kernel)",
+           "spectra_per_s": 1e3 / head["ms"], "ms_per_spectrum": head["ms"], "ms_runs_this_rank": head["ms_runs_this_rank"],
+           "pairs": pairs, "equivalent_pairs_per_s": pairs / (head["ms"] * 1e-3),
+           "scaling": "strong", "n_gpus": world, "chunk_points_rank0": nc, "launches": head["launches"],
+           "partition": "measured-class-cost model of the variant" + (", one feedback step on the warm-up run's per-rank times" if head["rebalanced"] else ""),
+           "gather": "none" if world == 1 else ("peer stores fused into K3" if use_peer else "nccl"),
+           "gather_parity": head["gather_parity"],
+           "rank0_stage_ms": head["rank0_stage_ms"], "max_rank_stage_ms": head["max_rank_stage_ms"],
+           "exact_kernel": {"ms_per_spectrum": exact["ms"], "pairs_per_s": pairs / (exact["ms"] * 1e-3),
+                            "ms_runs_this_rank": exact["ms_runs_this_rank"], "rank0_stage_ms": exact["rank0_stage_ms"],
+                            "max_rank_stage_ms": exact["max_rank_stage_ms"], "gather_parity": exact["gather_parity"]},
+           "roofline_k3": {"bound": "hbm", "achieved": k3_bytes / (k3_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                           "frac": k3_bytes / (k3_ms * 1e-3) / 1e9 / hbm,
+                           "traffic": load_traffic("k3_fold_f32@cfg4") if world == 1 and len(win) == 100 else None,
+                           "algorithmic_bytes": k3_bytes},
+           "roofline_k1": {"bound": "hbm", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                           "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": k1_bytes,
+                           "note": "56 B of line columns once + 36 B of records per line-layer; the kernel is FP64-pipe / "
+                                   "issue bound (DESIGN.md section 4)"}}
+    return out
 
 
 if __name__ == "__main__":

@@ -98,15 +98,16 @@ int prb_upload_lines(prb_engine *e, int64_t n,
                      const int32_t *group, int32_t n_groups);
 
 /* Grouped line list (section 8(b): per-group output rows in one pass; pyradClasses.py:350-359, 498-503, 566-576): the
- * host objects hold one line list per isotopologue, each ascending in nu0.  They are uploaded as they are -- group g is
- * entries [offsets[g], offsets[g+1]) of the columns, offsets[0] = 0, no merge sort -- and prb_line_sum_groups returns one
+ * host objects hold one line list per isotopologue, each ascending in nu0.  They are uploaded from where they are -- every
+ * column argument is a table of n_groups pointers, group g's column has counts[g] entries; no merge sort, no host-side
+ * concatenation -- and prb_line_sum_groups returns one
  * cross-section row per group from ONE prepass + ONE line-sum launch (every group walks only its own lines).  Replaces
  * prb_upload_lines; prb_set_grid / prb_layer_prepass / prb_pair_count / prb_line_survey work as before, prb_line_sum and
  * prb_atmosphere need the single ascending list of prb_upload_lines. */
-int prb_upload_line_groups(prb_engine *e, int32_t n_groups, const int64_t *offsets,
-                           const double *nu0, const double *s296,
-                           const double *gamma_air, const double *gamma_self,
-                           const double *elower, const double *n_air, const double *delta_air);
+int prb_upload_line_groups(prb_engine *e, int32_t n_groups, const int64_t *counts,
+                           const double *const *nu0, const double *const *s296,
+                           const double *const *gamma_air, const double *const *gamma_self,
+                           const double *const *elower, const double *const *n_air, const double *const *delta_air);
 
 /* Line list straight from HITRAN-online CSV text (section 8(f) row 1; pyradUtilities.py:173-189, 421-448): `text`
  * is the concatenation of the segment files (host memory; rows molec,iso,nu,sw,a,elower,gamma_air,gamma_self,

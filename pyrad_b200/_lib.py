@@ -43,7 +43,7 @@ PROTOTYPES = {
     "prb_set_k2_variant": (C.c_int, [_vp, C.c_int, C.c_int]),
     "prb_set_narrow_threshold": (C.c_int, [_vp, _i64]),
     "prb_upload_lines": (C.c_int, [_vp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _i32]),
-    "prb_upload_line_groups": (C.c_int, [_vp, _i32, _lp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "prb_upload_line_groups": (C.c_int, [_vp, _i32, _lp] + [C.POINTER(_dp)] * 7),
     "prb_ingest_hitran_csv": (C.c_int, [_vp, C.c_char_p, _i64, _d, _d, _lp]),
     "prb_download_lines": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "prb_line_count": (_i64, [_vp]),

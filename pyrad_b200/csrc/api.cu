@@ -543,21 +543,27 @@ extern "C" int prb_upload_lines(prb_engine *e, int64_t n, const double *nu0, con
 // sort -- and every group becomes its own work-item row of ONE K2 launch (prb_line_sum_groups), walking only its own
 // lines.  Segments start 16-byte aligned on the device (the TMA staging of K2 aligns its first record down by up to
 // three entries); the gap entries carry group -1 and are inert.
-extern "C" int prb_upload_line_groups(prb_engine *e, int32_t n_groups, const int64_t *offsets, const double *nu0,
-                                      const double *s296, const double *gamma_air, const double *gamma_self,
-                                      const double *elower, const double *n_air, const double *delta_air) {
+extern "C" int prb_upload_line_groups(prb_engine *e, int32_t n_groups, const int64_t *counts,
+                                      const double *const *nu0, const double *const *s296,
+                                      const double *const *gamma_air, const double *const *gamma_self,
+                                      const double *const *elower, const double *const *n_air,
+                                      const double *const *delta_air) {
     if (!e) return fail(PRB_ERR_ARG, "null engine");
-    if (n_groups < 1 || !offsets || offsets[0] != 0) return fail(PRB_ERR_ARG, "prb_upload_line_groups: bad offsets");
-    for (int g = 0; g < n_groups; ++g)
-        if (offsets[g + 1] < offsets[g]) return fail(PRB_ERR_ARG, "prb_upload_line_groups: offsets must be non-decreasing");
-    const int64_t n = offsets[n_groups];
+    if (n_groups < 1 || !counts) return fail(PRB_ERR_ARG, "prb_upload_line_groups: bad group count");
+    if (!nu0 || !s296 || !gamma_air || !gamma_self || !elower || !n_air || !delta_air)
+        return fail(PRB_ERR_ARG, "prb_upload_line_groups: NULL column table");
+    int64_t n = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        if (counts[g] < 0) return fail(PRB_ERR_ARG, "prb_upload_line_groups: negative line count");
+        if (counts[g] > 0 && (!nu0[g] || !s296[g] || !gamma_air[g] || !gamma_self[g] || !elower[g] || !n_air[g] || !delta_air[g]))
+            return fail(PRB_ERR_ARG, "prb_upload_line_groups: NULL column");
+        n += counts[g];
+    }
     if (n > 2000000000LL) return fail(PRB_ERR_ARG, "prb_upload_line_groups: too many lines");
-    if (n > 0 && (!nu0 || !s296 || !gamma_air || !gamma_self || !elower || !n_air || !delta_air))
-        return fail(PRB_ERR_ARG, "prb_upload_line_groups: NULL column");
     CK(cudaSetDevice(e->device));
     std::vector<int64_t> seg(n_groups + 1, 0), cnt(n_groups, 0);
     for (int g = 0; g < n_groups; ++g) {
-        cnt[g] = offsets[g + 1] - offsets[g];
+        cnt[g] = counts[g];
         seg[g + 1] = (seg[g] + cnt[g] + 3) & ~int64_t(3);
     }
     const int64_t n_dev = seg[n_groups];
@@ -566,20 +572,19 @@ extern "C" int prb_upload_line_groups(prb_engine *e, int32_t n_groups, const int
     const int64_t na = e->n_alloc;
     CK(e->group.ensure(na));
     DevBuf<double> *cols[7] = {&e->nu0, &e->s296, &e->gair, &e->gself, &e->elower, &e->nair, &e->delta};
-    const double *src[7] = {nu0, s296, gamma_air, gamma_self, elower, n_air, delta_air};
+    const double *const *src[7] = {nu0, s296, gamma_air, gamma_self, elower, n_air, delta_air};
     for (int g = 0; g < n_groups; ++g)
         for (int c = 0; c < 7 && cnt[g]; ++c)
-            CK(cudaMemcpyAsync(cols[c]->p + seg[g], src[c] + offsets[g], sizeof(double) * cnt[g], cudaMemcpyHostToDevice,
-                               e->stream));
+            CK(cudaMemcpyAsync(cols[c]->p + seg[g], src[c][g], sizeof(double) * cnt[g], cudaMemcpyHostToDevice, e->stream));
     std::vector<int32_t> grp((size_t)std::max<int64_t>(n_dev, 1), -1);
     double smax = 0;
     bool sorted = true;
     for (int g = 0; g < n_groups; ++g) {
         std::fill(grp.begin() + seg[g], grp.begin() + seg[g] + cnt[g], g);
-        for (int64_t i = offsets[g]; i < offsets[g + 1]; ++i) {
-            const double sa = std::fabs(s296[i]);
+        for (int64_t i = 0; i < cnt[g]; ++i) {
+            const double sa = std::fabs(s296[g][i]);
             smax = sa > smax ? sa : smax;
-            if (i > offsets[g] && !(nu0[i] >= nu0[i - 1])) sorted = false;
+            if (i && !(nu0[g][i] >= nu0[g][i - 1])) sorted = false;
         }
     }
     if (n_dev) {

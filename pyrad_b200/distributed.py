@@ -13,13 +13,14 @@ from . import partition as pt
 class ShardPlan:
     """Everything a rank needs to know about its chunk."""
 
-    def __init__(self, nu0, range_min, res, n_total, windows, rank, world, balance=True, chunks=None, cost=None):
+    def __init__(self, nu0, range_min, res, n_total, windows, rank, world, balance=True, chunks=None, cost=None,
+                 farfield=False):
         idx = pt.line_index(nu0, range_min, res)
         self.cost = cost
         if chunks is not None:
             self.chunks = [tuple(c) for c in chunks]
         elif balance and world > 1:
-            self.cost = pt.block_time_cost(idx, n_total, windows)
+            self.cost = pt.block_time_cost(idx, n_total, windows, farfield=farfield)
             self.chunks = pt.balanced_chunks(self.cost, n_total, world)
         else:
             self.chunks = pt.equal_chunks(n_total, world)

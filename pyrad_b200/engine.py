@@ -116,17 +116,17 @@ class Engine:
         self.n_groups = int(n_groups)
 
     def upload_line_groups(self, groups):
-        """groups: one dict of SoA columns per isotopologue, each ascending in nu -- uploaded as they are (no merge);
-        line_sum_groups() then returns one row per group from one prepass + one line-sum launch."""
+        """groups: one dict of SoA columns per isotopologue, each ascending in nu -- uploaded from where they are (a table
+        of column pointers per group: no merge, no concatenation); line_sum_groups() then returns one row per group from
+        one prepass + one line-sum launch."""
         names = ("nu", "sw", "gamma_air", "gamma_self", "elower", "n_air", "delta_air")
-        off = np.zeros(len(groups) + 1, dtype=np.int64)
-        off[1:] = np.cumsum([np.asarray(g["nu"]).size for g in groups])
-        cols = [_f64(np.concatenate([np.asarray(g[k], dtype=np.float64).ravel() for g in groups])) if len(groups) > 1
-                else _f64(groups[0][k]) for k in names]
-        _lib.check(self._lib.prb_upload_line_groups(self._h, len(groups), off.ctypes.data_as(C.POINTER(C.c_int64)),
-                                                    *[_dp(c) for c in cols]))
-        self.n_lines = int(off[-1])
-        self.n_groups = len(groups)
+        G = len(groups)
+        keep = [[_f64(g[k]) for g in groups] for k in names]
+        counts = np.array([c.size for c in keep[0]], dtype=np.int64)
+        tables = [(C.POINTER(C.c_double) * G)(*[_dp(c) for c in col]) for col in keep]
+        _lib.check(self._lib.prb_upload_line_groups(self._h, G, counts.ctypes.data_as(C.POINTER(C.c_int64)), *tables))
+        self.n_lines = int(counts.sum())
+        self.n_groups = G
 
     def ingest_csv(self, text, wave_min, wave_max):
         """HITRAN-online CSV bytes -> the engine's line list, parsed on the device (K5).  Returns the line count."""

@@ -67,11 +67,35 @@ def _class_cost(wm):
     return 1 / 1.5e12, 1.5e-11            # k2_narrow: a few lines per point, per-point overhead dominates
 
 
-def block_time_cost(idx, n_total, windows, block=ALIGN):
+#: far-field variant (PRB_K2_FARFIELD): a node evaluation costs about two exact pair evaluations (measured,
+#: profiles/r02_k2_farfield.txt), 16 nodes per span (level 1) or per 2048-point tile (level 2, windows >= 8192)
+FAR_NODES, FAR_NODE_COST, FAR_TILE, FAR_L2_MIN_WM = 16, 2.0, 2048, 8192
+
+
+def _farfield_pair_equivalents(idx, n_total, w, block):
+    """What the far-field kernel evaluates for one layer of window w, per grid block, in exact-pair equivalents: the lines
+    within 1.5 spans of a point and the partially covering ones (about one more span at either window edge) point by
+    point, every other line of the window at the span's nodes -- or at the tile's nodes beyond 1.5 tiles (level 2)."""
+    wm = max(w - 2, 0)
+    span = 256 if wm >= 1024 else 128
+    near_w = min(w, int(2.5 * span) + 2)
+    near = block_pair_cost(idx, n_total, [near_w], block)
+    all_pairs = block_pair_cost(idx, n_total, [w], block)
+    if wm >= FAR_L2_MIN_WM:
+        mid_w = min(w, int(1.5 * FAR_TILE) + FAR_TILE // 2 + 2)
+        mid = block_pair_cost(idx, n_total, [mid_w], block)
+        far = (mid - near) * FAR_NODES / span + (all_pairs - mid) * FAR_NODES / FAR_TILE
+    else:
+        far = (all_pairs - near) * FAR_NODES / span
+    return near + FAR_NODE_COST * np.maximum(far, 0.0)
+
+
+def block_time_cost(idx, n_total, windows, block=ALIGN, farfield=False):
     """Estimated K2 seconds per grid block over all layers: the pair counts of block_pair_cost weighted by the
     measured cost of the kernel class each window runs on, plus the per-point overhead of the thread-per-point
     kernels.  Balancing on this instead of the raw pair count evens out ranks whose chunks differ in width (edge
-    chunks see one-sided windows, so equal pair counts give them more points -- and more narrow-layer work)."""
+    chunks see one-sided windows, so equal pair counts give them more points -- and more narrow-layer work).
+    farfield=True: the wide classes (W-2 >= 256) run the far-field variant, whose far pairs are nearly free."""
     windows = [int(w) for w in np.atleast_1d(windows)]
     nb = (n_total + block - 1) // block
     a = np.arange(nb, dtype=np.int64) * block
@@ -81,7 +105,11 @@ def block_time_cost(idx, n_total, windows, block=ALIGN):
     for w in windows:
         by_class.setdefault(_class_cost(max(w - 2, 0)), []).append(w)
     for (c_pair, c_point), ws in by_class.items():
-        cost += c_pair * block_pair_cost(idx, n_total, ws, block) + c_point * len(ws) * pts
+        if farfield and max(ws[0] - 2, 0) >= 256:
+            for w in set(ws):
+                cost += ws.count(w) * c_pair * _farfield_pair_equivalents(idx, n_total, w, block)
+        else:
+            cost += c_pair * block_pair_cost(idx, n_total, ws, block) + c_point * len(ws) * pts
     return cost
 
 

@@ -173,3 +173,24 @@ def test_farfield_work_accounting_matches_brute_force():
     assert pt.farfield_work(idx, 0, 4096, 2600, 256, level2_spans=4, level2_min_domains=0)[1] < pt.farfield_work(idx, 0, 4096, 2600, 256, level2_spans=0)[1]
     # the kernel's own rule: no level 2 below four domain lengths of window
     assert pt.farfield_work(idx, 0, 4096, 2600, 256) == pt.farfield_work(idx, 0, 4096, 2600, 256, level2_spans=0)
+
+
+def test_farfield_cost_model_tracks_the_far_field_work():
+    """block_time_cost(farfield=True) prices the wide classes by what the far-field kernel evaluates: per block it stays
+    within a small factor of the exact accounting (partition.farfield_work) and far below the all-pairs cost."""
+    rng = np.random.default_rng(11)
+    n = 65536
+    idx = np.sort(rng.integers(-6000, n + 6000, 40000))
+    for window in (5000, 1400):
+        exact_cost = pt.block_time_cost(idx, n, [window])
+        far_cost = pt.block_time_cost(idx, n, [window], farfield=True)
+        assert far_cost.shape == exact_cost.shape and np.all(far_cost > 0)
+        assert far_cost.sum() < (0.4 if window == 5000 else 0.7) * exact_cost.sum()
+        span = 256 if window - 2 >= 1024 else 128
+        c_pair = pt._class_cost(window - 2)[0]
+        for b in (2, 7, 12):
+            ex, nodes = pt.farfield_work(idx, b * 4096, (b + 1) * 4096, window, span)
+            want = c_pair * (ex + 2.0 * nodes)
+            assert 0.6 * want <= far_cost[b] <= 1.6 * want, (window, b, far_cost[b], want)
+    # level 2 (cfg5-like window): the far term shrinks again
+    assert pt.block_time_cost(idx, n, [25000], farfield=True).sum() < 0.1 * pt.block_time_cost(idx, n, [25000]).sum()
