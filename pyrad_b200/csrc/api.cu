@@ -229,6 +229,7 @@ extern "C" int prb_create(int device, prb_engine **out) {
     CK(cudaSetDevice(device));
     prb_engine *e = new prb_engine();
     e->device = device;
+    k1_fill_constants(e->k1_host);
     if (cudaGetDeviceProperties(&e->prop, device) != cudaSuccess) {
         delete e;
         return fail(PRB_ERR_CUDA, "prb_create: cudaGetDeviceProperties failed");

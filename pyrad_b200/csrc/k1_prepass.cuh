@@ -136,57 +136,107 @@ struct K1Layer {
 // The layer table travels as a kernel parameter: per-layer constants are then constant-bank operands of the
 // FP64 instructions (no registers, no loads), which is what lets the register budget hold the line's own data.
 constexpr int K1_MAX_LAYERS = 128;
+// Every 64-bit literal of the per-line arithmetic also travels in the parameter block: a double that is not a kernel
+// parameter reaches a DFMA as an immediate pair (two moves into uniform registers per use -- a __constant__ array with an
+// initialiser is folded into the same thing), and the layer loop re-materialises them every trip.  ptxas showed 210 such
+// moves; from the parameter bank they are plain operands.
+enum K1Const {
+    K1C_EXP_INV = 0, K1C_EXP_MAGIC, K1C_EXP_HI, K1C_EXP_LO, K1C_EXP_5, K1C_EXP_4, K1C_EXP_3,     // exp_k1
+    K1C_T7, K1C_T6, K1C_T5, K1C_T4, K1C_T3,                                                  // exp_tiny 1/5040 .. 1/6
+    K1C_V1, K1C_V2, K1C_V3, K1C_V4,                                                          // f5: 2.69269 2.42843 4.47163 .07842
+    K1C_E1, K1C_E2, K1C_E3,                                                                  // eta: 1.36603 .47719 .11116
+    K1C_LOG2E, K1C_INV_SQRTPI, K1C_INV_PI, K1C_FIFTH, K1C_C2, K1C_NEG_C2_T0,
+    K1C_LO_A, K1C_LO_B, K1C_HI_A, K1C_HI_B,                                                  // regime thresholds with their 1e-14 margins
+    K1C_BIG, K1C_COUNT
+};
 struct K1Table {
     int n;
     int pad;
+    double c[K1C_COUNT];
     K1Layer rows[K1_MAX_LAYERS];
 };
+inline void k1_fill_constants(K1Table &t) {
+    const double eps = 1e-14, c2 = cLight * hPlanck * 100 / kBoltz;
+    const double v[K1C_COUNT] = {
+        92.33248261689366, 6755399441055744.0, -0.01083042469326756, -2.9815858269852933e-12, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,
+        1.0 / 5040, 1.0 / 720, 1.0 / 120, 1.0 / 24, 1.0 / 6,
+        2.69269, 2.42843, 4.47163, .07842,
+        1.36603, .47719, .11116,
+        1.4426950408889634, 0.5641895835477563, 1.0 / kPi, 0.2, c2, -c2 / kT0,
+        .01 * (1 - eps), .01 * (1 + eps), 100 * (1 + eps), 100 * (1 - eps),
+        8.0e37};
+    for (int i = 0; i < K1C_COUNT; ++i) t.c[i] = v[i];
+}
 
-// exp(x) for the arguments this kernel meets (|x| <= 700), coefficients in constant memory so that every DFMA takes
-// its constant straight from the constant bank (the profile of the library exp showed 28 % of K1's instructions
-// moving 64-bit immediates into registers).  x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor (remainder 4e-18),
-// result scaled by adding k to the exponent field.  ~2 ulp; the parity tests hold K1's outputs to 1e-12.
-__constant__ double K1_EXP[18] = {
-    1.4426950408889634,            // [0] log2(e)
-    6755399441055744.0,            // [1] 1.5 * 2^52: rounds to the nearest integer in the low word
-    -6.93147180369123816490e-01,   // [2] -ln2 (high part)
-    -1.90821492927058770002e-10,   // [3] -ln2 (low part)
-    1.0 / 6227020800.0,            // [4] 1/13!
-    1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
-    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
-__device__ __forceinline__ double exp_k1(double x) {
-    if (!(fabs(x) <= 700.0)) return exp(x);                       // out of range / NaN: the library routine
-    const double t = fma(x, K1_EXP[0], K1_EXP[1]);
-    const int k = __double2loint(t);
-    const double kf = t - K1_EXP[1];
-    double r = fma(kf, K1_EXP[2], x);
-    r = fma(kf, K1_EXP[3], r);
-    double p = K1_EXP[4];
-#pragma unroll
-    for (int i = 5; i < 18; ++i) p = fma(p, r, K1_EXP[i]);
-    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+// exp(x) for the arguments this kernel meets (|x| <= 700): table driven.  x = (64 k + j) ln2/64 + r with |r| <= ln2/128,
+//   exp(x) = 2^k * 2^(j/64) * exp(r),  exp(r) - 1 = r + r^2 (1/2 + r/6 + r^2/24 + r^3/120)   (remainder r^6/720 < 4e-17)
+// -- ten FP64 instructions instead of the eighteen of a degree-13 polynomial (the kernel is FP64-pipe bound and spends
+// three of these per line and layer).  The 64 values 2^(j/64) are correctly rounded literals, copied into shared memory
+// by the CTA (a constant-bank lookup with a per-thread index would serialise); ln2/64 is split so that n * hi is exact.
+// ~1 ulp; the parity tests hold K1's outputs to 1e-12.
+__constant__ double K1_EXP_TAB[64] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+// (Arguments are clamped to [-708, 709] instead of branching to the library routine: below, the true value is a
+// denormal that every later product flushes anyway; above, 1.6e308 overflows the range guards just as inf would.  NaN
+// inputs never get here unnoticed: the kernel flags non-finite line data once per line.)
+__device__ __forceinline__ double exp_k1(double x, const double *__restrict__ tab, const double *__restrict__ c) {
+    x = fmin(fmax(x, -708.0), 709.0);
+    const double t = fma(x, c[K1C_EXP_INV], c[K1C_EXP_MAGIC]);
+    const int n = __double2loint(t);
+    const double nf = t - c[K1C_EXP_MAGIC];
+    double r = fma(nf, c[K1C_EXP_HI], x);
+    r = fma(nf, c[K1C_EXP_LO], r);
+    double p = fma(r, c[K1C_EXP_5], c[K1C_EXP_4]);
+    p = fma(p, r, c[K1C_EXP_3]);
+    p = fma(p, r, 0.5);
+    const double em1 = fma(p * r, r, r);
+    const double tj = tab[n & 63];
+    const double v = fma(tj, em1, tj);
+    return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+}
+
+// 1 / x to ~1 ulp without the IEEE division sequence: hardware seed (MUFU.RCP64H) and two Newton steps.
+__device__ __forceinline__ double rcp_k1(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
 }
 
 // f5^(-1/5) without log/exp/division: FP32 seed (two MUFU) and two Newton steps on g(r) = r^-5 - f5,
 //   r <- r (1 + (1 - f5 r^5)/5)   (quadratic: 1e-6 -> ~3e-12 -> below FP64 resolution).
-__device__ __forceinline__ double inv_fifth_root(double f5) {
+__device__ __forceinline__ double inv_fifth_root(double f5, const double *__restrict__ c) {
     double r = (double)__powf((float)f5, -0.2f);
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
         const double r2 = r * r;
         const double r5 = r2 * r2 * r;
-        r = fma(r, fma(-f5, r5, 1.0) * 0.2, r);
+        r = fma(r, fma(-f5, r5, 1.0) * c[K1C_FIFTH], r);
     }
     return r;
 }
 
 // exp(x) for |x| <= 0.02 (degree-7 Taylor, truncation < 1e-18)
-__device__ __forceinline__ double exp_tiny(double x) {
-    double p = 1.0 / 5040;
-    p = fma(p, x, 1.0 / 720);
-    p = fma(p, x, 1.0 / 120);
-    p = fma(p, x, 1.0 / 24);
-    p = fma(p, x, 1.0 / 6);
+__device__ __forceinline__ double exp_tiny(double x, const double *__restrict__ c) {
+    double p = fma(c[K1C_T7], x, c[K1C_T6]);
+    p = fma(p, x, c[K1C_T5]);
+    p = fma(p, x, c[K1C_T4]);
+    p = fma(p, x, c[K1C_T3]);
     p = fma(p, x, 0.5);
     p = fma(p, x, 1.0);
     return fma(p, x, 1.0);
@@ -194,10 +244,21 @@ __device__ __forceinline__ double exp_tiny(double x) {
 
 // One thread per line; the thread keeps the line's seven constants in registers and walks the layers of the
 // batch, so the SoA columns are read once per launch instead of once per layer.
-__global__ void __launch_bounds__(256, 3)
+#ifndef PRB_K1_UNROLL
+#define PRB_K1_UNROLL 1
+#endif
+constexpr int K1_UNROLL = PRB_K1_UNROLL;   // layers per trip of the layer loop
+#ifndef PRB_K1_MINB
+#define PRB_K1_MINB 4
+#endif
+__global__ void __launch_bounds__(256, PRB_K1_MINB)
 k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ K1Table tab,
            int64_t l_begin, int64_t l_end, int64_t n_lines, int64_t i_base, DebugOut dbg) {
-    const double c2 = cLight * hPlanck * 100 / kBoltz;          // pyradIntensity.py:13
+    __shared__ double exp_tab[64];
+    if (threadIdx.x < 64) exp_tab[threadIdx.x] = K1_EXP_TAB[threadIdx.x];
+    __syncthreads();
+    const double *__restrict__ cst = tab.c;                     // parameter-bank constants (K1Const)
+    const double c2 = cst[K1C_C2];                              // cLight * hPlanck * 100 / kBoltz, pyradIntensity.py:13
     const int64_t l = l_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = l < l_end;
     // (grouped line lists keep every group's segment 16-byte aligned: the few gap entries between segments carry
@@ -212,11 +273,13 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
         g = L.group ? L.group[l] : 0;
         nf = -(float)((double)((int64_t)idx[l] - i_base));
     }
+    // bad line data (NaN / inf in any column) is reported once per line, whatever the arithmetic below makes of it
+    const bool bad_line = real && !isfinite(nu + delta + gair + gself + nair + elower + s296);
     // exp(-c2 nu0 / t0): the layer-independent factor of the stimulated-emission denominator
-    const double e296 = exp_k1(-c2 / kT0 * nu);
+    const double e296 = exp_k1(cst[K1C_NEG_C2_T0] * nu, exp_tab, cst);
     const double neg_c2_e = -c2 * elower;
     const int n_layers = tab.n;
-#pragma unroll 1
+#pragma unroll K1_UNROLL
     for (int ly = 0; ly < n_layers; ++ly) {
         const K1Layer &K = tab.rows[ly];
         unsigned int flags = 0;
@@ -239,18 +302,16 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
             const double dshift = delta * pp0;
             const double nus = nu + dshift;
             // (t0/T)^n = exp(n * log(t0/T)): the log is a per-layer constant
-            const double gl = ((1 - p.conc) * gair + p.conc * gself) * pp0 * exp_k1(nair * K.lc.log_t0_over_t);
+            const double gl = ((1 - p.conc) * gair + p.conc * gself) * pp0 * exp_k1(nair * K.lc.log_t0_over_t, exp_tab, cst);
             const double gd = nus * p.dopp;
             // regime (pyradClasses.py:378-387): ratio = gl / gd compared with .01 and 100.  Away from the two
             // thresholds products decide; within 1e-14 of one (or for gd <= 0: inf / negative ratios, as numpy)
             // the division itself does, so the tag is exactly the reference's.
             int regime;
             {
-                const double lo = .01 * gd, hi = 100 * gd;
-                const double eps = 1e-14;
-                if (gd > 0 && gl < lo * (1 - eps)) regime = REGIME_GAUSS;
-                else if (gd > 0 && gl > hi * (1 + eps)) regime = REGIME_LORENTZ;
-                else if (gd > 0 && gl > lo * (1 + eps) && gl < hi * (1 - eps)) regime = REGIME_VOIGT;
+                if (gd > 0 && gl < gd * cst[K1C_LO_A]) regime = REGIME_GAUSS;
+                else if (gd > 0 && gl > gd * cst[K1C_HI_A]) regime = REGIME_LORENTZ;
+                else if (gd > 0 && gl > gd * cst[K1C_LO_B] && gl < gd * cst[K1C_HI_B]) regime = REGIME_VOIGT;
                 else {
                     const double ratio = gl / gd;                 // gd == 0 -> inf -> Lorentz, as numpy
                     regime = ratio < .01 ? REGIME_GAUSS : (ratio > 100 ? REGIME_LORENTZ : REGIME_VOIGT);
@@ -259,15 +320,18 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
             // stimulated emission (1 - e^{-c2 nu*/T}) / (1 - e^{-c2 nu*/t0}); e^{-c2 nu*/t0} = e296 * e^{-c2 dshift/t0}
             const double x0 = K.lc.neg_c2_over_t0 * dshift;
             // (next to 0 cm^-1 the denominator cancels: keep the reference's own single exponential there)
-            const double e_t0 = (fabs(x0) <= 0.02 && nu > 1.0) ? e296 * exp_tiny(x0) : exp_k1(K.lc.neg_c2_over_t0 * nus);
-            const double stim = (1 - exp_k1(K.lc.neg_c2_over_t * nus)) / (1 - e_t0);
+            const double e_t0 = (fabs(x0) <= 0.02 && nu > 1.0) ? e296 * exp_tiny(x0, cst) : exp_k1(K.lc.neg_c2_over_t0 * nus, exp_tab, cst);
+            // (the quotient by reciprocal + multiply: ~1 ulp, a third of the IEEE division's instructions; a denominator that
+            // is 0, denormal or huge -- nu* at or below 0 cm^-1 -- takes the division itself)
+            const double den = 1 - e_t0, num = 1 - exp_k1(K.lc.neg_c2_over_t * nus, exp_tab, cst);
+            const double stim = (fabs(den) > 1e-300 && fabs(den) < 1e300) ? num * rcp_k1(den) : num / den;
             // exp(-c2 E/T) / exp(-c2 E/t0) evaluated as one exponential (same value to ~1e-16)
-            const double boltz = exp_k1(neg_c2_e * K.lc.inv_t_minus_inv_t0);
+            const double boltz = exp_k1(neg_c2_e * K.lc.inv_t_minus_inv_t0, exp_tab, cst);
             const double S = s296 * p.qratio * stim * boltz;
             const double sw = S * p.weight * (K.scale_dev ? __ldg(K.scale_dev) : K.scale);
             const double inv_res2 = K.lc.inv_res2;
-            const double log2e = 1.4426950408889634;
-            const double inv_sqrtpi = 0.5641895835477563;         // 1/sqrt(pi)
+            const double log2e = cst[K1C_LOG2E];
+            const double inv_sqrtpi = cst[K1C_INV_SQRTPI];        // 1/sqrt(pi)
             double A, B, G, C, bg;                                // bg: Gaussian (h/res)^2
             float dg = -1.0f;
             if (regime == REGIME_GAUSS) {
@@ -277,24 +341,29 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
                 bg = gd * gd * inv_res2;
                 C = -log2e * K.lc.res2 * inv_gd * inv_gd;
             } else if (regime == REGIME_LORENTZ) {
-                A = sw * gl * (inv_res2 / kPi);
+                A = sw * gl * (inv_res2 * cst[K1C_INV_PI]);
                 B = gl * gl * inv_res2;
                 G = 0.0; C = -1.0; bg = 0.0;
             } else {
                 const double gFW = 2 * gd, lFW = 2 * gl;
-                const double g2 = gFW * gFW, l2 = lFW * lFW;
-                const double f5 = pow5(gFW) + 2.69269 * g2 * g2 * lFW + 2.42843 * g2 * gFW * l2 +
-                                  4.47163 * g2 * l2 * lFW + .07842 * gFW * l2 * l2 + pow5(lFW);
+                // f5 = g^5 + 2.69269 g^4 l + 2.42843 g^3 l^2 + 4.47163 g^2 l^3 + .07842 g l^4 + l^5 (pyradLineshape.py:62-66),
+                // Horner in g with the powers of l: 13 FP64 operations instead of 27 (same value to a few 1e-16)
+                const double l2 = lFW * lFW, l3 = l2 * lFW, l4 = l2 * l2;
+                double f5 = fma(cst[K1C_V1], lFW, gFW);
+                f5 = fma(f5, gFW, cst[K1C_V2] * l2);
+                f5 = fma(f5, gFW, cst[K1C_V3] * l3);
+                f5 = fma(f5, gFW, cst[K1C_V4] * l4);
+                f5 = fma(f5, gFW, l4 * lFW);
                 // f = f5 ** .2 (pyradLineshape.py:66): 1/f by Newton when f5 sits in the FP32 seed's range
                 double inv_f;
-                if (f5 > 1e-30 && f5 < 1e30) inv_f = inv_fifth_root(f5);
+                if (f5 > 1e-30 && f5 < 1e30) inv_f = inv_fifth_root(f5, cst);
                 else inv_f = 1.0 / exp(.2 * log(f5));
                 const double r2 = inv_f * inv_f;
                 const double hh = 0.5 * (f5 * (r2 * r2));         // f / 2, f = f5 * f5^(-4/5)
                 const double inv_hh = 2 * inv_f;
                 const double rho = gl * inv_hh;                   // lFW / f
-                const double eta = 1.36603 * rho - .47719 * rho * rho + .11116 * rho * rho * rho;
-                A = sw * eta * hh * (inv_res2 / kPi);
+                const double eta = rho * fma(rho, fma(cst[K1C_E3], rho, -cst[K1C_E2]), cst[K1C_E1]);
+                A = sw * eta * hh * (inv_res2 * cst[K1C_INV_PI]);
                 B = hh * hh * inv_res2;
                 G = sw * (1 - eta) * inv_hh * inv_sqrtpi;
                 bg = B;
@@ -309,7 +378,7 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
             if (G != 0.0) {
                 float t2 = 160.f;
                 if (A != 0.0) {
-                    const float rho9 = (float)fabs(2e-7 * A / (B * G));
+                    const float rho9 = fabsf(2e-7f * (float)A / ((float)B * (float)G));   // (FP32: the scaled records' own range)
                     if (rho9 >= 1.f) t2 = -1.f;
                     else {
                         const float ln = -__logf(fmaxf(rho9, 1e-37f));
@@ -321,9 +390,9 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
             // FP32 range guards: the paired far path forms A*(d^2+B) with |d| <= wm.
             const double wq = K.wm + 4096.0;                      // partial lines reach one warp span past the window
             const double qmax = wq * wq + B;
-            if (!(isfinite(A) && isfinite(G) && isfinite(B) && isfinite(C))) flags |= FLAG_NONFINITE;
+            if (bad_line || !(isfinite(A) && isfinite(G) && isfinite(B) && isfinite(C))) flags |= FLAG_NONFINITE;
             // the triple-reciprocal path forms |A| q^2 and q^3
-            else if (fabs(A) * qmax * qmax > 8.0e37 || fabs(G) > 8.0e37 || qmax * qmax * qmax > 8.0e37) flags |= FLAG_OVERFLOW;
+            else if (fabs(A) * qmax * qmax > cst[K1C_BIG] || fabs(G) > cst[K1C_BIG] || qmax * qmax * qmax > cst[K1C_BIG]) flags |= FLAG_OVERFLOW;
             const float Af = (float)A, Bf = (float)B;
             if (K.narrow) {                                       // compact layout of k2_point / k2_narrow
                 K.recA[l] = make_float4(nf, Af, Bf, (float)G);
