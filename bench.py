@@ -857,6 +857,8 @@ def run_sharded_column(e, w, windows, column_args, rank, world, ext, use_peer, v
 
     e.set_k2_variant(variant, 0)
     e.set_timing(True)
+    # strong scaling over small chunks: short K2 launches hand every tile out as line-range parts (no idle last wave)
+    e.set_option(eng.OPT_SPLIT_TILES, 1 if world > 1 else 0)
     try:
         place(pd.ShardPlan(w["lines"]["nu"], w["range_min"], w["res"], n_total, windows, rank, world, farfield=far))
         run()
@@ -880,9 +882,11 @@ def run_sharded_column(e, w, windows, column_args, rank, world, ext, use_peer, v
         parity = gather_parity(e, state["plan"].chunks, state["nc"], rank, world, dist) if (world > 1 and use_peer) else None
         return {"ms": ms, "ms_runs_this_rank": [float(t) for t in times], "rank0_stage_ms": tim,
                 "max_rank_stage_ms": {"k1_ms": k1, "k2_ms": k2, "k3_ms": k3}, "launches": e.atmosphere_launches(),
-                "chunk_points_rank0": state["nc"], "rebalanced": rebalanced, "gather_parity": parity}
+                "chunk_points_rank0": state["nc"], "rebalanced": rebalanced, "gather_parity": parity,
+                "split_tiles": world > 1}
     finally:
         e.set_timing(False)
+        e.set_option(eng.OPT_SPLIT_TILES, 0)
         e.set_k2_variant(eng.K2_CLASSED, 0)
 
 

@@ -67,6 +67,11 @@ extern "C" {
 #define PRB_OPT_FUSE_SINGLE_LAYER   2   /* single-layer prb_atmosphere: layer physics in K2's epilogue (default 1) */
 #define PRB_OPT_RECORD_BUDGET_MB    3   /* device memory for resident per-layer line records; 0 = auto */
 #define PRB_OPT_FOLD_TMA            5   /* layer fold: k matrix staged through shared memory by TMA (default 1) or register-held loads (0) */
+#define PRB_OPT_SPLIT_TILES         6   /* K2 launches of a few waves: every tile becomes up to 8 work items over parts of its line
+                                           range, FP64 partials combined in part order by the CTA that finishes last (default 0).
+                                           Removes the idle tail of short launches (strong scaling over small chunks); the
+                                           regrouped FP64 sums differ from the unsplit run in the last bits, so the bitwise
+                                           shard invariance of the default holds only with the option off */
 #define PRB_OPT_POINT_KERNEL        4   /* narrow windows: table-driven k2_point (default 1) or binary-search k2_narrow (0) */
 
 #define PRB_PEER_HANDLE_BYTES      64   /* sizeof(cudaIpcMemHandle_t) */

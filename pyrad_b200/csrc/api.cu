@@ -157,6 +157,9 @@ struct prb_engine {
     bool k3_tma = true;          // layer fold: k matrix staged by TMA (k3_fold_tma) instead of register-held loads
     bool point_kernel = true;    // windows up to 511 points: k2_point instead of k2_narrow
     bool fuse_single = true;     // single wide layer: layer physics + peer stores in K2's epilogue
+    bool split_tiles = false;    // PRB_OPT_SPLIT_TILES: short K2 launches split every tile into line-range parts
+    DevBuf<double> part_sums;    // [items][parts][tile] FP64 partials of such a launch
+    DevBuf<unsigned int> part_count;
     int64_t rec_budget_mb = 0;   // 0 = auto (a quarter of the free memory)
     PeerState peer;
     DevBuf<unsigned int> peer_err;
@@ -299,6 +302,7 @@ extern "C" int prb_destroy(prb_engine *e) {
     e->tile_bounds_buf[0].release(); e->tile_bounds_buf[1].release();
     e->far_lag[0].release(); e->far_lag[1].release(); e->far_lag2[0].release(); e->far_lag2[1].release();
     e->dev_scal.release();
+    e->part_sums.release(); e->part_count.release();
     e->xsc_rows.release();
     for (auto &x : e->xsc) { x.fx.release(); x.fy.release(); }
     if (e->pin_scal) cudaFreeHost(e->pin_scal);
@@ -849,6 +853,20 @@ extern "C" int prb_debug_line_params(prb_engine *e, double *nu_shift, double *ga
 }
 
 // ------------------------------------------------------------------------------------ K2
+// Line-range parts (PRB_OPT_SPLIT_TILES): how many work items a (layer, tile) becomes.  A launch of a few waves ends on a
+// mostly idle last wave -- 306 equal tiles on 296 resident CTAs take two tile times --; split into S parts of the line
+// range the same work is ceil(items S / slots) / S tile times.  Long launches (the batched atmosphere) stay unsplit.
+static int pick_parts(const prb_engine *e, int64_t items, int64_t slots) {
+    if (!e->split_tiles || items <= 0 || items > 4 * slots) return 1;
+    int best = 1;
+    double best_t = 1e30;
+    for (int s = 1; s <= 8; s *= 2) {
+        const double t = (double)((items * s + slots - 1) / slots) / s + 0.015 * s;   // + per-part overhead (search, combine)
+        if (t < best_t - 1e-9) { best_t = t; best = s; }
+    }
+    return best;
+}
+
 template <int P>
 static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
     const int tile = K2_CONSUMERS * 32 * P;
@@ -856,8 +874,19 @@ static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
     if (a.n_tiles == 0) return cudaSuccess;
     const bool staging = a.fuse.enabled && a.fuse.n_dst > 1;
     const size_t smem = K2_SMEM_BYTES<P>(staging);
-    const int64_t items = (int64_t)a.n_tiles * a.n_layers;
-    const int grid = (int)std::min<int64_t>(items, (int64_t)K2_MIN_CTAS * e->prop.multiProcessorCount);
+    int64_t items = (int64_t)a.n_tiles * a.n_layers;
+    const int64_t slots = (int64_t)K2_MIN_CTAS * e->prop.multiProcessorCount;
+    a.parts = pick_parts(e, items, slots);
+    if (a.parts > 1) {
+        cudaError_t ce = e->part_sums.ensure((size_t)items * a.parts * tile);
+        if (ce == cudaSuccess) ce = e->part_count.ensure((size_t)items);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(e->part_count.p, 0, sizeof(unsigned int) * items, e->stream);
+        if (ce != cudaSuccess) return ce;
+        a.part_sums = e->part_sums.p;
+        a.part_count = e->part_count.p;
+        items *= a.parts;
+    }
+    const int grid = (int)std::min<int64_t>(items, slots);
     if (far_args<P>(e, a)) k2_line_sum_far<(P == 4 ? 4 : 8)><<<grid, K2_THREADS, smem, e->stream>>>(a);
     else k2_line_sum<P><<<grid, K2_THREADS, smem, e->stream>>>(a);
     return cudaGetLastError();
@@ -1697,6 +1726,7 @@ extern "C" int prb_set_option(prb_engine *e, int option, int64_t value) {
         case PRB_OPT_FUSE_SINGLE_LAYER: e->fuse_single = value != 0; return PRB_OK;
         case PRB_OPT_POINT_KERNEL: e->point_kernel = value != 0; e->last.valid = false; return PRB_OK;
         case PRB_OPT_FOLD_TMA: e->k3_tma = value != 0; return PRB_OK;
+        case PRB_OPT_SPLIT_TILES: e->split_tiles = value != 0; return PRB_OK;
         case PRB_OPT_RECORD_BUDGET_MB: e->rec_budget_mb = value < 0 ? 0 : value; return PRB_OK;
         default: return fail(PRB_ERR_ARG, "prb_set_option: unknown option");
     }

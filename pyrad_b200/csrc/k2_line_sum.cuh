@@ -137,6 +137,13 @@ struct K2Args {
     const double *xsc_sigma;
     long long xsc_ld;
     int n_xsc;
+    // line-range parts (PRB_OPT_SPLIT_TILES; launches of a few waves only): every (layer, tile) is `parts` work items,
+    // part s sums the staged chunks [s nch / parts, (s+1) nch / parts) of the tile's line range into its own FP64
+    // partials (part_sums[item][TILE]); the CTA that finishes a tile's last part adds the partials in part order and
+    // runs the epilogue.  part_count[layer * n_tiles + tile] counts finished parts (zeroed before the launch).
+    int parts;
+    double *part_sums;
+    unsigned int *part_count;
 };
 
 // k of one grid point: the line sum plus the layer's xsc molecules (Layer.absCoef adds molecule by molecule, :707-712).
@@ -187,6 +194,7 @@ struct K2Desc {
     int cnt;        // staged lines to process (padding excluded)
     int flags;      // K2_FIRST | K2_LAST | K2_END
     int layer;      // index into K2Args::layers
+    int part;       // which line-range part of the tile this work item is (0 when tiles are not split)
 };
 constexpr int K2_FIRST = 1, K2_LAST = 2, K2_END = 4;
 
@@ -200,6 +208,7 @@ struct K2Smem {
     double far2[2][K2_CONSUMERS][K2_FAR_NODES];   // far-field level 2: every warp's node sums, double buffered by tile parity
     double2 faracc[2][K2_CONSUMERS * 32];         // far-field: every lane's two FP64 node sums, level 1 and level 2 (touched
                                                   // once per far_pass call: eight registers the hot loops get back)
+    int part_last;                                // line-range parts: this CTA finished the tile's last outstanding part
 };
 
 // Dynamic shared memory of k2_line_sum<P>: K2Smem | FP64 accumulators (PRB_K2_ACC_SMEM) | peer staging (2 x TILE floats).
@@ -473,14 +482,24 @@ __device__ __forceinline__ void k2_line_sum_body(const K2Args &a) {
             stage = it % K2_STAGES;
             mbar_wait_parked(&sm.empty[stage], ((it / K2_STAGES) & 1) ^ 1);   // fresh barrier: passes at once
         };
-        const int n_items = a.n_layers * a.n_tiles;
+        const int parts = a.parts > 1 ? a.parts : 1;
+        const int n_items = a.n_layers * a.n_tiles * parts;
         while (true) {
             int item = 0;
             if (lane == 0) item = (int)atomicAdd(&a.st->tile_counter, 1u);
             item = __shfl_sync(0xffffffffu, item, 0);
             if (item >= n_items) break;
-            const int layer = item / a.n_tiles;
-            const int tile = a.tile_base + item - layer * a.n_tiles;
+            // part-major order, the parts that can carry the most work first: in the far-field variant the lines near
+            // the tile (the middle of its line range) and the ones whose window edge crosses it (both ends) are evaluated
+            // point by point, everything between at a few nodes -- handing the heavy parts out first keeps the launch's
+            // tail short; for the exact kernel all parts cost the same and the order does not matter
+            const int n_lt = a.n_layers * a.n_tiles;
+            const int pidx = item / n_lt;
+            const int lt = item - pidx * n_lt;
+            const int half = parts >> 1, step = pidx >> 2, r = pidx & 3;
+            const int part = parts < 4 ? pidx : (r == 0 ? half - 1 - step : r == 1 ? half + step : r == 2 ? step : parts - 1 - step);
+            const int layer = lt / a.n_tiles;
+            const int tile = a.tile_base + lt - layer * a.n_tiles;
             const K2Layer *L = a.layers + layer;
             const int wm = __ldg(&L->wm), l_begin = __ldg(&L->l_begin), l_end = __ldg(&L->l_end);
             const float4 *recA = L->recA;
@@ -493,13 +512,17 @@ __device__ __forceinline__ void k2_line_sum_body(const K2Args &a) {
             const int hi = warp_lower_bound(a.idx, lo, l_end, k_hi);
             lo &= ~3;                                  // 16-byte alignment of the float stream
             const int nch = hi > lo ? (hi - lo + K2_CHUNK - 1) / K2_CHUNK : 1;   // empty tile: one empty chunk
-            for (int c = 0; c < nch; ++c, ++it) {
+            // this work item's chunks of the tile (all of them unless the tile is split into line-range parts)
+            const int c0 = (int)((long long)part * nch / parts), c1 = (int)((long long)(part + 1) * nch / parts);
+            const int cn = c1 > c0 ? c1 - c0 : 1;      // a part without chunks still reports in with an empty one
+            for (int k = 0; k < cn; ++k, ++it) {
+                const int c = c0 + k;
                 uint32_t stage;
                 slot_acquire(stage);
                 if (lane == 0) {
                     const int first = lo + c * K2_CHUNK;
-                    const int cnt = max(min(K2_CHUNK, hi - first), 0);
-                    sm.desc[stage] = K2Desc{tile0, cnt, (c == 0 ? K2_FIRST : 0) | (c == nch - 1 ? K2_LAST : 0), layer};
+                    const int cnt = c1 > c0 ? max(min(K2_CHUNK, hi - first), 0) : 0;
+                    sm.desc[stage] = K2Desc{tile0, cnt, (k == 0 ? K2_FIRST : 0) | (k == cn - 1 ? K2_LAST : 0), layer, part};
                     if (cnt > 0) {
                         const uint32_t ce = (uint32_t)((cnt + 3) & ~3);   // padding records exist past l_end
                         mbar_expect_tx(&sm.full[stage], ce * 36u);
@@ -516,7 +539,7 @@ __device__ __forceinline__ void k2_line_sum_body(const K2Args &a) {
         uint32_t stage;
         slot_acquire(stage);
         if (lane == 0) {
-            sm.desc[stage] = K2Desc{0, 0, K2_END, 0};
+            sm.desc[stage] = K2Desc{0, 0, K2_END, 0, 0};
             mbar_arrive(&sm.full[stage]);
         }
         return;
@@ -735,45 +758,71 @@ __device__ __forceinline__ void k2_line_sum_body(const K2Args &a) {
                     }
                 }
             }
+            bool finish = true;                            // this CTA runs the tile's epilogue (always, unless tiles are split)
+            if (a.parts > 1) {
+                // line-range parts: park this part's sums (far-field contributions included); the CTA that completes the
+                // tile adds all parts in part order -- a fixed order, whoever finishes last
+                const int lt = d.layer * a.n_tiles + (d.tile0 / TILE - a.tile_base);
+                double *mine = a.part_sums + ((size_t)lt * a.parts + d.part) * TILE + warp * SPAN + lane;
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const int i = wb + 32 * p + lane;
-                if (i < a.n_chunk) {
-                    const double v = k2_add_xsc(a, L, i, s.acc(p) * inv_scale);
-                    if (a.out_mode == 0) reinterpret_cast<double *>(out)[i] = v;
-                    else reinterpret_cast<float *>(out)[i] = (float)v;
-                    if (a.fuse.enabled) {
-                        // same operations, in the same order, as k3_fold_f32 with one layer
-                        const double x = axis_value(a.i_begin + i, a.fuse.n_total, a.fuse.x0, a.fuse.dx, a.fuse.x_last);
-                        const float nu = (float)x;
-                        const float a3 = (float)(2E8 * hPlanck * (cLight * cLight) * (x * x * x));
-                        const float e = (float)v * a.fuse.neg_depth_log2e;
-                        const float b = planck_f32(a3, a.fuse.c2_over_t * nu);
-                        const float rad = k3_fold_step(planck_f32(a3, a.fuse.c2_over_tsurf * nu), e, b);
-                        const float tr = exp2f(0.f + e);
-                        if (bulk) {
-                            stage_rad[i - d.tile0] = rad;
-                            stage_tr[i - d.tile0] = tr;
-                        } else {
+                for (int p = 0; p < P; ++p) __stcg(mine + 32 * p, s.acc(p));
+                __threadfence();
+                consumer_barrier();
+                if (tid == 0) sm.part_last = atomicAdd(a.part_count + lt, 1u) == (unsigned int)(a.parts - 1);
+                consumer_barrier();
+                finish = sm.part_last != 0;
+                if (finish) {
+                    __threadfence();
+                    const double *all = a.part_sums + (size_t)lt * a.parts * TILE + warp * SPAN + lane;
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        double v = 0.0;
+                        for (int q = 0; q < a.parts; ++q) v += __ldcg(all + (size_t)q * TILE + 32 * p);
+                        s.acc(p) = v;
+                    }
+                }
+            }
+            if (finish) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const int i = wb + 32 * p + lane;
+                    if (i < a.n_chunk) {
+                        const double v = k2_add_xsc(a, L, i, s.acc(p) * inv_scale);
+                        if (a.out_mode == 0) reinterpret_cast<double *>(out)[i] = v;
+                        else reinterpret_cast<float *>(out)[i] = (float)v;
+                        if (a.fuse.enabled) {
+                            // same operations, in the same order, as k3_fold_f32 with one layer
+                            const double x = axis_value(a.i_begin + i, a.fuse.n_total, a.fuse.x0, a.fuse.dx, a.fuse.x_last);
+                            const float nu = (float)x;
+                            const float a3 = (float)(2E8 * hPlanck * (cLight * cLight) * (x * x * x));
+                            const float e = (float)v * a.fuse.neg_depth_log2e;
+                            const float b = planck_f32(a3, a.fuse.c2_over_t * nu);
+                            const float rad = k3_fold_step(planck_f32(a3, a.fuse.c2_over_tsurf * nu), e, b);
+                            const float tr = exp2f(0.f + e);
+                            if (bulk) {
+                                stage_rad[i - d.tile0] = rad;
+                                stage_tr[i - d.tile0] = tr;
+                            } else {
 #pragma unroll 1
-                            for (int dst = 0; dst < a.fuse.n_dst; ++dst) {
-                                a.fuse.rad[dst][i] = rad;      // own slot of every rank's gather buffer
-                                a.fuse.trans[dst][i] = tr;
+                                for (int dst = 0; dst < a.fuse.n_dst; ++dst) {
+                                    a.fuse.rad[dst][i] = rad;      // own slot of every rank's gather buffer
+                                    a.fuse.trans[dst][i] = tr;
+                                }
                             }
                         }
                     }
                 }
-            }
-            if (bulk) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                consumer_barrier();
-                if (tid == 0) {
+                if (bulk) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    consumer_barrier();
+                    if (tid == 0) {
 #pragma unroll 1
-                    for (int dst = 0; dst < a.fuse.n_dst; ++dst) {
-                        tma_bulk_s2g(a.fuse.rad[dst] + d.tile0, stage_rad, TILE * 4u);
-                        tma_bulk_s2g(a.fuse.trans[dst] + d.tile0, stage_tr, TILE * 4u);
+                        for (int dst = 0; dst < a.fuse.n_dst; ++dst) {
+                            tma_bulk_s2g(a.fuse.rad[dst] + d.tile0, stage_rad, TILE * 4u);
+                            tma_bulk_s2g(a.fuse.trans[dst] + d.tile0, stage_tr, TILE * 4u);
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         }

@@ -10,7 +10,7 @@ P0 = 1013.25
 
 OUT_F64, OUT_F32 = 0, 1
 K2_GENERAL, K2_CLASSED, K2_FARFIELD = 0, 1, 2
-OPT_BATCH_LAYERS, OPT_FUSE_SINGLE_LAYER, OPT_RECORD_BUDGET_MB, OPT_POINT_KERNEL, OPT_FOLD_TMA = 1, 2, 3, 4, 5
+OPT_BATCH_LAYERS, OPT_FUSE_SINGLE_LAYER, OPT_RECORD_BUDGET_MB, OPT_POINT_KERNEL, OPT_FOLD_TMA, OPT_SPLIT_TILES = 1, 2, 3, 4, 5, 6
 PEER_HANDLE_BYTES = 64
 
 

@@ -445,6 +445,45 @@ def test_error_behaviour_is_loud_and_specific(engine):
     assert np.isfinite(engine.line_sum()).all()
 
 
+# ---------------------------------------------------------------- line-range parts (PRB_OPT_SPLIT_TILES)
+@pytest.mark.parametrize("variant", [eng.K2_CLASSED, eng.K2_FARFIELD])
+def test_split_tiles_regroups_the_same_sum(engine, variant):
+    """Short launches with PRB_OPT_SPLIT_TILES: every tile's line range is summed in parts by different CTAs and the FP64
+    partials are added in part order by whichever CTA finishes last.  Same sum, regrouped: equal to the unsplit result to
+    FP64 rounding (far below the FP32 evaluation noise), identical from run to run, and through the fused epilogue."""
+    w = workloads.gas_cell(["h2o", "co2", "ch4", "o3"], 40000, 1000.0, 1040.0, 0.001, 296, 1013.25,
+                           [0.01, 400e-6, 1.8e-6, 5e-8], 10.0, 47)
+    n = H.engine_setup(engine, w)
+    wts = [eng.number_density_weight(c, w["P"], w["T"]) for c in w["conc"]]
+    sp = w["species"]
+    win = eng.window_len(w["cutoff"], w["res"])
+    col = ([w["depth_cm"]], [w["T"]], [w["P"]], [w["conc"]], [s.molmass for s in sp], [[s.q(w["T"]) for s in sp]],
+           [s.q296 for s in sp], [win], 288.0, w["range_max"])
+    engine.set_k2_variant(variant, 0)
+    try:
+        H.engine_prepass(engine, w, weights=wts)
+        plain = engine.line_sum()
+        engine.atmosphere(*col)
+        rad0, tr0 = engine.atmosphere_read()
+        engine.set_option(eng.OPT_SPLIT_TILES, 1)
+        H.engine_prepass(engine, w, weights=wts)
+        split = engine.line_sum()
+        again = engine.line_sum()
+        engine.atmosphere(*col)
+        rad1, tr1 = engine.atmosphere_read()
+    finally:
+        engine.set_option(eng.OPT_SPLIT_TILES, 0)
+        engine.set_k2_variant(eng.K2_CLASSED, 0)
+    assert np.array_equal(split, again)                              # deterministic: fixed part order
+    assert not np.array_equal(split, plain)                          # (the tiles really were split: 20 tiles on 296 CTA slots)
+    assert H.k_rel_err(split, plain).max() <= 1e-13
+    assert np.abs(tr1 - tr0).max() <= 2e-7
+    np.testing.assert_allclose(rad1[1:], rad0[1:], rtol=2e-6, atol=0)
+    pts = H.boundary_points(n, 200, 3, n_tiles=6)
+    ref = H.oracle_layer_k_at(w, pts, w["T"], w["P"], w["conc"], w["cutoff"])
+    assert H.k_rel_err(split[pts], ref).max() <= H.K_REL_TOL
+
+
 # ---------------------------------------------------------------- per-group rows in one pass (SURVEY 8(b))
 @pytest.mark.parametrize("P,T", [(1013.25, 296), (60.0, 230), (3.0, 250)])
 def test_line_sum_groups_equals_one_run_per_group(engine, P, T):
