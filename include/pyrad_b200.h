@@ -58,9 +58,12 @@ extern "C" {
 /* K2 kernel variants (for A/B parity tests and profiling) */
 #define PRB_K2_GENERAL       0   /* every staged line through the predicated two-term path */
 #define PRB_K2_CLASSED       1   /* per-warp window classes + paired-reciprocal far path (default) */
-#define PRB_K2_FARFIELD      2   /* CLASSED, and for windows of >= 1024 points the Lorentz wings of lines more than 512 grid
-                                    points from a warp's 256-point span are summed at 8 Chebyshev nodes of the span and
-                                    interpolated (error < 1e-6 of k, median 3e-9; opt-in) */
+#define PRB_K2_FARFIELD      2   /* CLASSED, and for windows of >= 256 points the Lorentz wings of lines more than one span length
+                                    from a warp's 128/256-point span (and covering it fully) are summed at 16 Chebyshev nodes of
+                                    the span and interpolated once per tile; for windows of four tile lengths and more, lines far
+                                    from the whole 2048-point tile once per tile.  Interpolation error <= 2e-8 of k (FP64 model of
+                                    the algorithm); opt-in -- the default and every headline number are the exact kernel; see
+                                    DESIGN.md section 4 */
 
 /* prb_set_option */
 #define PRB_OPT_BATCH_LAYERS        1   /* prb_atmosphere: one K1 + one K2 launch per kernel class (default 1) */

@@ -259,6 +259,12 @@ extern "C" int prb_create(int device, prb_engine **out) {
     want((const void *)k2_line_sum<16>, K2_SMEM_BYTES<16>(true));
     want((const void *)k2_line_sum_far<4>, K2_SMEM_BYTES<4>(true));
     want((const void *)k2_line_sum_far<8>, K2_SMEM_BYTES<8>(true));
+    want((const void *)k2_line_sum<2, true>, K2_SMEM_BYTES<2>(true));
+    want((const void *)k2_line_sum<4, true>, K2_SMEM_BYTES<4>(true));
+    want((const void *)k2_line_sum<8, true>, K2_SMEM_BYTES<8>(true));
+    want((const void *)k2_line_sum<16, true>, K2_SMEM_BYTES<16>(true));
+    want((const void *)k2_line_sum_far<4, true>, K2_SMEM_BYTES<4>(true));
+    want((const void *)k2_line_sum_far<8, true>, K2_SMEM_BYTES<8>(true));
     want((const void *)k2_point, sizeof(KPSmem));
     want((const void *)k3_fold_tma, sizeof(K3TSmem));
     if (ae != cudaSuccess) {
@@ -687,6 +693,13 @@ static int pick_ppt(const prb_engine *e, int64_t wm) {
     if (e->k2_ppt) return e->k2_ppt;
     // a warp spans 32*P points: keep the span well inside the window so most lines cover it fully
     // (thresholds measured per layer on B200, profiles/r01_k2_experiments.txt)
+#ifndef PRB_FAR_P8_MIN
+#define PRB_FAR_P8_MIN 3072
+#endif
+    // (far-field variant: a 128-point span halves the near zone and the partly covered lines at twice the node
+    // evaluations, which pays up to wider windows than in the exact kernel: cfg4 K2 67.3 ms with the 256-point span
+    // from W-2 >= 1024, 66.2 / 65.5 / 64.9 / 65.2 / 64.7 from 1536 / 2048 / 3072 / 4096 / never)
+    if (e->k2_variant == PRB_K2_FARFIELD) return wm >= PRB_FAR_P8_MIN ? 8 : (wm >= 256 ? 4 : 2);
     if (wm >= 1024) return 8;
     if (wm >= 256) return 4;
     return 2;
@@ -887,8 +900,14 @@ static cudaError_t launch_k2_t(prb_engine *e, K2Args a) {
         items *= a.parts;
     }
     const int grid = (int)std::min<int64_t>(items, slots);
-    if (far_args<P>(e, a)) k2_line_sum_far<(P == 4 ? 4 : 8)><<<grid, K2_THREADS, smem, e->stream>>>(a);
-    else k2_line_sum<P><<<grid, K2_THREADS, smem, e->stream>>>(a);
+    const bool far = far_args<P>(e, a);
+    if (a.parts > 1) {
+        if (far) k2_line_sum_far<(P == 4 ? 4 : 8), true><<<grid, K2_THREADS, smem, e->stream>>>(a);
+        else k2_line_sum<P, true><<<grid, K2_THREADS, smem, e->stream>>>(a);
+    } else {
+        if (far) k2_line_sum_far<(P == 4 ? 4 : 8)><<<grid, K2_THREADS, smem, e->stream>>>(a);
+        else k2_line_sum<P><<<grid, K2_THREADS, smem, e->stream>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -454,7 +454,9 @@ __device__ __forceinline__ void general_all(const float4 *sA, const float4 *sB, 
     }
 }
 
-template <int P, bool FAR>
+// SPLIT: the launch hands tiles out as line-range parts (PRB_OPT_SPLIT_TILES).  A template parameter, not a run-time
+// test: with the hand-over code merely present in the epilogue the unsplit fused gas-cell step measured 9 % slower.
+template <int P, bool FAR, bool SPLIT>
 __device__ __forceinline__ void k2_line_sum_body(const K2Args &a) {
     static_assert(P >= 2 && P % 2 == 0, "points per thread must be even (packed FP32x2)");
     static_assert(!FAR || P == 4 || P == 8, "far-field tables exist for 128- and 256-point spans");
@@ -482,7 +484,7 @@ __device__ __forceinline__ void k2_line_sum_body(const K2Args &a) {
             stage = it % K2_STAGES;
             mbar_wait_parked(&sm.empty[stage], ((it / K2_STAGES) & 1) ^ 1);   // fresh barrier: passes at once
         };
-        const int parts = a.parts > 1 ? a.parts : 1;
+        const int parts = (SPLIT && a.parts > 1) ? a.parts : 1;
         const int n_items = a.n_layers * a.n_tiles * parts;
         while (true) {
             int item = 0;
@@ -759,7 +761,7 @@ __device__ __forceinline__ void k2_line_sum_body(const K2Args &a) {
                 }
             }
             bool finish = true;                            // this CTA runs the tile's epilogue (always, unless tiles are split)
-            if (a.parts > 1) {
+            if (SPLIT && a.parts > 1) {
                 // line-range parts: park this part's sums (far-field contributions included); the CTA that completes the
                 // tile adds all parts in part order -- a fixed order, whoever finishes last
                 const int lt = d.layer * a.n_tiles + (d.tile0 / TILE - a.tile_base);
@@ -830,16 +832,16 @@ __device__ __forceinline__ void k2_line_sum_body(const K2Args &a) {
 }
 
 // The exact kernel: 96 registers (2 CTAs x 288 threads, ptxas' own bound for that launch shape).
-template <int P>
+template <int P, bool SPLIT = false>
 __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum(const K2Args a) {
-    k2_line_sum_body<P, false>(a);
+    k2_line_sum_body<P, false, SPLIT>(a);
 }
 // The far-field variant (same launch shape: 96 registers is the most that lets two CTAs share an SM -- the register
 // file is per SM sub-partition, 16 384 each, and two CTAs put five warps on one of them; 112 was tried and halves the
 // occupancy).
-template <int P>
+template <int P, bool SPLIT = false>
 __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) k2_line_sum_far(const K2Args a) {
-    k2_line_sum_body<P, true>(a);
+    k2_line_sum_body<P, true, SPLIT>(a);
 }
 
 }  // namespace prb
