@@ -776,10 +776,35 @@ def run_mirror(e, w, e2e_ms):
         t0 = time.perf_counter()
         rows = [C.getCrossSection(m[0]) for m in layer]          # the rows are still on the device: one D2H for all four
         comp_ms = (time.perf_counter() - t0) * 1e3
+        # where the cold call's time goes: the same engine calls, one by one (host wall clock, synchronised)
+        isos = [m[0] for m in layer]
+        stage = {}
+
+        def lap(name, fn):
+            e.synchronize()
+            t = time.perf_counter()
+            out = fn()
+            e.synchronize()
+            stage[name] = (time.perf_counter() - t) * 1e3
+            return out
+        n_pts = len(tr)
+        win = eng_window = None
+        from pyrad_b200 import engine as eng
+        win = eng.window_len(layer.distanceFromCenter, layer.resolution)
+        lap("upload_line_groups_ms", lambda: e.upload_line_groups([iso._cols for iso in isos]))
+        lap("set_grid_ms", lambda: e.set_grid(layer.rangeMin, layer.resolution, n_pts))
+        lap("layer_prepass_ms", lambda: e.layer_prepass(layer.T, layer.P, [iso.molecule.concentration for iso in isos],
+                                                        [iso.molmass for iso in isos], [iso.q[layer.T] for iso in isos],
+                                                        [iso.q296 for iso in isos], win))
+        lap("line_sum_groups_ms", lambda: e.line_sum_groups(to_host=False))
+        wts = [eng.number_density_weight(iso.molecule.concentration, layer.P, layer.T) for iso in isos]
+        lap("layer_spectra_resident_ms", lambda: e.layer_spectra_resident(wts, layer.depth, layer.T, layer.rangeMax,
+                                                                          want=("transmittance",)))
+        C._RESIDENT_KEY = None
         return {"workload": "cfg2 through pyrad_b200.classes (Layer > Molecule > Isotope), pageable numpy line arrays, float64 results",
                 "lines": n_lines, "points": len(tr), "build_objects_ms": build_ms,
                 "get_transmittance_cold_ms": cold_ms, "vs_c_abi_e2e": cold_ms / e2e_ms if e2e_ms else None,
-                "per_isotopologue_rows_ms": comp_ms, "rows": len(rows),
+                "per_isotopologue_rows_ms": comp_ms, "rows": len(rows), "cold_call_stages": stage,
                 "bytes": {"h2d": int(n_lines * 7 * 8), "d2h_transmittance": int(8 * len(tr)), "d2h_rows": int(8 * len(tr) * len(rows))},
                 "mean_transmittance": float(np.nanmean(tr)),
                 "api": "classes.getTransmittance(layer): prb_upload_line_groups + prb_set_grid + prb_layer_prepass + "

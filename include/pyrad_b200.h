@@ -88,6 +88,10 @@ int         prb_create(int device, prb_engine **out);
 int         prb_destroy(prb_engine *e);
 void       *prb_stream(prb_engine *e);                  /* the engine's cudaStream_t */
 int         prb_synchronize(prb_engine *e);             /* stream sync + deferred device status */
+/* page-locked host memory (cudaHostAlloc) for line columns / result buffers a caller keeps: copies to and from it run at
+ * PCIe speed instead of through the driver's staging buffer; NULL when no CUDA device is usable */
+void       *prb_host_alloc(size_t bytes);
+int         prb_host_free(void *p);
 int         prb_device_info(prb_engine *e, int *sm_count, int *cc_major, int *cc_minor,
                             int *sm_clock_khz, size_t *free_bytes, size_t *total_bytes);
 /* Roofline denominators measured on this device (bench.py): FP32 lane-FMAs per second of a packed-FFMA2 and of a scalar

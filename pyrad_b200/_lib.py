@@ -37,6 +37,8 @@ PROTOTYPES = {
     "prb_destroy": (C.c_int, [_vp]),
     "prb_stream": (_vp, [_vp]),
     "prb_synchronize": (C.c_int, [_vp]),
+    "prb_host_alloc": (_vp, [C.c_size_t]),
+    "prb_host_free": (C.c_int, [_vp]),
     "prb_device_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "prb_measure_peaks": (C.c_int, [_vp, _dp, _dp, _dp]),

@@ -107,7 +107,7 @@ def getEmissivity(obj):
 def resetCrossSection(obj):
     if not isinstance(obj, Layer):
         if not obj.exotic:
-            obj.crossSection = np.zeros(_n_base(obj))
+            obj.crossSection = None                   # reads as np.zeros(N) (the reference's reset value), made on demand
             obj.progressCrossSection = False
     else:
         obj.progressCrossSection = False
@@ -252,6 +252,21 @@ class Line:
         return self.broadenedLine * np.sqrt(2 * k * self.layer.T / self.isotope.molMass / c ** 2)
 
 
+class _LazyCrossSection:
+    """crossSection of an Isotope / Molecule: an array, or None for "reset" -- which reads as np.zeros(N), built when
+    somebody looks (resetting a layer of 3 M-point spectra is then free instead of eight 24 MB memsets)."""
+
+    @property
+    def crossSection(self):
+        if self._cs is None:
+            self._cs = np.zeros(_n_base(self))
+        return self._cs
+
+    @crossSection.setter
+    def crossSection(self, value):
+        self._cs = value
+
+
 class _Spectral:
     """Pointwise spectra shared by Isotope / Molecule / Layer: all evaluated by K3 on the device."""
 
@@ -288,7 +303,7 @@ class _Spectral:
         return self._stream(("radiance",), np.asarray(surfaceSpectrum, dtype=np.float64))[2]
 
 
-class Isotope(list, _Spectral):
+class Isotope(list, _Spectral, _LazyCrossSection):
     """An isotopologue and its lines.  The reference fills the list with one Line object per transition
     (pyradClasses.py:350-359); here the transitions live in SoA columns and the list protocol hands out Line VIEWS on
     demand (len / iteration / indexing / linelist()), so a 5 M-line list costs its columns, not 5 M Python objects."""
@@ -297,7 +312,7 @@ class Isotope(list, _Spectral):
         list.__init__(self)
         self.molecule = molecule
         self.layer = molecule.layer
-        self.crossSection = np.copy(self.layer.crossSection)
+        self.crossSection = None                      # zeros until computed (the reference copies the fresh layer's zeros)
         self.exotic = molecule.exotic
         self._cols = {kname: np.zeros(0) for kname in _io.LINE_COLUMNS}
         if not isinstance(number, str):
@@ -366,8 +381,15 @@ class Isotope(list, _Spectral):
         """Attach a line list directly (SoA float64 columns, ascending nu) instead of reading the data tree.  A column
         that is absent (the Einstein A of a synthetic list) reads as zeros."""
         n = len(cols["nu"])
-        self._cols = {kname: (np.ascontiguousarray(cols[kname], dtype=np.float64) if kname in cols else np.zeros(n))
-                      for kname in _io.LINE_COLUMNS}
+        # the isotopologue owns its columns, in page-locked memory when a device is there: every later upload of the
+        # list then runs at PCIe speed instead of through the driver's staging buffer
+        block = _eng.PinnedBlock((8 * n + 64) * len(_io.LINE_COLUMNS))
+        self._cols = {}
+        for kname in _io.LINE_COLUMNS:
+            a = block.array(n)
+            a[:] = cols[kname] if kname in cols else 0.0
+            self._cols[kname] = a
+        self._cols_block = block
         if q_table is not None:
             self.q = q_table
         self.progressCrossSection = False
@@ -440,14 +462,14 @@ class Isotope(list, _Spectral):
         return self.crossSection[None, :], [w]
 
 
-class Molecule(list, _Spectral):
+class Molecule(list, _Spectral, _LazyCrossSection):
     def __init__(self, shortNameOrMolNum, layer, isotopeDepth=1, **abundance):
         list.__init__(self)
         self.layer = layer
         self.concText = ""
         self.concentration = 0
         self.exotic = False
-        self.crossSection = np.copy(layer.crossSection)
+        self.crossSection = None                      # zeros until computed (the reference copies the fresh layer's zeros)
         self.progressCrossSection = False
         for key, val in abundance.items():
             if key == "ppm":

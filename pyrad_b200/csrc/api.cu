@@ -325,6 +325,21 @@ extern "C" int prb_destroy(prb_engine *e) {
 
 extern "C" void *prb_stream(prb_engine *e) { return e ? (void *)e->stream : nullptr; }
 
+// Page-locked host memory for callers that keep line columns / result buffers around (the host mirror's Isotope): copies
+// from and to it run at PCIe speed instead of through the driver's staging buffer.  NULL when no device is usable.
+extern "C" void *prb_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" int prb_host_free(void *p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) return fail(PRB_ERR_CUDA, "prb_host_free: cudaFreeHost failed");
+    return PRB_OK;
+}
+
 static int report_flags(const DevState *h, int n_states) {
     unsigned int f = 0;
     for (int k = 0; k < n_states; ++k) f |= h[k].flags;

@@ -22,6 +22,41 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
 
 
+class PinnedBlock:
+    """A block of page-locked host memory (prb_host_alloc) carved into numpy arrays; freed with the last reference.
+    `ok` is False when no CUDA device is usable (the arrays are then ordinary numpy arrays)."""
+
+    def __init__(self, nbytes):
+        self._lib = _lib.load()
+        self.nbytes = int(nbytes)
+        self.ptr = self._lib.prb_host_alloc(self.nbytes) if self.nbytes else None
+        self.ok = bool(self.ptr)
+        self._used = 0
+
+    def array(self, n, dtype=np.float64):
+        """The next n elements of the block as a numpy array (64-byte aligned); an ordinary array when not pinned."""
+        dt = np.dtype(dtype)
+        start = (self._used + 63) & ~63
+        if not self.ok or start + n * dt.itemsize > self.nbytes:
+            return np.empty(n, dtype=dt)
+        self._used = start + n * dt.itemsize
+        buf = (C.c_char * (n * dt.itemsize)).from_address(self.ptr + start)
+        arr = np.frombuffer(buf, dtype=dt, count=n)
+        arr = arr.view()
+        arr.flags.writeable = True
+        self._keep = getattr(self, "_keep", [])
+        self._keep.append(buf)
+        return arr
+
+    def __del__(self):
+        try:
+            if self.ok and self.ptr:
+                self._lib.prb_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
 def window_len(cutoff, res):
     """W = len(np.arange(0, cutoff, res)) (pyradClasses.py:377) -- numpy's own length rule."""
     return len(np.arange(0, cutoff, res))
