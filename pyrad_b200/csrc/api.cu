@@ -20,6 +20,7 @@
 #include "k4_derived.cuh"
 #include "k5_ingest.cuh"
 #include "k9_peaks.cuh"
+#include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
 using namespace prb;
@@ -2014,6 +2015,38 @@ extern "C" int prb_ingest_hitran_csv(prb_engine *e, const char *text, int64_t n_
         }
         CKI(cudaMemcpyAsync(h_scal, d_scal.p, sizeof h_scal, cudaMemcpyDeviceToHost, e->stream));
         CKI(cudaStreamSynchronize(e->stream));
+        if ((h_scal[3] & 0xffffffffull) && n_kept > 1) {
+            // out of order: stable radix sort of the kept rows by wavenumber, last row of every equal-wavenumber run wins,
+            // columns gathered back into the engine's SoA (the parse buffers t[] serve as the source copy)
+            IngestCols cur{e->nu0.p, e->s296.p, e->einstein_a.p, e->elower.p, e->gair.p, e->gself.p, e->delta.p, e->nair.p};
+            const unsigned gk = (unsigned)((n_kept + 255) / 256);
+            for (int c = 0; c < 8; ++c) {
+                double *src8[8] = {cur.nu, cur.sw, cur.a, cur.elower, cur.gair, cur.gself, cur.delta, cur.nair};
+                CKI(cudaMemcpyAsync(t[c].p, src8[c], sizeof(double) * n_kept, cudaMemcpyDeviceToDevice, e->stream));
+            }
+            DevBuf<double> keys_out;
+            DevBuf<int32_t> perm_in, perm_out;
+            CKI(keys_out.ensure(n_kept)); CKI(perm_in.ensure(n_kept)); CKI(perm_out.ensure(n_kept));
+            k5_iota<<<gk, 256, 0, e->stream>>>(perm_in.p, n_kept);
+            size_t tmp3 = 0;
+            CKI(cub::DeviceRadixSort::SortPairs(nullptr, tmp3, t[0].p, keys_out.p, perm_in.p, perm_out.p, (int)n_kept, 0, 64, e->stream));
+            CKI(d_tmp.ensure(tmp3));
+            CKI(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp3, t[0].p, keys_out.p, perm_in.p, perm_out.p, (int)n_kept, 0, 64, e->stream));
+            k5_keep_last_of_run<<<gk, 256, 0, e->stream>>>(keys_out.p, n_kept, d_keep.p);
+            size_t tmp4 = 0;
+            CKI(cub::DeviceScan::ExclusiveSum(nullptr, tmp4, d_keep.p, d_pos.p, n_kept, e->stream));
+            CKI(d_tmp.ensure(tmp4));
+            CKI(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp4, d_keep.p, d_pos.p, n_kept, e->stream));
+            k5_gather_sorted<<<gk, 256, 0, e->stream>>>(tc, perm_out.p, d_keep.p, d_pos.p, n_kept, cur);
+            CKI(cudaGetLastError());
+            int32_t lp = 0, lk = 0;
+            CKI(cudaMemcpyAsync(&lp, d_pos.p + (n_kept - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+            CKI(cudaMemcpyAsync(&lk, d_keep.p + (n_kept - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+            CKI(cudaStreamSynchronize(e->stream));
+            n_kept = (int64_t)lp + lk;
+            keys_out.release(); perm_in.release(); perm_out.release();
+            h_scal[3] = 0;                                      // ascending now (NaN wavenumbers cannot get here: the range filter drops them)
+        }
     } else {
         e->lines_set = false;
         int rc = alloc_line_storage(e, 0);

@@ -187,6 +187,30 @@ k5_scatter_kept(IngestCols tmp, const int32_t *__restrict__ keep, const int32_t 
     dst.gair[o] = tmp.gair[r]; dst.gself[o] = tmp.gself[r]; dst.delta[o] = tmp.delta[r]; dst.nair[o] = tmp.nair[r];
 }
 
+// Out-of-order segment files (the reference's reader keys a dict by nu and takes any order, pyradUtilities.py:421-448):
+// the kept rows are stably sorted by wavenumber (row numbers as the payload of a radix sort), which also brings equal
+// wavenumbers from anywhere in the file next to each other in FILE order -- the last of every run is the row the
+// reference's dict ends up with.
+__global__ void __launch_bounds__(256) k5_iota(int32_t *__restrict__ v, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int32_t)i;
+}
+__global__ void __launch_bounds__(256)
+k5_keep_last_of_run(const double *__restrict__ nu_sorted, int64_t n, int32_t *__restrict__ keep) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keep[i] = (i + 1 == n || nu_sorted[i + 1] != nu_sorted[i]) ? 1 : 0;
+}
+// dst[pos[i]] = src[perm[i]] for the kept entries of the sorted order
+__global__ void __launch_bounds__(256)
+k5_gather_sorted(IngestCols src, const int32_t *__restrict__ perm, const int32_t *__restrict__ keep,
+                 const int32_t *__restrict__ pos, int64_t n, IngestCols dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const int64_t r = perm[i], o = pos[i];
+    dst.nu[o] = src.nu[r]; dst.sw[o] = src.sw[r]; dst.a[o] = src.a[r]; dst.elower[o] = src.elower[r];
+    dst.gair[o] = src.gair[r]; dst.gself[o] = src.gself[r]; dst.delta[o] = src.delta[r]; dst.nair[o] = src.nair[r];
+}
+
 // What prb_upload_lines validates on the host, here on the device: ascending nu0 and max |S296|.
 __global__ void __launch_bounds__(256)
 k5_finalize(const double *__restrict__ nu, const double *__restrict__ sw, int64_t n, unsigned long long *__restrict__ smax_bits,

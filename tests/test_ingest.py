@@ -46,8 +46,32 @@ def test_number_parser_matches_python_float():
         ref = float(s)
         assert rc == 0, s
         assert v == ref and np.signbit(v) == np.signbit(ref), (s, v, ref)
-    for s in ["", "abc", "1e", "--1", "1.2.3", "#", "nan", "inf", "1_0", "12345678901234567890", "0x10", "1 2"]:
+    for s in ["", "abc", "1e", "--1", "1.2.3", "#", "nan", "inf", "1_0", "0x10", "1 2"]:
         assert _parse(lib, s)[0] == -7, s                      # PRB_ERR_PARSE: fail loudly, as float() raises
+
+
+def test_number_parser_long_literals():
+    """More than 19 significant digits (float() parses them; a HITRAN field padded with zeros is one): the first 19 digits
+    and "were the rest zero" decide the result whenever both ends of that interval round to the same double -- always
+    for trailing zeros.  Whatever is accepted equals float(); the rare undecided literal is refused, never guessed."""
+    lib = _lib.load()
+    rng = random.Random(11)
+    for s in ["12345678901234567890", "667.661000000000000000000000", "1.00000000000000000000000000E-5",
+              "0.000000000000000000000000000001234567890123456789012345", "123456789012345678901234567890E-20",
+              "9007199254740993.00000000000000", "5000.0000010000000000000000000"]:
+        rc, v = _parse(lib, s)
+        assert rc == 0 and v == float(s), (s, v)
+    accepted = 0
+    for _ in range(20000):
+        digits = "".join(rng.choice("0123456789") for _ in range(rng.randint(20, 40)))
+        cut = rng.randint(0, len(digits))
+        s = (digits[:cut] + "." + digits[cut:] if rng.random() < 0.7 else digits) + ("E%d" % rng.randint(-330, 290) if rng.random() < 0.5 else "")
+        rc, v = _parse(lib, s)
+        if rc == 0:
+            accepted += 1
+            ref = float(s)
+            assert v == ref or (np.isinf(ref) and np.isinf(v)), (s, v, ref)
+    assert accepted > 19000                                     # undecided (refused) literals are rare
 
 
 def test_number_parser_property_any_decimal_literal():
@@ -130,8 +154,33 @@ def test_device_ingest_edge_cases(engine):
     assert ei.value.code == -7 and "row 0" in str(ei.value)
     with pytest.raises(_lib.EngineError):
         engine.ingest_csv(b"2,1,5.5,1e-20\n", 0.0, 10.0)               # too few cells
-    with pytest.raises(_lib.EngineError):
-        engine.ingest_csv(one + b"\n" + one.replace(b"5.5", b"4.5") + b"\n", 0.0, 10.0)   # descending wavenumbers
+    # descending wavenumbers: sorted on the device (the reference's reader takes any order)
+    assert engine.ingest_csv(one + b"\n" + one.replace(b"5.5", b"4.5") + b"\n", 0.0, 10.0) == 2
+    np.testing.assert_array_equal(engine.download_lines()["nu"], [4.5, 5.5])
+
+
+@pytest.mark.gpu
+def test_device_ingest_takes_rows_in_any_order(engine):
+    """readHitranOnlineFile keys a dict by wavenumber (pyradUtilities.py:421-448): the rows may come in any order and a
+    later row replaces an earlier one of the same wavenumber WHEREVER it stands.  The device path sorts the kept rows
+    (stable radix sort) and keeps the last row of every wavenumber: the same set of lines, ascending."""
+    ln = synth.make_lines(4000, 480.0, 830.0, 321)
+    rows = _csv(ln)
+    rng = np.random.default_rng(3)
+    dup = [rows[i].rsplit(",", 1)[0] + ",0.%03d" % i for i in (7, 1500, 3999)]      # same nu, new n_air
+    order = rng.permutation(len(rows))
+    shuffled = [rows[i] for i in order] + dup                                        # the replacements come last
+    text = ("\n".join(shuffled) + "\n").encode()
+    lo, hi = 500.0, 800.0
+    ref = ph.read_hitran_online_rows(shuffled, lo, hi)                               # dict semantics, insertion order
+    asc = np.argsort(ref["nu"], kind="stable")
+    n = engine.ingest_csv(text, lo, hi)
+    got = engine.download_lines()
+    assert n == len(ref["nu"]) and np.all(np.diff(got["nu"]) > 0)
+    for k in hitran_io.LINE_COLUMNS:
+        np.testing.assert_array_equal(got[k], ref[k][asc], err_msg=k)
+    inside = [i for i in (7, 1500, 3999) if lo < ln["nu"][i] < hi]
+    assert inside and all(got["n_air"][np.searchsorted(got["nu"], ln["nu"][i])] == float("0.%03d" % i) for i in inside)
 
 
 @pytest.mark.gpu
