@@ -21,7 +21,11 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     e = eng.Engine(local)
     torch.cuda.set_stream(torch.cuda.ExternalStream(e.stream))
-    for n_layers, top in ((1, 2.0), (6, 45.0)):
+    for n_layers, top, variant, split in ((1, 2.0, eng.K2_CLASSED, 0), (6, 45.0, eng.K2_CLASSED, 0),
+                                          (1, 2.0, eng.K2_FARFIELD, 1), (6, 45.0, eng.K2_FARFIELD, 1)):
+        # (the far-field variant with line-range parts: the configuration bench.py strong-scales with)
+        e.set_k2_variant(variant, 0)
+        e.set_option(eng.OPT_SPLIT_TILES, split)
         w = workloads.atmosphere(n_layers=n_layers, n_lines=20000, rmin=600.0, rmax=700.0, res=0.001, top_km=top)
         sp = w["species"]
         n_total = eng.grid_len(w["range_min"], w["range_max"], w["res"])
@@ -44,12 +48,14 @@ def main():
             e.atmosphere(*args)
             g_r, g_t = pd.gathered_spectra(e)
             for r, (a, b) in enumerate(plan.chunks):
-                assert torch.equal(g_r[r, : b - a], ref_r[r, : b - a]), (n_layers, step, rank, r, "radiance")
-                assert torch.equal(g_t[r, : b - a], ref_t[r, : b - a]), (n_layers, step, rank, r, "transmittance")
+                assert torch.equal(g_r[r, : b - a], ref_r[r, : b - a]), (n_layers, variant, step, rank, r, "radiance")
+                assert torch.equal(g_t[r, : b - a], ref_t[r, : b - a]), (n_layers, variant, step, rank, r, "transmittance")
         full = pd.assemble(g_t, plan)
         assert full.numel() == n_total
         dist.barrier()
         e.peer_disconnect()
+    e.set_k2_variant(eng.K2_CLASSED, 0)
+    e.set_option(eng.OPT_SPLIT_TILES, 0)
     if rank == 0:
         print("peer_check ok: world %d" % world, flush=True)
     dist.barrier()
