@@ -904,20 +904,34 @@ def run_sharded_column(e, w, windows, column_args, rank, world, ext, use_peer, v
     e.set_option(eng.OPT_SPLIT_TILES, 1 if world > 1 else 0)
     try:
         place(pd.ShardPlan(w["lines"]["nu"], w["range_min"], w["res"], n_total, windows, rank, world, farfield=far))
-        run()
-        torch.cuda.synchronize()
+        for _ in range(2 if world > 1 else 1):          # (the first run allocates; the feedback step reads a warm one)
+            run()
+            torch.cuda.synchronize()
         rebalanced = False
         if world > 1:
-            t0 = e.atmosphere_timing()
-            mine = torch.tensor([t0["k1_ms"] + t0["k2_ms"] + t0["k3_ms"]], dtype=torch.float64, device="cuda")
-            allt = torch.empty(world, dtype=torch.float64, device="cuda")
-            dist.all_gather_into_tensor(allt, mine)
-            plan2 = state["plan"].rebalanced([float(x) for x in allt.tolist()])
-            if plan2 is not state["plan"]:
+            def slowest_rank_ms():
+                t = e.atmosphere_timing()
+                mine = torch.tensor([t["k1_ms"] + t["k2_ms"] + t["k3_ms"]], dtype=torch.float64, device="cuda")
+                allt = torch.empty(world, dtype=torch.float64, device="cuda")
+                dist.all_gather_into_tensor(allt, mine)
+                return [float(x) for x in allt.tolist()]
+            before = slowest_rank_ms()
+            plan1 = state["plan"]
+            plan2 = plan1.rebalanced(before)
+            if plan2 is not plan1:
                 place(plan2)
-                rebalanced = True
-                run()
-                torch.cuda.synchronize()
+                for _ in range(2):
+                    run()
+                    torch.cuda.synchronize()
+                after = slowest_rank_ms()
+                # the feedback step is linear in the chunk's cost; a launch of a few waves is a step function of its tile
+                # count, so the moved cuts are kept only if the slowest rank really got faster
+                if max(after) < max(before):
+                    rebalanced = True
+                else:
+                    place(plan1)
+                    run()
+                    torch.cuda.synchronize()
             dist.barrier()
         times = timed_runs(ext, run, reps, world, dist)
         tim = e.atmosphere_timing()

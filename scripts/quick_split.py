@@ -14,13 +14,17 @@ def main():
     stream = torch.cuda.ExternalStream(e.stream)
     n = eng.grid_len(w["range_min"], w["range_max"], w["res"])
     win = eng.window_len(w["cutoff"], w["res"])
-    plan = pd.ShardPlan(w["lines"]["nu"], w["range_min"], w["res"], n, [win], 3, 8)
+    rank = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    far_plan = len(sys.argv) > 2 and sys.argv[2] == "far"
+    plan = pd.ShardPlan(w["lines"]["nu"], w["range_min"], w["res"], n, [win], rank, 8, farfield=far_plan)
+    print("rank", rank, "plan", "far-field" if far_plan else "exact", "chunks", [(b - a + 2047) // 2048 for a, b in plan.chunks])
     e.upload_lines(plan.subset(w["lines"]), len(sp)); e.set_grid(w["range_min"], w["res"], n, plan.i_begin, plan.i_end)
     T, P = w["T"], w["P"]
     args = ([w["depth_cm"]], [T], [P], [w["conc"]], [s.molmass for s in sp], [[s.q(T) for s in sp]], [s.q296 for s in sp],
             [win], 288.0, w["range_max"])
     print("chunk", plan.i_begin, plan.i_end, "tiles", (plan.i_end - plan.i_begin + 2047) // 2048)
     ref = {}
+    e.set_timing(True)
     for variant in (1, 2):
         for split in (0, 1):
             e.set_k2_variant(variant, 0); e.set_option(eng.OPT_SPLIT_TILES, split)
@@ -34,7 +38,7 @@ def main():
                 ms.append(a.elapsed_time(b))
             rad, tr = e.atmosphere_read()
             ref.setdefault(variant, tr)
-            print("variant", variant, "split", split, "ms %.3f" % np.median(ms), "max |dT| vs unsplit %.2e" % np.nanmax(np.abs(tr - ref[variant])))
+            print("variant", variant, "split", split, "ms %.3f" % np.median(ms), e.atmosphere_timing(), "max |dT| vs unsplit %.2e" % np.nanmax(np.abs(tr - ref[variant])))
     e.set_option(eng.OPT_SPLIT_TILES, 0); e.set_k2_variant(1, 0)
 
 
