@@ -39,6 +39,10 @@ DATA_ROOT = None
 #: largest grid span handed to one K2 launch: FP32 offsets must stay exact integers (< 2^24)
 _MAX_SPAN = 1 << 23
 
+import itertools as _it
+#: unique tokens for "this object / this line list" in Layer._state_key (id() values are reused after a free)
+_TOKEN = _it.count(1)
+
 _ENGINE = None
 #: state key of the Layer whose per-isotopologue rows the engine currently holds (Layer._device_rows)
 _RESIDENT_KEY = None
@@ -315,6 +319,7 @@ class Isotope(list, _Spectral, _LazyCrossSection):
         self.crossSection = None                      # zeros until computed (the reference copies the fresh layer's zeros)
         self.exotic = molecule.exotic
         self._cols = {kname: np.zeros(0) for kname in _io.LINE_COLUMNS}
+        self._lines_token = next(_TOKEN)
         if not isinstance(number, str):
             p = _io.read_mol_params(number, DATA_ROOT)
             self.globalIsoNumber = p["globalIso"]
@@ -376,6 +381,7 @@ class Isotope(list, _Spectral, _LazyCrossSection):
 
     def clearLines(self):
         self._cols = {kname: np.zeros(0) for kname in _io.LINE_COLUMNS}
+        self._lines_token = next(_TOKEN)
 
     def setLines(self, cols, q_table=None):
         """Attach a line list directly (SoA float64 columns, ascending nu) instead of reading the data tree.  A column
@@ -390,6 +396,7 @@ class Isotope(list, _Spectral, _LazyCrossSection):
             a[:] = cols[kname] if kname in cols else 0.0
             self._cols[kname] = a
         self._cols_block = block
+        self._lines_token = next(_TOKEN)
         if q_table is not None:
             self.q = q_table
         self.progressCrossSection = False
@@ -626,6 +633,7 @@ class Layer(list, _Spectral):
             self.hasAtmosphere = atmosphere
         self._cs = np.zeros(int((rangeMax - rangeMin) / BASE_RESOLUTION))
         self._rows_cache = (None, None)
+        self._token = next(_TOKEN)
         self.progressCrossSection = False
         self.exotic = False
         self.name = name or "layer %s" % self.atmosphere.nextLayerName()
@@ -703,8 +711,9 @@ class Layer(list, _Spectral):
 
     def _state_key(self):
         isos = self._isos()
-        return (id(self), self.T, self.P, self.rangeMin, self.rangeMax, self.resolution, self.distanceFromCenter, BASE_RESOLUTION,
-                tuple((id(iso._cols["nu"]), len(iso), iso.molmass, iso.q296, iso.molecule.concentration) for iso in isos),
+        return (self._token, self.T, self.P, self.rangeMin, self.rangeMax, self.resolution, self.distanceFromCenter, BASE_RESOLUTION,
+                tuple((iso._lines_token, len(iso), iso.molmass, iso.q296, iso.molecule.concentration, iso.q.get(self.T))
+                      for iso in isos),
                 tuple(m._xsc_key for m in self if m.exotic))
 
     def _device_rows(self):

@@ -23,7 +23,8 @@ def _dp(a):
 
 
 class PinnedBlock:
-    """A block of page-locked host memory (prb_host_alloc) carved into numpy arrays; freed with the last reference.
+    """A block of page-locked host memory (prb_host_alloc) carved into numpy arrays; freed when the block object and every
+    array carved from it are gone (each array's base keeps the block alive).
     `ok` is False when no CUDA device is usable (the arrays are then ordinary numpy arrays)."""
 
     def __init__(self, nbytes):
@@ -41,12 +42,8 @@ class PinnedBlock:
             return np.empty(n, dtype=dt)
         self._used = start + n * dt.itemsize
         buf = (C.c_char * (n * dt.itemsize)).from_address(self.ptr + start)
-        arr = np.frombuffer(buf, dtype=dt, count=n)
-        arr = arr.view()
-        arr.flags.writeable = True
-        self._keep = getattr(self, "_keep", [])
-        self._keep.append(buf)
-        return arr
+        buf._block = self                    # array -> its ctypes base -> this block: freed with the LAST array, not before
+        return np.frombuffer(buf, dtype=dt, count=n)
 
     def __del__(self):
         try:

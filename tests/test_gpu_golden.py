@@ -272,3 +272,42 @@ def test_merge_xsc_is_byte_identical_to_the_reference(data_root):
     assert sorted(written) == sorted(want) == sorted(got)
     for name in want:
         assert got[name] == want[name], name
+
+
+def test_mirror_resident_rows_follow_the_layer_state(data_root):
+    """The engine holds ONE layer's per-isotopologue rows at a time; the mirror re-uploads whenever another layer, another
+    line list, another mole fraction or another T / P is asked for -- and only then."""
+    g = G.load("cell_fine_grid")
+    species = [str(s) for s in g["species"]]
+    for i, s in enumerate(species):
+        seed(data_root, g, i, s)
+    C.BASE_RESOLUTION = float(g["base"])
+    rmin, rmax = float(g["range_min"]), float(g["range_max"])
+    a = C.Layer(float(g["depth"]), int(g["T"]), float(g["P"]), rmin, rmax, dynamicResolution=False)
+    b = C.Layer(3.0 * float(g["depth"]), 250, 300.0, rmin, rmax, dynamicResolution=False)
+    for layer in (a, b):
+        for s, c in zip(species, g["conc"]):
+            layer.addMolecule(s, concentration=float(c))
+    ta = C.getTransmittance(a)
+    assert np.abs(ta - g["layer_transmittance"]).max() <= H.T_ABS_TOL
+    key_a = C._RESIDENT_KEY
+    tb = C.getTransmittance(b)
+    assert C._RESIDENT_KEY != key_a and not np.array_equal(ta, tb)
+    assert np.array_equal(C.getTransmittance(a), ta)                      # a again: uploaded again, same spectrum
+    assert np.array_equal(a.transmittance, ta) and C._RESIDENT_KEY == key_a  # ... and now straight from the resident rows
+    # per-isotopologue rows come from the same launch
+    for i, m in enumerate(a):
+        assert H.k_rel_err(C.getCrossSection(m[0]), g["sigma_%d" % i]).max() <= H.K_REL_TOL
+    # a new mole fraction invalidates; the result is the one of a fresh layer built with it
+    a[0].setPPM(a[0].concentration * 2e6)
+    t2 = C.getTransmittance(a)
+    fresh = C.Layer(float(g["depth"]), int(g["T"]), float(g["P"]), rmin, rmax, dynamicResolution=False)
+    for k, (s, c) in enumerate(zip(species, g["conc"])):
+        fresh.addMolecule(s, concentration=float(c) * (2 if k == 0 else 1))
+    assert np.array_equal(C.getTransmittance(fresh), t2) and not np.array_equal(t2, ta)
+    # a new line list of the same length invalidates too (tokens, not ids or lengths, identify a list)
+    iso = a[1][0]
+    cols = {k: v.copy() for k, v in iso._cols.items()}
+    cols["sw"] = cols["sw"] * 3.0
+    iso.setLines(cols)
+    assert not np.array_equal(C.getTransmittance(a), t2)
