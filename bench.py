@@ -578,6 +578,17 @@ def main():
         from pyrad_b200 import workloads as wl
         small = {"cfg1": run_small_cell(e, ext, wl.cfg1(), "cfg1: CO2 cell 500-800 cm-1 @ 0.01 cm-1 (30 000 points, 50k lines, W = 500)", flush_buf),
                  "cfg3": run_small_cell(e, ext, wl.cfg3(), "cfg3: CO2 + H2O line by line + CFC-11 / HCFC-22 xsc tables, 500-800 cm-1 @ 0.01 cm-1", flush_buf)}
+        try:
+            # the REAL reference on this very workload, timed in the build container where its sources are mounted
+            # (scripts/time_reference_cfg1.py; committed next to the goldens): same inputs, same pair count
+            real = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_cfg1_timing.json")))
+            if real["pairs"] == small["cfg1"]["pairs"]:
+                small["cfg1"]["reference_real"] = {
+                    "get_transmittance_s": real["get_transmittance_s"], "pairs_per_s": real["pairs_per_s"], "cores": 1,
+                    "machine": real["machine"], "what": real["what"],
+                    "e2e_speedup_vs_real_reference": real["get_transmittance_s"] * 1e3 / small["cfg1"]["e2e"]["ms_per_step"]}
+        except Exception:
+            pass
         mirror = run_mirror(e, w, e2e["ms_per_step"])
     if rank == 0 and world == 1 and not args.no_cpu:
         ingest = run_ingest(e, w)

@@ -27,3 +27,20 @@ def test_gpu_arm_declares_the_same_metric():
     assert bench.METRIC == "line-gridpoint evals/s" and bench.UNIT == "pairs/s"
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     assert bench.METRIC.split()[0] in base["metric"]
+
+
+def test_real_reference_timing_fixture_describes_cfg1():
+    """tests/golden/reference_cfg1_timing.json (the real, unmodified reference timed on cfg1 in the build container,
+    scripts/time_reference_cfg1.py) is on the workload bench.py's cfg1 object runs: same lines, same accumulate count, and the
+    timed run itself agreed with the oracle."""
+    import numpy as np
+    from oracle import physics as ph
+    from pyrad_b200 import workloads
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_cfg1_timing.json")))
+    w = workloads.cfg1()
+    n = ph.grid_len(w["range_min"], w["range_max"], w["res"])
+    ln = w["per_group_lines"][0]
+    lo, hi = ph.effective_range(w["range_min"], w["range_max"], w["cutoff"])
+    nu = ln["nu"][(ln["nu"] > lo) & (ln["nu"] < hi)]
+    assert d["pairs"] == ph.pair_count(ph.line_index(nu, w["range_min"], w["res"]), n, ph.window_len(w["cutoff"], w["res"]))
+    assert d["cores"] == 1 and d["get_transmittance_s"] > 1.0 and d["max_abs_T_diff_oracle_vs_reference"] <= 1e-13
