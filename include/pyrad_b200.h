@@ -124,8 +124,11 @@ int prb_upload_line_groups(prb_engine *e, int32_t n_groups, const int64_t *count
 /* Line list straight from HITRAN-online CSV text (section 8(f) row 1; pyradUtilities.py:173-189, 421-448): `text`
  * is the concatenation of the segment files (host memory; rows molec,iso,nu,sw,a,elower,gamma_air,gamma_self,
  * delta_air,n_air; rows starting with '#' are skipped).  Parsed ON THE DEVICE with exact decimal->double
- * conversion (the value float() returns), kept when wave_min < nu < wave_max (strict), duplicate wavenumbers
- * collapse to the last row, file order preserved.  Replaces prb_upload_lines (single group).  prb_download_lines
+ * conversion (the value float() returns; numbers of more than 19 significant digits included whenever their first 19
+ * digits decide the rounding), kept when wave_min < nu < wave_max (strict), duplicate wavenumbers collapse to the
+ * last row.  Ascending files (HITRAN's) keep their order; rows in any other order are sorted by wavenumber on the
+ * device, the last row of a wavenumber winning wherever it stands (the reference keys a dict by nu).  Replaces
+ * prb_upload_lines (single group).  prb_download_lines
  * copies the resulting columns to host buffers (n = prb_line_count entries each; any may be NULL). */
 int     prb_ingest_hitran_csv(prb_engine *e, const char *text, int64_t n_bytes, double wave_min, double wave_max,
                               int64_t *n_lines_out);
