@@ -788,7 +788,7 @@ static int run_prepass(prb_engine *e, const LayerJob *jobs, int n, DebugOut dbg,
         if (cnt > 0) {
             LinesSoA L{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
                        e->has_group ? e->group.p : nullptr};
-            k1_prepass<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, tab, kb, ke, e->n_lines,
+            k1_prepass<false><<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, tab, kb, ke, e->n_lines,
                                                                             e->i_begin, dbg);
             CK(cudaGetLastError());
             if (launches) ++*launches;
@@ -866,7 +866,7 @@ extern "C" int prb_debug_line_params(prb_engine *e, double *nu_shift, double *ga
     row.narrow = 0; row.pad = 0;
     LinesSoA L{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
                e->has_group ? e->group.p : nullptr};
-    k1_prepass<<<(unsigned)((na + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, tab, 0, na, n, e->i_begin, dbg);
+    k1_prepass<true><<<(unsigned)((na + 255) / 256), 256, 0, e->stream>>>(L, e->idx.p, tab, 0, na, n, e->i_begin, dbg);
     CK(cudaGetLastError());
     if (nu_shift) CK(cudaMemcpyAsync(nu_shift, e->scratch_a.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
     if (gamma_l) CK(cudaMemcpyAsync(gamma_l, e->scratch_b.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
@@ -1545,7 +1545,7 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
                 fill_k1_row(e, jj, tab.rows[0]);
                 LinesSoA Ls{e->nu0.p, e->s296.p, e->gair.p, e->gself.p, e->elower.p, e->nair.p, e->delta.p,
                             e->has_group ? e->group.p : nullptr};
-                k1_prepass<<<(unsigned)((b - a + 255) / 256), 256, 0, st>>>(Ls, e->idx.p, tab, a, b, n, e->i_begin, DebugOut{});
+                k1_prepass<false><<<(unsigned)((b - a + 255) / 256), 256, 0, st>>>(Ls, e->idx.p, tab, a, b, n, e->i_begin, DebugOut{});
                 CK(cudaGetLastError());
                 launches += 2;
             }

@@ -195,7 +195,8 @@ __constant__ double K1_EXP_TAB[64] = {
 // denormal that every later product flushes anyway; above, 1.6e308 overflows the range guards just as inf would.  NaN
 // inputs never get here unnoticed: the kernel flags non-finite line data once per line.)
 __device__ __forceinline__ double exp_k1(double x, const double *__restrict__ tab, const double *__restrict__ c) {
-    x = fmin(fmax(x, -708.0), 709.0);
+    // |x| >= 704 (one integer compare on the high word; NaN and inf land here too): clamp, out of the common path
+    if ((__double2hiint(x) & 0x7fffffff) >= 0x40860000) x = fmin(fmax(x, -708.0), 709.0);
     const double t = fma(x, c[K1C_EXP_INV], c[K1C_EXP_MAGIC]);
     const int n = __double2loint(t);
     const double nf = t - c[K1C_EXP_MAGIC];
@@ -251,6 +252,9 @@ constexpr int K1_UNROLL = PRB_K1_UNROLL;   // layers per trip of the layer loop
 #ifndef PRB_K1_MINB
 #define PRB_K1_MINB 4
 #endif
+// DEBUG: also write the FP64 per-line values of the parity tests (prb_debug_line_params); compiled out of the product
+// launches (five pointer tests per line and layer otherwise).
+template <bool DEBUG = false>
 __global__ void __launch_bounds__(256, PRB_K1_MINB)
 k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ K1Table tab,
            int64_t l_begin, int64_t l_end, int64_t n_lines, int64_t i_base, DebugOut dbg) {
@@ -403,11 +407,13 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
                 K.recB[l] = make_float4(Bf, Bf, (float)G, (float)C);
                 K.recD[l] = dg;
             }
-            if (dbg.nu_shift) dbg.nu_shift[l] = nus;
-            if (dbg.gl) dbg.gl[l] = gl;
-            if (dbg.gd) dbg.gd[l] = gd;
-            if (dbg.st) dbg.st[l] = S;
-            if (dbg.regime) dbg.regime[l] = regime;
+            if (DEBUG) {
+                if (dbg.nu_shift) dbg.nu_shift[l] = nus;
+                if (dbg.gl) dbg.gl[l] = gl;
+                if (dbg.gd) dbg.gd[l] = gd;
+                if (dbg.st) dbg.st[l] = S;
+                if (dbg.regime) dbg.regime[l] = regime;
+            }
         }
         // OR of the status flags, one atomic per warp that has something to report (order independent).
         flags = __reduce_or_sync(0xffffffffu, flags);
