@@ -13,6 +13,9 @@ def main():
         w = workloads.cfg2()
     elif what == "cfg5":
         w = workloads.cfg5()
+    elif what.startswith("p"):
+        w = workloads.cfg5(cutoff=5.0 * float(what[1:]) / 1013.25)   # a cfg4 layer of that pressure [hPa] on the cfg4 line density
+        w["P"], w["T"] = float(what[1:]), 230
     else:
         w = workloads.cfg5(cutoff=5.0 * 971.9 / 1013.25)          # the widest cfg4 layer's window on the cfg4 line density
     sp = w["species"]
