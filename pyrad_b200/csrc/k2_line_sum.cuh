@@ -325,6 +325,11 @@ __device__ __forceinline__ void lorentz_paired(const float4 *sA, const float4 *s
     s.flush();
 }
 
+#ifndef PRB_K2_GAUSS_PAIR_H
+#define PRB_K2_GAUSS_PAIR_H 2
+#endif
+constexpr int K2_GAUSS_PAIR_H = PRB_K2_GAUSS_PAIR_H;   // spans of up to this many 64-point blocks take two hit lines per trip
+
 // Gaussian cores of lines [js, je): only lines whose near zone meets the span (warp-uniform test).
 // MASKED: the window |d| <= wm may cover only part of the span -> zero G per point outside it.
 template <int H, bool MASKED>
@@ -343,11 +348,9 @@ __device__ __forceinline__ void gauss_pass(const float4 *sA, const float4 *sB, c
             hit = (dg >= 0.f) && (f + dg >= wbf) && (f - dg <= we1f);
         }
         unsigned int m = __ballot_sync(0xffffffffu, hit);
-        while (m) {
-            const int j = jb + __ffs(m) - 1;
-            m &= m - 1;
-            const float4 b = sB[j];
-            const float2 nf = splat(sA[j].x), C2 = splat(b.w);
+        // one hit line on all H blocks of the span: term(b, nf) -> a32 += G exp2(C d^2)
+        auto one = [&](const float4 &b, float nf1) {
+            const float2 nf = splat(nf1), C2 = splat(b.w);
 #pragma unroll
             for (int h = 0; h < H; ++h) {
                 const float2 e = __fadd2_rn(s.fi[h], nf);
@@ -359,7 +362,42 @@ __device__ __forceinline__ void gauss_pass(const float4 *sA, const float4 *sB, c
                 }
                 s.a32[h] = __ffma2_rn(g, make_float2(ex2_approx(arg.x), ex2_approx(arg.y)), s.a32[h]);
             }
-            if (++since == K2_FLUSH) { s.flush(); since = 0; }
+        };
+        while (m) {
+            const int j = jb + __ffs(m) - 1;
+            m &= m - 1;
+            if (H <= K2_GAUSS_PAIR_H && m) {
+                // spans of few blocks: two hit lines per trip, so that twice as many exponentials are in flight (the sums
+                // still take the lines in ascending order: same roundings as one line per trip)
+                const int j2 = jb + __ffs(m) - 1;
+                m &= m - 1;
+                const float4 b1 = sB[j], b2 = sB[j2];
+                const float n1 = sA[j].x, n2 = sA[j2].x;
+                const float2 nfa = splat(n1), nfb = splat(n2), Ca = splat(b1.w), Cb = splat(b2.w);
+                float2 ta[H], tb[H], ga[H], gb[H];
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const float2 ea = __fadd2_rn(s.fi[h], nfa), eb = __fadd2_rn(s.fi[h], nfb);
+                    const float2 xa = __fmul2_rn(Ca, __fmul2_rn(ea, ea)), xb = __fmul2_rn(Cb, __fmul2_rn(eb, eb));
+                    ga[h] = splat(b1.z);
+                    gb[h] = splat(b2.z);
+                    if (MASKED) {
+                        ga[h].x = fabsf(ea.x) <= wmf ? b1.z : 0.f;
+                        ga[h].y = fabsf(ea.y) <= wmf ? b1.z : 0.f;
+                        gb[h].x = fabsf(eb.x) <= wmf ? b2.z : 0.f;
+                        gb[h].y = fabsf(eb.y) <= wmf ? b2.z : 0.f;
+                    }
+                    ta[h] = make_float2(ex2_approx(xa.x), ex2_approx(xa.y));
+                    tb[h] = make_float2(ex2_approx(xb.x), ex2_approx(xb.y));
+                }
+#pragma unroll
+                for (int h = 0; h < H; ++h) s.a32[h] = __ffma2_rn(gb[h], tb[h], __ffma2_rn(ga[h], ta[h], s.a32[h]));
+                since += 2;
+                if (since >= K2_FLUSH) { s.flush(); since = 0; }
+                continue;
+            }
+            one(sB[j], sA[j].x);
+            if (++since >= K2_FLUSH) { s.flush(); since = 0; }
         }
     }
     if (since) s.flush();
