@@ -224,7 +224,10 @@ int prb_atmosphere(prb_engine *e, int32_t n_layers, int32_t n_groups,
  * compute: = prb_upload_lines + prb_set_grid + prb_atmosphere(1 layer), bit for bit, but the columns cross PCIe in
  * wavenumber pieces and each piece's prepass and line sum (one wave of K2 tiles) start as soon as it has landed.
  * Combine with prb_set_result_host for results that arrive in host memory the same way (pinned buffers recommended
- * for the inputs too).  Leaves the line list, grid and results on the device like the three separate calls. */
+ * for the inputs too).  Leaves the line list, grid and results on the device like the three separate calls.
+ * The line list is validated ON THE DEVICE while it is being used (ascending nu0, group ids in range): on PRB_ERR_ARG
+ * from that check the result buffers (device arrays, and the host buffers of prb_set_result_host) hold undefined values.
+ * Resident xsc tables (prb_xsc_resident + prb_set_xsc_conc for one layer) are included like in prb_atmosphere. */
 int prb_gas_cell_host(prb_engine *e, int64_t n, const double *nu0, const double *s296, const double *gamma_air,
                       const double *gamma_self, const double *elower, const double *n_air, const double *delta_air,
                       const int32_t *group, int32_t n_groups, double range_min, double res, int64_t n_total,
