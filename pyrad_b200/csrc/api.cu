@@ -2210,10 +2210,17 @@ extern "C" int prb_gas_cell_host(prb_engine *e, int64_t n, const double *nu0, co
     const int ppt = pick_ppt(e, wm);
     const int tile_pts = K2_CONSUMERS * 32 * ppt;
     const int n_tiles = (int)((nc + tile_pts - 1) / tile_pts);
-    // K2 tiles per piece in waves of resident CTAs: measured on cfg2 (ms per call) 1 wave 1.72, 2 waves 1.65, 3 waves 1.65
+    // K2 tiles per piece in waves of resident CTAs: measured on cfg2 (ms per call) 1 wave 1.72, 2 waves 1.65, 3 waves 1.65.
+    // The FIRST piece is a single wave: its lines are across PCIe in half the time, so the first line sum starts earlier
+    // while the second piece still lands under it (PRB_PIPE_FIRST_WAVES).
+#ifndef PRB_PIPE_FIRST_WAVES
+#define PRB_PIPE_FIRST_WAVES 1
+#endif
     const int waves_per_piece = 2;
-    const int wave = waves_per_piece * K2_MIN_CTAS * e->prop.multiProcessorCount;
-    const int S = (n_tiles + wave - 1) / wave;
+    const int wave1 = K2_MIN_CTAS * e->prop.multiProcessorCount;
+    const int wave = waves_per_piece * wave1;
+    const int first = std::min(n_tiles, PRB_PIPE_FIRST_WAVES * wave1);
+    const int S = (first > 0 ? 1 : 0) + (n_tiles - first + wave - 1) / wave;
     const bool pipelined = k2_classed(e) && e->fuse_single && wm >= e->narrow_wm && S >= 2 && n >= 4096;
     if (!pipelined) {
         int rc = prb_upload_lines(e, n, nu0, s296, gamma_air, gamma_self, elower, n_air, delta_air, group, n_groups);
@@ -2266,7 +2273,7 @@ extern "C" int prb_gas_cell_host(prb_engine *e, int64_t n, const double *nu0, co
     pipe.smax_bits_dev = e->dev_scal.p;
     pipe.scale_dev = reinterpret_cast<double *>(e->dev_scal.p + 2);
     for (int sidx = 0; sidx < S; ++sidx) {
-        const int t0 = sidx * wave, t1 = std::min(n_tiles, t0 + wave);
+        const int t0 = sidx == 0 ? 0 : first + (sidx - 1) * wave, t1 = sidx == 0 ? first : std::min(n_tiles, t0 + wave);
         const int64_t p0 = (int64_t)t0 * tile_pts, p1 = std::min<int64_t>(nc, (int64_t)t1 * tile_pts);
         const double nu_lo = range_min + (double)(i_begin + p0 - wm - 2) * res;
         const double nu_hi = range_min + (double)(i_begin + p1 - 1 + wm + 3) * res;
