@@ -44,3 +44,14 @@ def test_real_reference_timing_fixture_describes_cfg1():
     nu = ln["nu"][(ln["nu"] > lo) & (ln["nu"] < hi)]
     assert d["pairs"] == ph.pair_count(ph.line_index(nu, w["range_min"], w["res"]), n, ph.window_len(w["cutoff"], w["res"]))
     assert d["cores"] == 1 and d["get_transmittance_s"] > 1.0 and d["max_abs_T_diff_oracle_vs_reference"] <= 1e-13
+
+
+def test_rank_affinity_helper_never_fails_and_never_widens():
+    """bench.pin_rank_to_gpu_numa binds a rank to its GPU's CPUs when the box tells which those are; without nvidia-smi or
+    sysfs (here) it reports why nothing changed and leaves the affinity alone."""
+    import bench
+    before = os.sched_getaffinity(0)
+    msg = bench.pin_rank_to_gpu_numa(0)
+    assert isinstance(msg, str) and msg
+    assert os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
