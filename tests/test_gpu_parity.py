@@ -613,3 +613,14 @@ def test_k2_farfield_variant_is_shard_invariant_and_feeds_the_fused_paths(engine
     finally:
         engine.set_k2_variant(eng.K2_CLASSED, 0)
     assert np.abs(tr_far - tr_exact).max() <= 1e-6
+
+
+def test_measured_peaks_are_plausible_roofline_denominators(engine):
+    """prb_measure_peaks (the denominators of bench.py's rooflines): the packed-FFMA2 and scalar-FFMA streams both reach the
+    FP32 pipe's rate (148 SMs x 128 lanes x clock, within 15 %), the float4 copy a few TB/s."""
+    info = engine.device_info()
+    p = engine.measure_peaks()
+    nominal = info["sm_count"] * 128 * info["sm_clock_khz"] * 1e3
+    assert 0.85 * nominal <= p["ffma2_lane_fma_per_s"] <= 1.02 * nominal, (p, nominal)
+    assert 0.85 * nominal <= p["ffma_lane_fma_per_s"] <= 1.02 * nominal, (p, nominal)
+    assert 3e12 <= p["copy_bytes_per_s"] <= 9e12, p
