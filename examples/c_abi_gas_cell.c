@@ -5,6 +5,11 @@
  *   gcc -O2 -I include examples/c_abi_gas_cell.c -o build/c_abi_gas_cell -L pyrad_b200 -lpyrad_b200 \
  *       -Wl,-rpath,$PWD/pyrad_b200 -lm
  *
+ * Then the same cell with its lines held as TWO isotopologue lists (odd / even lines), uploaded from where they are with
+ * prb_upload_line_groups: one prepass + one line-sum launch give a cross-section row per list (the per-isotopologue loop
+ * of Layer.createCrossSection, :498-503, 566-576), and prb_layer_spectra_resident forms the transmittance on the device
+ * from those rows -- it must agree with the single-list result.
+ *
  * Prints the pair count, the largest absorption coefficient and the mean transmittance; exits 0 on success and
  * non-zero with the library's error text otherwise (on a machine without a B200 that is PRB_ERR_NODEVICE: there is
  * no CPU fallback). */
@@ -52,7 +57,33 @@ int main(void) {
     for (int64_t i = 0; i < n_grid; ++i) { kmax = k[i] > kmax ? k[i] : kmax; tmean += t[i]; }
     printf("c_abi_gas_cell ok: abi %d, %lld pairs, k_max %.6e cm^-1, mean transmittance %.6f\n", prb_abi_version(),
            (long long)prb_pair_count(e), kmax, tmean / n_grid);
-    free(sigma); free(k); free(t);
+    /* --- the same lines as two groups, per-group rows in one pass, spectra from the device-resident rows --- */
+    enum { HALF = N_LINES / 2 };
+    static double g_nu[2][HALF], g_sw[2][HALF], g_ga[2][HALF], g_gs[2][HALF], g_el[2][HALF], g_na[2][HALF], g_da[2][HALF];
+    for (int i = 0; i < N_LINES; ++i) {
+        const int g = i & 1, j = i >> 1;
+        g_nu[g][j] = nu[i]; g_sw[g][j] = sw[i]; g_ga[g][j] = ga[i]; g_gs[g][j] = gs[i];
+        g_el[g][j] = el[i]; g_na[g][j] = na[i]; g_da[g][j] = da[i];
+    }
+    const int64_t counts[2] = {HALF, HALF};
+    const double *p_nu[2] = {g_nu[0], g_nu[1]}, *p_sw[2] = {g_sw[0], g_sw[1]}, *p_ga[2] = {g_ga[0], g_ga[1]},
+                 *p_gs[2] = {g_gs[0], g_gs[1]}, *p_el[2] = {g_el[0], g_el[1]}, *p_na[2] = {g_na[0], g_na[1]},
+                 *p_da[2] = {g_da[0], g_da[1]};
+    const double conc2[2] = {conc, conc}, mass2[2] = {molmass, molmass}, q2[2] = {q296, q296}, w2[2] = {weight, weight};
+    CHECK(prb_upload_line_groups(e, 2, counts, p_nu, p_sw, p_ga, p_gs, p_el, p_na, p_da));
+    CHECK(prb_set_grid(e, range_min, res, n_grid, 0, n_grid));
+    CHECK(prb_layer_prepass(e, T, P, 2, conc2, mass2, q2, q2, NULL, window));
+    double *rows = malloc(sizeof(double) * 2 * n_grid), *t2 = malloc(sizeof(double) * n_grid);
+    CHECK(prb_line_sum_groups(e, rows));
+    CHECK(prb_layer_spectra_resident(e, w2, NULL, depth_cm, T, range_max, NULL, NULL, t2, NULL));
+    double dmax = 0, smax = 0;
+    for (int64_t i = 0; i < n_grid; ++i) {
+        const double ds = fabs(rows[i] + rows[n_grid + i] - sigma[i]), dt = fabs(t2[i] - t[i]);
+        smax = ds > smax * sigma[i] ? ds / (sigma[i] > 0 ? sigma[i] : 1) : smax;
+        dmax = dt > dmax ? dt : dmax;
+    }
+    printf("c_abi_gas_cell groups: 2 rows in one pass, max |dT| vs the single list %.2e, max rel d(sigma) %.2e\n", dmax, smax);
+    free(sigma); free(k); free(t); free(rows); free(t2);
     CHECK(prb_destroy(e));
-    return (kmax > 0 && tmean > 0) ? 0 : 1;
+    return (kmax > 0 && tmean > 0 && dmax <= 1e-6 && smax <= 1e-5) ? 0 : 1;
 }

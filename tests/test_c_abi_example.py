@@ -35,3 +35,4 @@ def test_c_example_runs_on_the_gpu(tmp_path):
     out = subprocess.run([build(tmp_path)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "c_abi_gas_cell ok" in out.stdout and "pairs" in out.stdout
+    assert "2 rows in one pass" in out.stdout                      # the grouped API from C pointer tables
