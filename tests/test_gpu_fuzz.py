@@ -1,0 +1,124 @@
+"""Seeded random sweep of gas cells through the C ABI against the oracle: pressure (window length and line-shape regime),
+temperature, grid resolution, cutoff, line density, species mix, the wavenumber chunk a rank would own, the K2 variant
+(exact / far-field) and line-range parts all drawn together, so that the class boundaries of the kernels (span sizes,
+window classes, far-field thresholds, narrow-window kernels, chunk edges) are met in combinations the hand-picked
+parity cases do not list.  The oracle is evaluated in its gather form at boundary-inclusive sample points, so windows
+of tens of thousands of points stay cheap on the CPU.  Tolerance: the north_star's rel <= 1e-5 on k(nu)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import physics as ph
+from pyrad_b200 import engine as eng
+from pyrad_b200 import workloads
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+#: cases per sweep in the suite; PRB_FUZZ_SCALE=25 runs the long sweep (1500 cells, 500 columns: a few minutes of oracle time)
+SCALE = int(os.environ.get("PRB_FUZZ_SCALE", "1"))
+TILE = 2048
+SPECIES = ["h2o", "co2", "ch4", "o3"]
+CONC = {"h2o": 0.01, "co2": 400e-6, "ch4": 1.8e-6, "o3": 5e-8}
+
+
+def draw_case(seed):
+    rng = np.random.default_rng(1000 + seed)
+    res = float(rng.choice([0.1, 0.01, 0.005, 0.002, 0.001]))
+    P = float(np.exp(rng.uniform(np.log(0.05), np.log(3000.0))))
+    T = int(rng.integers(180, 330))
+    # the layer's own cutoff (5 cm-1 * P / p0) most of the time, else a cutoff drawn for a window of 1 .. 40 000 points
+    cutoff = None if rng.random() < 0.6 else float(res * np.exp(rng.uniform(0.0, np.log(40000.0))))
+    n_grid = int(np.exp(rng.uniform(np.log(300.0), np.log(400000.0))))
+    rmin = float(rng.choice([0.0, 2.5, 600.0, 1000.0, 2349.0]))
+    rmax = rmin + n_grid * res
+    names = list(rng.choice(SPECIES, size=int(rng.integers(1, 5)), replace=False))
+    # mean line spacing of 0.2 .. 50 grid points, bounded so that the whole case stays small
+    n_lines = int(min(max(n_grid / np.exp(rng.uniform(np.log(0.2), np.log(50.0))), 8), 120000))
+    w = workloads.gas_cell(names, n_lines, rmin, rmax, res, T, P, [CONC[s] for s in names], 10.0, 500 + seed, cutoff=cutoff)
+    n = eng.grid_len(rmin, rmax, res)
+    # chunk: the whole grid, or a tile-aligned slice as a rank of a sharded run owns it
+    lo, hi = 0, n
+    if n > 3 * TILE and rng.random() < 0.5:
+        t = np.sort(rng.choice(np.arange(0, n // TILE + 1), size=2, replace=False))
+        lo, hi = int(t[0]) * TILE, min(int(t[1]) * TILE, n)
+    variant = eng.K2_FARFIELD if rng.random() < 0.5 else eng.K2_CLASSED
+    split = bool(rng.random() < 0.3)
+    return w, n, lo, hi, variant, split
+
+
+@pytest.mark.parametrize("seed", range(60 * SCALE))
+def test_random_cell_matches_oracle(engine, seed):
+    w, n, lo, hi, variant, split = draw_case(seed)
+    H.engine_setup(engine, w, lo, hi)
+    wts = [eng.number_density_weight(c, w["P"], w["T"]) for c in w["conc"]]
+    engine.set_k2_variant(variant, 0)
+    engine.set_option(eng.OPT_SPLIT_TILES, 1 if split else 0)
+    try:
+        H.engine_prepass(engine, w, weights=wts)
+        out = engine.line_sum()
+    finally:
+        engine.set_option(eng.OPT_SPLIT_TILES, 0)
+        engine.set_k2_variant(eng.K2_CLASSED, 0)
+    assert out.shape == (hi - lo,)
+    pts = H.boundary_points(n, 150, seed, n_tiles=8)
+    pts = np.unique(np.concatenate([pts, [lo, min(lo + 1, hi - 1), hi - 2 if hi - 2 >= lo else lo, hi - 1]]))
+    pts = pts[(pts >= lo) & (pts < hi)]
+    ref = H.oracle_layer_k_at(w, pts, w["T"], w["P"], w["conc"], w["cutoff"])
+    # (the sample of a chunk may hold no line centre: the FP32 floor is taken from the line list's tallest core)
+    err = H.k_rel_err(out[pts - lo], ref, peak=max(H.gaussian_peak(w, wts), float(np.abs(ref).max())))
+    info = dict(seed=seed, P=w["P"], T=w["T"], res=w["res"], cutoff=w["cutoff"], n=n, chunk=(lo, hi),
+                lines=len(w["lines"]["nu"]), variant=variant, split=split, window=eng.window_len(w["cutoff"], w["res"]))
+    assert err.max() <= H.K_REL_TOL, (info, float(err.max()), int(pts[err.argmax()]))
+    # the metric's numerator on the owned chunk (integer work: exact)
+    if lo == 0 and hi == n:
+        idx = ph.line_index(w["lines"]["nu"], w["range_min"], w["res"])
+        assert engine.pair_count() == ph.pair_count(idx, n, eng.window_len(w["cutoff"], w["res"])), info
+
+
+def draw_column(seed):
+    rng = np.random.default_rng(7000 + seed)
+    res = float(rng.choice([0.01, 0.005, 0.002, 0.001]))
+    n_layers = int(rng.integers(1, 41))
+    top_km = float(rng.uniform(15.0, 90.0))
+    n_grid = int(np.exp(rng.uniform(np.log(2000.0), np.log(200000.0))))
+    rmin = float(rng.choice([2.5, 600.0, 1000.0, 2349.0, 4300.0]))
+    rmax = rmin + n_grid * res
+    n_lines = int(min(max(n_grid / np.exp(rng.uniform(np.log(0.5), np.log(40.0))), 40), 100000))
+    fixed = None if rng.random() < 0.7 else float(res * np.exp(rng.uniform(np.log(3.0), np.log(20000.0))))
+    w = workloads.atmosphere(n_layers=n_layers, n_lines=n_lines, rmin=rmin, rmax=rmax, res=res, top_km=top_km,
+                             fixed_cutoff=fixed, seed=900 + seed)
+    # layer depth scaled so that columns from transparent to opaque are met (the fold's thin and thick forms)
+    w["depth_cm"] = w["depth_cm"] * float(np.exp(rng.uniform(np.log(1e-7), np.log(1e-2))))
+    w["t_surface"] = float(rng.uniform(220.0, 320.0))
+    variant = eng.K2_FARFIELD if rng.random() < 0.5 else eng.K2_CLASSED
+    split = bool(rng.random() < 0.3)
+    return w, variant, split
+
+
+@pytest.mark.parametrize("seed", range(20 * SCALE))
+def test_random_column_matches_oracle(engine, seed):
+    """The column path (one batched K1, K2 per layer class, K3 fold or the fused epilogue) on random columns: total
+    transmittance to 1e-6 absolute, radiance to 2e-5 relative, at boundary-inclusive sample points."""
+    w, variant, split = draw_column(seed)
+    n = H.engine_setup(engine, w)
+    sp = w["species"]
+    win = [eng.window_len(c, w["res"]) for c in w["cutoff"]]
+    qt = np.array([[s.q(T) for s in sp] for T in w["T"]])
+    engine.set_k2_variant(variant, 0)
+    engine.set_option(eng.OPT_SPLIT_TILES, 1 if split else 0)
+    try:
+        engine.atmosphere(w["depth_cm"], w["T"], w["P"], w["conc"], [s.molmass for s in sp], qt, [s.q296 for s in sp],
+                          win, w["t_surface"], w["range_max"])
+        rad, tr = engine.atmosphere_read()
+    finally:
+        engine.set_option(eng.OPT_SPLIT_TILES, 0)
+        engine.set_k2_variant(eng.K2_CLASSED, 0)
+    pts = H.boundary_points(n, 120, seed, n_tiles=6)
+    rad_ref, tr_ref = H.oracle_column_at(w, pts, w["t_surface"])
+    info = dict(seed=seed, layers=len(w["T"]), res=w["res"], n=n, lines=len(w["lines"]["nu"]), variant=variant, split=split,
+                windows=(min(win), max(win)), rmin=w["range_min"], depth=float(w["depth_cm"][0]))
+    dt = np.abs(tr[pts] - tr_ref)
+    assert dt.max() <= H.T_ABS_TOL, (info, float(dt.max()), int(pts[dt.argmax()]))
+    np.testing.assert_allclose(rad[pts], rad_ref, rtol=2e-5, atol=0, err_msg=str(info))
