@@ -23,6 +23,29 @@ SPECIES = ["h2o", "co2", "ch4", "o3"]
 CONC = {"h2o": 0.01, "co2": 400e-6, "ch4": 1.8e-6, "o3": 5e-8}
 
 
+def cluster_lines(w, rng):
+    """Replace the jittered lattice of line positions by an uneven one: a few dense clusters (band heads: many lines on
+    the same few grid points), repeated wavenumbers, and empty stretches in between."""
+    from pyrad_b200 import synth
+    lo = max(w["range_min"] - w["cutoff"], 0.0) + 1e-6
+    hi = w["range_max"] + w["cutoff"] - 1e-6
+    for ln in w["per_group_lines"]:
+        m = len(ln["nu"])
+        if m < 4:
+            continue
+        k = int(rng.integers(1, 6))
+        centre = rng.uniform(lo, hi, k)
+        width = w["res"] * np.exp(rng.uniform(np.log(0.5), np.log(3000.0), k))
+        which = rng.integers(0, k, m)
+        nu = centre[which] + width[which] * rng.standard_normal(m)
+        stray = rng.random(m) < 0.2
+        nu[stray] = rng.uniform(lo, hi, int(stray.sum()))
+        nu[rng.random(m) < 0.05] = centre[0]                          # a pile of lines on one wavenumber
+        ln["nu"] = np.sort(np.clip(np.round(nu, 6), lo, hi))
+    w["lines"] = synth.merge_species_lines(w["per_group_lines"])
+    w.pop("_idx_cache", None)
+
+
 def draw_case(seed):
     rng = np.random.default_rng(1000 + seed)
     res = float(rng.choice([0.1, 0.01, 0.005, 0.002, 0.001]))
@@ -37,6 +60,8 @@ def draw_case(seed):
     # mean line spacing of 0.2 .. 50 grid points, bounded so that the whole case stays small
     n_lines = int(min(max(n_grid / np.exp(rng.uniform(np.log(0.2), np.log(50.0))), 8), 120000))
     w = workloads.gas_cell(names, n_lines, rmin, rmax, res, T, P, [CONC[s] for s in names], 10.0, 500 + seed, cutoff=cutoff)
+    if rng.random() < 0.4:
+        cluster_lines(w, rng)
     n = eng.grid_len(rmin, rmax, res)
     # chunk: the whole grid, or a tile-aligned slice as a rank of a sharded run owns it
     lo, hi = 0, n
@@ -122,3 +147,95 @@ def test_random_column_matches_oracle(engine, seed):
     dt = np.abs(tr[pts] - tr_ref)
     assert dt.max() <= H.T_ABS_TOL, (info, float(dt.max()), int(pts[dt.argmax()]))
     np.testing.assert_allclose(rad[pts], rad_ref, rtol=2e-5, atol=0, err_msg=str(info))
+
+
+@pytest.mark.parametrize("seed", range(24 * SCALE))
+def test_random_line_groups_rows_match_oracle(engine, seed):
+    """prb_upload_line_groups / prb_line_sum_groups on random groupings: every species' list cut into a random number of
+    isotopologue lists (some of them empty or a single line), per-group cross-section rows against the oracle."""
+    rng = np.random.default_rng(3000 + seed)
+    w, n, lo, hi, variant, _ = draw_case(5000 + seed)
+    groups, meta = [], []
+    for g, sp in enumerate(w["species"]):
+        ln = w["per_group_lines"][g]
+        m = len(ln["nu"])
+        parts = int(rng.integers(1, 4))
+        tag = rng.integers(0, parts, m) if rng.random() < 0.8 else np.zeros(m, dtype=np.int64)   # (then the others are empty)
+        for q in range(parts):
+            sel = tag == q
+            groups.append({k: np.ascontiguousarray(np.asarray(v)[sel]) for k, v in ln.items()})
+            meta.append(g)
+    sp = [w["species"][g] for g in meta]
+    conc = [w["conc"][g] for g in meta]
+    win = eng.window_len(w["cutoff"], w["res"])
+    engine.upload_line_groups(groups)
+    engine.set_grid(w["range_min"], w["res"], n, lo, hi)
+    engine.set_k2_variant(variant, 0)
+    try:
+        engine.layer_prepass(w["T"], w["P"], conc, [s.molmass for s in sp], [s.q(w["T"]) for s in sp], [s.q296 for s in sp], win)
+        rows = engine.line_sum_groups()
+    finally:
+        engine.set_k2_variant(eng.K2_CLASSED, 0)
+    assert rows.shape == (len(groups), hi - lo)
+    pts = H.boundary_points(n, 100, seed, n_tiles=6)
+    pts = pts[(pts >= lo) & (pts < hi)]
+    wm = max(win - 2, 0)
+    for j, (ln, s) in enumerate(zip(groups, sp)):
+        if len(ln["nu"]) == 0:
+            assert not rows[j].any(), j
+            continue
+        idx = ph.line_index(ln["nu"], w["range_min"], w["res"])
+        sub = H._lines_near(idx, ln, pts, wm)
+        ref = np.zeros(len(pts))
+        if len(sub["nu"]):
+            ref = ph.cross_section_at(pts, sub, w["T"], w["P"], conc[j], s.molmass, s.q(w["T"]), s.q296, w["range_min"],
+                                      w["range_max"], w["res"], w["cutoff"])
+        p = ph.LineParams(ln, w["T"], w["P"], conc[j], s.molmass, s.q(w["T"]), s.q296)
+        ok = p.gD > 0
+        peak = max(float(np.max(np.abs(p.S[ok]) / p.gD[ok])) / np.sqrt(np.pi) if ok.any() else 0.0, float(np.abs(ref).max()))
+        err = H.k_rel_err(rows[j][pts - lo], ref, peak=peak)
+        assert err.max() <= H.K_REL_TOL, (seed, j, len(ln["nu"]), float(err.max()), int(pts[err.argmax()]), win, variant)
+
+
+@pytest.mark.parametrize("seed", range(12 * SCALE))
+def test_random_cell_from_host_buffers_matches_oracle(engine, seed):
+    """prb_gas_cell_host (pipelined upload, fused epilogue, results stored into host buffers) on random cells and chunks:
+    transmittance to 1e-6 absolute against the oracle, and bitwise what upload + set_grid + atmosphere return."""
+    import torch
+    rng = np.random.default_rng(4000 + seed)
+    w, n, lo, hi, variant, _ = draw_case(9000 + seed)
+    sp = w["species"]
+    win = eng.window_len(w["cutoff"], w["res"])
+    depth = float(np.exp(rng.uniform(np.log(1e-2), np.log(1e5))))
+    mol, q296, qt = [s.molmass for s in sp], [s.q296 for s in sp], [s.q(w["T"]) for s in sp]
+    h_rad = torch.zeros(hi - lo, dtype=torch.float32).pin_memory()
+    h_tr = torch.zeros(hi - lo, dtype=torch.float32).pin_memory()
+    engine.set_k2_variant(variant, 0)
+    engine.set_result_host(h_rad.numpy(), h_tr.numpy())
+    try:
+        engine.gas_cell_host(w["lines"], len(sp), w["range_min"], w["res"], n, lo, hi, depth, w["T"], w["P"], w["conc"],
+                             mol, qt, q296, win, 288.0, w["range_max"])
+        engine.synchronize()
+        tr = h_tr.numpy().copy(); rad = h_rad.numpy().copy()
+        engine.set_result_host()
+        engine.upload_lines(w["lines"], n_groups=len(sp))
+        engine.set_grid(w["range_min"], w["res"], n, lo, hi)
+        engine.atmosphere([depth], [w["T"]], [w["P"]], [w["conc"]], mol, [qt], q296, [win], 288.0, w["range_max"])
+        rad2 = np.empty(hi - lo, dtype=np.float32); tr2 = np.empty(hi - lo, dtype=np.float32)
+        engine.atmosphere_read_f32(rad2, tr2)
+    finally:
+        engine.set_result_host()
+        engine.set_k2_variant(eng.K2_CLASSED, 0)
+    assert np.array_equal(tr, tr2) and np.array_equal(rad, rad2, equal_nan=True)
+    pts = H.boundary_points(n, 100, seed, n_tiles=6)
+    pts = pts[(pts >= lo) & (pts < hi)]
+    k = H.oracle_layer_k_at(w, pts, w["T"], w["P"], w["conc"], w["cutoff"])
+    t_ref = ph.transmittance(k, depth)
+    got = tr[pts - lo]
+    # (lines piled next to 0 cm-1 with a negative pressure shift get a negative Doppler width in the reference and with it
+    # a negative k: exp(-k u) overflows there, in the reference's FP64 and in the engine's FP32 result alike)
+    huge = ~np.isfinite(t_ref) | (t_ref > 1e30)
+    assert np.all(~np.isfinite(got[huge]) | (got[huge] > 1e30))
+    dt = np.abs(got[~huge] - t_ref[~huge])
+    assert dt.size == 0 or dt.max() <= H.T_ABS_TOL * max(1.0, float(np.abs(t_ref[~huge]).max())), \
+        (seed, float(dt.max()), int(pts[~huge][dt.argmax()]), win, variant, depth)
