@@ -198,7 +198,9 @@ def _merge_plan(newX, oldX):
     else:
         final_new, final_old = len(nx) - 1, src0 + len(nx) - 1
     count = max(final_old - src0, 0)
-    out_len = dst0 + count + (len(nx) - final_new)
+    if src0 + count > len(ox):
+        raise IndexError("list index out of range")               # the reference's copy loop runs off oldY (:224-226)
+    out_len = dst0 + count + max(len(nx) - final_new, 0)          # ([0] * negative is an empty list, :229)
     return dst0, src0, count, out_len
 
 

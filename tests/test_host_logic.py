@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 from oracle import physics as ph
 from pyrad_b200 import classes as C
@@ -81,6 +82,38 @@ def test_merge_plan_matches_oracle_merge_array():
     mine = np.zeros(out_len)
     mine[dst0:dst0 + count] = old_y[src0:src0 + count]
     assert np.array_equal(mine, ref)
+
+
+def test_merge_plan_random_ranges_behave_like_the_oracle():
+    """Random layer / table ranges (table inside, around, overlapping one end of, or away from the layer's range; edges
+    on and off the 0.01 grid): the plan reproduces mergeArray's result or fails where it fails (its `.index` lookups
+    raise ValueError when a rounded edge is not on the other axis)."""
+    rng = np.random.default_rng(17)
+    same, raised = 0, 0
+    for _ in range(300):
+        a = round(float(rng.uniform(500.0, 600.0)), int(rng.integers(0, 4)))
+        b = a + round(float(rng.uniform(0.5, 40.0)), int(rng.integers(0, 3)))
+        new_x = np.linspace(a, b, int((b - a) / .01))                         # Layer.xAxis, pyradClasses.py:659
+        lo = round(float(rng.uniform(a - 30.0, b + 10.0)), int(rng.integers(0, 4)))
+        hi = lo + round(float(rng.uniform(0.2, 60.0)), int(rng.integers(0, 3)))
+        old_x = np.arange(lo, hi, .01)
+        if len(new_x) < 2 or len(old_x) < 2:
+            continue
+        old_y = rng.uniform(1, 2, old_x.size)
+        try:
+            ref = ph.merge_array(new_x, old_x, old_y)
+        except (ValueError, IndexError) as err:
+            with pytest.raises(type(err)):
+                C._merge_plan(new_x, old_x)
+            raised += 1
+            continue
+        dst0, src0, count, out_len = C._merge_plan(new_x, old_x)
+        assert out_len == len(ref)
+        mine = np.zeros(max(out_len, dst0 + count))
+        mine[dst0:dst0 + count] = old_y[src0:src0 + count]
+        assert np.array_equal(mine[:out_len], ref)
+        same += 1
+    assert same > 50 and raised > 5
 
 
 def test_unit_conversions_and_concentration_setters():
