@@ -194,3 +194,24 @@ def test_farfield_cost_model_tracks_the_far_field_work():
             assert 0.6 * want <= far_cost[b] <= 1.6 * want, (window, b, far_cost[b], want)
     # level 2 (cfg5-like window): the far term shrinks again
     assert pt.block_time_cost(idx, n, [25000], farfield=True).sum() < 0.1 * pt.block_time_cost(idx, n, [25000]).sum()
+
+
+def test_shard_plans_on_random_inputs_are_partitions_of_the_grid():
+    """Random grids (ten points to millions), line lists (empty, one line, tens of thousands), window sets, world sizes
+    (also more ranks than tiles) and both cost models: every rank derives the same chunks; they are contiguous,
+    tile-aligned, cover [0, n_total) exactly and may be empty but never overlap."""
+    rng = np.random.default_rng(0)
+    for _ in range(150):
+        world = int(rng.choice([1, 2, 3, 4, 8]))
+        n_total = int(np.exp(rng.uniform(np.log(10), np.log(3e6))))
+        res = float(rng.choice([0.1, 0.01, 0.001]))
+        rmin = float(rng.choice([0.0, 600.0]))
+        nu = np.sort(rng.uniform(max(rmin - 5, 0), rmin + n_total * res + 5, int(rng.choice([0, 1, 5, 1000, 50000]))))
+        wins = [int(np.exp(rng.uniform(0, np.log(30000)))) for _ in range(int(rng.integers(1, 5)))]
+        ff = bool(rng.random() < 0.5)
+        plans = [pd.ShardPlan(nu, rmin, res, n_total, wins, r, world, farfield=ff) for r in range(world)]
+        ch = plans[0].chunks
+        assert all(p.chunks == ch for p in plans) and len(ch) == world
+        assert ch[0][0] == 0 and ch[-1][1] == n_total
+        assert all(a[1] == b[0] for a, b in zip(ch[:-1], ch[1:])) and all(a <= b for a, b in ch)
+        assert all(a % pt.ALIGN == 0 or a == n_total for a, _ in ch)
