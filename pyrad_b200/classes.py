@@ -67,6 +67,17 @@ def _n_base(obj):
 
 
 # ---------------------------------------------------------------------------------- module-level getters
+def printProgress(text, obj):
+    """Progress line of the reference's per-isotopologue loop (pyradClasses.py:98-102); kept for callers that print it."""
+    print('Processing %s: %s; %s; isotope %s' % (text, obj.layer.name, obj.molecule.name, obj.name))
+
+
+def cacheCurves():
+    """The reference writes its memoised line-shape curves to disk here (pyradClasses.py:947-948, pyradLineshape.py).
+    The device path evaluates every shape in place and keeps no curve cache: nothing to write."""
+    return None
+
+
 def integrateSpectrum(spectrum, unitAngle=pi, res=None):
     res = BASE_RESOLUTION if res is None else res
     return engine().integrate_spectrum(spectrum, unitAngle, res)          # device reduction (K4)
