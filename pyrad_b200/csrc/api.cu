@@ -532,27 +532,35 @@ extern "C" int prb_upload_lines(prb_engine *e, int64_t n, const double *nu0, con
     const int64_t na = e->n_alloc;
     DevBuf<double> *cols[7] = {&e->nu0, &e->s296, &e->gair, &e->gself, &e->elower, &e->nair, &e->delta};
     const double *src[7] = {nu0, s296, gamma_air, gamma_self, elower, n_air, delta_air};
-    for (int c = 0; c < 7; ++c)
-        if (n) CK(cudaMemcpyAsync(cols[c]->p, src[c], sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    if (!e->pin_scal) CK(cudaMallocHost((void **)&e->pin_scal, 64));
+    CK(e->dev_scal.ensure(8));
     e->has_group = group != nullptr;
-    if (group) {
-        CK(e->group.ensure(na));
-        if (n) CK(cudaMemcpyAsync(e->group.p, group, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
-    }
-    // (the H2D copies above are in flight from pinned memory while the host validates)
-    // one validation pass over the host columns: ascending nu0, max |S296|, group ids in range
-    double smax = 0;
-    bool sorted = true, group_ok = true;
-    for (int64_t i = 0; i < n; ++i) {
-        const double sa = std::fabs(s296[i]);
-        smax = sa > smax ? sa : smax;
-        if (i && !(nu0[i] >= nu0[i - 1])) sorted = false;
-        if (group && (group[i] < 0 || group[i] >= n_groups)) group_ok = false;
+    if (group) CK(e->group.ensure(na));
+    if (n) {
+        CK(cudaMemsetAsync(e->dev_scal.p, 0, 2 * sizeof(unsigned long long), e->stream));
+        CK(cudaMemcpyAsync(cols[0]->p, src[0], sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(cols[1]->p, src[1], sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+        if (group) CK(cudaMemcpyAsync(e->group.p, group, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+        // the checks of the line list -- ascending nu0, group ids in range -- and max|S296| run on the device over the
+        // columns just uploaded, while the other five cross the bus (a host pass over the caller's arrays costs as much
+        // as their PCIe time)
+        k0_validate_lines<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->nu0.p, group ? e->group.p : nullptr, n, n_groups,
+                                                                            reinterpret_cast<unsigned int *>(e->dev_scal.p + 1));
+        k0_absmax<<<e->prop.multiProcessorCount * 4, 256, 0, e->stream>>>(e->s296.p, n, e->dev_scal.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(e->pin_scal, e->dev_scal.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+        for (int c = 2; c < 7; ++c)
+            CK(cudaMemcpyAsync(cols[c]->p, src[c], sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
     }
     CK(cudaStreamSynchronize(e->stream));
     e->lines_set = false;
-    if (!sorted) return fail(PRB_ERR_ARG, "prb_upload_lines: nu0 must be ascending");
-    if (!group_ok) return fail(PRB_ERR_ARG, "prb_upload_lines: group id out of range");
+    double smax = 0;
+    if (n) {
+        memcpy(&smax, e->pin_scal, sizeof(double));
+        const unsigned int vf = (unsigned int)e->pin_scal[1];
+        if (vf & 1u) return fail(PRB_ERR_ARG, "prb_upload_lines: nu0 must be ascending");
+        if (vf & 2u) return fail(PRB_ERR_ARG, "prb_upload_lines: group id out of range");
+    }
     e->n_lines = n;
     e->n_groups = n_groups;
     e->s_max = smax;
@@ -600,28 +608,39 @@ extern "C" int prb_upload_line_groups(prb_engine *e, int32_t n_groups, const int
     CK(e->group.ensure(na));
     DevBuf<double> *cols[7] = {&e->nu0, &e->s296, &e->gair, &e->gself, &e->elower, &e->nair, &e->delta};
     const double *const *src[7] = {nu0, s296, gamma_air, gamma_self, elower, n_air, delta_air};
-    for (int g = 0; g < n_groups; ++g)
-        for (int c = 0; c < 7 && cnt[g]; ++c)
-            CK(cudaMemcpyAsync(cols[c]->p + seg[g], src[c][g], sizeof(double) * cnt[g], cudaMemcpyHostToDevice, e->stream));
-    std::vector<int32_t> grp((size_t)std::max<int64_t>(n_dev, 1), -1);
-    double smax = 0;
-    bool sorted = true;
-    for (int g = 0; g < n_groups; ++g) {
-        std::fill(grp.begin() + seg[g], grp.begin() + seg[g] + cnt[g], g);
-        for (int64_t i = 0; i < cnt[g]; ++i) {
-            const double sa = std::fabs(s296[g][i]);
-            smax = sa > smax ? sa : smax;
-            if (i && !(nu0[g][i] >= nu0[g][i - 1])) sorted = false;
+    if (!e->pin_scal) CK(cudaMallocHost((void **)&e->pin_scal, 64));
+    CK(e->dev_scal.ensure(8));
+    CK(cudaMemsetAsync(e->dev_scal.p, 0, 2 * sizeof(unsigned long long), e->stream));
+    // the S296 and nu0 columns first: their checks run on the device while the other columns cross the bus
+    for (int c = 0; c < 7; ++c) {
+        for (int g = 0; g < n_groups; ++g)
+            if (cnt[g])
+                CK(cudaMemcpyAsync(cols[c]->p + seg[g], src[c][g], sizeof(double) * cnt[g], cudaMemcpyHostToDevice, e->stream));
+        if (c != 1 || !n_dev) continue;
+        // group ids, gap entries, and what prb_upload_lines checks in its host pass -- max|S296| and "ascending within
+        // every group" -- as device kernels over the uploaded columns (a host pass over 0.5 M lines costs as much as
+        // their PCIe time): no host vector of group ids, no second read of the caller's columns
+        CK(cudaMemsetAsync(e->group.p, 0xFF, sizeof(int32_t) * n_dev, e->stream));
+        for (int g = 0; g < n_groups; ++g) {
+            if (!cnt[g]) continue;
+            const unsigned nb = (unsigned)((cnt[g] + 255) / 256);
+            k0_set_group<<<nb, 256, 0, e->stream>>>(e->group.p + seg[g], cnt[g], g);
+            k0_validate_lines<<<nb, 256, 0, e->stream>>>(e->nu0.p + seg[g], nullptr, cnt[g], n_groups,
+                                                        reinterpret_cast<unsigned int *>(e->dev_scal.p + 1));
         }
-    }
-    if (n_dev) {
-        CK(cudaMemcpyAsync(e->group.p, grp.data(), sizeof(int32_t) * n_dev, cudaMemcpyHostToDevice, e->stream));
         k0_fill_gaps<<<(unsigned)((n_dev + 255) / 256), 256, 0, e->stream>>>(e->nu0.p, e->s296.p, e->group.p, n_dev);
+        k0_absmax<<<e->prop.multiProcessorCount * 4, 256, 0, e->stream>>>(e->s296.p, n_dev, e->dev_scal.p);
         CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(e->pin_scal, e->dev_scal.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     }
     CK(cudaStreamSynchronize(e->stream));
     e->lines_set = false;
-    if (!sorted) return fail(PRB_ERR_ARG, "prb_upload_line_groups: nu0 must be ascending within every group");
+    double smax = 0;
+    if (n_dev) {
+        memcpy(&smax, e->pin_scal, sizeof(double));
+        if ((unsigned int)e->pin_scal[1] & 1u)
+            return fail(PRB_ERR_ARG, "prb_upload_line_groups: nu0 must be ascending within every group");
+    }
     e->has_group = true;
     e->n_lines = n_dev;
     e->n_groups = n_groups;
@@ -2234,7 +2253,7 @@ extern "C" int prb_gas_cell_host(prb_engine *e, int64_t n, const double *nu0, co
     if (!e->copy_stream) {
         CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
-        CK(cudaMallocHost((void **)&e->pin_scal, 64));
+        if (!e->pin_scal) CK(cudaMallocHost((void **)&e->pin_scal, 64));
         CK(e->dev_scal.ensure(8));
     }
     while ((int)e->pipe_ev.size() < 2 * (S + 1)) {

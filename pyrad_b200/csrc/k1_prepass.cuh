@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(256)
 k0_absmax(const double *__restrict__ x, int64_t n, unsigned long long *__restrict__ out_bits) {
     unsigned long long b = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long v = (unsigned long long)__double_as_longlong(fabs(x[i]));
+        const double a = fabs(x[i]);
+        const unsigned long long v = a == a ? (unsigned long long)__double_as_longlong(a) : 0ull;   // (NaN: skipped, as `>` does on the host)
         b = v > b ? v : b;
     }
     const unsigned int hi = __reduce_max_sync(0xffffffffu, (unsigned int)(b >> 32));
@@ -107,6 +108,13 @@ k0_validate_lines(const double *__restrict__ nu0, const int32_t *__restrict__ gr
     }
     f = __reduce_or_sync(0xffffffffu, f);
     if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
+// Group ids of one segment of a grouped line list (the gaps between segments keep the -1 of the memset before).
+__global__ void __launch_bounds__(256)
+k0_set_group(int32_t *__restrict__ group, int64_t n, int32_t g) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) group[i] = g;
 }
 
 // Gap entries of a grouped line list (group < 0): a wavenumber that maps to the sentinel index, zero intensity.
