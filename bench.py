@@ -796,7 +796,13 @@ def run_mirror(e, w, e2e_ms):
             C.resetCrossSection(layer)
             C._RESIDENT_KEY = None
             return C.getTransmittance(layer)
+        # the first calls also page-lock the result arrays the mirror's pool then reuses (engine.ResultPool: ~15 ms per
+        # 24 MB block, once per result size); the figure quoted is the steady state of a session that recomputes a layer
+        t0 = time.perf_counter()
         tr = cold_transmittance()
+        first_ms = (time.perf_counter() - t0) * 1e3
+        for _ in range(2):
+            tr = cold_transmittance()
         reps = 5
         t0 = time.perf_counter()
         for _ in range(reps):
@@ -832,7 +838,7 @@ def run_mirror(e, w, e2e_ms):
         C._RESIDENT_KEY = None
         return {"workload": "cfg2 through pyrad_b200.classes (Layer > Molecule > Isotope), pageable numpy line arrays, float64 results",
                 "lines": n_lines, "points": len(tr), "build_objects_ms": build_ms,
-                "get_transmittance_cold_ms": cold_ms, "vs_c_abi_e2e": cold_ms / e2e_ms if e2e_ms else None,
+                "get_transmittance_cold_ms": cold_ms, "first_call_ms": first_ms, "vs_c_abi_e2e": cold_ms / e2e_ms if e2e_ms else None,
                 "per_isotopologue_rows_ms": comp_ms, "rows": len(rows), "cold_call_stages": stage,
                 "bytes": {"h2d": int(n_lines * 7 * 8), "d2h_transmittance": int(8 * len(tr)), "d2h_rows": int(8 * len(tr) * len(rows))},
                 "mean_transmittance": float(np.nanmean(tr)),

@@ -52,7 +52,7 @@ def engine():
     """The process-wide CUDA engine (created on first use; raises EngineUnavailable without a B200)."""
     global _ENGINE
     if _ENGINE is None:
-        _ENGINE = _eng.Engine(0)
+        set_engine(_eng.Engine(0))
     return _ENGINE
 
 
@@ -60,6 +60,9 @@ def set_engine(e):
     global _ENGINE, _RESIDENT_KEY
     _ENGINE = e
     _RESIDENT_KEY = None
+    # spectra handed to the caller come from a pool of page-locked arrays that are reused once dropped (engine.ResultPool)
+    if e is not None and getattr(e, "result_pool", None) is None:
+        e.result_pool = _eng.ResultPool()
 
 
 def _n_base(obj):

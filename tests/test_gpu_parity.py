@@ -626,3 +626,41 @@ def test_measured_peaks_are_plausible_roofline_denominators(engine):
     assert 0.5 * nominal <= p["ffma_lane_fma_per_s"] <= 1.05 * nominal, (p, nominal)
     assert abs(p["ffma2_lane_fma_per_s"] / p["ffma_lane_fma_per_s"] - 1) < 0.1       # two forms of the same pipe
     assert 2e12 <= p["copy_bytes_per_s"] <= 9e12, p
+
+
+def test_result_pool_hands_out_and_takes_back_page_locked_arrays(engine):
+    """engine.ResultPool (the mirror's result arrays): a dropped array's block is reused by the next request of that size,
+    arrays alive at the same time never share memory, views keep a block leased, small results stay ordinary arrays."""
+    import gc
+    pool = eng.ResultPool(max_free=2)
+    a = pool.array(1 << 18)                                         # 2 MB of doubles
+    assert a.shape == (1 << 18,) and a.dtype == np.float64 and not a.flags.owndata and a.flags.writeable
+    addr = a.ctypes.data
+    a[:] = 1.0
+    view = a[10:20]
+    del a
+    gc.collect()
+    b = pool.array(1 << 18)
+    assert b.ctypes.data != addr and view[0] == 1.0                 # the view still leases the first block
+    del view
+    gc.collect()
+    c = pool.array(1 << 18)
+    assert c.ctypes.data == addr                                    # handed back, reused
+    m = pool.array((4, 1 << 16))
+    assert m.shape == (4, 1 << 16) and m.ctypes.data not in (b.ctypes.data, c.ctypes.data)
+    assert pool.array(10).flags.owndata                             # small: plain numpy
+    del b, c, m
+    gc.collect()
+    assert sum(len(v) for v in pool.free.values()) == 2             # max_free bounds what is kept
+    # the engine fills pooled arrays like any other host buffer
+    w = small_cell()
+    H.engine_setup(engine, w)
+    H.engine_prepass(engine, w)
+    ref = engine.line_sum()
+    engine.result_pool = pool
+    try:
+        axis = eng.linspace_axis(w["range_min"], w["range_max"], len(ref))
+        k, t, _ = engine.layer_stream(ref[None, :], [1.0], 10.0, 296, axis)
+    finally:
+        engine.result_pool = None
+    assert np.isfinite(k).all() and np.isfinite(t).all()

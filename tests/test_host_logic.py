@@ -211,3 +211,12 @@ def test_isotope_lines_are_views_over_soa_columns(tmp_path, monkeypatch):
     iso.clearLines()
     assert len(iso) == 0 and list(iso) == []
     np.testing.assert_raises(IndexError, lambda: iso[0])
+
+
+def test_result_pool_without_a_device_returns_ordinary_arrays():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by the gpu test")
+    pool = eng.ResultPool()
+    a = pool.array((3, 1 << 18))
+    assert a.shape == (3, 1 << 18) and a.dtype == np.float64 and a.flags.owndata
