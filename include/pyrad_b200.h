@@ -102,7 +102,9 @@ int         prb_set_k2_variant(prb_engine *e, int variant, int points_per_thread
 /* windows with W-2 < wm_below use the thread-per-point kernel k2_narrow (0 = never, <0 = default 100) */
 int         prb_set_narrow_threshold(prb_engine *e, int64_t wm_below);
 
-/* ---- line list (a1): SoA float64, ascending nu0; group[i] in [0, n_groups) or NULL (all 0) - */
+/* ---- line list (a1): SoA float64, ascending nu0; group[i] in [0, n_groups) or NULL (all 0) -
+ * The list is checked before the call returns (ascending nu0, NaN included; group ids in range -> PRB_ERR_ARG and no
+ * list is set) by device kernels over the uploaded columns; the caller's arrays are read once, by the copies. */
 int prb_upload_lines(prb_engine *e, int64_t n,
                      const double *nu0, const double *s296,
                      const double *gamma_air, const double *gamma_self,
