@@ -48,3 +48,87 @@ def test_real_reference_loop_equals_oracle(tmp_path):
     idx = ph.line_index(sub["nu"], 600, .01)
     brute = sum(sum(1 for d in range(-(W - 2), W - 1) if 0 <= i + d <= n - 1) for i in idx)
     assert ph.pair_count(idx, n, W) == brute
+
+
+def test_real_reference_merge_array_random_ranges(tmp_path):
+    """mergeArray of the real reference against the oracle's restatement on random layer / table ranges: the same array
+    or the same exception (its `.index` lookups raise ValueError off the 0.01 lattice, its copy loop IndexError)."""
+    ref = rh.load_reference(str(tmp_path))
+    rng = np.random.default_rng(23)
+    same = raised = 0
+    for _ in range(250):
+        a = round(float(rng.uniform(500.0, 600.0)), int(rng.integers(0, 4)))
+        b = a + round(float(rng.uniform(0.5, 30.0)), int(rng.integers(0, 3)))
+        new_x = np.linspace(a, b, int((b - a) / .01))
+        lo = round(float(rng.uniform(a - 25.0, b + 8.0)), int(rng.integers(0, 4)))
+        hi = lo + round(float(rng.uniform(0.2, 50.0)), int(rng.integers(0, 3)))
+        old_x = np.arange(lo, hi, .01)
+        if len(new_x) < 2 or len(old_x) < 2:
+            continue
+        old_y = rng.uniform(1, 2, old_x.size)
+        try:
+            want = ref.classes.mergeArray(new_x, old_x, old_y)
+        except (ValueError, IndexError) as err:
+            with pytest.raises(type(err)):
+                ph.merge_array(new_x, old_x, old_y)
+            raised += 1
+            continue
+        got = ph.merge_array(new_x, old_x, old_y)
+        assert np.array_equal(got, want)
+        same += 1
+    assert same > 40 and raised > 5
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_real_reference_random_cells_equal_oracle(tmp_path, seed):
+    """Random small gas cells through the REAL reference (its scalar loop: a second or two each) against the oracle:
+    pressure decides the line-shape regime and the window, temperature the Q lookup, two species, base resolution
+    0.01 or (overridden) 0.002."""
+    rng = np.random.default_rng(900 + seed)
+    wd = str(tmp_path)
+    P = float(np.exp(rng.uniform(np.log(0.05), np.log(2000.0))))
+    T = int(rng.integers(190, 320))
+    base = float(rng.choice([0.01, 0.002]))
+    dynamic = bool(base == 0.01 and rng.random() < 0.5)                  # pyradClasses.py:659-662: coarser grid above 10 atm
+    if dynamic:
+        P = float(np.exp(rng.uniform(np.log(10200.0), np.log(30000.0))))
+    rmin = float(rng.choice([600.0, 1000.0, 2349.0]))
+    rmax = rmin + float(rng.uniform(2.0, 12.0)) * (base / 0.01) * (10.0 if dynamic else 1.0)
+    names = ["co2", "h2o"][: int(rng.integers(1, 3))]
+    conc = [400e-6, 0.01][: len(names)]
+    cutoff = ph.layer_cutoff(P)
+    rh.seed_workdir(wd)
+    per = []
+    for g, nme in enumerate(names):
+        sp = synth.species(nme)
+        n_ln = int(rng.integers(20, 120))
+        ln = synth.make_lines(n_ln, max(rmin - cutoff - 1.0, 0.0), rmax + cutoff + 1.0, 40 + 7 * seed + g)
+        per.append((sp, ln))
+        rh.write_params(wd, sp.global_iso, nme, sp.mol_id, 1, 0.99, sp.q296, 1, sp.molmass)
+        rh.write_q_table(wd, sp.global_iso, range(100, 400), [sp.q(t) for t in range(100, 400)])
+        rh.write_line_segments(wd, sp.global_iso, sp.mol_id, 1, ln, int(max(rmin - cutoff - 1.0, 0.0) / 100) * 100,
+                               rmax + cutoff + 102)
+    ref = rh.load_reference(wd)
+    ref.set_base_resolution(base)
+    C = ref.classes
+    with rh.quiet():
+        layer = C.Layer(25.0, T, P, rmin, rmax, dynamicResolution=dynamic)
+        mols = [layer.addMolecule(nme, concentration=c) for nme, c in zip(names, conc)]
+        sig = [np.asarray(C.getCrossSection(m[0])) for m in mols]
+        k = np.asarray(C.getAbsCoef(layer))
+        tr = np.asarray(C.getTransmittance(layer))
+    res = ph.layer_resolution(P, base, dynamic)
+    assert layer.resolution == res and (not dynamic or res > base)
+    lo, hi = ph.effective_range(rmin, rmax, cutoff)
+    k_or = 0
+    for (sp, ln), c, s_ref, m in zip(per, conc, sig, mols):
+        keep = (ln["nu"] > lo) & (ln["nu"] < hi)
+        sub = {kk: v[keep] for kk, v in ln.items()}
+        assert np.array_equal([l.wavenumber for l in m[0]], sub["nu"])
+        o = ph.cross_section(sub, T, P, c, sp.molmass, sp.q(T), sp.q296, rmin, rmax, res, cutoff)
+        if res != base:
+            o = ph.interp_to_base(o, rmin, rmax, res, base)
+        np.testing.assert_allclose(o, s_ref, rtol=1e-12, atol=0)
+        k_or = k_or + ph.abs_coef(o, c, P, T)
+    np.testing.assert_allclose(k_or, k, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(ph.transmittance(k_or, 25.0), tr, rtol=1e-12, atol=0)
