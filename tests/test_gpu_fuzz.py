@@ -239,3 +239,55 @@ def test_random_cell_from_host_buffers_matches_oracle(engine, seed):
     dt = np.abs(got[~huge] - t_ref[~huge])
     assert dt.size == 0 or dt.max() <= H.T_ABS_TOL * max(1.0, float(np.abs(t_ref[~huge]).max())), \
         (seed, float(dt.max()), int(pts[~huge][dt.argmax()]), win, variant, depth)
+
+
+@pytest.mark.parametrize("seed", range(24 * SCALE))
+def test_random_xsc_tables_through_the_mirror_match_oracle(engine, tmp_path, seed):
+    """xsc molecules through the host mirror (file on disk -> device parse -> np.interp onto the 0.01 grid when coarser ->
+    aligned placement, pyradClasses.py:466-505) for random table ranges and resolutions relative to the layer's range:
+    inside it, around it, on and off the 0.01 lattice, disjoint.  Where the reference's mergeArray is undefined (partial
+    overlap: wrong-length result; off-lattice edge: ValueError) the mirror must raise, never return a guess."""
+    from oracle import ref_harness as rh
+    from pyrad_b200 import classes as C
+    from pyrad_b200 import synth
+    rng = np.random.default_rng(6000 + seed)
+    C.set_engine(engine)
+    old = (C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere)
+    C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere = str(tmp_path), 0.01, False
+    try:
+        l_min = float(rng.choice([600.0, 800.0, 1000.5, 1234.25]))
+        l_max = l_min + float(rng.choice([20.0, 57.5, 100.0, 300.0]))
+        kind = rng.integers(0, 4)
+        if kind == 0:      # inside the layer range
+            f_min = l_min + round(float(rng.uniform(1.0, 5.0)), int(rng.integers(0, 3)))
+            f_max = l_max - round(float(rng.uniform(1.0, 5.0)), int(rng.integers(0, 3)))
+        elif kind == 1:    # around it
+            f_min = l_min - round(float(rng.uniform(0.0, 40.0)), int(rng.integers(0, 3)))
+            f_max = l_max + round(float(rng.uniform(0.0, 40.0)), int(rng.integers(0, 3)))
+        elif kind == 2:    # overlapping one end
+            f_min = l_min - round(float(rng.uniform(1.0, 30.0)), 1)
+            f_max = l_min + round(float(rng.uniform(1.0, 15.0)), 1)
+        else:              # disjoint
+            f_min = l_max + round(float(rng.uniform(1.0, 30.0)), 1)
+            f_max = f_min + round(float(rng.uniform(5.0, 40.0)), 1)
+        f_min = max(f_min, 0.5)
+        f_res = float(rng.choice([0.01, 0.01, 0.02, 0.05, 0.1]))
+        fx, fy = synth.make_xsc_table(f_min, f_max, f_res, 70 + seed)
+        fname = rh.write_xsc_file(str(tmp_path), "CFC11", 296.0, 760.0, f_min, f_max, f_res, fx, fy)
+        layer = C.Layer(10.0, 296, 1013.25, l_min, l_max)
+        try:
+            want = ph.xsc_cross_section(layer.xAxis, fx, fy, f_min, f_max, f_res)
+        except (ValueError, IndexError):
+            want = None
+        info = (seed, int(kind), l_min, l_max, f_min, f_max, f_res)
+        if want is None or len(want) != len(layer.xAxis):
+            from pyrad_b200 import _lib
+            with pytest.raises((ValueError, IndexError, _lib.EngineError)):
+                layer.addMolecule({"CFC11": fname}, concentration=1e-9)
+            return
+        xm = layer.addMolecule({"CFC11": fname}, concentration=1e-9)
+        got = C.getCrossSection(xm)
+        assert got.shape == want.shape, info
+        np.testing.assert_allclose(got, want, rtol=1e-14, atol=0, err_msg=str(info))
+    finally:
+        C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere = old
