@@ -144,3 +144,110 @@ def oracle_column_at(w, points, t_surface):
         rad = ph.transmission(t, rad, ph.planck_wavenumber(xa, T))
         total = total * t
     return rad, total
+
+
+class LayerModel:
+    """What a reference Layer holds and computes, restated with the oracle (pyradClasses.py:640-780): the state the
+    change* methods move, the line subset getData keeps (effective range as it stood when the data was last loaded --
+    changePressure does not update it, changeRange does), and k / T of the layer on the base grid."""
+
+    def __init__(self, species, lines, conc, depth, T, P, rmin, rmax, base=.01, dynamic=True):
+        self.species, self.lines, self.conc = species, lines, list(conc)
+        self.depth, self.T, self.P, self.rmin, self.rmax, self.base, self.dynamic = depth, T, P, rmin, rmax, base, dynamic
+        self.cutoff = ph.layer_cutoff(P)
+        self.eff = ph.effective_range(rmin, rmax, self.cutoff)
+        self.res = ph.layer_resolution(P, base, dynamic)
+
+    def change_temperature(self, T):
+        self.T = T
+
+    def change_pressure(self, P):
+        self.P = P
+        self.cutoff = ph.layer_cutoff(P)                 # effectiveRange* stay as they were (:746-753)
+        self.res = ph.layer_resolution(P, self.base, self.dynamic)
+
+    def change_range(self, rmin, rmax):
+        self.rmin, self.rmax = rmin, rmax
+        self.eff = ph.effective_range(rmin, rmax, self.cutoff)
+
+    def change_depth(self, depth):
+        self.depth = depth
+
+    def kept(self, g):
+        ln = self.lines[g]
+        m = (ln["nu"] > self.eff[0]) & (ln["nu"] < self.eff[1])
+        return {k: np.asarray(v)[m] for k, v in ln.items()}
+
+    def sigma(self, g):
+        sp = self.species[g]
+        o = ph.cross_section(self.kept(g), self.T, self.P, self.conc[g], sp.molmass, sp.q(self.T), sp.q296, self.rmin,
+                             self.rmax, self.res, self.cutoff)
+        return o if self.res == self.base else ph.interp_to_base(o, self.rmin, self.rmax, self.res, self.base)
+
+    def abs_coef(self):
+        return sum(ph.abs_coef(self.sigma(g), self.conc[g], self.P, self.T) for g in range(len(self.species)))
+
+    def transmittance(self):
+        return ph.transmittance(self.abs_coef(), self.depth)
+
+
+def random_layer_case(seed, max_points=2500, max_lines=60):
+    """A small random layer and a sequence of mutations for the mirror / reference state tests."""
+    from pyrad_b200 import synth
+    rng = np.random.default_rng(1234 + seed)
+    names = [str(s) for s in rng.choice(["co2", "h2o", "ch4", "o3"], size=int(rng.integers(1, 4)), replace=False)]
+    conc = [float(c) for c in rng.choice([400e-6, 0.01, 1.8e-6, 5e-6], size=len(names))]
+    P = float(np.exp(rng.uniform(np.log(0.5), np.log(1500.0))))
+    T = int(rng.integers(200, 320))
+    rmin = float(rng.choice([600.0, 1000.0, 2349.0]))
+    rmax = rmin + float(rng.integers(4, max_points // 100))
+    species = [synth.species(n) for n in names]
+    # (lines over everything a later changeRange / changePressure can reach)
+    lines = [synth.make_lines(int(rng.integers(10, max_lines)), max(rmin - 30.0, 0.0), rmin + max_points // 100 + 30.0, 11 * seed + g)
+             for g in range(len(names))]
+    steps = []
+    for _ in range(int(rng.integers(2, 5))):
+        kind = str(rng.choice(["T", "P", "depth", "ppm", "range"]))
+        if kind == "T":
+            steps.append((kind, int(rng.integers(200, 320))))
+        elif kind == "P":
+            steps.append((kind, float(np.exp(rng.uniform(np.log(0.5), np.log(1500.0))))))
+        elif kind == "depth":
+            steps.append((kind, float(np.exp(rng.uniform(np.log(1.0), np.log(1e4))))))
+        elif kind == "ppm":
+            steps.append((kind, (int(rng.integers(0, len(names))), float(np.round(np.exp(rng.uniform(np.log(1.0), np.log(2e4))), 3)))))
+        else:
+            a = rmin + float(rng.integers(-3, 4))
+            steps.append((kind, (a, a + float(rng.integers(3, max_points // 100)))))
+    return dict(names=names, conc=conc, P=P, T=T, rmin=rmin, rmax=rmax, depth=float(rng.choice([10.0, 100.0, 1000.0])),
+                species=species, lines=lines, steps=steps)
+
+
+def seed_layer_case(root, case, rh):
+    """Write the case's species files (params, Q table, 100 cm-1 line segments) into a data tree."""
+    for sp, ln in zip(case["species"], case["lines"]):
+        rh.write_params(root, sp.global_iso, sp.name, sp.mol_id, 1, 0.99, sp.q296, 1, sp.molmass)
+        rh.write_q_table(root, sp.global_iso, range(100, 501), [sp.q(t) for t in range(100, 501)])
+        rh.write_line_segments(root, sp.global_iso, sp.mol_id, 1, ln, int(max(ln["nu"].min() - 100, 0) / 100) * 100,
+                               ln["nu"].max() + 201)
+
+
+def drive_layer_case(C, case, model, check, dynamic=True):
+    """Build the layer through an object model `C` (the real reference's pyradClasses or the mirror), apply the case's
+    mutations to it and to the LayerModel in step, and call check(layer, model, tag) after the build and every step."""
+    layer = C.Layer(case["depth"], case["T"], case["P"], case["rmin"], case["rmax"], dynamicResolution=dynamic)
+    mols = [layer.addMolecule(n, concentration=c) for n, c in zip(case["names"], case["conc"])]
+    check(layer, model, "built")
+    for kind, v in case["steps"]:
+        if kind == "T":
+            layer.changeTemperature(v); model.change_temperature(v)
+        elif kind == "P":
+            layer.changePressure(v); model.change_pressure(v)
+        elif kind == "depth":
+            layer.changeDepth(v); model.change_depth(v)
+        elif kind == "ppm":
+            mols[v[0]].setPPM(v[1]); model.conc[v[0]] = v[1] * 10 ** -6
+        else:
+            layer.changeRange(*v); model.change_range(*v)
+        check(layer, model, (kind, v))
+    return layer

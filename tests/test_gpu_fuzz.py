@@ -291,3 +291,34 @@ def test_random_xsc_tables_through_the_mirror_match_oracle(engine, tmp_path, see
         np.testing.assert_allclose(got, want, rtol=1e-14, atol=0, err_msg=str(info))
     finally:
         C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere = old
+
+
+@pytest.mark.parametrize("seed", range(16 * SCALE))
+def test_random_mirror_layers_follow_the_reference_through_mutations(engine, tmp_path, seed):
+    """The host mirror on an on-disk data tree (device CSV ingestion, kept-line filter, one-pass per-isotopologue rows,
+    resident-state keys) through random changeTemperature / changePressure / changeDepth / setPPM / changeRange sequences:
+    k to 1e-5 relative and T to 1e-6 after every step against tests.helpers.LayerModel, which
+    tests/test_oracle_vs_reference.py holds the REAL reference to on the same cases."""
+    from oracle import ref_harness as rh
+    from pyrad_b200 import classes as C
+    case = H.random_layer_case(seed if seed < 8 else 100 + seed, max_points=40000 if seed >= 8 else 2500,
+                               max_lines=2000 if seed >= 8 else 60)
+    C.set_engine(engine)
+    old = (C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere)
+    C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere = str(tmp_path), 0.01, False
+    try:
+        H.seed_layer_case(str(tmp_path), case, rh)
+        model = H.LayerModel(case["species"], case["lines"], case["conc"], case["depth"], case["T"], case["P"], case["rmin"],
+                             case["rmax"])
+
+        def check(layer, model, tag):
+            k, t = C.getAbsCoef(layer), C.getTransmittance(layer)
+            assert layer.resolution == model.res and layer.distanceFromCenter == model.cutoff, tag
+            k_ref = model.abs_coef()
+            assert k.shape == k_ref.shape, tag
+            assert H.k_rel_err(k, k_ref).max() <= H.K_REL_TOL, (seed, tag)
+            assert np.abs(t - model.transmittance()).max() <= H.T_ABS_TOL, (seed, tag)
+
+        H.drive_layer_case(C, case, model, check)
+    finally:
+        C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere = old

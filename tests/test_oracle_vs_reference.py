@@ -132,3 +132,28 @@ def test_real_reference_random_cells_equal_oracle(tmp_path, seed):
         k_or = k_or + ph.abs_coef(o, c, P, T)
     np.testing.assert_allclose(k_or, k, rtol=1e-12, atol=0)
     np.testing.assert_allclose(ph.transmittance(k_or, 25.0), tr, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_real_reference_layer_mutations_equal_the_state_model(tmp_path, seed):
+    """changeTemperature / changePressure / changeDepth / setPPM / changeRange on a REAL reference layer, k and T after
+    every step against tests.helpers.LayerModel -- the model the GPU sweep then holds the host mirror to."""
+    from tests import helpers as H
+    case = H.random_layer_case(seed)
+    wd = str(tmp_path)
+    rh.seed_workdir(wd)
+    H.seed_layer_case(wd, case, rh)
+    ref = rh.load_reference(wd)
+    model = H.LayerModel(case["species"], case["lines"], case["conc"], case["depth"], case["T"], case["P"], case["rmin"],
+                         case["rmax"])
+
+    def check(layer, model, tag):
+        with rh.quiet():
+            k = np.asarray(ref.classes.getAbsCoef(layer))
+            t = np.asarray(ref.classes.getTransmittance(layer))
+        assert layer.resolution == model.res and layer.distanceFromCenter == model.cutoff, tag
+        np.testing.assert_allclose(k, model.abs_coef(), rtol=1e-12, atol=0, err_msg=str(tag))
+        np.testing.assert_allclose(t, model.transmittance(), rtol=1e-12, atol=0, err_msg=str(tag))
+
+    with rh.quiet():
+        H.drive_layer_case(ref.classes, case, model, check)
