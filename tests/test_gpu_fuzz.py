@@ -322,3 +322,47 @@ def test_random_mirror_layers_follow_the_reference_through_mutations(engine, tmp
         H.drive_layer_case(C, case, model, check)
     finally:
         C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere = old
+
+
+@pytest.mark.parametrize("seed", range(10 * SCALE))
+def test_random_mirror_columns_match_the_layer_by_layer_chain(engine, tmp_path, seed):
+    """Atmosphere.columnSpectrum (ONE prb_atmosphere call) on random stacks of mirror layers against the reference's own
+    way of doing a column -- layer.transmission(spectrum) chained bottom to top (pyradClasses.py:784-787) -- evaluated
+    with the oracle state model, and against the mirror's own chained calls."""
+    from oracle import ref_harness as rh
+    from pyrad_b200 import classes as C
+    rng = np.random.default_rng(8000 + seed)
+    case = H.random_layer_case(300 + seed, max_points=20000, max_lines=800)
+    C.set_engine(engine)
+    old = (C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere)
+    C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere = str(tmp_path), 0.01, False
+    try:
+        H.seed_layer_case(str(tmp_path), case, rh)
+        atm = C.Atmosphere("random column")
+        models = []
+        for _ in range(int(rng.integers(2, 9))):
+            T = int(rng.integers(200, 310))
+            P = float(np.exp(rng.uniform(np.log(0.2), np.log(1100.0))))
+            depth = float(np.exp(rng.uniform(np.log(1.0), np.log(3e4))))
+            conc = [c * float(rng.uniform(0.2, 2.0)) for c in case["conc"]]
+            layer = atm.addLayer(depth, T, P, case["rmin"], case["rmax"], dynamicResolution=False)
+            for n, c in zip(case["names"], conc):
+                layer.addMolecule(n, concentration=c)
+            models.append(H.LayerModel(case["species"], case["lines"], conc, depth, T, P, case["rmin"], case["rmax"],
+                                       dynamic=False))
+        t_surf = float(rng.uniform(230.0, 320.0))
+        rad, tot = atm.columnSpectrum(t_surf)
+        xa = ph.x_axis(case["rmin"], case["rmax"], .01)
+        rad_ref, tot_ref = ph.planck_wavenumber(xa, t_surf), np.ones(len(xa))
+        chain = atm[0].planck(t_surf)
+        for layer, m in zip(atm, models):
+            t = m.transmittance()
+            rad_ref = ph.transmission(t, rad_ref, ph.planck_wavenumber(xa, m.T))
+            tot_ref = tot_ref * t
+            chain = layer.transmission(chain)
+        info = (seed, len(models), [round(m.P, 2) for m in models])
+        assert np.abs(tot - tot_ref).max() <= H.T_ABS_TOL, info
+        np.testing.assert_allclose(rad, rad_ref, rtol=2e-5, atol=0, err_msg=str(info))
+        np.testing.assert_allclose(chain, rad_ref, rtol=2e-5, atol=0, err_msg=str(info))
+    finally:
+        C.DATA_ROOT, C.BASE_RESOLUTION, C.Layer.hasAtmosphere = old
