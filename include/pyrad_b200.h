@@ -212,6 +212,15 @@ int prb_xsc_resident(prb_engine *e, int32_t slot, int64_t n_out, int64_t dst0, i
 int prb_set_xsc_conc(prb_engine *e, int32_t n_layers, int32_t n_xsc, const double *conc);
 int prb_xsc_clear(prb_engine *e);
 
+/* ---- per-layer line ranges.  The reference loads every layer's lines from that layer's own effective range, strictly
+ * inside (Isotope.getData -> gatherData(effectiveRangeMin, effectiveRangeMax), pyradClasses.py:350-352,
+ * pyradUtilities.py:437-438).  When ONE uploaded list serves a column of layers with different cutoffs, a layer whose
+ * cutoff is shorter than a grid step would otherwise pick up a line the reference never loaded for it (a line within one
+ * step below rangeMin lands on grid index 0: int() truncates towards zero, pyradClasses.py:390).  With ranges set, layer l
+ * of the following prb_atmosphere / prb_gas_cell_host calls (same n_layers) uses only lines with
+ * nu_lo[l] < nu0 < nu_hi[l]; n_layers = 0 clears. */
+int prb_set_layer_line_range(prb_engine *e, int32_t n_layers, const double *nu_lo, const double *nu_hi);
+
 /* ---- atmosphere (cfg 4): L layers bottom -> top on the owned chunk, everything on the device:
  * per layer K1 + K2 (absorption-coefficient mode, FP32 row of the k matrix), then ONE K3 pass
  * folding I <- T_l*I + (1-T_l)*B(nu, t[l]) with I_0 = B(nu, t_surface).  Per-layer arrays have L

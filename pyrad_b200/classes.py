@@ -885,8 +885,11 @@ class Atmosphere(list):
                     tables.setdefault(m._xsc_key, m)
         if len(tables) > 8:
             raise ValueError("columnSpectrum carries at most eight distinct xsc tables")
-        # line source: the layer with the widest cutoff read the widest wavenumber range from the data tree
-        widest = max(layers, key=lambda l: l.distanceFromCenter)
+        # line source: the layer that read the widest wavenumber range from the data tree; every layer then takes part
+        # with the lines of its OWN effective range only, as its getData kept them (prb_set_layer_line_range)
+        widest = max(layers, key=lambda l: l.effectiveRangeMax - l.effectiveRangeMin)
+        if any(l.effectiveRangeMin < widest.effectiveRangeMin or l.effectiveRangeMax > widest.effectiveRangeMax for l in layers):
+            raise ValueError("columnSpectrum needs one layer whose loaded line range covers every other layer's")
         isos = [iso for m in widest if not m.exotic for iso in m]
         cols = {k: np.concatenate([iso._cols[k] for iso in isos]) if isos else np.zeros(0)
                 for k in ("nu", "sw", "gamma_air", "gamma_self", "elower", "n_air", "delta_air")}
@@ -914,12 +917,16 @@ class Atmosphere(list):
                                 for l in layers])
             if not isos:                                           # xsc molecules only: an empty line list
                 conc, q_t = [[0.0]] * len(layers), [[1.0]] * len(layers)
+            if any((l.effectiveRangeMin, l.effectiveRangeMax) != (widest.effectiveRangeMin, widest.effectiveRangeMax)
+                   for l in layers):
+                e.set_layer_line_range([l.effectiveRangeMin for l in layers], [l.effectiveRangeMax for l in layers])
             e.atmosphere([l.depth for l in layers], [l.T for l in layers], [l.P for l in layers], conc,
                          [iso.molmass for iso in isos] or [1.0], q_t, [iso.q296 for iso in isos] or [1.0], window,
                          surfaceTemperature, ref.rangeMax)
             return e.atmosphere_read()
         finally:
             e.xsc_clear()
+            e.set_layer_line_range()
 
 
 def getGlobalIsotope(ID, isotopeDepth):

@@ -76,6 +76,8 @@ struct LayerJob {
     void *out_dev = nullptr;
     bool valid = false;
     double xsc_w[K2_MAX_XSC] = {};   // absCoef weights of the resident xsc tables in this layer (0: none)
+    bool filter = false;             // only lines with nu_lo < nu0 < nu_hi take part (prb_set_layer_line_range)
+    double nu_lo = 0, nu_hi = 0;
 };
 
 // A resident xsc cross-section table (prb_xsc_resident): the file's samples and its placement plan.
@@ -192,6 +194,7 @@ struct prb_engine {
     int xsc_build_launches = 0;                       // resampling kernels enqueued so far (a running count)
     std::vector<double> xsc_conc;                     // [xsc_conc_layers][n_xsc]
     int xsc_conc_layers = 0;
+    std::vector<double> line_lo, line_hi;             // per-layer line ranges of the next prb_atmosphere calls (may be empty)
 
     // outputs / scratch
     DevBuf<double> out64;
@@ -811,6 +814,25 @@ static int run_prepass(prb_engine *e, const LayerJob *jobs, int n, DebugOut dbg,
                                                                             e->i_begin, dbg);
             CK(cudaGetLastError());
             if (launches) ++*launches;
+            // layers that use only the lines of their own range (prb_set_layer_line_range): blank the records of the others
+            LineRangeTable lr;
+            lr.n = 0; lr.pad = 0;
+            const size_t na = (size_t)e->n_alloc;
+            for (int k = 0; k < m; ++k) {
+                const LayerJob &j = jobs[k0 + k];
+                if (!j.filter) continue;
+                LineRangeRow &r = lr.rows[lr.n++];
+                r.recA = e->recA.p + na * j.slot;
+                r.recB = e->recB.p + na * j.slot;
+                r.recD = e->recD.p + na * j.slot;
+                r.lo = j.nu_lo; r.hi = j.nu_hi;
+                r.narrow = j.narrow; r.pad = 0;
+            }
+            if (lr.n) {
+                k1_mask_line_range<<<lr.n, 256, 0, e->stream>>>(e->nu0.p, 0, e->n_lines, lr);
+                CK(cudaGetLastError());
+                if (launches) ++*launches;
+            }
         }
     }
     return PRB_OK;
@@ -1291,6 +1313,16 @@ extern "C" int prb_xsc_clear(prb_engine *e) {
     return PRB_OK;
 }
 
+// Per-layer line ranges (the reference's gatherData(effectiveRangeMin, effectiveRangeMax) filter, strict on both sides).
+extern "C" int prb_set_layer_line_range(prb_engine *e, int32_t n_layers, const double *nu_lo, const double *nu_hi) {
+    if (!e) return fail(PRB_ERR_ARG, "null engine");
+    if (n_layers < 0 || (n_layers > 0 && (!nu_lo || !nu_hi)))
+        return fail(PRB_ERR_ARG, "prb_set_layer_line_range: bad arguments");
+    e->line_lo.assign(nu_lo, nu_lo + n_layers);
+    e->line_hi.assign(nu_hi, nu_hi + n_layers);
+    return PRB_OK;
+}
+
 extern "C" int prb_set_xsc_conc(prb_engine *e, int32_t n_layers, int32_t n_xsc, const double *conc) {
     if (!e) return fail(PRB_ERR_ARG, "null engine");
     if (n_layers < 0 || n_xsc != e->n_xsc || (n_layers > 0 && n_xsc > 0 && !conc))
@@ -1380,6 +1412,9 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
     if (e->n_xsc > 0 && e->xsc_conc_layers != n_layers)
         return fail(PRB_ERR_ARG, "prb_atmosphere: resident xsc tables need their mole fractions for these layers "
                                  "(prb_set_xsc_conc with the same n_layers), or prb_xsc_clear");
+    if (!e->line_lo.empty() && (int)e->line_lo.size() != n_layers)
+        return fail(PRB_ERR_ARG, "prb_atmosphere: the per-layer line ranges were set for another number of layers "
+                                 "(prb_set_layer_line_range with the same n_layers, or with 0 to clear)");
     const int xsc_before = e->xsc_build_launches;
     if ((rc = ensure_xsc_rows(e))) return rc;
     const int xsc_launches = e->xsc_build_launches - xsc_before;   // table resamplings this call had to enqueue
@@ -1443,6 +1478,11 @@ static int atmosphere_impl(prb_engine *e, int32_t n_layers, int32_t n_groups, co
         }
         for (int x = 0; x < e->n_xsc; ++x)                      // absCoef of an xsc molecule, same factor (:581-583)
             jobs[l].xsc_w[x] = e->xsc_conc[(size_t)l * e->n_xsc + x] * p_layer[l] / 1E4 / kBoltz / t_layer[l];
+        if (!e->line_lo.empty()) {
+            jobs[l].filter = true;
+            jobs[l].nu_lo = e->line_lo[l];
+            jobs[l].nu_hi = e->line_hi[l];
+        }
         jobs[l].gp_dev = gp_dev + (size_t)l * n_groups;
         jobs[l].st_dev = st_dev + l;
         jobs[l].out_dev = e->kmat.p + (size_t)l * e->kmat_ld;
@@ -2240,7 +2280,8 @@ extern "C" int prb_gas_cell_host(prb_engine *e, int64_t n, const double *nu0, co
     const int wave = waves_per_piece * wave1;
     const int first = std::min(n_tiles, PRB_PIPE_FIRST_WAVES * wave1);
     const int S = (first > 0 ? 1 : 0) + (n_tiles - first + wave - 1) / wave;
-    const bool pipelined = k2_classed(e) && e->fuse_single && wm >= e->narrow_wm && S >= 2 && n >= 4096;
+    // (per-layer line ranges: the separate calls apply them)
+    const bool pipelined = k2_classed(e) && e->fuse_single && wm >= e->narrow_wm && S >= 2 && n >= 4096 && e->line_lo.empty();
     if (!pipelined) {
         int rc = prb_upload_lines(e, n, nu0, s296, gamma_air, gamma_self, elower, n_air, delta_air, group, n_groups);
         if (rc) return rc;

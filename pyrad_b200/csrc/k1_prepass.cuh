@@ -429,4 +429,44 @@ k1_prepass(LinesSoA L, const int32_t *__restrict__ idx, const __grid_constant__ 
     }
 }
 
+// Per-layer line ranges (prb_set_layer_line_range): the reference loads a layer's lines from that layer's own effective
+// range, strictly inside (pyradUtilities.py:437-438); with ONE list for a column, layer l leaves out the lines with
+// nu0 <= lo or nu0 >= hi.  The list is ascending, so those are a prefix and a suffix -- found by binary search, a few
+// hundred records per layer -- and K1 itself stays as it is (the test inside its layer loop cost 2.5 % of K1).  A record
+// that is left out keeps its place in the list (K2 searches the records by position) with zero amplitudes and no Gaussian
+// near zone: it adds exactly nothing.
+struct LineRangeRow {
+    float4 *recA, *recB;
+    float *recD;
+    double lo, hi;
+    int narrow, pad;
+};
+struct LineRangeTable {
+    int n, pad;
+    LineRangeRow rows[K1_MAX_LAYERS];
+};
+__global__ void __launch_bounds__(256)
+k1_mask_line_range(const double *__restrict__ nu0, int64_t l_begin, int64_t l_end, const __grid_constant__ LineRangeTable tab) {
+    const LineRangeRow &R = tab.rows[blockIdx.x];
+    int64_t a = l_begin, b = l_end;                               // first line with nu0 > lo
+    while (a < b) { const int64_t m = (a + b) >> 1; if (nu0[m] > R.lo) b = m; else a = m + 1; }
+    const int64_t keep0 = a;
+    a = keep0; b = l_end;                                         // first line with nu0 >= hi
+    while (a < b) { const int64_t m = (a + b) >> 1; if (nu0[m] >= R.hi) b = m; else a = m + 1; }
+    const int64_t keep1 = a;
+    const int64_t n_out = (keep0 - l_begin) + (l_end - keep1);
+    for (int64_t t = threadIdx.x; t < n_out; t += blockDim.x) {
+        const int64_t l = t < keep0 - l_begin ? l_begin + t : keep1 + (t - (keep0 - l_begin));
+        const float pos = R.recA[l].x;
+        if (R.narrow) {
+            R.recA[l] = make_float4(pos, 0.f, 1.f, 0.f);
+            reinterpret_cast<float2 *>(R.recB)[l] = make_float2(-1.f, -1.f);
+        } else {
+            R.recA[l] = make_float4(pos, pos, 0.f, 0.f);
+            R.recB[l] = make_float4(1.f, 1.f, 0.f, -1.f);
+        }
+        R.recD[l] = -1.f;
+    }
+}
+
 }  // namespace prb

@@ -356,6 +356,18 @@ class Engine:
         _lib.check(self._lib.prb_xsc_resident(self._h, int(slot), int(n_out), int(dst0), int(src0), int(count),
                                               int(bool(interp)), float(ax0), float(adelta), fy.size, _dp(fx), _dp(fy)))
 
+    def set_layer_line_range(self, nu_lo=None, nu_hi=None):
+        """Per-layer open intervals (nu_lo[l], nu_hi[l]) of the line wavenumbers that take part in layer l of the following
+        atmosphere() calls -- the reference's gatherData(effectiveRangeMin, effectiveRangeMax) filter when ONE line list
+        serves a column of layers with different cutoffs; no arguments: every line takes part again."""
+        if nu_lo is None:
+            _lib.check(self._lib.prb_set_layer_line_range(self._h, 0, None, None))
+            return
+        lo, hi = _f64(nu_lo), _f64(nu_hi)
+        if lo.shape != hi.shape or lo.ndim != 1:
+            raise ValueError("set_layer_line_range: nu_lo and nu_hi must be 1-d arrays of one length")
+        _lib.check(self._lib.prb_set_layer_line_range(self._h, lo.size, _dp(lo), _dp(hi)))
+
     def set_xsc_conc(self, conc):
         """conc: (L, n_xsc) mole fractions of the resident xsc tables in every layer of the next atmosphere() call."""
         c = _f64(np.atleast_2d(conc))

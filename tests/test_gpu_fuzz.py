@@ -178,6 +178,7 @@ def test_random_line_groups_rows_match_oracle(engine, seed):
         engine.set_k2_variant(eng.K2_CLASSED, 0)
     assert rows.shape == (len(groups), hi - lo)
     pts = H.boundary_points(n, 100, seed, n_tiles=6)
+    pts = np.unique(np.concatenate([pts, [lo, hi - 1]]))
     pts = pts[(pts >= lo) & (pts < hi)]
     wm = max(win - 2, 0)
     for j, (ln, s) in enumerate(zip(groups, sp)):
@@ -236,9 +237,9 @@ def test_random_cell_from_host_buffers_matches_oracle(engine, seed):
     # a negative k: exp(-k u) overflows there, in the reference's FP64 and in the engine's FP32 result alike)
     huge = ~np.isfinite(t_ref) | (t_ref > 1e30)
     assert np.all(~np.isfinite(got[huge]) | (got[huge] > 1e30))
-    dt = np.abs(got[~huge] - t_ref[~huge])
-    assert dt.size == 0 or dt.max() <= H.T_ABS_TOL * max(1.0, float(np.abs(t_ref[~huge]).max())), \
-        (seed, float(dt.max()), int(pts[~huge][dt.argmax()]), win, variant, depth)
+    # (T > 1 where k < 0: an FP32 result, compared to FP32 resolution of exp(|k u|))
+    dt = np.abs(got[~huge] - t_ref[~huge]) / np.maximum(1.0, 10.0 * np.abs(t_ref[~huge]))
+    assert dt.size == 0 or dt.max() <= H.T_ABS_TOL, (seed, float(dt.max()), int(pts[~huge][dt.argmax()]), win, variant, depth)
 
 
 @pytest.mark.parametrize("seed", range(24 * SCALE))

@@ -664,3 +664,46 @@ def test_result_pool_hands_out_and_takes_back_page_locked_arrays(engine):
     finally:
         engine.result_pool = None
     assert np.isfinite(k).all() and np.isfinite(t).all()
+
+
+def test_layer_line_ranges_keep_a_column_on_the_references_per_layer_line_sets(engine):
+    """ONE line list for a column whose layers have different cutoffs (prb_set_layer_line_range): the reference loads
+    each layer's lines from that layer's own effective range (pyradUtilities.py:437-438), and a layer whose cutoff is
+    shorter than a grid step (W = 1: centre samples only) must not pick up the line that sits within one grid step below
+    rangeMin -- int() truncation puts it on index 0 (pyradClasses.py:390) -- although a wider layer needs it."""
+    sp = workloads.synth.species("co2")
+    rmin, rmax, res = 600.0, 610.0, 0.01
+    n = eng.grid_len(rmin, rmax, res)
+    ln = workloads.synth.make_lines(40, 598.0, 612.0, 5)
+    ln["nu"] = np.sort(np.concatenate([ln["nu"][:-1], [rmin - 0.004]]))         # 0.4 grid steps below rangeMin
+    P = [800.0, 0.5]                                                            # cutoffs 3.95 and 0.0025 cm-1: W = 395 and 1
+    T = [280, 230]
+    win = [eng.window_len(ph.layer_cutoff(p), res) for p in P]
+    assert win[1] == 1
+    conc = [[400e-6], [400e-6]]
+    depth = [1e4, 1e6]
+    engine.upload_lines(ln, 1)
+    engine.set_grid(rmin, res, n)
+    args = (depth, T, P, conc, [sp.molmass], [[sp.q(t)] for t in T], [sp.q296], win, 288.0, rmax)
+    engine.atmosphere(*args)
+    _, tr_all = engine.atmosphere_read()
+    lo = [max(rmin - ph.layer_cutoff(p), 0) for p in P]
+    hi = [rmax + ph.layer_cutoff(p) for p in P]
+    engine.set_layer_line_range(lo, hi)
+    try:
+        engine.atmosphere(*args)
+        _, tr = engine.atmosphere_read()
+        with pytest.raises(_lib.EngineError):
+            engine.atmosphere(depth[:1], T[:1], P[:1], conc[:1], [sp.molmass], [[sp.q(T[0])]], [sp.q296], win[:1], 288.0, rmax)
+    finally:
+        engine.set_layer_line_range()
+    want = np.ones(n)
+    for l in range(2):
+        m = (ln["nu"] > lo[l]) & (ln["nu"] < hi[l])
+        sub = {k: v[m] for k, v in ln.items()}
+        sig = ph.cross_section(sub, T[l], P[l], conc[l][0], sp.molmass, sp.q(T[l]), sp.q296, rmin, rmax, res, ph.layer_cutoff(P[l]))
+        want = want * ph.transmittance(ph.abs_coef(sig, conc[l][0], P[l], T[l]), depth[l])
+    assert np.abs(tr - want).max() <= H.T_ABS_TOL
+    assert np.abs(tr_all[0] - want[0]) > 1e-4 and np.abs(tr_all[1:] - want[1:]).max() <= H.T_ABS_TOL   # (the line matters)
+    engine.atmosphere(*args)                                                    # cleared: every line takes part again
+    assert np.array_equal(engine.atmosphere_read()[1], tr_all)
