@@ -162,7 +162,8 @@ k5_scatter2(const double *__restrict__ a, const double *__restrict__ b, const in
 }
 
 // The reference's dict keyed by nu: a later row with the same wavenumber replaces the earlier one.  Files are
-// ascending in nu, so duplicates are adjacent (only comment rows can sit between them).
+// ascending in nu, so duplicates are adjacent (only comment rows can sit between them); whatever this fast path misses
+// shows up as two equal neighbours among the kept rows and takes the sort path (k5_finalize flags it).
 __global__ void __launch_bounds__(256)
 k5_resolve_duplicates(const double *__restrict__ nu, const unsigned char *__restrict__ state, int64_t n_rows,
                       int32_t *__restrict__ keep) {
@@ -220,7 +221,9 @@ k5_finalize(const double *__restrict__ nu, const double *__restrict__ sw, int64_
     unsigned int bad = 0;
     if (i < n) {
         b = (unsigned long long)__double_as_longlong(fabs(sw[i]));                // |S| >= 0: bit order == value order
-        if (i + 1 < n && !(nu[i + 1] >= nu[i])) bad = 1;
+        // not STRICTLY ascending: out of order, or two kept rows of one wavenumber that k5_resolve_duplicates did not see
+        // as neighbours (rows outside the wavenumber range stood between them) -> the sort path keeps the last of the run
+        if (i + 1 < n && !(nu[i + 1] > nu[i])) bad = 1;
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
     // warp max of a 64-bit key: two 32-bit reductions (high word first)
