@@ -420,3 +420,43 @@ def test_random_hitran_csv_text_is_ingested_like_the_reference_reader(engine, se
         got = engine.download_lines()
         for k in hitran_io.LINE_COLUMNS:
             np.testing.assert_array_equal(got[k], ref[k][asc], err_msg="%s seed %d" % (k, seed))
+
+
+def make_xsc_text(seed):
+    """Random two-column xsc table text: good rows in several number formats and spacings mixed with everything
+    returnXscFileContents skips (pyradUtilities.py:680-696)."""
+    rng = np.random.default_rng(15000 + seed)
+    n = int(rng.choice([0, 1, 3, 50, 2000]))
+    fmts = [repr, lambda v: "%.6f" % v, lambda v: "%.4E" % v, lambda v: "%.12e" % v, lambda v: "%+.5E" % v]
+    rows = []
+    for j in range(n):
+        a, b = 700.0 + 0.02 * j, float(10.0 ** rng.uniform(-24, -17))
+        kind = rng.random()
+        fa, fb = fmts[int(rng.integers(0, len(fmts)))](a), fmts[int(rng.integers(0, len(fmts)))](b)
+        sep = " " * int(rng.integers(1, 8))
+        if kind < 0.75:
+            rows.append(" " * int(rng.integers(0, 3)) + fa + sep + fb + " " * int(rng.integers(0, 3)))
+        elif kind < 0.80:
+            rows.append(fa + "\t" + fb)                 # a tab is not a separator: one token, skipped
+        elif kind < 0.85:
+            rows.append(fa + sep + fb + sep + "7")      # three tokens: skipped
+        elif kind < 0.90:
+            rows.append("abc" + sep + fb)               # not a number: skipped
+        elif kind < 0.94:
+            rows.append("")                             # blank: skipped
+        elif kind < 0.97:
+            rows.append("# a comment" if j else fa + sep + fb)    # (a LEADING '#' row is dropped before the parse)
+        else:
+            rows.append(fa + sep + fb + "\t")           # trailing tab: stripped
+    eol = "\r\n" if rng.random() < 0.3 else "\n"
+    return "# header line" + eol + eol.join(rows) + (eol if rows and rng.random() < 0.5 else ""), eol
+
+
+@pytest.mark.parametrize("seed", range(12 * SCALE))
+def test_random_xsc_table_text_is_parsed_like_the_reference_reader(engine, seed):
+    text, eol = make_xsc_text(seed)
+    ref_rows = text.split("\n")[1:]                      # (the reader sees rows split at LF; a CR stays and is stripped)
+    wn_ref, xs_ref = ph.read_xsc_rows(ref_rows)
+    wn, xs = engine.parse_xsc_text(text.encode())
+    np.testing.assert_array_equal(wn, wn_ref, err_msg=str(seed))
+    np.testing.assert_array_equal(xs, xs_ref, err_msg=str(seed))
