@@ -157,3 +157,46 @@ def test_real_reference_layer_mutations_equal_the_state_model(tmp_path, seed):
 
     with rh.quiet():
         H.drive_layer_case(ref.classes, case, model, check)
+
+
+def test_real_reference_readers_on_random_text(tmp_path):
+    """readHitranOnlineFile and returnXscFileContents of the real reference on random well-formed files (the cell formats,
+    row orders, repeated wavenumbers, CRLF, range bounds of tests/test_gpu_fuzz.py's text sweeps; the reference crashes
+    on a comment row below the header and on a malformed xsc row, so those stay out here) against the oracle's readers,
+    which the device parsers are then held to on the GPU."""
+    import os
+    from tests.test_gpu_fuzz import make_csv_case
+    ref = rh.load_reference(str(tmp_path))
+    rng = np.random.default_rng(5)
+    checked = 0
+    for seed in range(60):
+        text, data_rows, lo, hi = make_csv_case(seed)
+        if not data_rows:
+            continue
+        eol = "\r\n" if text.startswith("# header\r") else "\n"
+        path = os.path.join(str(tmp_path), "seg_%d.pyr" % seed)
+        with open(path, "w", newline="") as f:
+            f.write("# header" + eol + eol.join(r.rstrip("\r") for r in data_rows) + eol)
+        want = ref.utils.readHitranOnlineFile(path, lo, hi)
+        got = ph.read_hitran_online_rows(data_rows, lo, hi)
+        assert list(want.keys()) == list(got["nu"])
+        for j, (nu, c) in enumerate(want.items()):
+            assert (c["intensity"], c["einsteinA"], c["lowerEnergy"], c["airHalfWidth"], c["selfHalfWidth"], c["tempExponent"],
+                    c["pressureShift"]) == (got["sw"][j], got["a"][j], got["elower"][j], got["gamma_air"][j],
+                                            got["gamma_self"][j], got["n_air"][j], got["delta_air"][j])
+        checked += 1
+    assert checked > 40
+    for seed in range(20):
+        n = int(rng.integers(1, 400))
+        x = 700.0 + 0.02 * np.arange(n)
+        y = 10.0 ** rng.uniform(-24, -17, n)
+        fm = [repr, lambda v: "%.6f" % v, lambda v: "%.4E" % v, lambda v: "%+.5E" % v]
+        rows = [" " * int(rng.integers(0, 3)) + fm[int(rng.integers(0, 4))](float(a)) + " " * int(rng.integers(1, 8)) +
+                fm[int(rng.integers(0, 4))](float(b)) + " " * int(rng.integers(0, 3)) for a, b in zip(x, y)]
+        path = os.path.join(str(tmp_path), "xsc_%d.txt" % seed)
+        with open(path, "w") as f:
+            f.write("# header\n" + "\n".join(rows) + "\n")
+        with rh.quiet():
+            want = ref.utils.returnXscFileContents(path)
+        wn, xs = ph.read_xsc_rows(rows)
+        assert want["wavenumber"] == list(wn) and want["intensity"] == list(xs)
