@@ -187,6 +187,15 @@ class LayerModel:
     def abs_coef(self):
         return sum(ph.abs_coef(self.sigma(g), self.conc[g], self.P, self.T) for g in range(len(self.species)))
 
+    def line_survey(self):
+        """Layer.lineSurvey (pyradClasses.py:409-428, 589-594, 691-696): made when the data is loaded, from the kept lines."""
+        n = ph.grid_len(self.rmin, self.rmax, self.base)
+        out = np.zeros(n)
+        for g in range(len(self.species)):
+            k = self.kept(g)
+            out += ph.line_survey(k["nu"], k["sw"], self.rmin, self.res, n)
+        return out
+
     def transmittance(self):
         return ph.transmittance(self.abs_coef(), self.depth)
 

@@ -318,7 +318,18 @@ def test_random_mirror_layers_follow_the_reference_through_mutations(engine, tmp
             k_ref = model.abs_coef()
             assert k.shape == k_ref.shape, tag
             assert H.k_rel_err(k, k_ref).max() <= H.K_REL_TOL, (seed, tag)
-            assert np.abs(t - model.transmittance()).max() <= H.T_ABS_TOL, (seed, tag)
+            tm = model.transmittance()
+            assert np.abs(t - tm).max() <= H.T_ABS_TOL, (seed, tag)
+            # the line survey made at load time (bit exact: S296 summed per bin in file order) and the derived spectra
+            assert np.array_equal(layer.lineSurvey, model.line_survey()), (seed, tag)
+            with np.errstate(all="ignore"):
+                tau_ref, ab_ref = ph.optical_depth(tm), ph.absorbance(tm)
+            fin = np.isfinite(tau_ref)
+            np.testing.assert_allclose(C.getOpticalDepth(layer)[fin], tau_ref[fin], rtol=2e-5, atol=1e-6, err_msg=str((seed, tag)))
+            np.testing.assert_allclose(C.getAbsorbance(layer)[fin], ab_ref[fin], rtol=2e-5, atol=1e-6, err_msg=str((seed, tag)))
+            em = C.getEmissivity(layer)
+            assert np.abs(em - ph.emissivity(tm)).max() <= H.T_ABS_TOL, (seed, tag)
+            assert C.integrateSpectrum(em, res=.01) == pytest.approx(ph.integrate_spectrum(em, res=.01), rel=1e-12)
 
         H.drive_layer_case(C, case, model, check)
     finally:

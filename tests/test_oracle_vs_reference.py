@@ -154,6 +154,18 @@ def test_real_reference_layer_mutations_equal_the_state_model(tmp_path, seed):
         assert layer.resolution == model.res and layer.distanceFromCenter == model.cutoff, tag
         np.testing.assert_allclose(k, model.abs_coef(), rtol=1e-12, atol=0, err_msg=str(tag))
         np.testing.assert_allclose(t, model.transmittance(), rtol=1e-12, atol=0, err_msg=str(tag))
+        # what the menus derive from it (pyradClasses.py:26-29, 73-88) and the line survey made at load time
+        with rh.quiet():
+            tau, ab, em = (np.asarray(f(layer)) for f in (ref.classes.getOpticalDepth, ref.classes.getAbsorbance,
+                                                           ref.classes.getEmissivity))
+            surv = np.asarray(layer.lineSurvey)
+            total = ref.classes.integrateSpectrum(em, res=.01)
+        tm = model.transmittance()
+        np.testing.assert_allclose(tau, ph.optical_depth(tm), rtol=1e-9, atol=1e-15, err_msg=str(tag))
+        np.testing.assert_allclose(ab, ph.absorbance(tm), rtol=1e-9, atol=1e-15, err_msg=str(tag))
+        np.testing.assert_allclose(em, ph.emissivity(tm), rtol=1e-9, atol=1e-15, err_msg=str(tag))
+        assert np.array_equal(surv, model.line_survey()), tag
+        assert total == pytest.approx(ph.integrate_spectrum(ph.emissivity(tm), res=.01), rel=1e-9)
 
     with rh.quiet():
         H.drive_layer_case(ref.classes, case, model, check)
