@@ -2364,7 +2364,7 @@ extern "C" int prb_gas_cell_host(prb_engine *e, int64_t n, const double *nu0, co
 
     rc = atmosphere_impl(e, 1, n_groups, &depth_cm, &t_layer, &p_layer, conc, molmass, q_t, q_296, &window_len, t_surface,
                          range_max, &pipe);
-    // what prb_upload_lines checks on the host, checked on the device after the fact (the header says so: on
+    // what prb_upload_lines checks before it returns, checked here after the fact (the header says so: on
     // PRB_ERR_ARG from this check the output buffers hold garbage)
     k0_validate_lines<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->nu0.p, group ? e->group.p : nullptr, n, n_groups,
                                                                         reinterpret_cast<unsigned int *>(e->dev_scal.p + 1));

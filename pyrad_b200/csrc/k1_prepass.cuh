@@ -54,8 +54,8 @@ __global__ void k0_line_index(const double *__restrict__ nu0, int64_t n, int64_t
     idx[l] = (int32_t)t;
 }
 
-// max |x| of a column as its bit pattern (|x| >= 0: bit order == value order), and -- for the line list checks the
-// host does in prb_upload_lines -- "ascending nu0" / "group id in range" as device flags.
+// max |x| of a column as its bit pattern (|x| >= 0: bit order == value order), and the checks of an uploaded line list --
+// "ascending nu0" / "group id in range" -- as device flags (prb_upload_lines, prb_upload_line_groups, prb_gas_cell_host).
 __global__ void __launch_bounds__(256)
 k0_absmax(const double *__restrict__ x, int64_t n, unsigned long long *__restrict__ out_bits) {
     unsigned long long b = 0;

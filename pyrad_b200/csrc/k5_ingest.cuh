@@ -212,7 +212,7 @@ k5_gather_sorted(IngestCols src, const int32_t *__restrict__ perm, const int32_t
     dst.gair[o] = src.gair[r]; dst.gself[o] = src.gself[r]; dst.delta[o] = src.delta[r]; dst.nair[o] = src.nair[r];
 }
 
-// What prb_upload_lines validates on the host, here on the device: ascending nu0 and max |S296|.
+// What prb_upload_lines checks for a caller-supplied list, for the ingested one: strictly ascending nu0 and max |S296|.
 __global__ void __launch_bounds__(256)
 k5_finalize(const double *__restrict__ nu, const double *__restrict__ sw, int64_t n, unsigned long long *__restrict__ smax_bits,
             unsigned int *__restrict__ unsorted) {
